@@ -1,0 +1,462 @@
+// b200_deflate.cu -- C ABI (include/b200_deflate.h) and host orchestration of the sm_100a kernels.
+//
+// Pipeline (compress):  K1 lz77_kernel -> K2 huffman_kernel -> K3 scan_sizes_kernel -> K4 encode_kernel,
+// per batch of chunks, all on one stream; chunk sizes are exact after K2 so K4 writes every chunk at
+// its final byte offset (no compaction pass).
+// Pipeline (inflate, single stream): find_sync (count, scan, write) -> inflate_chunks (one warp per
+// candidate chunk, optimistic layout) -> validate; a stream that does not have this library's chunk
+// structure falls back to one warp decoding it sequentially (inflate_batch_kernel with one stream).
+// There is no CPU fallback anywhere in this file.
+#include "../../include/b200_deflate.h"
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+#include "common.cuh"
+#include "corpus.cuh"
+#include "encode.cuh"
+#include "huffman.cuh"
+#include "inflate.cuh"
+#include "lz77.cuh"
+
+using namespace b200;
+
+namespace {
+
+std::atomic<uint64_t> g_launches{0};
+
+#define CK(expr)                                                                                 \
+    do {                                                                                         \
+        cudaError_t e__ = (expr);                                                                \
+        if (e__ != cudaSuccess) {                                                                \
+            if (getenv("B200_DEBUG"))                                                            \
+                fprintf(stderr, "[b200] %s failed: %s (%s:%d)\n", #expr, cudaGetErrorString(e__), \
+                        __FILE__, __LINE__);                                                     \
+            return B200_E_CUDA;                                                                  \
+        }                                                                                        \
+    } while (0)
+
+#define LAUNCHED()                       \
+    do {                                 \
+        g_launches.fetch_add(1);         \
+        CK(cudaGetLastError());          \
+    } while (0)
+
+struct Buf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t need) {
+        if (need <= cap) return B200_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = need + need / 8 + 256;
+        if (cudaMalloc(&p, want) != cudaSuccess) {
+            if (cudaMalloc(&p, need) != cudaSuccess) { cudaGetLastError(); return B200_E_NOMEM; }
+            want = need;
+        }
+        cap = want;
+        return B200_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct b200_ctx {
+    int device = 0;
+    bool attrs_set = false;
+    uint32_t batch_chunks = 4096;
+    // compress scratch
+    Buf tok, ntok, hist, codes, hdr, desc, sizes, offsets, total;
+    // inflate scratch
+    Buf counts, woffs, cand, res, result, one_off;
+    // host-API staging
+    Buf d_in, d_out;
+    cudaStream_t stream = nullptr;   // used by the host-buffer API
+    std::mutex mu;
+};
+
+namespace {
+
+int set_attrs(b200_ctx* c) {
+    if (c->attrs_set) return B200_OK;
+    CK(cudaFuncSetAttribute(lz77_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LZ_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(lz77_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LZ_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_SMEM_BYTES));
+    c->attrs_set = true;
+    return B200_OK;
+}
+
+b200_ctx* g_default = nullptr;
+std::mutex g_default_mu;
+
+int default_ctx(b200_ctx** out) {
+    std::lock_guard<std::mutex> lk(g_default_mu);
+    if (!g_default) {
+        int dev = 0;
+        if (const char* e = getenv("B200_DEVICE")) dev = atoi(e);
+        else if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return B200_E_CUDA; }
+        int rc = b200_ctx_create(dev, &g_default);
+        if (rc) return rc;
+    }
+    *out = g_default;
+    return B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200_abi_version(void) { return B200_DEFLATE_ABI_VERSION; }
+
+const char* b200_strerror(int code) {
+    switch (code) {
+        case B200_OK: return "ok";
+        case B200_E_OVERRUN: return "Reading bits beyond the alloted buffer size!";   // the reference's message
+        case B200_E_DATA: return "invalid deflate stream";
+        case B200_E_OUTPUT: return "output buffer too small";
+        case B200_E_CUDA: return "CUDA error or no sm_100 device (this library has no CPU path)";
+        case B200_E_ARG: return "bad argument";
+        case B200_E_NOMEM: return "out of memory";
+        default: return "unknown error";
+    }
+}
+
+uint64_t b200_launch_count(void) { return g_launches.load(); }
+
+int b200_ctx_create(int device, b200_ctx** ctx) {
+    if (!ctx) return B200_E_ARG;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) { cudaGetLastError(); return B200_E_CUDA; }
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return B200_E_CUDA;   // kernels are built for sm_100a only
+    CK(cudaSetDevice(device));
+    b200_ctx* c = new (std::nothrow) b200_ctx();
+    if (!c) return B200_E_NOMEM;
+    c->device = device;
+    if (const char* e = getenv("B200_BATCH_CHUNKS")) { int v = atoi(e); if (v > 0) c->batch_chunks = (uint32_t)v; }
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return B200_E_CUDA; }
+    int rc = set_attrs(c);
+    if (rc) { cudaStreamDestroy(c->stream); delete c; return rc; }
+    *ctx = c;
+    return B200_OK;
+}
+
+void b200_ctx_destroy(b200_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    Buf* all[] = {&c->tok, &c->ntok, &c->hist, &c->codes, &c->hdr, &c->desc, &c->sizes, &c->offsets, &c->total,
+                  &c->counts, &c->woffs, &c->cand, &c->res, &c->result, &c->one_off, &c->d_in, &c->d_out};
+    for (Buf* b : all) b->release();
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+size_t b200_deflate_bound(size_t n) {
+    const size_t nchunks = (n + CHUNK - 1) / CHUNK;
+    return n + 15 * nchunks + 16;
+}
+
+void b200_free(void* p) { free(p); }
+
+// ------------------------------------------------------------------------------------------------
+int b200_deflate_compress_dev(b200_ctx* c, const void* d_in, size_t n, int level, unsigned flags, void* d_out,
+                              size_t cap, uint64_t* d_out_n, size_t* h_out_n, uint64_t* d_chunk_off,
+                              void* stream_) {
+    if (!c || (!d_in && n) || !d_out || level < 0 || level > 3) return B200_E_ARG;
+    if (cap < b200_deflate_bound(n)) return B200_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream_;
+    CK(cudaSetDevice(c->device));
+    const bool final_here = !(flags & B200_F_NOT_LAST);
+    const uint64_t nchunks = (n + CHUNK - 1) / CHUNK;
+    int rc;
+    if ((rc = c->total.ensure(16))) return rc;
+    uint64_t* d_total = (uint64_t*)c->total.p;
+
+    if (nchunks == 0) {
+        // empty input: a final empty fixed block (BFINAL=1, BTYPE=01, EOB) = 03 00
+        static const uint8_t empty_final[2] = {0x03, 0x00};
+        const uint64_t tot = final_here ? 2 : 0;
+        if (final_here) CK(cudaMemcpyAsync(d_out, empty_final, 2, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_total, &tot, 8, cudaMemcpyHostToDevice, st));
+        if (d_chunk_off) CK(cudaMemcpyAsync(d_chunk_off, d_total, 8, cudaMemcpyDeviceToDevice, st));
+        if (d_out_n) CK(cudaMemcpyAsync(d_out_n, d_total, 8, cudaMemcpyDeviceToDevice, st));
+        if (h_out_n) { CK(cudaStreamSynchronize(st)); *h_out_n = (size_t)tot; }
+        return B200_OK;
+    }
+
+    const uint64_t B = nchunks < c->batch_chunks ? nchunks : c->batch_chunks;
+    if ((rc = c->tok.ensure(B * CHUNK * 4))) return rc;
+    if ((rc = c->ntok.ensure(B * NSEG * 4))) return rc;
+    if ((rc = c->hist.ensure(B * NSEG * NSYM * 4))) return rc;
+    if ((rc = c->codes.ensure(B * NSYM * 4))) return rc;
+    if ((rc = c->hdr.ensure(B * HDR_WORDS * 4))) return rc;
+    if ((rc = c->desc.ensure(B * sizeof(BlockDesc)))) return rc;
+    if ((rc = c->sizes.ensure(B * 4))) return rc;
+    uint64_t* offs = d_chunk_off;
+    if (!offs) {
+        if ((rc = c->offsets.ensure((nchunks + 1) * 8))) return rc;
+        offs = (uint64_t*)c->offsets.p;
+    }
+
+    const uint8_t* in = (const uint8_t*)d_in;
+    for (uint64_t b0 = 0; b0 < nchunks; b0 += B) {
+        const uint32_t nb = (uint32_t)((nchunks - b0 < B) ? nchunks - b0 : B);
+        const uint8_t* bin = in + b0 * CHUNK;
+        const uint64_t bn = n - b0 * CHUNK;
+        const bool last_batch = b0 + nb == nchunks;
+        if (level >= 1) {
+            if (level == 1)
+                lz77_kernel<1><<<nb, LZ_THREADS, LZ_SMEM_BYTES, st>>>(bin, bn, (uint32_t*)c->tok.p, (uint32_t*)c->ntok.p, (uint32_t*)c->hist.p);
+            else
+                lz77_kernel<0><<<nb, LZ_THREADS, LZ_SMEM_BYTES, st>>>(bin, bn, (uint32_t*)c->tok.p, (uint32_t*)c->ntok.p, (uint32_t*)c->hist.p);
+            LAUNCHED();
+        }
+        huffman_kernel<<<(nb + HUF_WARPS - 1) / HUF_WARPS, HUF_THREADS, 0, st>>>(
+            (const uint32_t*)c->hist.p, bn, nb, level, (last_batch && final_here) ? 1 : 0, (uint32_t*)c->codes.p,
+            (uint32_t*)c->hdr.p, (BlockDesc*)c->desc.p, (uint32_t*)c->sizes.p);
+        LAUNCHED();
+        scan_sizes_kernel<<<1, SCAN_THREADS, 0, st>>>((const uint32_t*)c->sizes.p, nb, b0 ? offs + b0 : nullptr,
+                                                     offs + b0, d_total);
+        LAUNCHED();
+        encode_kernel<<<nb, ENC_THREADS, ENC_SMEM_BYTES, st>>>(bin, (const uint32_t*)c->tok.p, (const uint32_t*)c->ntok.p,
+                                                              (const uint32_t*)c->codes.p, (const uint32_t*)c->hdr.p,
+                                                              (const BlockDesc*)c->desc.p, offs + b0, (uint8_t*)d_out);
+        LAUNCHED();
+    }
+    if (d_out_n) CK(cudaMemcpyAsync(d_out_n, d_total, 8, cudaMemcpyDeviceToDevice, st));
+    if (h_out_n) {
+        uint64_t tot = 0;
+        CK(cudaMemcpyAsync(&tot, d_total, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        *h_out_n = (size_t)tot;
+    }
+    return B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+int b200_inflate_batch_dev(b200_ctx* c, const void* d_in, const uint64_t* d_in_off, const uint64_t* d_in_len,
+                           void* d_out, const uint64_t* d_out_off, const uint64_t* d_out_cap, uint64_t* d_out_len,
+                           int32_t* d_status, size_t n_streams, unsigned flags, void* stream_) {
+    if (!c || !d_in_off || !d_in_len || !d_out_off || !d_out_cap || !d_out_len || !d_status) return B200_E_ARG;
+    if (n_streams == 0) return B200_OK;
+    cudaStream_t st = (cudaStream_t)stream_;
+    CK(cudaSetDevice(c->device));
+    const uint64_t grid = (n_streams + INF_WARPS - 1) / INF_WARPS;
+    if (grid > 0x7FFFFFFFull) return B200_E_ARG;
+    inflate_batch_kernel<<<(uint32_t)grid, INF_THREADS, 0, st>>>((const uint8_t*)d_in, d_in_off, d_in_len, (uint8_t*)d_out,
+                                                               d_out_off, d_out_cap, d_out_len, d_status, n_streams, flags);
+    LAUNCHED();
+    return B200_OK;
+}
+
+// Single stream.  Synchronizes `stream` internally (the candidate count and the validation verdict
+// steer the launches).
+int b200_inflate_dev(b200_ctx* c, const void* d_in, size_t n, void* d_out, size_t cap, uint64_t* d_out_n,
+                     size_t* h_out_n, size_t* h_full_n, int32_t* d_status, unsigned flags, void* stream_) {
+    if (!c || (!d_in && n) || (!d_out && cap)) return B200_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream_;
+    CK(cudaSetDevice(c->device));
+    int rc;
+    const uint8_t* in = (const uint8_t*)d_in;
+    int status = B200_OK;
+    uint64_t full = 0;
+    bool done = false;
+
+    if ((rc = c->result.ensure(64))) return rc;
+    unsigned long long* d_result = (unsigned long long*)c->result.p;   // [0] valid, [1] total, [2..] fallback scratch
+
+    if (n >= 8 && !getenv("B200_INFLATE_SEQUENTIAL")) {
+        // ---- candidates ----
+        const uint64_t nwarps = (n + SYNC_REGION - 1) / SYNC_REGION;
+        const uint64_t cand_cap = n / 64 + 1024;
+        if ((rc = c->counts.ensure(nwarps * 4))) return rc;
+        if ((rc = c->woffs.ensure((nwarps + 1) * 8))) return rc;
+        if ((rc = c->cand.ensure((cand_cap + 1) * 8))) return rc;
+        uint64_t* cand = (uint64_t*)c->cand.p;
+        const uint32_t g = (uint32_t)((nwarps * 32 + 255) / 256);
+        find_sync_kernel<false><<<g, 256, 0, st>>>(in, n, (uint32_t*)c->counts.p, nullptr, nullptr, 0);
+        LAUNCHED();
+        scan_sizes_kernel<<<1, SCAN_THREADS, 0, st>>>((const uint32_t*)c->counts.p, (uint32_t)nwarps, nullptr,
+                                                     (uint64_t*)c->woffs.p, (uint64_t*)d_result + 2);
+        LAUNCHED();
+        uint64_t nmark = 0;
+        CK(cudaMemcpyAsync(&nmark, d_result + 2, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (nmark + 1 <= cand_cap) {
+            const uint64_t ncand = nmark + 1;
+            CK(cudaMemsetAsync(cand, 0, 8, st));   // cand[0] = 0
+            if (nmark) {
+                find_sync_kernel<true><<<g, 256, 0, st>>>(in, n, nullptr, (const uint64_t*)c->woffs.p, cand + 1, nmark);
+                LAUNCHED();
+            }
+            if ((rc = c->res.ensure(ncand * sizeof(ChunkResult)))) return rc;
+            const unsigned long long init[2] = {1ull, 0ull};
+            CK(cudaMemcpyAsync(d_result, init, 16, cudaMemcpyHostToDevice, st));
+            inflate_chunks_kernel<<<(uint32_t)((ncand + INF_WARPS - 1) / INF_WARPS), INF_THREADS, 0, st>>>(
+                in, n, cand, ncand, (uint8_t*)d_out, cap, (ChunkResult*)c->res.p, flags);
+            LAUNCHED();
+            validate_chunks_kernel<<<(uint32_t)((ncand + 255) / 256), 256, 0, st>>>(cand, ncand, (const ChunkResult*)c->res.p, d_result);
+            LAUNCHED();
+            unsigned long long verdict[2] = {0, 0};
+            CK(cudaMemcpyAsync(verdict, d_result, 16, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (verdict[0] == 1) { done = true; full = verdict[1]; }
+        }
+    }
+    if (!done) {
+        // ---- sequential fallback: one warp, whole stream ----
+        if ((rc = c->one_off.ensure(64))) return rc;
+        uint64_t* d = (uint64_t*)c->one_off.p;   // [0] in_off [1] in_len [2] out_off [3] out_cap [4] out_len [5] status
+        const uint64_t h[6] = {0, (uint64_t)n, 0, (uint64_t)cap, 0, 0};
+        CK(cudaMemcpyAsync(d, h, sizeof(h), cudaMemcpyHostToDevice, st));
+        inflate_batch_kernel<<<1, INF_THREADS, 0, st>>>(in, d, d + 1, (uint8_t*)d_out, d + 2, d + 3, d + 4, (int32_t*)(d + 5), 1, flags);
+        LAUNCHED();
+        uint64_t r[2] = {0, 0};
+        CK(cudaMemcpyAsync(r, d + 4, 16, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        full = r[0];
+        status = (int)(int32_t)(r[1] & 0xFFFFFFFFu);
+    }
+    const uint64_t written = full < cap ? full : cap;
+    if (d_out_n) CK(cudaMemcpyAsync(d_out_n, &written, 8, cudaMemcpyHostToDevice, st));
+    if (d_status) { int32_t s32 = status; CK(cudaMemcpyAsync(d_status, &s32, 4, cudaMemcpyHostToDevice, st)); }
+    if (d_out_n || d_status) CK(cudaStreamSynchronize(st));
+    if (h_out_n) *h_out_n = (size_t)written;
+    if (h_full_n) *h_full_n = (size_t)full;
+    return status;
+}
+
+int b200_corpus_generate_dev(void* d_out, uint64_t seed, uint64_t first_chunk, uint64_t n_chunks, void* stream_) {
+    if (!d_out && n_chunks) return B200_E_ARG;
+    if (!n_chunks) return B200_OK;
+    cudaStream_t st = (cudaStream_t)stream_;
+    corpus_text_kernel<<<(uint32_t)((n_chunks + 63) / 64), 64, 0, st>>>((uint8_t*)d_out, seed, first_chunk, n_chunks);
+    LAUNCHED();
+    const uint64_t words = n_chunks * (CHUNK / 8);
+    corpus_flat_kernel<<<(uint32_t)((words + 255) / 256), 256, 0, st>>>((uint8_t*)d_out, seed, first_chunk, n_chunks);
+    LAUNCHED();
+    return B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host-buffer API
+int b200_deflate_compress_into(const void* in, size_t n, int level, void* out, size_t cap, size_t* out_n) {
+    if ((!in && n) || !out_n || level < 0 || level > 3) return B200_E_ARG;
+    b200_ctx* c;
+    int rc = default_ctx(&c);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    const size_t bound = b200_deflate_bound(n);
+    if ((rc = c->d_in.ensure(n + 64))) return rc;
+    if ((rc = c->d_out.ensure(bound + 64))) return rc;
+    if (n) CK(cudaMemcpyAsync(c->d_in.p, in, n, cudaMemcpyHostToDevice, c->stream));
+    size_t cn = 0;
+    rc = b200_deflate_compress_dev(c, c->d_in.p, n, level, 0, c->d_out.p, c->d_out.cap, nullptr, &cn, nullptr, c->stream);
+    if (rc) return rc;
+    *out_n = cn;
+    if (cn > cap || (!out && cn)) return B200_E_OUTPUT;
+    if (cn) CK(cudaMemcpyAsync(out, c->d_out.p, cn, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return B200_OK;
+}
+
+int b200_deflate_compress(const void* in, size_t n, int level, void** out, size_t* out_n) {
+    if (!out || !out_n) return B200_E_ARG;
+    *out = nullptr; *out_n = 0;
+    b200_ctx* c;
+    int rc = default_ctx(&c);
+    if (rc) return rc;
+    size_t cn = 0;
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        CK(cudaSetDevice(c->device));
+        const size_t bound = b200_deflate_bound(n);
+        if ((rc = c->d_in.ensure(n + 64))) return rc;
+        if ((rc = c->d_out.ensure(bound + 64))) return rc;
+        if (n) CK(cudaMemcpyAsync(c->d_in.p, in, n, cudaMemcpyHostToDevice, c->stream));
+        rc = b200_deflate_compress_dev(c, c->d_in.p, n, level, 0, c->d_out.p, c->d_out.cap, nullptr, &cn, nullptr, c->stream);
+        if (rc) return rc;
+        void* buf = malloc(cn ? cn : 1);
+        if (!buf) return B200_E_NOMEM;
+        if (cn && cudaMemcpyAsync(buf, c->d_out.p, cn, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) { free(buf); return B200_E_CUDA; }
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess) { free(buf); return B200_E_CUDA; }
+        *out = buf;
+    }
+    *out_n = cn;
+    return B200_OK;
+}
+
+static int inflate_host(const uint8_t* in, size_t n, void* out, size_t cap, void** out_alloc, size_t* out_n,
+                        size_t* full_n, unsigned flags) {
+    b200_ctx* c;
+    int rc = default_ctx(&c);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    if ((rc = c->d_in.ensure(n + 64))) return rc;
+    if (n) CK(cudaMemcpyAsync(c->d_in.p, in, n, cudaMemcpyHostToDevice, c->stream));
+    size_t dcap = cap;
+    if (out_alloc) dcap = n * 4 + 65536 > (size_t)1 << 20 ? n * 4 + 65536 : (size_t)1 << 20;   // first guess
+    size_t written = 0, full = 0;
+    for (int attempt = 0; attempt < 3; attempt++) {
+        if ((rc = c->d_out.ensure(dcap + 64))) return rc;
+        rc = b200_inflate_dev(c, c->d_in.p, n, c->d_out.p, dcap, nullptr, &written, &full, nullptr, flags, c->stream);
+        if (!out_alloc || full <= dcap) break;
+        dcap = full;                       // decoded size is now known exactly: one more pass
+    }
+    if (out_alloc) {
+        void* buf = malloc(written ? written : 1);
+        if (!buf) return B200_E_NOMEM;
+        if (written && cudaMemcpyAsync(buf, c->d_out.p, written, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) { free(buf); return B200_E_CUDA; }
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess) { free(buf); return B200_E_CUDA; }
+        *out_alloc = buf;
+    } else if (written) {
+        CK(cudaMemcpyAsync(out, c->d_out.p, written, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    if (out_n) *out_n = written;
+    if (full_n) *full_n = full;
+    return rc;
+}
+
+int b200_inflate(const void* in, size_t n, void* out, size_t cap, size_t* out_n, size_t* full_n, unsigned flags) {
+    if ((!in && n) || (!out && cap)) return B200_E_ARG;
+    return inflate_host((const uint8_t*)in, n, out, cap, nullptr, out_n, full_n, flags);
+}
+
+int b200_inflate_alloc(const void* in, size_t n, void** out, size_t* out_n, unsigned flags) {
+    if ((!in && n) || !out || !out_n) return B200_E_ARG;
+    *out = nullptr; *out_n = 0;
+    return inflate_host((const uint8_t*)in, n, nullptr, 0, out, out_n, nullptr, flags);
+}
+
+static size_t zlib_header_skip(const uint8_t* in, size_t n) {
+    // RFC 1950: CMF, FLG; FLG bit 5 = FDICT -> 4 more bytes (DICTID).  (The reference always skips 2:
+    // its FDICT test reads bit 26 of a byte value, inflate.hpp:329,355.)
+    if (n < 2) return n;
+    size_t skip = 2;
+    if (in[1] & 0x20) skip = 6;
+    return skip < n ? skip : n;
+}
+
+int b200_inflate_zlib(const void* in, size_t n, void* out, size_t cap, size_t* out_n, size_t* full_n, unsigned flags) {
+    if (!in || n < 2) return B200_E_OVERRUN;
+    const size_t s = zlib_header_skip((const uint8_t*)in, n);
+    return b200_inflate((const uint8_t*)in + s, n - s, out, cap, out_n, full_n, flags);
+}
+
+int b200_inflate_zlib_alloc(const void* in, size_t n, void** out, size_t* out_n, unsigned flags) {
+    if (!in || n < 2) { if (out) *out = nullptr; if (out_n) *out_n = 0; return B200_E_OVERRUN; }
+    const size_t s = zlib_header_skip((const uint8_t*)in, n);
+    return b200_inflate_alloc((const uint8_t*)in + s, n - s, out, out_n, flags);
+}
+
+}  // extern "C"

@@ -1,0 +1,83 @@
+// common.cuh -- shared constants, RFC 1951 symbol arithmetic and small device helpers.
+//
+// Replaces the reference's linear-scan RangeLookup tables (include/common.hpp:408-440, 508-575)
+// with closed-form arithmetic (count-leading-zeros), and its token word (deflate.hpp:11-13) with a
+// compact one-word-per-TOKEN format (the reference stores one word per input BYTE).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200 {
+
+constexpr uint32_t CHUNK = 65536;          // independent unit: one DEFLATE block, one CTA
+constexpr uint32_t NSEG = 8;               // segments per chunk: one warp each
+constexpr uint32_t SEG = CHUNK / NSEG;     // 8192 bytes parsed by one warp
+constexpr uint32_t NLIT = 288;             // literal/length alphabet slots (286 used)
+constexpr uint32_t NDIST = 32;             // distance alphabet slots (30 used)
+constexpr uint32_t NSYM = NLIT + NDIST;    // 320: [0,288) lit/len, [288,320) dist
+constexpr uint32_t HDR_WORDS = 160;        // >= 4498 bits worst-case dynamic header
+constexpr uint32_t MIN_MATCH = 3;
+constexpr uint32_t MAX_MATCH = 258;
+constexpr uint32_t MAX_DIST = 32768;
+
+// Token: literal -> byte value (dist field 0); match -> length in bits [0,9), distance in [16,32).
+__host__ __device__ __forceinline__ uint32_t tok_match(uint32_t len, uint32_t dist) { return len | (dist << 16); }
+__host__ __device__ __forceinline__ uint32_t tok_dist(uint32_t t) { return t >> 16; }
+__host__ __device__ __forceinline__ uint32_t tok_len(uint32_t t) { return t & 0x1FFu; }
+
+// Block descriptor written by the Huffman kernel, read by the encoder.
+struct BlockDesc {
+    uint32_t btype;          // 0 stored, 1 fixed, 2 dynamic
+    uint32_t hdr_bits;       // bits in hdr[] (3-bit block header + dynamic tables)
+    uint32_t total_bits;     // whole Huffman block incl. header and EOB (btype 1/2)
+    uint32_t nbytes;         // bytes this chunk occupies in the stream (incl. sync marker if any)
+    uint32_t clen;           // uncompressed bytes in this chunk
+    uint32_t last;           // 1 = carries BFINAL, no sync marker
+    uint32_t eob;            // bit-reversed EOB code | len << 16
+    uint32_t pad;
+    uint32_t seg_bitoff[NSEG];  // bit offset of each segment's first token, relative to block start
+};
+
+// ---- RFC 1951 3.2.5 symbol arithmetic ------------------------------------------------------
+
+// length 3..258 -> symbol index 0..28 (symbol = 257 + index), extra-bit count, extra value
+__device__ __forceinline__ void len_symbol(uint32_t len, uint32_t& idx, uint32_t& nextra, uint32_t& extra) {
+    uint32_t l = len - 3;
+    if (l < 8) { idx = l; nextra = 0; extra = 0; return; }
+    if (len == 258) { idx = 28; nextra = 0; extra = 0; return; }
+    uint32_t k = 31 - __clz(l);               // >= 3
+    nextra = k - 2;
+    idx = 4 * (k - 1) + ((l >> nextra) & 3);
+    extra = l & ((1u << nextra) - 1);
+}
+
+// distance 1..32768 -> symbol 0..29, extra-bit count, extra value
+__device__ __forceinline__ void dist_symbol(uint32_t dist, uint32_t& sym, uint32_t& nextra, uint32_t& extra) {
+    uint32_t d = dist - 1;
+    if (d < 4) { sym = d; nextra = 0; extra = 0; return; }
+    uint32_t k = 31 - __clz(d);               // >= 2
+    nextra = k - 1;
+    sym = 2 * k + ((d >> nextra) & 1);
+    extra = d & ((1u << nextra) - 1);
+}
+
+__host__ __device__ __forceinline__ uint32_t len_extra_bits(uint32_t idx) {   // idx = symbol - 257
+    return (idx < 8 || idx == 28) ? 0 : (idx - 4) >> 2;
+}
+__host__ __device__ __forceinline__ uint32_t dist_extra_bits(uint32_t sym) {
+    return sym < 4 ? 0 : (sym - 2) >> 1;
+}
+__host__ __device__ __forceinline__ uint32_t fixed_lit_len(uint32_t sym) {   // common.hpp:442-482
+    return sym < 144 ? 8 : sym < 256 ? 9 : sym < 280 ? 7 : 8;
+}
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ uint32_t bitrev(uint32_t code, uint32_t len) { return __brev(code) >> (32 - len); }
+
+// 4 bytes at an arbitrary byte offset of a shared-memory buffer (two aligned words + funnel shift).
+__device__ __forceinline__ uint32_t ld4_unaligned(const uint8_t* base, uint32_t off) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(base) + (off >> 2);
+    return __funnelshift_r(w[0], w[1], (off & 3) * 8);
+}
+
+}  // namespace b200

@@ -1,0 +1,177 @@
+// encode.cuh -- K3 (chunk offset scan) and K4 (token -> bit packing, written straight to its final
+// place in the output stream).
+//
+// Replaces the reference's compressBuffer (include/deflate.hpp:630-674), makeUncompressedBlock
+// (:387-399), Bitstream::addBits (:97-116, one byte-loop per code) and Bitstream::copyBitstream
+// (:143-150, a second byte-by-byte re-pack of every block to concatenate at bit granularity).
+// Here chunk sizes are exact before encoding (K2), an exclusive scan gives every chunk its final
+// byte offset, and one CTA per chunk packs the bits in shared memory -- each warp owns one segment
+// whose starting bit offset K2 computed -- then copies the bytes out with 16-byte stores.
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+// ---- K3: exclusive scan of per-chunk byte sizes (single CTA) --------------------------------------
+// offsets[i] = base + sum(sizes[0..i)), offsets[n] = base + total.  *total_out = offsets[n].
+constexpr uint32_t SCAN_THREADS = 1024;
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_sizes_kernel(const uint32_t* __restrict__ sizes, uint32_t n, const uint64_t* __restrict__ base_ptr,
+                  uint64_t* __restrict__ offsets, uint64_t* __restrict__ total_out) {
+    __shared__ uint64_t s_warp[32];
+    __shared__ uint64_t s_carry;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = base_ptr ? *base_ptr : 0;
+    __syncthreads();
+    const uint32_t per = (n + SCAN_THREADS - 1) / SCAN_THREADS;   // contiguous items per thread
+    const uint32_t lo = min(n, tid * per), hi = min(n, lo + per);
+    uint64_t sum = 0;
+    for (uint32_t i = lo; i < hi; i++) sum += sizes[i];
+    uint64_t incl = sum;
+    for (int o = 1; o < 32; o <<= 1) {
+        uint64_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if ((int)lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint64_t w = s_warp[lane];
+        uint64_t wi = w;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint64_t v = __shfl_up_sync(0xFFFFFFFFu, wi, o);
+            if ((int)lane >= o) wi += v;
+        }
+        s_warp[lane] = wi - w;   // exclusive
+    }
+    __syncthreads();
+    uint64_t run = s_carry + s_warp[warp] + (incl - sum);
+    for (uint32_t i = lo; i < hi; i++) { offsets[i] = run; run += sizes[i]; }
+    if (tid == SCAN_THREADS - 1) { offsets[n] = run; if (total_out) *total_out = run; }
+}
+
+// ---- K4: encode ------------------------------------------------------------------------------------
+constexpr uint32_t ENC_THREADS = NSEG * 32;
+constexpr uint32_t ENC_STAGE_BYTES = CHUNK + 64;       // block bytes (<= stored size) + phase + marker
+constexpr size_t ENC_SMEM_BYTES = ENC_STAGE_BYTES + NSYM * 4;
+
+// OR `nbits` (<= 48) of v into the staging bit array at absolute bit position `bit`.
+__device__ __forceinline__ void stage_bits(uint32_t* stage, uint32_t bit, uint64_t v, uint32_t nbits) {
+    (void)nbits;
+    const uint32_t w = bit >> 5, ph = bit & 31;
+    const uint64_t a = v << ph;
+    const uint32_t lo = (uint32_t)a, mid = (uint32_t)(a >> 32);
+    const uint32_t hi = ph ? (uint32_t)(v >> (64 - ph)) : 0;
+    if (lo) atomicOr(&stage[w], lo);
+    if (mid) atomicOr(&stage[w + 1], mid);
+    if (hi) atomicOr(&stage[w + 2], hi);
+}
+
+// grid = chunks, block = 256 (warp s encodes segment s).
+__global__ void __launch_bounds__(ENC_THREADS, 3)
+encode_kernel(const uint8_t* __restrict__ in, const uint32_t* __restrict__ tok, const uint32_t* __restrict__ ntok,
+              const uint32_t* __restrict__ codes, const uint32_t* __restrict__ hdr,
+              const BlockDesc* __restrict__ desc, const uint64_t* __restrict__ offsets,
+              uint8_t* __restrict__ out) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint32_t* stage = reinterpret_cast<uint32_t*>(smem);
+    uint32_t* s_codes = reinterpret_cast<uint32_t*>(smem + ENC_STAGE_BYTES);
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint64_t chunk = blockIdx.x;
+    const BlockDesc& d = desc[chunk];
+    const uint64_t dst = offsets[chunk];
+    const uint32_t phase = (uint32_t)(dst & 15);          // staging byte k <-> out[(dst & ~15) + k]
+    const uint32_t nbytes = d.nbytes;
+    const uint32_t stage_bytes = phase + nbytes;
+    const uint32_t stage_words = (stage_bytes + 3) / 4;
+
+    for (uint32_t i = tid; i < ((stage_words + 3) & ~3u) + 4; i += ENC_THREADS) stage[i] = 0;
+    if (d.btype) for (uint32_t i = tid; i < NSYM; i += ENC_THREADS) s_codes[i] = codes[chunk * NSYM + i];
+    __syncthreads();
+
+    if (d.btype == 0) {
+        // stored blocks: [hdr byte][LEN][NLEN][raw bytes], <= 65535 bytes each (deflate.hpp:387-399)
+        uint8_t* sb = smem + phase;
+        const uint8_t* src = in + chunk * CHUNK;
+        const uint32_t nblk = (d.clen + 65534u) / 65535u;
+        uint32_t done = 0, o = 0;
+        for (uint32_t b = 0; b < nblk; b++) {
+            const uint32_t bl = min(65535u, d.clen - done);
+            if (tid == 0) {
+                sb[o] = (d.last && b == nblk - 1) ? 1 : 0;
+                sb[o + 1] = bl & 0xFF; sb[o + 2] = bl >> 8;
+                sb[o + 3] = (~bl) & 0xFF; sb[o + 4] = ((~bl) >> 8) & 0xFF;
+            }
+            for (uint32_t i = tid; i < bl; i += ENC_THREADS) sb[o + 5 + i] = src[done + i];
+            o += 5 + bl; done += bl;
+        }
+        if (!d.last && tid == 0) { sb[o] = 0; sb[o + 1] = 0; sb[o + 2] = 0; sb[o + 3] = 0xFF; sb[o + 4] = 0xFF; }
+    } else {
+        const uint32_t bit0 = phase * 8;
+        // header bits
+        const uint32_t hw = (d.hdr_bits + 31) / 32;
+        for (uint32_t i = tid; i < hw; i += ENC_THREADS) {
+            uint32_t v = hdr[chunk * HDR_WORDS + i];
+            const uint32_t rem = d.hdr_bits - i * 32;
+            if (rem < 32) v &= (1u << rem) - 1u;
+            stage_bits(stage, bit0 + i * 32, v, 32);
+        }
+        // payload: warp = segment; 32 tokens per step, warp scan of bit lengths
+        const uint32_t nt = ntok[chunk * NSEG + warp];
+        const uint32_t* mytok = tok + chunk * CHUNK + warp * SEG;
+        uint32_t bit = bit0 + d.seg_bitoff[warp];
+        for (uint32_t b = 0; b < nt; b += 32) {
+            const uint32_t i = b + lane;
+            uint64_t v = 0;
+            uint32_t nb = 0;
+            if (i < nt) {
+                const uint32_t t = mytok[i];
+                const uint32_t dist = tok_dist(t);
+                if (dist == 0) {
+                    const uint32_t c = s_codes[t & 0xFFu];
+                    v = c >> 8; nb = c & 0xFFu;
+                } else {
+                    uint32_t idx, ne, ev;
+                    len_symbol(tok_len(t), idx, ne, ev);
+                    uint32_t c = s_codes[257 + idx];
+                    v = c >> 8; nb = c & 0xFFu;
+                    v |= (uint64_t)ev << nb; nb += ne;
+                    uint32_t ds;
+                    dist_symbol(dist, ds, ne, ev);
+                    c = s_codes[NLIT + ds];
+                    v |= (uint64_t)(c >> 8) << nb; nb += c & 0xFFu;
+                    v |= (uint64_t)ev << nb; nb += ne;
+                }
+            }
+            uint32_t incl = nb;
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if ((int)lane >= o) incl += u;
+            }
+            if (nb) stage_bits(stage, bit + incl - nb, v, nb);
+            bit += __shfl_sync(0xFFFFFFFFu, incl, 31);
+        }
+        if (tid == 0) {
+            const uint32_t c = s_codes[256];
+            const uint32_t eob_len = c & 0xFFu;
+            stage_bits(stage, bit0 + d.total_bits - eob_len, c >> 8, eob_len);
+            if (!d.last) {   // empty stored block: 3 zero bits, pad, 00 00 FF FF
+                const uint32_t mb = phase + (d.total_bits + 3 + 7) / 8;
+                stage_bits(stage, (mb + 2) * 8, 0xFFFFu, 16);   // atomic: may share a word with payload bits
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- copy out: aligned 16-byte vectors in the middle, bytes at the ragged ends ------------
+    uint8_t* gbase = out + (dst - phase);                 // 16-byte aligned iff out is
+    const bool valigned = ((reinterpret_cast<uintptr_t>(gbase) & 15) == 0);
+    const uint32_t vlo = valigned ? ((phase + 15) & ~15u) : stage_bytes;   // first fully-owned vector
+    const uint32_t vhi = valigned ? max(vlo, stage_bytes & ~15u) : stage_bytes;
+    for (uint32_t i = phase + tid; i < min(vlo, stage_bytes); i += ENC_THREADS) gbase[i] = smem[i];
+    for (uint32_t i = vlo + tid * 16; i < vhi; i += ENC_THREADS * 16)
+        *reinterpret_cast<uint4*>(gbase + i) = *reinterpret_cast<const uint4*>(smem + i);
+    for (uint32_t i = max(vhi, min(vlo, stage_bytes)) + tid; i < stage_bytes; i += ENC_THREADS) gbase[i] = smem[i];
+}
+
+}  // namespace b200

@@ -1,0 +1,402 @@
+// huffman.cuh -- K2: per-chunk histogram reduce, length-limited Huffman code construction,
+// dynamic-header generation, exact block-type selection and segment bit offsets.  One warp per chunk.
+//
+// Replaces (not ports) the reference's
+//   CodeMap / constructDynamicHuffmanTree          include/deflate.hpp:35-79, 402-418
+//   FlatHuffmanTree::generateCodeLengths           include/common.hpp:322-404   (priority queue + DFS)
+//   FlatHuffmanTree::construct (canonical codes)   include/common.hpp:104-145
+//   writeDynamicHuffmanTree & friends              include/deflate.hpp:419-626
+//   the "encode twice, keep the smaller" choice    include/deflate.hpp:728-746
+// Differences that matter: symbols are sorted once (warp bitonic sort) and code lengths come from the
+// in-place Moffat-Katajainen pass instead of a heap + per-symbol tree search; over-long codes are
+// repaired to an exact Kraft sum instead of throwing (common.hpp:398-402 falls back to fixed codes);
+// block sizes are computed exactly from the histograms so nothing is encoded twice; the literal
+// histogram counts emitted tokens only (the reference also counts bytes hidden under matches,
+// deflate.hpp:406-414).  The literal/length and distance code-length lists are run-length coded
+// SEPARATELY (the reference inflater cannot parse a run that crosses the two lists).
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr uint32_t HUF_WARPS = 4;
+constexpr uint32_t HUF_THREADS = HUF_WARPS * 32;
+
+__constant__ uint8_t PRECODE_ORDER[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+struct HufScratch {
+    uint32_t freq[NSYM];     // reduced histogram (lit/len incl. EOB, dist)
+    uint32_t keys[512];      // sort keys (freq << 9 | sym); reused per alphabet
+    uint32_t A[NLIT];        // Moffat-Katajainen work array
+    uint32_t next_code[16];
+    uint32_t count[16];
+    uint32_t pfreq[32];      // precode histogram
+    uint16_t rle[NSYM + 8];  // precode symbol | extra << 8
+    uint8_t lens[NSYM];      // code lengths, lit/len then dist
+    uint8_t plens[32];       // precode lengths
+    uint16_t pcodes[32];     // precode (bit-reversed) codes
+    uint32_t misc[8];
+};
+
+// Bitonic sort of N (power of two, >= 32) keys in shared memory by one warp.
+__device__ __forceinline__ void warp_sort(uint32_t* keys, uint32_t N, uint32_t lane) {
+    for (uint32_t k = 2; k <= N; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = lane; i < N; i += 32) {
+                uint32_t ixj = i ^ j;
+                if (ixj > i) {
+                    uint32_t a = keys[i], b = keys[ixj];
+                    bool up = (i & k) == 0;
+                    if ((a > b) == up) { keys[i] = b; keys[ixj] = a; }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// Code lengths for one alphabet.  freq[0..nsym) -> lens[0..nsym), every length <= maxbits, Kraft sum
+// exactly 1 (at least two codes are always emitted, as zlib does, so single-symbol alphabets stay
+// decodable by strict decoders).  Returns false only if the repair could not reach Kraft == 1.
+// Warp-cooperative: sort and scatter are parallel, the O(n) tree pass runs on lane 0.
+__device__ bool build_lengths(HufScratch* s, const uint32_t* freq, uint8_t* lens, uint32_t nsym,
+                              uint32_t maxbits, uint32_t lane) {
+    const uint32_t N = nsym > 32 ? 512 : 32;
+    for (uint32_t i = lane; i < N; i += 32) {
+        uint32_t f = i < nsym ? freq[i] : 0;
+        s->keys[i] = f ? ((f << 9) | i) : 0xFFFFFFFFu;
+    }
+    for (uint32_t i = lane; i < nsym; i += 32) lens[i] = 0;
+    __syncwarp();
+    uint32_t used = 0;
+    for (uint32_t i = lane; i < N; i += 32) used += __popc(__ballot_sync(0xFFFFFFFFu, s->keys[i] != 0xFFFFFFFFu));
+    // force at least two symbols (zlib build_tree does the same): add the lowest unused symbols, freq 1
+    if (used < 2) {
+        if (lane == 0) {
+            uint32_t have = 0xFFFFu, hk = 0;
+            for (uint32_t i = 0; i < N; i++)
+                if (s->keys[i] != 0xFFFFFFFFu) { hk = s->keys[i]; have = hk & 511u; }
+            for (uint32_t i = 0; i < N; i++) s->keys[i] = 0xFFFFFFFFu;
+            uint32_t k = 0;
+            if (have != 0xFFFFu) s->keys[k++] = hk;
+            for (uint32_t c = 0; k < 2; c++)
+                if (c != have) s->keys[k++] = (1u << 9) | c;
+        }
+        used = 2;
+        __syncwarp();
+    }
+    warp_sort(s->keys, N, lane);
+    const uint32_t n = used;
+    bool ok = true;
+    if (lane == 0) {
+        uint32_t* A = s->A;
+        for (uint32_t i = 0; i < n; i++) A[i] = s->keys[i] >> 9;
+        if (n == 2) {
+            A[0] = A[1] = 1;
+        } else {
+            // Moffat & Katajainen, "In-place calculation of minimum-redundancy codes" (1995)
+            A[0] += A[1];
+            uint32_t root = 0, leaf = 2;
+            for (uint32_t next = 1; next < n - 1; next++) {
+                if (leaf >= n || A[root] < A[leaf]) { A[next] = A[root]; A[root++] = next; }
+                else A[next] = A[leaf++];
+                if (leaf >= n || (root < next && A[root] < A[leaf])) { A[next] += A[root]; A[root++] = next; }
+                else A[next] += A[leaf++];
+            }
+            A[n - 2] = 0;
+            for (int next = (int)n - 3; next >= 0; next--) A[next] = A[A[next]] + 1;
+            int avbl = 1, usedn = 0, dpth = 0, rt = (int)n - 2, nx = (int)n - 1;
+            while (avbl > 0) {
+                while (rt >= 0 && (int)A[rt] == dpth) { usedn++; rt--; }
+                while (avbl > usedn) { A[nx--] = dpth; avbl--; }
+                avbl = 2 * usedn; dpth++; usedn = 0;
+            }
+        }
+        // A[i] = length of the i-th least frequent symbol (non-increasing in i).  Limit to maxbits.
+        if (A[0] > maxbits) {
+            uint32_t* cnt = s->count;
+            for (uint32_t l = 0; l < 16; l++) cnt[l] = 0;
+            for (uint32_t i = 0; i < n; i++) cnt[min(A[i], maxbits)]++;
+            const uint32_t cap = 1u << maxbits;
+            uint32_t K = 0;
+            for (uint32_t l = 1; l <= maxbits; l++) K += cnt[l] << (maxbits - l);
+            while (K > cap) {   // demote the deepest code that is still above the limit
+                uint32_t l = maxbits - 1;
+                while (l > 0 && cnt[l] == 0) l--;
+                if (l == 0) break;
+                cnt[l]--; cnt[l + 1]++;
+                K -= 1u << (maxbits - l - 1);
+            }
+            for (uint32_t l = maxbits; l >= 2 && K < cap; l--) {   // refill exactly, cheapest moves first
+                const uint32_t unit = 1u << (maxbits - l);
+                while (cnt[l] > 0 && cap - K >= unit) { cnt[l]--; cnt[l - 1]++; K += unit; }
+            }
+            ok = (K == cap);
+            uint32_t i = 0;
+            for (uint32_t l = maxbits; l >= 1; l--)
+                for (uint32_t c = 0; c < cnt[l]; c++) A[i++] = l;
+        }
+    }
+    __syncwarp();
+    ok = __shfl_sync(0xFFFFFFFFu, (int)ok, 0);
+    for (uint32_t i = lane; i < n; i += 32) lens[s->keys[i] & 511u] = (uint8_t)s->A[i];
+    __syncwarp();
+    return ok;
+}
+
+// Canonical codes (RFC 1951 3.2.2) for lens[0..nsym): out[i] = len | bit-reversed code << 8.
+__device__ void assign_codes(HufScratch* s, const uint8_t* lens, uint32_t nsym, uint32_t* out, uint32_t lane) {
+    if (lane < 16) s->count[lane] = 0;
+    __syncwarp();
+    for (uint32_t i = lane; i < nsym; i += 32)
+        if (lens[i]) atomicAdd(&s->count[lens[i]], 1u);
+    __syncwarp();
+    if (lane == 0) {
+        uint32_t code = 0;
+        s->next_code[0] = 0;
+        for (uint32_t l = 1; l <= 15; l++) {
+            code = (code + (l > 1 ? s->count[l - 1] : 0)) << 1;
+            s->next_code[l] = code;
+        }
+    }
+    __syncwarp();
+    for (uint32_t b = 0; b < nsym; b += 32) {
+        const uint32_t i = b + lane;
+        const uint32_t l = i < nsym ? lens[i] : 0;
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, l);
+        const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+        uint32_t code = l ? s->next_code[l] + rank : 0;
+        __syncwarp();
+        if (l && rank == 0) s->next_code[l] += __popc(peers);
+        __syncwarp();
+        if (i < nsym) out[i] = l ? (l | (bitrev(code, l) << 8)) : 0;
+    }
+}
+
+struct BitSink {   // lane-0 serial bit writer into a global word array
+    uint32_t* dst;
+    uint64_t acc;
+    uint32_t nacc, nwords;
+    __device__ void put(uint32_t v, uint32_t nb) {
+        acc |= (uint64_t)v << nacc;
+        nacc += nb;
+        if (nacc >= 32) { dst[nwords++] = (uint32_t)acc; acc >>= 32; nacc -= 32; }
+    }
+    __device__ void flush() { if (nacc) { dst[nwords++] = (uint32_t)acc; acc = 0; nacc = 0; } }
+};
+
+// Run-length code one code-length list (RFC 1951 3.2.7) into s->rle[pos..]; returns new pos.
+__device__ uint32_t rle_lengths(HufScratch* s, const uint8_t* lens, uint32_t n, uint32_t pos) {
+    uint32_t i = 0;
+    while (i < n) {
+        const uint32_t v = lens[i];
+        uint32_t run = 1;
+        while (i + run < n && lens[i + run] == v) run++;
+        i += run;
+        if (v == 0) {
+            while (run >= 11) { uint32_t r = min(run, 138u); s->rle[pos++] = (uint16_t)(18 | ((r - 11) << 8)); run -= r; }
+            if (run >= 3) { s->rle[pos++] = (uint16_t)(17 | ((run - 3) << 8)); run = 0; }
+            while (run--) s->rle[pos++] = 0;
+        } else {
+            s->rle[pos++] = (uint16_t)v; run--;
+            while (run >= 3) { uint32_t r = min(run, 6u); s->rle[pos++] = (uint16_t)(16 | ((r - 3) << 8)); run -= r; }
+            while (run--) s->rle[pos++] = (uint16_t)v;
+        }
+    }
+    return pos;
+}
+
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    return v;
+}
+
+// grid = ceil(nchunks / HUF_WARPS), block = 128.
+//   hist   : [nchunks][NSEG][NSYM] from K1
+//   codes  : [nchunks][NSYM]   len | reversed code << 8   (what the encoder indexes by symbol)
+//   hdr    : [nchunks][HDR_WORDS] block header bits (BFINAL/BTYPE + dynamic tables)
+//   desc   : [nchunks] BlockDesc;  sizes: [nchunks] bytes per chunk (input of the offset scan)
+// level 0 forces stored blocks.  last_is_final: the final chunk of this buffer carries BFINAL.
+__global__ void __launch_bounds__(HUF_THREADS)
+huffman_kernel(const uint32_t* __restrict__ hist, uint64_t n, uint32_t nchunks, int level, int last_is_final,
+               uint32_t* __restrict__ codes, uint32_t* __restrict__ hdr, BlockDesc* __restrict__ desc,
+               uint32_t* __restrict__ sizes) {
+    __shared__ HufScratch scratch[HUF_WARPS];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t chunk = blockIdx.x * HUF_WARPS + warp;
+    if (chunk >= nchunks) return;
+    HufScratch* s = &scratch[warp];
+    const uint32_t clen = (uint32_t)min((uint64_t)CHUNK, n - (uint64_t)chunk * CHUNK);
+    const bool last = last_is_final && chunk == nchunks - 1;
+    const uint32_t* h = hist + (size_t)chunk * NSEG * NSYM;
+    uint32_t* mycodes = codes + (size_t)chunk * NSYM;
+    uint32_t* myhdr = hdr + (size_t)chunk * HDR_WORDS;
+    BlockDesc* d = desc + chunk;
+
+    const uint32_t nstored = (clen + 65534u) / 65535u;
+    const uint32_t stored_bytes = clen + 5u * nstored + (last ? 0u : 5u);
+
+    if (level == 0) {
+        if (lane == 0) {
+            d->btype = 0; d->hdr_bits = 0; d->total_bits = 0; d->nbytes = stored_bytes; d->clen = clen;
+            d->last = last; d->eob = 0;
+            sizes[chunk] = stored_bytes;
+        }
+        return;
+    }
+
+    // ---- reduce the per-segment histograms ------------------------------------------------
+    for (uint32_t i = lane; i < NSYM; i += 32) {
+        uint32_t f = 0;
+        for (uint32_t sgm = 0; sgm < NSEG; sgm++) f += h[sgm * NSYM + i];
+        s->freq[i] = f + (i == 256 ? 1u : 0u);
+    }
+    __syncwarp();
+
+    // ---- code lengths + canonical codes ----------------------------------------------------
+    bool ok = build_lengths(s, s->freq, s->lens, 286, 15, lane);
+    ok &= build_lengths(s, s->freq + NLIT, s->lens + NLIT, 30, 15, lane);
+    if (lane < 2) s->lens[286 + lane] = 0;
+    if (lane < 2) s->lens[NLIT + 30 + lane] = 0;
+    __syncwarp();
+
+    // ---- dynamic header: HLIT/HDIST, RLE of both lists (separately), precode ---------------
+    uint32_t hlit = 286, hdist = 30;
+    if (lane == 0) {
+        while (hlit > 257 && s->lens[hlit - 1] == 0) hlit--;
+        while (hdist > 1 && s->lens[NLIT + hdist - 1] == 0) hdist--;
+        uint32_t nr = rle_lengths(s, s->lens, hlit, 0);
+        nr = rle_lengths(s, s->lens + NLIT, hdist, nr);
+        for (uint32_t i = 0; i < 32; i++) s->pfreq[i] = 0;
+        for (uint32_t i = 0; i < nr; i++) s->pfreq[s->rle[i] & 31u]++;
+        s->misc[0] = hlit; s->misc[1] = hdist; s->misc[2] = nr;
+    }
+    __syncwarp();
+    hlit = s->misc[0]; hdist = s->misc[1];
+    const uint32_t nr = s->misc[2];
+    ok &= build_lengths(s, s->pfreq, s->plens, 19, 7, lane);
+    {   // precode canonical codes: 19 symbols, one batch
+        uint32_t tmp = 0;
+        if (lane < 16) s->count[lane] = 0;
+        __syncwarp();
+        const uint32_t l = lane < 19 ? s->plens[lane] : 0;
+        if (l) atomicAdd(&s->count[l], 1u);
+        __syncwarp();
+        if (lane == 0) {
+            uint32_t code = 0;
+            for (uint32_t b = 1; b <= 7; b++) { code = (code + (b > 1 ? s->count[b - 1] : 0)) << 1; s->next_code[b] = code; }
+        }
+        __syncwarp();
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, l);
+        const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+        if (l) tmp = bitrev(s->next_code[l] + rank, l);
+        if (lane < 32) s->pcodes[lane] = (uint16_t)tmp;
+        __syncwarp();
+    }
+
+    // ---- exact sizes -----------------------------------------------------------------------
+    uint32_t dyn = 0, fix = 0;
+    for (uint32_t i = lane; i < NSYM; i += 32) {
+        const uint32_t f = s->freq[i];
+        if (!f) continue;
+        if (i < NLIT) {
+            const uint32_t ex = i > 256 ? len_extra_bits(i - 257) : 0;
+            dyn += f * (s->lens[i] + ex);
+            fix += f * (fixed_lit_len(i) + ex);
+        } else {
+            const uint32_t ex = dist_extra_bits(i - NLIT);
+            dyn += f * (s->lens[i] + ex);
+            fix += f * (5 + ex);
+        }
+    }
+    dyn = warp_sum(dyn);
+    fix = warp_sum(fix);
+    const uint8_t* ORDER = PRECODE_ORDER;
+    uint32_t hclen = 19;
+    while (hclen > 4 && s->plens[ORDER[hclen - 1]] == 0) hclen--;
+    uint32_t hdr_bits = 3 + 5 + 5 + 4 + 3 * hclen;
+    {
+        uint32_t hb = 0;
+        for (uint32_t i = lane; i < nr; i += 32) {
+            const uint32_t r = s->rle[i], sym = r & 31u;
+            hb += s->plens[sym] + (sym == 16 ? 2u : sym == 17 ? 3u : sym == 18 ? 7u : 0u);
+        }
+        hdr_bits += warp_sum(hb);
+    }
+    const uint32_t dyn_bits = ok ? hdr_bits + dyn : 0xFFFFFFFFu;
+    const uint32_t fix_bits = 3 + fix;
+    const uint32_t use_dyn = dyn_bits < fix_bits;
+    const uint32_t bits = use_dyn ? dyn_bits : fix_bits;
+    const uint32_t huff_bytes = last ? (bits + 7) / 8 : (bits + 3 + 7) / 8 + 4;
+    const uint32_t btype = huff_bytes < stored_bytes ? (use_dyn ? 2u : 1u) : 0u;
+
+    // ---- emit codes, header, descriptor ---------------------------------------------------
+    if (btype == 2) {
+        assign_codes(s, s->lens, NLIT, mycodes, lane);
+        assign_codes(s, s->lens + NLIT, NDIST, mycodes + NLIT, lane);
+    } else if (btype == 1) {
+        for (uint32_t i = lane; i < NSYM; i += 32) {
+            uint32_t v;
+            if (i < NLIT) {   // common.hpp:442-482 (RFC 1951 3.2.6)
+                uint32_t l = fixed_lit_len(i);
+                uint32_t c = i < 144 ? 0x30 + i : i < 256 ? 0x190 + (i - 144) : i < 280 ? (i - 256) : 0xC0 + (i - 280);
+                v = l | (bitrev(c, l) << 8);
+            } else {
+                v = 5u | (bitrev(i - NLIT, 5) << 8);
+            }
+            mycodes[i] = v;
+        }
+    }
+    __syncwarp();
+    const uint32_t hb_final = btype == 2 ? hdr_bits : btype == 1 ? 3u : 0u;
+    if (lane == 0) {
+        if (btype == 2) {
+            BitSink bs{myhdr, 0, 0, 0};
+            bs.put((last ? 1u : 0u) | (2u << 1), 3);
+            bs.put(hlit - 257, 5);
+            bs.put(hdist - 1, 5);
+            bs.put(hclen - 4, 4);
+            for (uint32_t i = 0; i < hclen; i++) bs.put(s->plens[ORDER[i]], 3);
+            for (uint32_t i = 0; i < nr; i++) {
+                const uint32_t r = s->rle[i], sym = r & 31u;
+                bs.put(s->pcodes[sym], s->plens[sym]);
+                if (sym == 16) bs.put(r >> 8, 2);
+                else if (sym == 17) bs.put(r >> 8, 3);
+                else if (sym == 18) bs.put(r >> 8, 7);
+            }
+            bs.flush();
+        } else if (btype == 1) {
+            myhdr[0] = (last ? 1u : 0u) | (1u << 1);
+        }
+    }
+    // segment bit offsets (exclusive scan of per-segment payload bits)
+    uint32_t off = hb_final;
+    for (uint32_t sgm = 0; sgm < NSEG; sgm++) {
+        uint32_t sb = 0;
+        if (btype) {
+            for (uint32_t i = lane; i < NSYM; i += 32) {
+                const uint32_t f = h[sgm * NSYM + i];
+                if (!f) continue;
+                const uint32_t cl = btype == 2 ? s->lens[i] : (i < NLIT ? fixed_lit_len(i) : 5u);
+                const uint32_t ex = i < NLIT ? (i > 256 ? len_extra_bits(i - 257) : 0u) : dist_extra_bits(i - NLIT);
+                sb += f * (cl + ex);
+            }
+            sb = warp_sum(sb);
+        }
+        if (lane == 0) d->seg_bitoff[sgm] = off;
+        off += sb;
+    }
+    if (lane == 0) {
+        const uint32_t eob_len = btype == 2 ? s->lens[256] : 7u;
+        d->btype = btype;
+        d->hdr_bits = hb_final;
+        d->total_bits = btype ? off + eob_len : 0;
+        d->nbytes = btype ? huff_bytes : stored_bytes;
+        d->clen = clen;
+        d->last = last;
+        d->eob = btype ? mycodes[256] : 0;   // written above by this warp (same-thread visibility not needed: recomputed by encoder)
+        sizes[chunk] = d->nbytes;
+    }
+}
+
+}  // namespace b200

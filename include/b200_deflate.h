@@ -1,0 +1,139 @@
+/* b200_deflate.h -- C ABI of libb200deflate.so: the drop-in boundary for the DEFLATE / INFLATE hot
+ * path of HyperBitGore/deflate.hpp, executed by hand-written sm_100a CUDA kernels.
+ *
+ * Plain pointers and sizes only; no C++ or torch types.  Every entry point names the reference
+ * interface it replaces (file:line into the reference's include/).  The header-only C++17 drop-ins
+ * include/deflate.hpp and include/inflate.hpp are thin wrappers over this file; INTEGRATION.md shows
+ * the binding a maintainer of the reference would add.
+ *
+ * There is NO CPU fallback: every compute entry point returns B200_E_CUDA when no sm_100 device or
+ * driver is usable.
+ *
+ * Stream format produced by the compressor (one valid RFC 1951 raw stream):
+ *   input is cut into independent 64 KiB chunks; each chunk is ONE block (dynamic, fixed or stored,
+ *   whichever is smallest by exact bit count) that starts byte-aligned; every chunk except the last
+ *   is followed by an empty non-final stored block (pad bits, 00 00 FF FF) so that the next chunk is
+ *   byte-aligned again; the last chunk's block carries BFINAL.  No match crosses a chunk boundary.
+ */
+#ifndef B200_DEFLATE_H
+#define B200_DEFLATE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_DEFLATE_ABI_VERSION 1
+
+/* Return codes (0 = success). */
+#define B200_OK 0
+#define B200_E_OVERRUN 1  /* inflate: ran past the input  (reference: std::runtime_error("Reading bits \
+                             beyond the alloted buffer size!"), inflate.hpp:82,98,107) */
+#define B200_E_DATA 2     /* inflate: invalid stream (bad code lengths, bad symbol, bad block) */
+#define B200_E_OUTPUT 3   /* output buffer too small (only where truncation is not the contract) */
+#define B200_E_CUDA 4     /* CUDA runtime / driver error, or no sm_100 device: there is no CPU path */
+#define B200_E_ARG 5      /* bad argument */
+#define B200_E_NOMEM 6    /* host or device allocation failed */
+
+/* Compression levels: the reference's `int compression_level` (deflate.hpp:675-680). */
+#define B200_LEVEL_STORED 0  /* stored blocks only */
+#define B200_LEVEL_HUFFMAN 1 /* Huffman only, no matching */
+#define B200_LEVEL_FAST 2    /* greedy hash matcher      (reference "fast",   getMatches     :310) */
+#define B200_LEVEL_BETTER 3  /* lazy + deeper matcher    (reference "better", getMatchesSlow :268) */
+
+/* Flags for the compressor. */
+#define B200_F_NOT_LAST 1u /* this buffer is a shard that is NOT the end of the stream: its last chunk \
+                              is closed with the byte-aligning empty stored block instead of BFINAL */
+/* Flags for the inflater. */
+#define B200_F_STRICT 1u   /* reject what the reference silently accepts: distance beyond the output \
+                              produced so far, NLEN != ~LEN, BTYPE 3 (default: behave like the reference) */
+
+#define B200_CHUNK_BYTES 65536u
+
+typedef struct b200_ctx b200_ctx; /* per-device workspace; use one ctx from one thread at a time */
+
+int b200_abi_version(void);
+const char* b200_strerror(int code);
+/* Number of kernel launches issued by this library since load (bench.py reports it as gpu_launches). */
+uint64_t b200_launch_count(void);
+
+/* ---- context ------------------------------------------------------------------------------- */
+int b200_ctx_create(int device, b200_ctx** ctx);
+void b200_ctx_destroy(b200_ctx* ctx);
+
+/* Worst-case compressed size for n input bytes (all chunks stored + framing). */
+size_t b200_deflate_bound(size_t n);
+
+/* ---- host-buffer API: what the header-only drop-ins call ------------------------------------ */
+
+/* Replaces deflate::compress(char* data, size_t data_size, int compression_level) -> vector
+ * (reference include/deflate.hpp:779) and the vector overload (:798).
+ * *out is malloc'ed by the library; release with b200_free().  Never fails on valid arguments other
+ * than for CUDA / memory errors (the reference compressor never throws to its caller either). */
+int b200_deflate_compress(const void* in, size_t n, int level, void** out, size_t* out_n);
+
+/* Same, into a caller buffer of `cap` bytes (B200_E_OUTPUT if cap < compressed size; cap >=
+ * b200_deflate_bound(n) always suffices).  Pinned host memory is streamed without staging. */
+int b200_deflate_compress_into(const void* in, size_t n, int level, void* out, size_t cap, size_t* out_n);
+
+/* Replaces inflate::decompress(void* in, size_t in_size, void* out, size_t out_size) -> size_t
+ * (reference include/inflate.hpp:338): decodes the raw RFC 1951 stream, writes at most `cap` bytes
+ * and, like the reference (:345), silently truncates: *out_n = min(decoded size, cap).
+ * *full_n (may be NULL) receives the full decoded size. */
+int b200_inflate(const void* in, size_t n, void* out, size_t cap, size_t* out_n, size_t* full_n,
+                 unsigned flags);
+
+/* Replaces inflate::decompress(void* in, size_t in_size) -> vector (inflate.hpp:363) and the vector
+ * overload (:376).  *out is malloc'ed; release with b200_free(). */
+int b200_inflate_alloc(const void* in, size_t n, void** out, size_t* out_n, unsigned flags);
+
+/* Replaces inflate::decompressZlib (inflate.hpp:326,352): skips the 2-byte zlib header (and, unlike
+ * the reference whose FDICT test at :329/:355 can never fire, the 4-byte DICTID when FDICT is set);
+ * the Adler-32 trailer is ignored like the reference does. */
+int b200_inflate_zlib(const void* in, size_t n, void* out, size_t cap, size_t* out_n, size_t* full_n,
+                      unsigned flags);
+int b200_inflate_zlib_alloc(const void* in, size_t n, void** out, size_t* out_n, unsigned flags);
+
+void b200_free(void* p);
+
+/* ---- device-resident API (benchmarks, pipelines, multi-GPU shards) -------------------------- */
+/* All pointers prefixed d_ are device pointers on ctx's device; `stream` is a cudaStream_t passed as
+ * void* (NULL = default stream).  Work is enqueued on `stream`.  If h_out_n is non-NULL the call
+ * synchronizes the stream and stores the byte count there; d_out_n (may be NULL) receives it on the
+ * device without a sync. */
+
+/* Compress d_in[0..n) into d_out[0..cap).  cap must be >= b200_deflate_bound(n).
+ * d_chunk_off (may be NULL): n_chunks+1 uint64 byte offsets of each chunk's compressed bytes inside
+ * d_out (an optional index for chunk-parallel inflate; the stream is self-describing without it). */
+int b200_deflate_compress_dev(b200_ctx* ctx, const void* d_in, size_t n, int level, unsigned flags,
+                              void* d_out, size_t cap, uint64_t* d_out_n, size_t* h_out_n,
+                              uint64_t* d_chunk_off, void* stream);
+
+/* Inflate one raw stream.  Streams produced by this library (or any stream whose blocks are joined
+ * by byte-aligning empty stored blocks and whose chunks do not reference earlier chunks) are decoded
+ * chunk-parallel, one warp per chunk; anything else is decoded by a single warp.  Writes at most cap
+ * bytes; *h_out_n / *d_out_n = min(decoded, cap); status (B200_*) is the return value when h_out_n is
+ * given, else it is left in d_status (int32, may be NULL). */
+int b200_inflate_dev(b200_ctx* ctx, const void* d_in, size_t n, void* d_out, size_t cap,
+                     uint64_t* d_out_n, size_t* h_out_n, size_t* h_full_n, int32_t* d_status,
+                     unsigned flags, void* stream);
+
+/* Batch inflate: n_streams independent raw streams, one warp each (BASELINE config 4).
+ * Stream i is d_in + d_in_off[i], d_in_len[i] bytes; output goes to d_out + d_out_off[i], at most
+ * d_out_cap[i] bytes (truncating); d_out_len[i] = full decoded size; d_status[i] = B200_* code. */
+int b200_inflate_batch_dev(b200_ctx* ctx, const void* d_in, const uint64_t* d_in_off,
+                           const uint64_t* d_in_len, void* d_out, const uint64_t* d_out_off,
+                           const uint64_t* d_out_cap, uint64_t* d_out_len, int32_t* d_status,
+                           size_t n_streams, unsigned flags, void* stream);
+
+/* Synthetic corpus of BASELINE config 3/5 (definition: oracle/corpus_oracle.c):
+ * chunks first_chunk .. first_chunk+n_chunks-1 of 64 KiB each, written to d_out. */
+int b200_corpus_generate_dev(void* d_out, uint64_t seed, uint64_t first_chunk, uint64_t n_chunks,
+                             void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_DEFLATE_H */
