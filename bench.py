@@ -1,0 +1,419 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the DEFLATE hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--mib M] [--level 2|3]
+
+Workload (config.workload): BASELINE.json configs[2], the 1 GiB synthetic mixed-entropy corpus
+(text-like + image-like + random, 64 KiB chunks, definition in oracle/corpus_oracle.c / DESIGN.md),
+fast level, generated on the device.  One step = one pass of the whole compress path over the corpus
+(K1 lz77 -> K2 huffman -> K3 scan -> K4 encode, per batch).  With N > 1 (torchrun, one rank per GPU)
+every rank owns its own 1 GiB shard of one N GiB corpus (weak scaling), compresses it with
+B200_F_NOT_LAST on all but the last rank, and the compressed bytes are gathered to rank 0 over NCCL
+inside the timed region -- the only exchange step this path has.
+
+Printed JSON (one line, rank 0):
+  value      compress throughput, input GB/s, inputs resident in HBM, CUDA events, max over ranks
+  decompress output GB/s of b200_inflate_dev on the stream just produced (same timing rules)
+  e2e        the same compress metric through the host-buffer C-ABI call (b200_deflate_compress_into)
+             with pinned HOST buffers: H2D + kernels + D2H inside the timed region
+  roofline   dominant kernel vs measured HBM peak (MEASURED_PEAKS.json), algorithmic bytes = (1 + r)
+             bytes per input byte; per-kernel device time from CUDA events recorded by
+             the library around every launch on its stream
+  cpu_baseline  the UNMODIFIED reference (oracle/_ref) on the host cores over a bounded sample
+`--impl reference` times only that CPU arm and prints the same line shape with "impl": "reference".
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 20261018
+CHUNK = 65536
+METRIC = "compress_input_GBps_fast_level"
+UNIT = "GB/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mib", type=int, default=1024, help="corpus MiB per GPU")
+    ap.add_argument("--level", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--ref-budget-s", type=float, default=90.0, help="CPU seconds (wall) the reference arm may use")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: oracle/_ref (the unmodified reference) -- the only place bench.py
+# touches oracle/, and only as the baseline being reported, never on the product path
+class RefLib:
+    def __init__(self):
+        p = os.path.join(ROOT, "oracle", "_ref", "libref_deflate.so")
+        if not os.path.exists(p):
+            raise FileNotFoundError(p)
+        self.lib = ctypes.CDLL(p)
+        self.lib.ref_quiet(1)
+        self.lib.ref_compress_slices_mt.restype = ctypes.c_double
+        self.lib.ref_compress_slices_mt.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
+                                                    ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+
+    def compress_mt(self, buf_addr, nbytes, slice_bytes, level, threads):
+        import numpy as np
+        count = (nbytes + slice_bytes - 1) // slice_bytes
+        offs = (np.arange(count, dtype=np.uint64) * slice_bytes)
+        lens = np.minimum(slice_bytes, nbytes - offs).astype(np.uint64)
+        sizes = np.zeros(count, dtype=np.int64)
+        secs = self.lib.ref_compress_slices_mt(buf_addr, offs.ctypes.data, lens.ctypes.data, count, level, threads,
+                                               sizes.ctypes.data)
+        return secs, int(sizes.sum()), int((sizes < 0).sum())
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def host_corpus(nchunks, first_chunk=0):
+    """Sample of the workload generated on the host by the oracle's generator (same bytes as the device)."""
+    so = os.path.join(ROOT, "oracle", "liboracle.so")
+    if not os.path.exists(so):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), so], check=True, capture_output=True)
+    o = ctypes.CDLL(so)
+    o.oracle_corpus_generate.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_void_p]
+    import numpy as np
+    buf = np.empty(nchunks * CHUNK, dtype=np.uint8)
+    o.oracle_corpus_generate(SEED, first_chunk, nchunks, buf.ctypes.data)
+    return buf
+
+
+def cpu_reference_run(level, steps, warmup, budget_s=12.0):
+    """Times deflate::compress of the unmodified reference with all host threads on a bounded sample of
+    the corpus.  Returns dict(value GB/s, cores, sample, ratio, ms_per_step)."""
+    ref = RefLib()
+    cores = host_cores()
+    # calibrate on 3 chunks (one of each kind), single thread
+    cal = host_corpus(3)
+    secs, _, _ = ref.compress_mt(cal.ctypes.data, cal.size, cal.size, level, 1)
+    per_core = cal.size / max(secs, 1e-6)
+    total_steps = max(1, steps + warmup)
+    want = per_core * cores * budget_s / total_steps
+    nchunks = int(max(3 * cores, min(16384, want // CHUNK)))
+    nchunks -= nchunks % 3                                   # whole T/I/R triples
+    nchunks = max(nchunks, 3)
+    buf = host_corpus(nchunks)
+    slice_bytes = 3 * CHUNK                                  # one triple per task
+    times = []
+    comp = 0
+    for i in range(total_steps):
+        secs, comp, bad = ref.compress_mt(buf.ctypes.data, buf.size, slice_bytes, level, cores)
+        if i >= warmup:
+            times.append(secs)
+    t = sum(times) / len(times)
+    return {
+        "value": buf.size / t / 1e9, "unit": UNIT, "cores": cores, "kind": "reference",
+        "sample": f"first {nchunks} chunks ({buf.size / 2**20:.0f} MiB) of the same corpus, level {level}, "
+                  f"{cores} threads x 192 KiB slices, {len(times)} timed passes",
+        "ratio": comp / buf.size, "ms_per_step": t * 1e3, "bytes": int(buf.size),
+    }
+
+
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:  # noqa: BLE001
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(kernel):
+    """dram bytes per launch of `kernel` from the committed ncu capture summary, or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(kernel)
+        except Exception:  # noqa: BLE001
+            return None
+    return None
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        try:
+            r = cpu_reference_run(args.level, args.steps, args.warmup, budget_s=args.ref_budget_s)
+        except FileNotFoundError as e:
+            print(json.dumps({"impl": "reference", "unavailable": f"oracle/_ref not built: {e}"}))
+            return 0
+        line = {
+            "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "1 GiB synthetic mixed-entropy corpus (T/I/R 64 KiB chunks), fast level -- bounded sample",
+                       "level": args.level, "sample_bytes": r["bytes"]},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "ratio": {"reference_sample": r["ratio"]},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import deflate_hpp_b200 as d
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    ctx = d.Context(local_rank)
+    st = torch.cuda.current_stream().cuda_stream
+
+    nchunks = args.mib * 16
+    n = nchunks * CHUNK
+    src = torch.empty(n, dtype=torch.uint8, device=dev)
+    ctx.corpus_generate_dev(src.data_ptr(), SEED, rank * nchunks, nchunks, stream=st)
+    cap = d.deflate_bound(n)
+    dst = torch.empty(cap, dtype=torch.uint8, device=dev)
+    flags = d.F_NOT_LAST if rank != world - 1 else 0
+    gather_buf = None
+    if world > 1 and rank == 0:
+        gather_buf = torch.empty(cap * world, dtype=torch.uint8, device=dev)
+    sizes_t = torch.zeros(world, dtype=torch.int64, device=dev)
+
+    def step():
+        cn = ctx.compress_dev(src.data_ptr(), n, args.level, dst.data_ptr(), cap, flags=flags, stream=st)
+        if world > 1:
+            mine = torch.tensor([cn], dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(sizes_t, mine)
+            sz = sizes_t.tolist()
+            if rank == 0:
+                ops, off = [], sz[0]
+                for r in range(1, world):
+                    ops.append(dist.P2POp(dist.irecv, gather_buf[off:off + sz[r]], r))
+                    off += sz[r]
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()
+            else:
+                for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, dst[:cn], 0)]):
+                    w.wait()
+        return cn
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    launches0 = None
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    for _ in range(args.warmup):
+        cn = step()
+    barrier()
+    if sampler:
+        sampler.start()
+    ctx.profile(True)
+    launches0 = d.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        cn = step()
+    e1.record()
+    barrier()
+    launches = d.launch_count() - launches0
+    ctx.profile(False)
+    kern = ctx.profile_read()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        tot = torch.tensor([cn], dtype=torch.int64, device=dev)
+        dist.all_reduce(tot)
+        total_comp = int(tot.item())
+    else:
+        total_comp = cn
+    ms_per_step = ms / args.steps
+    total_in = n * world
+    value = total_in / (ms_per_step * 1e-3) / 1e9
+    ratio = total_comp / total_in
+
+    # ---- decompress (same stream, device resident) ----
+    back = torch.empty(n, dtype=torch.uint8, device=dev)
+    dec = None
+    if world == 1:
+        for _ in range(min(args.warmup, 3)):
+            ctx.inflate_dev(dst.data_ptr(), cn, back.data_ptr(), n, stream=st)
+        torch.cuda.synchronize()
+        ctx.profile(True)
+        dsteps = max(1, min(args.steps, 10))
+        e0.record()
+        for _ in range(dsteps):
+            w, full = ctx.inflate_dev(dst.data_ptr(), cn, back.data_ptr(), n, stream=st)
+        e1.record()
+        torch.cuda.synchronize()
+        ctx.profile(False)
+        dk = ctx.profile_read()
+        dms = e0.elapsed_time(e1) / dsteps
+        ok = bool(full == n and torch.equal(back, src))
+        dec = {"value": n / (dms * 1e-3) / 1e9, "unit": "GB/s (output bytes)", "ms_per_step": dms, "steps": dsteps,
+               "round_trip_bit_exact": ok,
+               "kernels_ms_per_step": {k: v[0] / dsteps for k, v in dk.items()}}
+    clocks = sampler.stop() if sampler else None
+
+    # ---- roofline of the dominant kernel ----
+    peak, peak_src = measured_peak()
+    per_step = {k: (v[0] / args.steps, v[1] // args.steps) for k, v in kern.items()}
+    dom = max(per_step, key=lambda k: per_step[k][0]) if per_step else None
+    roof = None
+    if dom:
+        dom_ms, dom_launches = per_step[dom]
+        alg_bytes_step = n * (1.0 + cn / n)                     # (1 + r) bytes per input byte, this rank
+        alg_per_launch = alg_bytes_step / max(1, dom_launches)
+        avg_launch_ms = dom_ms / max(1, dom_launches)
+        achieved = alg_per_launch / (avg_launch_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "peak_source": peak_src, "traffic": ncu_traffic(dom),
+                "algorithmic_bytes_per_launch": alg_per_launch, "avg_launch_ms": avg_launch_ms,
+                "launches_per_step": dom_launches,
+                "kernel_share_of_step": dom_ms / ms_per_step,
+                "kernels_ms_per_step": {k: v[0] for k, v in per_step.items()},
+                "whole_path_frac": (alg_bytes_step / (ms_per_step * 1e-3) / 1e9) / peak}
+
+    # ---- e2e: host-buffer C-ABI call, pinned host memory, H2D + D2H inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        L = d.lib()
+        h_in = torch.empty(n, dtype=torch.uint8).pin_memory()
+        h_in.copy_(src)
+        h_out = torch.empty(cap, dtype=torch.uint8).pin_memory()
+        out_n = ctypes.c_size_t()
+        esteps = max(1, min(args.steps, 5))
+        ewarm = max(1, min(args.warmup, 2))
+        barrier()
+        times = []
+        for i in range(ewarm + esteps):
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            rc = L.b200_deflate_compress_into(h_in.data_ptr(), n, args.level, h_out.data_ptr(), cap, ctypes.byref(out_n))
+            t1 = time.perf_counter()
+            if rc:
+                raise d.B200Error(rc, "b200_deflate_compress_into")
+            if i >= ewarm:
+                times.append(t1 - t0)
+        et = sum(times) / len(times)
+        if world > 1:
+            t = torch.tensor([et], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            et = float(t.item())
+        e2e = {"value": total_in / et / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(n), "d2h_bytes_per_step": int(out_n.value),
+               "ms_per_step": et * 1e3, "steps": esteps,
+               "api": "b200_deflate_compress_into(host in, host out) -- pinned host buffers, per rank"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            r = cpu_reference_run(args.level, 1, 0, budget_s=15.0)
+            cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            cpu["ratio"] = r["ratio"]
+        except Exception as e:  # noqa: BLE001
+            cpu = {"value": None, "unit": UNIT, "cores": host_cores(), "kind": "reference", "sample": f"unavailable: {e}"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": f"{args.mib} MiB per GPU of the synthetic mixed-entropy corpus (T/I/R, 64 KiB chunks), "
+                                   f"level {args.level} ({'fast' if args.level == 2 else 'better' if args.level == 3 else args.level}), "
+                                   f"device-resident; N>1: per-rank shards + NCCL gather of compressed bytes to rank 0",
+                       "bytes_per_gpu": int(n), "chunks_per_gpu": nchunks, "l2_hygiene": "inputs (>= 1 GiB) larger than the 126 MB L2",
+                       "seed": SEED},
+            "ratio": {"b200": ratio, "reference_sample": cpu.get("ratio") if cpu else None},
+            "decompress": dec, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+            "gpu_launches": int(launches),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

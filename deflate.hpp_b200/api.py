@@ -59,6 +59,12 @@ def lib():
     L.b200_launch_count.restype = c_u64
     L.b200_ctx_create.argtypes = [c_int, P(c_void_p)]
     L.b200_ctx_destroy.argtypes = [c_void_p]
+    L.b200_ctx_profile.argtypes = [c_void_p, c_int]
+    L.b200_ctx_profile.restype = c_int
+    L.b200_ctx_profile_read.argtypes = [c_void_p, c_int, P(ctypes.c_double), P(c_u64)]
+    L.b200_ctx_profile_read.restype = c_int
+    L.b200_kernel_name.argtypes = [c_int]
+    L.b200_kernel_name.restype = ctypes.c_char_p
     L.b200_deflate_bound.restype = c_size_t
     L.b200_deflate_bound.argtypes = [c_size_t]
     L.b200_deflate_compress.argtypes = [c_void_p, c_size_t, c_int, P(c_void_p), P(c_size_t)]
@@ -186,6 +192,28 @@ class Context:
             self.close()
         except Exception:
             pass
+
+    def profile(self, enable):
+        """Bracket every kernel launch of this context with CUDA events (bench.py roofline)."""
+        rc = lib().b200_ctx_profile(self._h, 1 if enable else 0)
+        if rc:
+            raise B200Error(rc, "b200_ctx_profile")
+
+    def profile_read(self):
+        """-> {kernel name: (total device ms, launches)} for the records since profile(True)."""
+        out = {}
+        k = 0
+        while True:
+            name = lib().b200_kernel_name(k)
+            if not name:
+                return out
+            ms, n = ctypes.c_double(), ctypes.c_uint64()
+            rc = lib().b200_ctx_profile_read(self._h, k, ctypes.byref(ms), ctypes.byref(n))
+            if rc:
+                raise B200Error(rc, "b200_ctx_profile_read")
+            if n.value:
+                out[name.decode()] = (ms.value, n.value)
+            k += 1
 
     def compress_dev(self, d_in, n, level, d_out, cap, flags=0, stream=0, d_out_n=0, d_chunk_off=0, sync=True):
         out_n = ctypes.c_size_t()

@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "common.cuh"
 #include "corpus.cuh"
@@ -46,6 +47,47 @@ std::atomic<uint64_t> g_launches{0};
         g_launches.fetch_add(1);         \
         CK(cudaGetLastError());          \
     } while (0)
+// bracket a launch with profiling events when the context has profiling switched on
+#define PROF_BEGIN(c, id, st) (c)->prof.begin((id), (st))
+#define PROF_END(c, st) (c)->prof.end((st))
+
+enum KernelId { K_LZ77 = 0, K_HUFFMAN, K_SCAN, K_ENCODE, K_FIND_SYNC, K_INFLATE_CHUNKS, K_VALIDATE, K_INFLATE_BATCH, K_CORPUS, K_COUNT };
+const char* const kKernelNames[K_COUNT] = {"lz77_kernel", "huffman_kernel", "scan_sizes_kernel", "encode_kernel",
+                                           "find_sync_kernel", "inflate_chunks_kernel", "validate_chunks_kernel",
+                                           "inflate_batch_kernel", "corpus_kernels"};
+
+// Optional per-kernel timing: CUDA events recorded on the launching stream around every launch.
+struct Prof {
+    bool on = false;
+    struct Rec { int id; cudaEvent_t a, b; };
+    std::vector<Rec> recs;
+    std::vector<cudaEvent_t> pool;
+    cudaEvent_t get() {
+        if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        return e;
+    }
+    void begin(int id, cudaStream_t st) {
+        if (!on) return;
+        Rec r{id, get(), get()};
+        cudaEventRecord(r.a, st);
+        recs.push_back(r);
+    }
+    void end(cudaStream_t st) {
+        if (!on) return;
+        cudaEventRecord(recs.back().b, st);
+    }
+    void clear() {
+        for (auto& r : recs) { pool.push_back(r.a); pool.push_back(r.b); }
+        recs.clear();
+    }
+    void destroy() {
+        clear();
+        for (auto e : pool) cudaEventDestroy(e);
+        pool.clear();
+    }
+};
 
 struct Buf {
     void* p = nullptr;
@@ -79,6 +121,7 @@ struct b200_ctx {
     Buf d_in, d_out;
     cudaStream_t stream = nullptr;   // used by the host-buffer API
     std::mutex mu;
+    Prof prof;
 };
 
 namespace {
@@ -154,8 +197,37 @@ void b200_ctx_destroy(b200_ctx* c) {
     Buf* all[] = {&c->tok, &c->ntok, &c->hist, &c->codes, &c->hdr, &c->desc, &c->sizes, &c->offsets, &c->total,
                   &c->counts, &c->woffs, &c->cand, &c->res, &c->result, &c->one_off, &c->d_in, &c->d_out};
     for (Buf* b : all) b->release();
+    c->prof.destroy();
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
+}
+
+int b200_ctx_profile(b200_ctx* c, int enable) {
+    if (!c) return B200_E_ARG;
+    c->prof.clear();
+    c->prof.on = enable != 0;
+    return B200_OK;
+}
+
+int b200_ctx_profile_read(b200_ctx* c, int kernel_id, double* total_ms, uint64_t* launches) {
+    if (!c || kernel_id < 0 || kernel_id >= K_COUNT) return B200_E_ARG;
+    CK(cudaSetDevice(c->device));
+    double ms = 0;
+    uint64_t n = 0;
+    for (auto& r : c->prof.recs) {
+        if (r.id != kernel_id) continue;
+        CK(cudaEventSynchronize(r.b));
+        float t = 0;
+        CK(cudaEventElapsedTime(&t, r.a, r.b));
+        ms += t; n++;
+    }
+    if (total_ms) *total_ms = ms;
+    if (launches) *launches = n;
+    return B200_OK;
+}
+
+const char* b200_kernel_name(int kernel_id) {
+    return (kernel_id >= 0 && kernel_id < K_COUNT) ? kKernelNames[kernel_id] : nullptr;
 }
 
 size_t b200_deflate_bound(size_t n) {
@@ -212,23 +284,31 @@ int b200_deflate_compress_dev(b200_ctx* c, const void* d_in, size_t n, int level
         const uint64_t bn = n - b0 * CHUNK;
         const bool last_batch = b0 + nb == nchunks;
         if (level >= 1) {
+            PROF_BEGIN(c, K_LZ77, st);
             if (level == 1)
                 lz77_kernel<1><<<nb, LZ_THREADS, LZ_SMEM_BYTES, st>>>(bin, bn, (uint32_t*)c->tok.p, (uint32_t*)c->ntok.p, (uint32_t*)c->hist.p);
             else
                 lz77_kernel<0><<<nb, LZ_THREADS, LZ_SMEM_BYTES, st>>>(bin, bn, (uint32_t*)c->tok.p, (uint32_t*)c->ntok.p, (uint32_t*)c->hist.p);
             LAUNCHED();
+            PROF_END(c, st);
         }
+        PROF_BEGIN(c, K_HUFFMAN, st);
         huffman_kernel<<<(nb + HUF_WARPS - 1) / HUF_WARPS, HUF_THREADS, 0, st>>>(
             (const uint32_t*)c->hist.p, bn, nb, level, (last_batch && final_here) ? 1 : 0, (uint32_t*)c->codes.p,
             (uint32_t*)c->hdr.p, (BlockDesc*)c->desc.p, (uint32_t*)c->sizes.p);
         LAUNCHED();
+        PROF_END(c, st);
+        PROF_BEGIN(c, K_SCAN, st);
         scan_sizes_kernel<<<1, SCAN_THREADS, 0, st>>>((const uint32_t*)c->sizes.p, nb, b0 ? offs + b0 : nullptr,
                                                      offs + b0, d_total);
         LAUNCHED();
+        PROF_END(c, st);
+        PROF_BEGIN(c, K_ENCODE, st);
         encode_kernel<<<nb, ENC_THREADS, ENC_SMEM_BYTES, st>>>(bin, (const uint32_t*)c->tok.p, (const uint32_t*)c->ntok.p,
                                                               (const uint32_t*)c->codes.p, (const uint32_t*)c->hdr.p,
                                                               (const BlockDesc*)c->desc.p, offs + b0, (uint8_t*)d_out);
         LAUNCHED();
+        PROF_END(c, st);
     }
     if (d_out_n) CK(cudaMemcpyAsync(d_out_n, d_total, 8, cudaMemcpyDeviceToDevice, st));
     if (h_out_n) {
@@ -250,9 +330,11 @@ int b200_inflate_batch_dev(b200_ctx* c, const void* d_in, const uint64_t* d_in_o
     CK(cudaSetDevice(c->device));
     const uint64_t grid = (n_streams + INF_WARPS - 1) / INF_WARPS;
     if (grid > 0x7FFFFFFFull) return B200_E_ARG;
+    PROF_BEGIN(c, K_INFLATE_BATCH, st);
     inflate_batch_kernel<<<(uint32_t)grid, INF_THREADS, 0, st>>>((const uint8_t*)d_in, d_in_off, d_in_len, (uint8_t*)d_out,
                                                                d_out_off, d_out_cap, d_out_len, d_status, n_streams, flags);
     LAUNCHED();
+    PROF_END(c, st);
     return B200_OK;
 }
 
@@ -281,11 +363,15 @@ int b200_inflate_dev(b200_ctx* c, const void* d_in, size_t n, void* d_out, size_
         if ((rc = c->cand.ensure((cand_cap + 1) * 8))) return rc;
         uint64_t* cand = (uint64_t*)c->cand.p;
         const uint32_t g = (uint32_t)((nwarps * 32 + 255) / 256);
+        PROF_BEGIN(c, K_FIND_SYNC, st);
         find_sync_kernel<false><<<g, 256, 0, st>>>(in, n, (uint32_t*)c->counts.p, nullptr, nullptr, 0);
         LAUNCHED();
+        PROF_END(c, st);
+        PROF_BEGIN(c, K_SCAN, st);
         scan_sizes_kernel<<<1, SCAN_THREADS, 0, st>>>((const uint32_t*)c->counts.p, (uint32_t)nwarps, nullptr,
                                                      (uint64_t*)c->woffs.p, (uint64_t*)d_result + 2);
         LAUNCHED();
+        PROF_END(c, st);
         uint64_t nmark = 0;
         CK(cudaMemcpyAsync(&nmark, d_result + 2, 8, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -293,17 +379,23 @@ int b200_inflate_dev(b200_ctx* c, const void* d_in, size_t n, void* d_out, size_
             const uint64_t ncand = nmark + 1;
             CK(cudaMemsetAsync(cand, 0, 8, st));   // cand[0] = 0
             if (nmark) {
+                PROF_BEGIN(c, K_FIND_SYNC, st);
                 find_sync_kernel<true><<<g, 256, 0, st>>>(in, n, nullptr, (const uint64_t*)c->woffs.p, cand + 1, nmark);
                 LAUNCHED();
+                PROF_END(c, st);
             }
             if ((rc = c->res.ensure(ncand * sizeof(ChunkResult)))) return rc;
             const unsigned long long init[2] = {1ull, 0ull};
             CK(cudaMemcpyAsync(d_result, init, 16, cudaMemcpyHostToDevice, st));
+            PROF_BEGIN(c, K_INFLATE_CHUNKS, st);
             inflate_chunks_kernel<<<(uint32_t)((ncand + INF_WARPS - 1) / INF_WARPS), INF_THREADS, 0, st>>>(
                 in, n, cand, ncand, (uint8_t*)d_out, cap, (ChunkResult*)c->res.p, flags);
             LAUNCHED();
+            PROF_END(c, st);
+            PROF_BEGIN(c, K_VALIDATE, st);
             validate_chunks_kernel<<<(uint32_t)((ncand + 255) / 256), 256, 0, st>>>(cand, ncand, (const ChunkResult*)c->res.p, d_result);
             LAUNCHED();
+            PROF_END(c, st);
             unsigned long long verdict[2] = {0, 0};
             CK(cudaMemcpyAsync(verdict, d_result, 16, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
@@ -316,8 +408,10 @@ int b200_inflate_dev(b200_ctx* c, const void* d_in, size_t n, void* d_out, size_
         uint64_t* d = (uint64_t*)c->one_off.p;   // [0] in_off [1] in_len [2] out_off [3] out_cap [4] out_len [5] status
         const uint64_t h[6] = {0, (uint64_t)n, 0, (uint64_t)cap, 0, 0};
         CK(cudaMemcpyAsync(d, h, sizeof(h), cudaMemcpyHostToDevice, st));
+        PROF_BEGIN(c, K_INFLATE_BATCH, st);
         inflate_batch_kernel<<<1, INF_THREADS, 0, st>>>(in, d, d + 1, (uint8_t*)d_out, d + 2, d + 3, d + 4, (int32_t*)(d + 5), 1, flags);
         LAUNCHED();
+        PROF_END(c, st);
         uint64_t r[2] = {0, 0};
         CK(cudaMemcpyAsync(r, d + 4, 16, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));

@@ -63,6 +63,15 @@ uint64_t b200_launch_count(void);
 int b200_ctx_create(int device, b200_ctx** ctx);
 void b200_ctx_destroy(b200_ctx* ctx);
 
+/* Per-kernel timing for benchmarks: when enabled, every kernel launch made through `ctx` is bracketed
+ * by CUDA events on its stream.  b200_ctx_profile(ctx, 1) clears earlier records and starts,
+ * b200_ctx_profile(ctx, 0) stops (records are kept for reading);
+ * b200_ctx_profile_read() synchronizes on the recorded events and returns the summed device time and the launch
+ * count of one kernel (ids 0.. as named by b200_kernel_name(); NULL past the last id). */
+int b200_ctx_profile(b200_ctx* ctx, int enable);
+int b200_ctx_profile_read(b200_ctx* ctx, int kernel_id, double* total_ms, uint64_t* launches);
+const char* b200_kernel_name(int kernel_id);
+
 /* Worst-case compressed size for n input bytes (all chunks stored + framing). */
 size_t b200_deflate_bound(size_t n);
 

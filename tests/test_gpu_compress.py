@@ -1,0 +1,149 @@
+"""GPU parity tests for the compressor (run with -m gpu on a B200), through the C ABI.
+
+Parity contract (BASELINE.json north star): identical compressed bytes are not
+required; every GPU-compressed stream must decode bit-exactly back to the input with BOTH the
+reference inflater (oracle/_ref when present, else its C restatement in oracle/) and zlib, and the
+size must be <= 1.03 x the reference's size at the same level."""
+import zlib
+
+import pytest
+
+from conftest import gold, zlib_raw_inflate
+import datagen
+
+pytestmark = pytest.mark.gpu
+
+LEVELS = [0, 1, 2, 3]
+# sizes the unmodified reference produces (re-checked by tests/test_oracle.py)
+REF_SIZES = {"test.bmp": {0: 21904, 1: 21904, 2: 5346, 3: 3124}, "tiny.bmp": {0: 264, 1: 264, 2: 99, 3: 67}}
+RATIO_TOL = 1.03
+
+
+def check_stream(c, data, oracle):
+    out, unused = zlib_raw_inflate(c)
+    assert out == data and unused == b""
+    rc, o = oracle.inflate(c)
+    assert rc == 0 and o == data
+
+
+@pytest.mark.parametrize("level", LEVELS)
+@pytest.mark.parametrize("name", ["test.bmp", "tiny.bmp"])
+def test_fixture_round_trip_and_ratio(b200, oracle, name, level):
+    """BASELINE config 1: test.bmp (and tiny.bmp) at every level."""
+    data = gold(name)
+    c = b200.compress(data, level)
+    check_stream(c, data, oracle)
+    assert b200.decompress(c) == data
+    assert len(c) <= RATIO_TOL * REF_SIZES[name][level], (len(c), REF_SIZES[name][level])
+
+
+@pytest.mark.parametrize("level", [2, 3])
+def test_fixture_through_reference_inflater(b200, ref, level):
+    for name in ("test.bmp", "tiny.bmp"):
+        data = gold(name)
+        c = b200.compress(data, level)
+        n, out = ref.inflate(c)
+        assert n == len(data) and out == data
+
+
+@pytest.mark.parametrize("level", LEVELS)
+def test_edge_sizes(b200, oracle, level):
+    src = datagen.text_like(210000, seed=7)
+    for n in datagen.EDGE_SIZES:
+        data = src[:n]
+        c = b200.compress(data, level)
+        check_stream(c, data, oracle)
+
+
+@pytest.mark.parametrize("kind", sorted(datagen.KINDS))
+@pytest.mark.parametrize("level", [1, 2, 3])
+def test_kinds(b200, oracle, kind, level):
+    data = datagen.KINDS[kind](300000)
+    c = b200.compress(data, level)
+    check_stream(c, data, oracle)
+    if kind != "random":
+        assert len(c) < len(data)
+    assert len(c) <= b200.deflate_bound(len(data))
+
+
+def test_reference_inflater_on_multi_chunk(b200, ref):
+    data = datagen.text_like(150000) + datagen.random_bytes(70000) + datagen.runs(100000)
+    for level in (2, 3):
+        c = b200.compress(data, level)
+        n, out = ref.inflate(c)
+        assert n == len(data) and out == data
+
+
+@pytest.mark.parametrize("level", [2, 3])
+def test_ratio_vs_reference(b200, ref, level):
+    """Ratio within 3 % of the reference at the same level on the three corpus kinds (the reference's
+    level 3 is O(n^2): 32 KB samples keep this test in seconds)."""
+    n = 32768 if level == 3 else 200000
+    for kind in ("text", "image", "lowent"):
+        data = datagen.KINDS[kind](n)
+        ours = len(b200.compress(data, level))
+        theirs = len(ref.compress(data, level))
+        assert ours <= RATIO_TOL * theirs, (kind, ours, theirs)
+
+
+def test_deterministic(b200):
+    data = datagen.text_like(500000)
+    a = b200.compress(data, 2)
+    assert a == b200.compress(data, 2)
+
+
+def test_accepts_bool_levels(b200, oracle):
+    data = gold("test.bmp")
+    fast, better = b200.compress(data, False), b200.compress(data, True)
+    assert fast == b200.compress(data, 2) and better == b200.compress(data, 3)
+    check_stream(better, data, oracle)
+
+
+def test_not_last_shards_concatenate(b200, oracle):
+    """Multi-GPU contract: shards compressed with F_NOT_LAST concatenate into one valid stream."""
+    import torch
+    data = datagen.text_like(200000) + datagen.image_like(131072)
+    cut = 131072
+    ctx = b200.Context(0)
+    parts = []
+    for piece, flags in ((data[:cut], b200.F_NOT_LAST), (data[cut:], 0)):
+        src = torch.frombuffer(bytearray(piece), dtype=torch.uint8).cuda()
+        cap = b200.deflate_bound(len(piece))
+        dst = torch.empty(cap, dtype=torch.uint8, device="cuda")
+        n = ctx.compress_dev(src.data_ptr(), len(piece), 2, dst.data_ptr(), cap, flags=flags)
+        parts.append(bytes(dst[:n].cpu().numpy()))
+    joined = b"".join(parts)
+    check_stream(joined, data, oracle)
+    assert b200.decompress(joined) == data
+    assert joined == b200.compress(data, 2)   # sharding at a chunk boundary does not change the bytes
+
+
+def test_large_device_resident(b200):
+    """BASELINE config 3 shape at reduced size + size-independent property: inflate(compress(x)) == x."""
+    import torch
+    nchunks = 2048   # 128 MiB
+    n = nchunks * b200.CHUNK
+    ctx = b200.Context(0)
+    src = torch.empty(n, dtype=torch.uint8, device="cuda")
+    ctx.corpus_generate_dev(src.data_ptr(), 20261018, 0, nchunks)
+    cap = b200.deflate_bound(n)
+    dst = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    back = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    for level in (2, 3):
+        cn = ctx.compress_dev(src.data_ptr(), n, level, dst.data_ptr(), cap)
+        assert cn < n
+        w, full = ctx.inflate_dev(dst.data_ptr(), cn, back.data_ptr(), n)
+        assert w == full == n and torch.equal(back, src)
+        # spot-check with zlib on the first 4 MiB worth of chunks is covered by test_kinds; here check
+        # that the whole stream is one valid raw deflate stream
+        host = bytes(dst[:cn].cpu().numpy())
+        o = zlib.decompressobj(-15)
+        total = 0
+        h = src.cpu().numpy().tobytes()
+        pos = 0
+        while pos < len(host):
+            piece = o.decompress(host[pos:pos + (1 << 24)])
+            assert piece == h[total:total + len(piece)]
+            total += len(piece)
+            pos += 1 << 24
+        assert o.eof and total == n

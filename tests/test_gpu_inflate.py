@@ -1,0 +1,170 @@
+"""GPU parity tests for the inflater (-m gpu): bit-exact against the oracle (C restatement of the
+reference inflater), the unmodified reference when its library travelled, and zlib."""
+import hashlib
+import zlib
+
+import numpy as np
+import pytest
+
+from conftest import gold
+import datagen
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name,sha,size", [("zlib.dat", "bcc0f00aa007", 72541), ("weird.dat", "ff59bf286819", 6050)])
+def test_reference_fixtures(b200, oracle, name, sha, size):
+    """zlib.dat: 3 dynamic blocks with cross-block back-references; weird.dat: HLIT 286, length 258."""
+    raw = gold(name)
+    out = b200.decompress_zlib(raw)
+    assert len(out) == size and hashlib.sha1(out).hexdigest().startswith(sha)
+    rc, o = oracle.inflate_zlib(raw)
+    assert rc == 0 and out == o
+    assert b200.decompress(raw[2:]) == out
+    # caller-buffer overload truncates silently (inflate.hpp:345)
+    assert b200.decompress_zlib(raw, out_size=size // 3) == out[:size // 3]
+    assert b200.decompress_zlib(raw, out_size=size + 100) == out
+
+
+@pytest.mark.parametrize("level", [0, 1, 2, 3])
+def test_reference_compressed_streams(b200, oracle, ref, level):
+    """GPU inflater == reference inflater on reference-compressed streams, including the level-2
+    streams that decode to wrong bytes (same wrong bytes expected)."""
+    for name in ("test.bmp", "tiny.bmp"):
+        c = ref.compress(gold(name), level)
+        n, r_out = ref.inflate(c)
+        assert n >= 0
+        assert b200.decompress(c) == r_out
+    data = datagen.text_like(40000)
+    c = ref.compress(data, level if level != 3 else 1)
+    n, r_out = ref.inflate(c)
+    if n >= 0:
+        assert b200.decompress(c) == r_out
+    else:
+        with pytest.raises(b200.B200Error):
+            b200.decompress(c)
+
+
+@pytest.mark.parametrize("kind", sorted(datagen.KINDS))
+def test_foreign_streams(b200, oracle, kind):
+    data = datagen.KINDS[kind](150000)
+    for name, stream in datagen.foreign_streams(data).items():
+        out = b200.decompress(stream)
+        assert out == data, name
+        rc, o = oracle.inflate(stream)
+        assert rc == 0 and o == out, name
+
+
+def test_edge_sizes(b200):
+    src = datagen.text_like(210000, seed=9)
+    for n in datagen.EDGE_SIZES:
+        for lvl in (0, 6):
+            c = datagen.foreign_streams(src[:n])["zlib6" if lvl else "stored"]
+            assert b200.decompress(c) == src[:n], (n, lvl)
+
+
+def test_errors(b200, oracle):
+    data = datagen.text_like(60000)
+    good = datagen.foreign_streams(data)["zlib6"]
+    for cut in (len(good) // 2, len(good) - 4, 7, 1):
+        rc, _ = oracle.inflate(good[:cut])
+        assert rc != 0
+        with pytest.raises(b200.B200Error) as e:
+            b200.decompress(good[:cut])
+        assert e.value.code in (1, 2)
+        if rc == -1:
+            assert e.value.code == 1 and "beyond the alloted buffer size" in str(e.value)
+    # garbage
+    junk = datagen.random_bytes(5000, seed=11)
+    rc, _ = oracle.inflate(junk)
+    if rc != 0:
+        with pytest.raises(b200.B200Error):
+            b200.decompress(junk)
+
+
+def test_reference_quirks_and_strict(b200, oracle):
+    bad_nlen = bytes([0x01, 0x03, 0x00, 0x00, 0x00]) + b"abc"
+    assert b200.decompress(bad_nlen) == oracle.inflate(bad_nlen)[1] == b"abc"
+    with pytest.raises(b200.B200Error):
+        b200.decompress(bad_nlen, flags=b200.F_STRICT)
+    # distance beyond the produced output: the reference copies nothing; strict mode rejects
+    stream = datagen.too_far_stream()
+    rc, o = oracle.inflate(stream)
+    assert rc == 0 and o == b"a"
+    assert b200.decompress(stream) == b"a"
+    with pytest.raises(b200.B200Error):
+        b200.decompress(stream, flags=b200.F_STRICT)
+    # BTYPE 3 is skipped by the reference (no case label): header 0b110 (non-final, type 3) then a
+    # final stored block.  After the 3 header bits the next block header follows immediately.
+    bt3 = bytes([0b00001110, 0x02, 0x00, 0xFD, 0xFF]) + b"hi"
+    rc, o = oracle.inflate(bt3)
+    assert rc == 0 and o == b"hi"
+    assert b200.decompress(bt3) == b"hi"
+    with pytest.raises(b200.B200Error):
+        b200.decompress(bt3, flags=b200.F_STRICT)
+
+
+def test_batch_mixed(b200, oracle):
+    """BASELINE config 4 at reduced count: many independent small streams, one warp each."""
+    import torch
+    rng = np.random.default_rng(5)
+    kinds = sorted(datagen.KINDS)
+    streams, expect = [], []
+    fixtures = [gold("zlib.dat")[2:], gold("weird.dat")[2:]]
+    for i in range(600):
+        n = int(np.exp(rng.uniform(np.log(1024), np.log(65536))))
+        data = datagen.KINDS[kinds[i % len(kinds)]](n, seed=100 + i)
+        prods = datagen.foreign_streams(data)
+        name = sorted(prods)[i % len(prods)]
+        streams.append(prods[name])
+        expect.append(data)
+    for f in fixtures:
+        streams.append(f)
+        expect.append(oracle.inflate(f)[1])
+    streams.append(streams[0][: len(streams[0]) // 2])   # one broken stream must not disturb the others
+    expect.append(None)
+    in_off = np.cumsum([0] + [len(s) + 3 for s in streams[:-1]]).astype(np.uint64)   # odd alignment on purpose
+    in_len = np.array([len(s) for s in streams], dtype=np.uint64)
+    blob = bytearray(int(in_off[-1] + in_len[-1]) + 64)
+    for o, s in zip(in_off, streams):
+        blob[int(o):int(o) + len(s)] = s
+    caps = np.array([len(e) if e is not None else 70000 for e in expect], dtype=np.uint64)
+    out_off = np.cumsum([0] + list(caps[:-1])).astype(np.uint64)
+    d_in = torch.frombuffer(blob, dtype=torch.uint8).cuda()
+    d_out = torch.zeros(int(out_off[-1] + caps[-1]), dtype=torch.uint8, device="cuda")
+    t = lambda a: torch.from_numpy(a.view(np.int64)).cuda()
+    d_in_off, d_in_len, d_out_off, d_caps = t(in_off), t(in_len), t(out_off), t(caps)
+    d_out_len = torch.zeros(len(streams), dtype=torch.int64, device="cuda")
+    d_status = torch.full((len(streams),), -1, dtype=torch.int32, device="cuda")
+    ctx = b200.Context(0)
+    ctx.inflate_batch_dev(d_in.data_ptr(), d_in_off.data_ptr(), d_in_len.data_ptr(), d_out.data_ptr(),
+                          d_out_off.data_ptr(), d_caps.data_ptr(), d_out_len.data_ptr(), d_status.data_ptr(),
+                          len(streams))
+    torch.cuda.synchronize()
+    status = d_status.cpu().numpy()
+    lens = d_out_len.cpu().numpy()
+    host = d_out.cpu().numpy().tobytes()
+    for i, e in enumerate(expect):
+        if e is None:
+            assert status[i] != 0
+            continue
+        assert status[i] == 0 and lens[i] == len(e), i
+        assert host[int(out_off[i]):int(out_off[i]) + len(e)] == e, i
+
+
+def test_own_streams_chunk_parallel_vs_sequential(b200, monkeypatch):
+    data = datagen.text_like(400000) + datagen.random_bytes(100000) + datagen.image_like(300000)
+    c = b200.compress(data, 2)
+    assert b200.decompress(c) == data
+    monkeypatch.setenv("B200_INFLATE_SEQUENTIAL", "1")
+    assert b200.decompress(c) == data
+
+
+def test_false_sync_markers(b200):
+    """Stored data full of 00 00 FF FF patterns must not confuse the chunk-parallel path."""
+    data = (b"\x00\x00\xff\xff" * 40000) + datagen.random_bytes(70000) + b"\x00\x00\xff\xff" * 10
+    for level in (0, 2):
+        c = b200.compress(data, level)
+        assert b200.decompress(c) == data
+    z = datagen.foreign_streams(datagen.random_bytes(200000) + b"\x00\x00\xff\xff" * 1000)["stored"]
+    assert b200.decompress(z) == datagen.random_bytes(200000) + b"\x00\x00\xff\xff" * 1000
