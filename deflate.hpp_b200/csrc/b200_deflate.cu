@@ -113,10 +113,12 @@ struct b200_ctx {
     int device = 0;
     bool attrs_set = false;
     uint32_t batch_chunks = 4096;
+    uint32_t better_depth = 128, better_nice = 258;   // "better" level: chain depth / good-enough length
     // compress scratch
     Buf tok, ntok, hist, codes, hdr, desc, sizes, offsets, total;
     // inflate scratch
-    Buf counts, woffs, cand, res, result, one_off;
+    Buf counts, woffs, cand, res, result, one_off, counter;
+    uint32_t inf_grid = 148 * 7;     // persistent inflate grid: SMs x resident CTAs
     // host-API staging
     Buf d_in, d_out;
     cudaStream_t stream = nullptr;   // used by the host-buffer API
@@ -130,6 +132,7 @@ int set_attrs(b200_ctx* c) {
     if (c->attrs_set) return B200_OK;
     CK(cudaFuncSetAttribute(lz77_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LZ_SMEM_BYTES));
     CK(cudaFuncSetAttribute(lz77_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LZ_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(lz77_better_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LZB_SMEM_BYTES));
     CK(cudaFuncSetAttribute(encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_SMEM_BYTES));
     c->attrs_set = true;
     return B200_OK;
@@ -183,6 +186,9 @@ int b200_ctx_create(int device, b200_ctx** ctx) {
     b200_ctx* c = new (std::nothrow) b200_ctx();
     if (!c) return B200_E_NOMEM;
     c->device = device;
+    c->inf_grid = (uint32_t)prop.multiProcessorCount * INF_MAX_CTAS_PER_SM;
+    if (const char* e = getenv("B200_BETTER_DEPTH")) { int v = atoi(e); if (v > 0) c->better_depth = (uint32_t)v; }
+    if (const char* e = getenv("B200_BETTER_NICE")) { int v = atoi(e); if (v >= 3) c->better_nice = (uint32_t)v; }
     if (const char* e = getenv("B200_BATCH_CHUNKS")) { int v = atoi(e); if (v > 0) c->batch_chunks = (uint32_t)v; }
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return B200_E_CUDA; }
     int rc = set_attrs(c);
@@ -195,7 +201,7 @@ void b200_ctx_destroy(b200_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     Buf* all[] = {&c->tok, &c->ntok, &c->hist, &c->codes, &c->hdr, &c->desc, &c->sizes, &c->offsets, &c->total,
-                  &c->counts, &c->woffs, &c->cand, &c->res, &c->result, &c->one_off, &c->d_in, &c->d_out};
+                  &c->counts, &c->woffs, &c->cand, &c->res, &c->result, &c->one_off, &c->counter, &c->d_in, &c->d_out};
     for (Buf* b : all) b->release();
     c->prof.destroy();
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -204,7 +210,7 @@ void b200_ctx_destroy(b200_ctx* c) {
 
 int b200_ctx_profile(b200_ctx* c, int enable) {
     if (!c) return B200_E_ARG;
-    c->prof.clear();
+    if (enable) c->prof.clear();   // records survive a stop so they can be read
     c->prof.on = enable != 0;
     return B200_OK;
 }
@@ -285,7 +291,10 @@ int b200_deflate_compress_dev(b200_ctx* c, const void* d_in, size_t n, int level
         const bool last_batch = b0 + nb == nchunks;
         if (level >= 1) {
             PROF_BEGIN(c, K_LZ77, st);
-            if (level == 1)
+            if (level == 3)
+                lz77_better_kernel<<<nb, LZB_THREADS, LZB_SMEM_BYTES, st>>>(bin, bn, (uint32_t*)c->tok.p, (uint32_t*)c->ntok.p,
+                                                                         (uint32_t*)c->hist.p, c->better_depth, c->better_nice);
+            else if (level == 1)
                 lz77_kernel<1><<<nb, LZ_THREADS, LZ_SMEM_BYTES, st>>>(bin, bn, (uint32_t*)c->tok.p, (uint32_t*)c->ntok.p, (uint32_t*)c->hist.p);
             else
                 lz77_kernel<0><<<nb, LZ_THREADS, LZ_SMEM_BYTES, st>>>(bin, bn, (uint32_t*)c->tok.p, (uint32_t*)c->ntok.p, (uint32_t*)c->hist.p);
@@ -328,11 +337,15 @@ int b200_inflate_batch_dev(b200_ctx* c, const void* d_in, const uint64_t* d_in_o
     if (n_streams == 0) return B200_OK;
     cudaStream_t st = (cudaStream_t)stream_;
     CK(cudaSetDevice(c->device));
-    const uint64_t grid = (n_streams + INF_WARPS - 1) / INF_WARPS;
-    if (grid > 0x7FFFFFFFull) return B200_E_ARG;
+    int rc;
+    if ((rc = c->counter.ensure(64))) return rc;
+    CK(cudaMemsetAsync(c->counter.p, 0, 8, st));
+    const uint64_t want = (n_streams + INF_WARPS - 1) / INF_WARPS;
+    const uint64_t grid = want < c->inf_grid ? want : c->inf_grid;
     PROF_BEGIN(c, K_INFLATE_BATCH, st);
     inflate_batch_kernel<<<(uint32_t)grid, INF_THREADS, 0, st>>>((const uint8_t*)d_in, d_in_off, d_in_len, (uint8_t*)d_out,
-                                                               d_out_off, d_out_cap, d_out_len, d_status, n_streams, flags);
+                                                               d_out_off, d_out_cap, d_out_len, d_status, n_streams, flags,
+                                                               (unsigned long long*)c->counter.p);
     LAUNCHED();
     PROF_END(c, st);
     return B200_OK;
@@ -388,8 +401,11 @@ int b200_inflate_dev(b200_ctx* c, const void* d_in, size_t n, void* d_out, size_
             const unsigned long long init[2] = {1ull, 0ull};
             CK(cudaMemcpyAsync(d_result, init, 16, cudaMemcpyHostToDevice, st));
             PROF_BEGIN(c, K_INFLATE_CHUNKS, st);
-            inflate_chunks_kernel<<<(uint32_t)((ncand + INF_WARPS - 1) / INF_WARPS), INF_THREADS, 0, st>>>(
-                in, n, cand, ncand, (uint8_t*)d_out, cap, (ChunkResult*)c->res.p, flags);
+            if ((rc = c->counter.ensure(64))) return rc;
+            CK(cudaMemsetAsync(c->counter.p, 0, 8, st));
+            const uint64_t want = (ncand + INF_WARPS - 1) / INF_WARPS;
+            inflate_chunks_kernel<<<(uint32_t)(want < c->inf_grid ? want : c->inf_grid), INF_THREADS, 0, st>>>(
+                in, n, cand, ncand, (uint8_t*)d_out, cap, (ChunkResult*)c->res.p, flags, (unsigned long long*)c->counter.p);
             LAUNCHED();
             PROF_END(c, st);
             PROF_BEGIN(c, K_VALIDATE, st);
@@ -406,10 +422,11 @@ int b200_inflate_dev(b200_ctx* c, const void* d_in, size_t n, void* d_out, size_
         // ---- sequential fallback: one warp, whole stream ----
         if ((rc = c->one_off.ensure(64))) return rc;
         uint64_t* d = (uint64_t*)c->one_off.p;   // [0] in_off [1] in_len [2] out_off [3] out_cap [4] out_len [5] status
-        const uint64_t h[6] = {0, (uint64_t)n, 0, (uint64_t)cap, 0, 0};
+        const uint64_t h[7] = {0, (uint64_t)n, 0, (uint64_t)cap, 0, 0, 0};   // [6] = work counter
         CK(cudaMemcpyAsync(d, h, sizeof(h), cudaMemcpyHostToDevice, st));
         PROF_BEGIN(c, K_INFLATE_BATCH, st);
-        inflate_batch_kernel<<<1, INF_THREADS, 0, st>>>(in, d, d + 1, (uint8_t*)d_out, d + 2, d + 3, d + 4, (int32_t*)(d + 5), 1, flags);
+        inflate_batch_kernel<<<1, INF_THREADS, 0, st>>>(in, d, d + 1, (uint8_t*)d_out, d + 2, d + 3, d + 4, (int32_t*)(d + 5), 1, flags,
+                                                        (unsigned long long*)(d + 6));
         LAUNCHED();
         PROF_END(c, st);
         uint64_t r[2] = {0, 0};

@@ -33,10 +33,14 @@ constexpr uint32_t END_SYNC = 2;            // stopped after an empty stored blo
 constexpr uint32_t END_NEEDS_HISTORY = 4;   // a distance reached before this chunk's first byte
 constexpr uint32_t END_TOO_BIG = 8;         // chunk mode: produced more than the chunk capacity
 
-// lit/len entry: [3:0] code length, [5:4] kind (0 literal, 1 length, 2 EOB, 3 long-or-invalid),
-//                literal: [15:8] byte; length: [16:8] base, [23:20] extra-bit count
+// lit/len entry (u32):
+//   literal(s)  : bit 31 = 0; [4:0] bits to consume (one or two codes), [15:8] first byte, [23:16] second
+//                 byte, [27:24] length of the first code alone, bit 30 = entry carries two literals
+//   non-literal : bit 31 = 1; [4:0] code length, [7:5] kind (1 length, 2 EOB, 3 long-or-invalid),
+//                 length: [16:8] base, [23:20] extra-bit count
 // dist entry   : [3:0] code length, [5:4] kind (0 ok, 3 long-or-invalid), [11:8] extra count, [31:16] base
-constexpr uint32_t K_LIT = 0, K_LEN = 1, K_EOB = 2, K_LONG = 3;
+constexpr uint32_t E_NONLIT = 0x80000000u, E_TWO = 0x40000000u;
+constexpr uint32_t K_LEN = 1, K_EOB = 2, K_LONG = 3;
 
 __constant__ uint16_t C_LEN_BASE[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31,
                                         35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
@@ -58,12 +62,14 @@ struct __align__(16) InfWarp {
     uint8_t lens[NSYM];
 };
 
+constexpr uint32_t LIT_INVALID = E_NONLIT | (K_LONG << 5);
+
 __device__ __forceinline__ uint32_t lit_entry(uint32_t sym, uint32_t len) {
-    if (sym < 256) return len | (K_LIT << 4) | (sym << 8);
-    if (sym == 256) return len | (K_EOB << 4);
-    if (sym > 285) return K_LONG << 4;     // 286/287 may appear in the fixed code but never in data
+    if (sym < 256) return len | (sym << 8) | (len << 24);
+    if (sym == 256) return E_NONLIT | len | (K_EOB << 5);
+    if (sym > 285) return LIT_INVALID;     // 286/287 exist in the fixed code but never in data
     const uint32_t idx = sym - 257;
-    return len | (K_LEN << 4) | ((uint32_t)C_LEN_BASE[idx] << 8) | (len_extra_bits(idx) << 20);
+    return E_NONLIT | len | (K_LEN << 5) | ((uint32_t)C_LEN_BASE[idx] << 8) | (len_extra_bits(idx) << 20);
 }
 __device__ __forceinline__ uint32_t dst_entry(uint32_t sym, uint32_t len) {
     if (sym > 29) return K_LONG << 4;
@@ -163,7 +169,7 @@ __device__ bool build_table(InfWarp* S, const uint8_t* lens, uint32_t n, uint32_
     }
     if (over) return false;
     if (lane < 16) { count[lane] = (uint16_t)(lane ? mycount : 0); first[lane] = (uint16_t)myfirst; offs[lane] = (uint16_t)myoff; next[lane] = 0; }
-    for (uint32_t i = lane; i < (1u << tbits); i += 32) table[i] = K_LONG << 4;
+    for (uint32_t i = lane; i < (1u << tbits); i += 32) table[i] = which ? (K_LONG << 4) : LIT_INVALID;
     __syncwarp();
 
     for (uint32_t b = 0; b < n; b += 32) {
@@ -186,6 +192,23 @@ __device__ bool build_table(InfWarp* S, const uint8_t* lens, uint32_t n, uint32_
         }
     }
     __syncwarp();
+    if (which == 0) {
+        // second pass: where a literal's code leaves room in the index for another complete literal code,
+        // let one lookup deliver both.  Entry j = i >> len1 holds the symbol whose code starts right
+        // after the first one; it is usable iff its own code fits in the remaining index bits.  The
+        // single-literal fields ([15:8], [27:24]) survive the rewrite, so in-place is race-free.
+        for (uint32_t i = lane; i < (1u << LIT_BITS); i += 32) {
+            const uint32_t e = table[i];
+            if (!(e & E_NONLIT)) {
+                const uint32_t l1 = (e >> 24) & 15u;
+                const uint32_t e2 = table[i >> l1];
+                const uint32_t l2 = (e2 >> 24) & 15u;
+                if (!(e2 & E_NONLIT) && l1 + l2 <= LIT_BITS)
+                    table[i] = (l1 + l2) | (e & 0x0F00FF00u) | (((e2 >> 8) & 0xFFu) << 16) | E_TWO;
+            }
+        }
+        __syncwarp();
+    }
     return true;
 }
 
@@ -244,7 +267,7 @@ __device__ int read_dynamic_header(InfWarp* S, BitReader& br, uint32_t lane) {
         br_need32(S, br, lane);
         const uint32_t e = S->pre[br_peek(br, 7)];
         const uint32_t l = e & 15u, sym = e >> 8;
-        if (l == 0) return ST_DATA;
+        if (l == 0) return ST_OVERRUN;   // no code matches: the reference reads on until it overruns (inflate.hpp:171-175)
         br_drop(br, l);
         uint32_t rep = 1, val = sym;
         if (sym == 16) { rep = 3 + br_peek(br, 2); br_drop(br, 2); val = prev; }   // prev starts at 0 (inflate.hpp:170)
@@ -274,71 +297,49 @@ __device__ void fixed_tables(InfWarp* S, uint32_t lane) {
     build_table(S, S->lens + NLIT, NDIST, 1, lane);
 }
 
-// ---- output side: literal gather + cooperative copies -----------------------------------------
-struct OutState {
-    uint8_t* out;
-    uint64_t cap;      // bytes that may be written / read back
-    uint64_t op;       // bytes produced so far (keeps counting past cap)
-    uint64_t pend;     // first position whose literal is still held in a lane register
-    uint32_t lit;      // this lane's pending literal
-};
-
-__device__ __forceinline__ void out_flush(OutState& o, uint32_t lane) {
-    if (o.op > o.pend) {
-        // the newest position < op that is congruent to this lane
-        const uint64_t p = (o.op - 1) - ((o.op - 1 - lane) & 31);
-        if (p >= o.pend && p < o.op && p < o.cap) o.out[p] = (uint8_t)o.lit;
-        o.pend = o.op;
-    }
-    __syncwarp();
-}
-__device__ __forceinline__ void out_literal(OutState& o, uint32_t byte, uint32_t lane) {
-    if ((uint32_t)(o.op & 31) == lane) o.lit = byte;
-    o.op++;
-    if ((o.op & 31) == 0) out_flush(o, lane);
-}
-// copy `len` bytes from `dist` back; the caller guarantees dist <= op
-__device__ __forceinline__ void out_match(OutState& o, uint32_t len, uint32_t dist, uint32_t lane) {
-    out_flush(o, lane);
-    const uint64_t dstp = o.op, src = o.op - dist;
-    if (dist >= 32) {
-        for (uint32_t b = 0; b < len; b += 32) {
-            // a 32-byte step only reads bytes written before this step started (dist >= 32)
-            const uint32_t i = b + lane;
-            if (i < len && dstp + i < o.cap) o.out[dstp + i] = o.out[src + i];
-            if (dist < len) __syncwarp();
-        }
-    } else {
-        uint32_t r = lane % dist;
-        const uint32_t step = 32 % dist;
-        for (uint32_t i = lane; i < len; i += 32) {
-            if (dstp + i < o.cap) o.out[dstp + i] = o.out[src + r];
-            r += step;
-            if (r >= dist) r -= dist;
-        }
-    }
-    o.op += len;
-    o.pend = o.op;
-    __syncwarp();
-}
-
 // ---- one stream ------------------------------------------------------------------------------------
-// Decodes blocks until BFINAL (or, if stop_at_sync, until an empty stored block).  Warp-uniform.
-// hist_floor: number of output bytes that precede `out` in the same logical stream and may be
-// referenced (0 for an independent stream/chunk).
-__device__ int inflate_warp(InfWarp* S, const uint8_t* in, uint64_t in_len, uint8_t* out, uint64_t cap,
-                            bool stop_at_sync, uint64_t max_out, unsigned flags, uint32_t lane,
+// s_mod[d][c] = c % d for d in 1..31, c in 0..32 (period-aware copies without integer division)
+struct ModLut { uint8_t m[32][36]; };
+__device__ __forceinline__ void modlut_init(ModLut* L, uint32_t tid, uint32_t nthreads) {
+    for (uint32_t i = tid; i < 32 * 33; i += nthreads) {
+        const uint32_t d = i / 33, c = i % 33;
+        L->m[d][c] = (uint8_t)(d ? c % d : 0);
+    }
+}
+
+// Decodes blocks until BFINAL (or, if stop_at_sync, until an empty stored block).  Warp-uniform: all
+// 32 lanes execute the same symbol decode; lanes differ only in which output bytes they store.
+// Output positions are 32-bit (one stream or chunk < 4 GiB).  `cap` bounds what may be written or read
+// back; decoding continues past it so the full size is still reported (the reference truncates the
+// same way, inflate.hpp:345).  max_out: stop (END_TOO_BIG) once more than this was produced.
+__device__ int inflate_warp(InfWarp* S, const ModLut* ML, const uint8_t* in, uint64_t in_len, uint8_t* out,
+                            uint64_t cap64, bool stop_at_sync, uint64_t max_out64, unsigned flags, uint32_t lane,
                             uint64_t& out_len, uint64_t& in_used, uint32_t& end_flags) {
     BitReader br;
     br.skip = (uint32_t)(reinterpret_cast<uintptr_t>(in) & 15);
     br.base16 = in - br.skip;
     br.limit = br.skip + in_len;
     br_seek(S, br, 0, lane);
-    OutState o{out, cap, 0, 0, 0};
+    const uint32_t cap = (uint32_t)min(cap64, (uint64_t)0xFFFFFFF0u);
+    const uint32_t max_out = (uint32_t)min(max_out64, (uint64_t)0xFFFFFF00u);
+    uint32_t op = 0;        // bytes produced
+    uint32_t pend = 0;      // first position whose literal still sits in a lane register
+    uint32_t lit = 0;       // this lane's pending literal
     const bool strict = flags & 1u;
     const uint64_t in_bits = in_len * 8;
+    const uint32_t wi_limit = (uint32_t)(br.limit >> 2) + 4;
     int st = ST_OK;
     end_flags = 0;
+
+    // store the literals held in lane registers: positions [pend, op), position p lives in lane p & 31
+    auto flush = [&]() {
+        if (op > pend) {
+            const uint32_t p = (op - 1) - ((op - 1 - lane) & 31);
+            if (p >= pend && p < op && p < cap) out[p] = (uint8_t)lit;
+            pend = op;
+        }
+        __syncwarp();
+    };
 
     for (;;) {
         if (br_bitpos(br) + 3 > in_bits) { st = ST_OVERRUN; break; }
@@ -354,11 +355,11 @@ __device__ int inflate_warp(InfWarp* S, const uint8_t* in, uint64_t in_len, uint
             if (strict && (len ^ nlen) != 0xFFFFu) { st = ST_DATA; break; }
             const uint64_t bpos = br_bitpos(br) >> 3;      // byte-aligned here
             if (bpos + len > in_len) { st = ST_OVERRUN; break; }
-            out_flush(o, lane);
+            flush();
             const uint8_t* sp = in + bpos;
             for (uint32_t i = lane; i < len; i += 32)
-                if (o.op + i < o.cap) o.out[o.op + i] = sp[i];
-            o.op += len; o.pend = o.op;
+                if (op + i < cap) out[op + i] = sp[i];
+            op += len; pend = op;
             __syncwarp();
             br_seek(S, br, bpos + len, lane);
             if (len == 0 && stop_at_sync && !bfinal) { end_flags |= END_SYNC; break; }
@@ -368,23 +369,52 @@ __device__ int inflate_warp(InfWarp* S, const uint8_t* in, uint64_t in_len, uint
             if (btype == 1) fixed_tables(S, lane);
             else { st = read_dynamic_header(S, br, lane); if (st) break; }
             // ---- symbol loop ----
-            const uint32_t wi_limit = (uint32_t)(br.limit >> 2) + 4;
             for (;;) {
-                if (br.wi > wi_limit) { st = ST_OVERRUN; break; }   // decoding padding zeros: stop
-                if (o.op > max_out) { end_flags |= END_TOO_BIG; st = ST_DATA; break; }
                 br_need32(S, br, lane);
                 uint32_t e = S->lit[br_peek(br, LIT_BITS)];
-                uint32_t kind = (e >> 4) & 3u, l = e & 15u;
+                if ((int32_t)e >= 0) {
+                    // one or two literals
+                    br_drop(br, e & 31u);
+                    if ((op & 31) == lane) lit = (e >> 8) & 0xFFu;
+                    op++;
+                    if ((op & 31) == 0) {
+                        const uint32_t p = op - 32 + lane;
+                        if (p >= pend && p < cap) out[p] = (uint8_t)lit;
+                        pend = op;
+                        __syncwarp();
+                        if (op > max_out || br.wi > wi_limit) break;    // resolved after the loop
+                    }
+                    if (e & E_TWO) {
+                        if ((op & 31) == lane) lit = (e >> 16) & 0xFFu;
+                        op++;
+                        if ((op & 31) == 0) {
+                            const uint32_t p = op - 32 + lane;
+                            if (p >= pend && p < cap) out[p] = (uint8_t)lit;
+                            pend = op;
+                            __syncwarp();
+                        }
+                    }
+                    continue;
+                }
+                uint32_t kind = (e >> 5) & 7u;
                 if (kind == K_LONG) {
                     uint32_t sl;
                     const int sym = slow_symbol(S, 0, (uint32_t)br.bb, sl);
-                    if (sym < 0) { st = br_bitpos(br) >= in_bits ? ST_OVERRUN : ST_DATA; break; }
+                    // no literal/length code matches: the reference keeps extending the code until it
+                    // runs off the input (inflate.hpp:231-235), i.e. it throws the overrun error
+                    if (sym < 0) { st = ST_OVERRUN; break; }
                     e = lit_entry((uint32_t)sym, sl);
-                    kind = (e >> 4) & 3u; l = sl;
-                    if (kind == K_LONG) { st = ST_DATA; break; }
+                    if (e == LIT_INVALID) { st = ST_DATA; break; }
+                    if ((int32_t)e >= 0) {
+                        br_drop(br, sl);
+                        if ((op & 31) == lane) lit = (e >> 8) & 0xFFu;
+                        op++;
+                        if ((op & 31) == 0) flush();
+                        continue;
+                    }
+                    kind = (e >> 5) & 7u;
                 }
-                br_drop(br, l);
-                if (kind == K_LIT) { out_literal(o, (e >> 8) & 0xFFu, lane); continue; }
+                br_drop(br, e & 31u);
                 if (kind == K_EOB) break;
                 const uint32_t ne = (e >> 20) & 15u;
                 const uint32_t length = ((e >> 8) & 0x1FFu) + br_peek(br, ne);
@@ -395,7 +425,7 @@ __device__ int inflate_warp(InfWarp* S, const uint8_t* in, uint64_t in_len, uint
                 if (((de >> 4) & 3u) == K_LONG) {
                     uint32_t sl;
                     const int sym = slow_symbol(S, 1, (uint32_t)br.bb, sl);
-                    if (sym < 0 || sym > 29) { st = br_bitpos(br) >= in_bits ? ST_OVERRUN : ST_DATA; break; }
+                    if (sym < 0 || sym > 29) { st = br_bitpos(br) + 16 > in_bits ? ST_OVERRUN : ST_DATA; break; }
                     de = dst_entry((uint32_t)sym, sl);
                     dl = sl;
                 }
@@ -403,44 +433,83 @@ __device__ int inflate_warp(InfWarp* S, const uint8_t* in, uint64_t in_len, uint
                 const uint32_t dne = (de >> 8) & 15u;
                 const uint32_t dist = (de >> 16) + br_peek(br, dne);
                 br_drop(br, dne);
-                if (dist > o.op) {
+                if (dist > op) {
                     // reaches before the first byte this warp produced
                     if (stop_at_sync) { end_flags |= END_NEEDS_HISTORY; st = ST_DATA; break; }
                     if (strict) { st = ST_DATA; break; }
                     continue;                              // reference: copies nothing (inflate.hpp:268-270)
                 }
-                out_match(o, length, dist, lane);
+                // ---- back-reference copy, all lanes ----
+                flush();
+                const uint32_t src = op - dist;
+                if (dist >= 32) {
+                    for (uint32_t b = 0; b < length; b += 32) {
+                        // a 32-byte step only reads bytes stored before the step began (dist >= 32)
+                        const uint32_t i = b + lane;
+                        if (i < length && op + i < cap) out[op + i] = out[src + i];
+                        if (dist < length) __syncwarp();
+                    }
+                } else if (dist == 1) {
+                    const uint8_t v = src < cap ? out[src] : 0;
+                    for (uint32_t i = lane; i < length; i += 32)
+                        if (op + i < cap) out[op + i] = v;
+                } else {
+                    uint32_t r = ML->m[dist][lane];
+                    const uint32_t step = ML->m[dist][32];
+                    for (uint32_t i = lane; i < length; i += 32) {
+                        if (op + i < cap) out[op + i] = out[src + r];
+                        r += step;
+                        if (r >= dist) r -= dist;
+                    }
+                }
+                op += length;
+                pend = op;
+                __syncwarp();
+                if (op > max_out || br.wi > wi_limit) break;
             }
             if (st) break;
-            if (br_bitpos(br) > in_bits) { st = ST_OVERRUN; break; }
+            if (br.wi > wi_limit || br_bitpos(br) > in_bits) { st = ST_OVERRUN; break; }
+            if (op > max_out) { end_flags |= END_TOO_BIG; st = ST_DATA; break; }
         }
-        if (o.op > max_out) { end_flags |= END_TOO_BIG; st = ST_DATA; break; }
+        if (op > max_out) { end_flags |= END_TOO_BIG; st = ST_DATA; break; }
         if (bfinal) { end_flags |= END_FINAL; break; }
     }
-    out_flush(o, lane);
-    if (st == ST_OK && br_bitpos(br) > in_bits) st = ST_OVERRUN;
-    out_len = o.op;
+    flush();
+    if (br_bitpos(br) > in_bits) st = ST_OVERRUN;   // whatever else went wrong, the reference would have thrown first
+    out_len = op;
     in_used = (br_bitpos(br) + 7) >> 3;
     return st;
 }
 
 // ---- kernels -----------------------------------------------------------------------------------
+// Both kernels are persistent: the grid is sized to the machine and every warp pulls the next stream
+// (or chunk) index from a global counter, because the cost of a unit varies a lot (a stored chunk is
+// a memcpy, a text chunk is ~25k symbols).  *counter must be zero at launch.
+constexpr uint32_t INF_MAX_CTAS_PER_SM = 7;
+
 // Batch: stream i = in + in_off[i] (in_len[i] bytes) -> out + out_off[i] (<= out_cap[i] bytes).
 __global__ void __launch_bounds__(INF_THREADS)
 inflate_batch_kernel(const uint8_t* __restrict__ in, const uint64_t* __restrict__ in_off,
                      const uint64_t* __restrict__ in_len, uint8_t* __restrict__ out,
                      const uint64_t* __restrict__ out_off, const uint64_t* __restrict__ out_cap,
                      uint64_t* __restrict__ out_len, int32_t* __restrict__ status, uint64_t n_streams,
-                     unsigned flags) {
+                     unsigned flags, unsigned long long* __restrict__ counter) {
     __shared__ InfWarp S[INF_WARPS];
+    __shared__ ModLut ML;
+    modlut_init(&ML, threadIdx.x, INF_THREADS);
+    __syncthreads();
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint64_t i = (uint64_t)blockIdx.x * INF_WARPS + warp;
-    if (i >= n_streams) return;
-    uint64_t ol = 0, used = 0;
-    uint32_t ef = 0;
-    const int st = inflate_warp(&S[warp], in + in_off[i], in_len[i], out + out_off[i], out_cap[i], false,
-                                ~0ull, flags, lane, ol, used, ef);
-    if (lane == 0) { out_len[i] = ol; status[i] = st; }
+    for (;;) {
+        unsigned long long i = 0;
+        if (lane == 0) i = atomicAdd(counter, 1ull);
+        i = __shfl_sync(0xFFFFFFFFu, i, 0);
+        if (i >= n_streams) break;
+        uint64_t ol = 0, used = 0;
+        uint32_t ef = 0;
+        const int st = inflate_warp(&S[warp], &ML, in + in_off[i], in_len[i], out + out_off[i], out_cap[i], false,
+                                    ~0ull, flags, lane, ol, used, ef);
+        if (lane == 0) { out_len[i] = ol; status[i] = st; }
+    }
 }
 
 // ---- single stream, chunk-parallel ---------------------------------------------------------------
@@ -509,22 +578,29 @@ struct ChunkResult { uint64_t in_end; uint32_t out_len; uint16_t status; uint16_
 __global__ void __launch_bounds__(INF_THREADS)
 inflate_chunks_kernel(const uint8_t* __restrict__ in, uint64_t n, const uint64_t* __restrict__ cand,
                       uint64_t ncand, uint8_t* __restrict__ out, uint64_t cap, ChunkResult* __restrict__ res,
-                      unsigned flags) {
+                      unsigned flags, unsigned long long* __restrict__ counter) {
     __shared__ InfWarp S[INF_WARPS];
+    __shared__ ModLut ML;
+    modlut_init(&ML, threadIdx.x, INF_THREADS);
+    __syncthreads();
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint64_t i = (uint64_t)blockIdx.x * INF_WARPS + warp;
-    if (i >= ncand) return;
-    const uint64_t start = cand[i];
-    const uint64_t o0 = i * CHUNK;
-    const uint64_t mycap = o0 >= cap ? 0 : min((uint64_t)CHUNK, cap - o0);
-    uint64_t ol = 0, used = 0;
-    uint32_t ef = 0;
-    const int st = inflate_warp(&S[warp], in + start, n - start, out + o0, mycap, true, CHUNK, flags, lane,
-                                ol, used, ef);
-    if (lane == 0) {
-        ChunkResult r;
-        r.in_end = start + used; r.out_len = (uint32_t)ol; r.status = (uint16_t)st; r.end_flags = (uint16_t)ef;
-        res[i] = r;
+    for (;;) {
+        unsigned long long i = 0;
+        if (lane == 0) i = atomicAdd(counter, 1ull);
+        i = __shfl_sync(0xFFFFFFFFu, i, 0);
+        if (i >= ncand) break;
+        const uint64_t start = cand[i];
+        const uint64_t o0 = i * CHUNK;
+        const uint64_t mycap = o0 >= cap ? 0 : min((uint64_t)CHUNK, cap - o0);
+        uint64_t ol = 0, used = 0;
+        uint32_t ef = 0;
+        const int st = inflate_warp(&S[warp], &ML, in + start, n - start, out + o0, mycap, true, CHUNK, flags, lane,
+                                    ol, used, ef);
+        if (lane == 0) {
+            ChunkResult r;
+            r.in_end = start + used; r.out_len = (uint32_t)ol; r.status = (uint16_t)st; r.end_flags = (uint16_t)ef;
+            res[i] = r;
+        }
     }
 }
 

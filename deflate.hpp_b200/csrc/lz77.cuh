@@ -181,4 +181,176 @@ lz77_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t* __restrict__ t
     for (uint32_t i = lane; i < NSYM; i += 32) gh[i] = h[i];
 }
 
+// =====================================================================================================
+// "better" level (reference level 3, LZ77::getMatchesSlow, include/deflate.hpp:268-304).
+//
+// The reference scans ALL earlier positions of a 32 KB chunk for every position (O(n^2), ~1.1 s per
+// chunk) and takes the longest match greedily.  Here one CTA owns a 64 KiB chunk for its whole
+// lifetime in ~224 KB of shared memory:
+//   phase A  warp 0 threads the chunk into hash chains (3-byte hash, 16 K heads + a 64 K-entry `prev`
+//            array, both u16 in shared memory); 32 positions per step, intra-step collisions resolved
+//            with __match_any_sync so the chains are strictly ordered by position
+//   phase B  all 16 warps search: each lane walks the chain of its own position (nearest first, up to
+//            `depth` candidates, 32 KiB distance limit, 4-byte-stride extension) and stores its best
+//            (length, distance) in the chunk's token scratch
+//   phase C  warps 0..7 parse one 8 KiB segment each over those candidates with lazy evaluation
+//            (a match is deferred when the next position has a longer one), emit tokens in place and
+//            build the histograms, exactly as the fast kernel does.
+// =====================================================================================================
+constexpr uint32_t LZB_THREADS = 512;
+constexpr uint32_t LZB_HASH_BITS = 14;
+constexpr uint32_t LZB_NIL = 0xFFFFu;           // position 65535 can never be anybody's predecessor
+constexpr uint32_t LZB_TOO_FAR = 4096;          // a 3-byte match farther than this costs more than literals
+constexpr size_t LZB_SMEM_BYTES = CHUNK + LZ_DATA_PAD + CHUNK * 2 + (2u << LZB_HASH_BITS) + 16;
+
+__device__ __forceinline__ uint32_t lzb_hash(uint32_t w4) { return ((w4 & 0xFFFFFFu) * 0x9E3779B1u) >> (32 - LZB_HASH_BITS); }
+
+__global__ void __launch_bounds__(LZB_THREADS, 1)
+lz77_better_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t* __restrict__ tok,
+                   uint32_t* __restrict__ ntok, uint32_t* __restrict__ hist, uint32_t depth, uint32_t nice) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* s_data = smem;
+    uint16_t* s_prev = reinterpret_cast<uint16_t*>(smem + CHUNK + LZ_DATA_PAD);
+    uint16_t* s_head = s_prev + CHUNK;
+    uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_head);          // phase C reuses the head table
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + CHUNK + LZ_DATA_PAD + CHUNK * 2 + (2u << LZB_HASH_BITS));
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint64_t chunk = blockIdx.x;
+    const uint64_t base = chunk * CHUNK;
+    const uint32_t clen = (uint32_t)min((uint64_t)CHUNK, n - base);
+    const uint8_t* src = in + base;
+    const uint32_t FULL = 0xFFFFFFFFu;
+
+    const bool aligned = ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    const uint32_t bulk = aligned ? (clen & ~15u) : 0;
+    if (tid == 0) mbar_init(s_bar, 1);
+    __syncthreads();
+    if (tid == 0 && bulk) tma_load_1d(s_data, src, bulk, s_bar);
+    for (uint32_t i = bulk + tid; i < clen; i += LZB_THREADS) s_data[i] = src[i];
+    for (uint32_t i = clen + tid; i < ((clen + 15u) & ~15u) + LZ_DATA_PAD && i < CHUNK + LZ_DATA_PAD; i += LZB_THREADS)
+        s_data[i] = 0;
+    for (uint32_t i = tid; i < (1u << LZB_HASH_BITS) / 2; i += LZB_THREADS) reinterpret_cast<uint32_t*>(s_head)[i] = 0xFFFFFFFFu;
+    if (bulk) mbar_wait(s_bar, 0);
+    __syncthreads();
+
+    // ---- phase A: ordered hash chains (one warp) -------------------------------------------------
+    if (warp == 0) {
+        for (uint32_t t0 = 0; t0 < clen; t0 += 32) {
+            const uint32_t p = t0 + lane;
+            const bool valid = p + 3 <= clen;
+            const uint32_t h = lzb_hash(ld4_unaligned(s_data, p));
+            const uint32_t key = valid ? h : (0x80000000u | lane);       // invalid lanes match nobody
+            const uint32_t peers = __match_any_sync(FULL, key);
+            const uint32_t lower = peers & ((1u << lane) - 1u);
+            if (valid) {
+                const uint32_t old = s_head[h];
+                s_prev[p] = (uint16_t)(lower ? t0 + (31 - __clz(lower)) : old);
+            } else if (p < clen) {
+                s_prev[p] = (uint16_t)LZB_NIL;
+            }
+            __syncwarp();
+            if (valid && (peers >> lane) == 1u) s_head[h] = (uint16_t)p;  // highest lane of its group
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+
+    // ---- phase B: chain search, every position, all warps ----------------------------------------
+    uint32_t* cand = tok + chunk * CHUNK;
+    for (uint32_t t0 = warp * 32; t0 < clen; t0 += LZB_THREADS) {
+        const uint32_t p = t0 + lane;
+        uint32_t best = 0, bdist = 0;
+        if (p + 3 <= clen) {
+            const uint32_t maxl = min(clen - p, MAX_MATCH);
+            const uint32_t stop = min(nice, maxl);
+            const uint32_t w4 = ld4_unaligned(s_data, p);
+            uint32_t q = s_prev[p];
+            uint32_t budget = depth;
+            best = 2;
+            while (q != LZB_NIL && budget-- && p - q <= MAX_DIST) {
+                // cheap reject: to beat `best` a candidate must agree on bytes [best-3, best] and at the head
+                if ((best < 3 || ld4_unaligned(s_data, q + best - 3) == ld4_unaligned(s_data, p + best - 3)) &&
+                    ((ld4_unaligned(s_data, q) ^ w4) & 0xFFFFFFu) == 0) {
+                    uint32_t l = 3;
+                    while (l < maxl) {
+                        const uint32_t x = ld4_unaligned(s_data, p + l) ^ ld4_unaligned(s_data, q + l);
+                        if (x) { l += (__ffs(x) - 1) >> 3; break; }
+                        l += 4;
+                    }
+                    l = min(l, maxl);
+                    if (l > best) { best = l; bdist = p - q; if (l >= stop) break; }
+                }
+                q = s_prev[q];
+            }
+            if (best < 3 || (best == 3 && bdist > LZB_TOO_FAR)) { best = 0; bdist = 0; }
+        }
+        if (p < clen) cand[p] = best | (bdist << 16);
+    }
+    __syncthreads();   // also orders the global cand[] stores before phase C's loads (same CTA)
+
+    // ---- phase C: lazy parse per segment (warps 0..7) --------------------------------------------
+    for (uint32_t i = tid; i < NSEG * NSYM; i += LZB_THREADS) s_hist[i] = 0;
+    __syncthreads();
+    if (warp >= NSEG) return;
+    const uint32_t seg_lo = warp * SEG;
+    const uint32_t seg_hi = min(clen, seg_lo + SEG);
+    uint32_t* h = s_hist + warp * NSYM;
+    uint32_t* mytok = tok + chunk * CHUNK + seg_lo;
+    uint32_t nt = 0;
+    if (seg_lo < clen) {
+        uint32_t pos = seg_lo;
+        while (pos < seg_hi) {
+            const uint32_t p = pos + lane;
+            const uint32_t valid = min(32u, seg_hi - pos);
+            uint32_t len = 0, dist = 0;
+            if (lane < valid) {
+                const uint32_t c = cand[p];
+                len = min(c & 0xFFFFu, seg_hi - p);          // tokens never cross a segment
+                dist = c >> 16;
+                if (len < 3 || (len == 3 && dist > LZB_TOO_FAR)) len = 0;
+            }
+            const uint8_t byte = s_data[p];
+            __syncwarp();                                     // all candidate loads done before tokens overwrite them
+            // lane 31 is only a lookahead unless the segment ends inside this window
+            const uint32_t limit = valid < 32 ? valid : 31;
+            const uint32_t mmask = __ballot_sync(FULL, len >= 3);
+            uint32_t litmask = 0, selmask = 0, cur = 0;
+            while (cur < limit) {
+                const uint32_t m = mmask & ~((1u << cur) - 1u) & ((limit >= 32) ? FULL : ((1u << limit) - 1u));
+                if (m == 0) { litmask |= mask_range(cur, limit); cur = limit; break; }
+                const uint32_t j = __ffs(m) - 1;
+                litmask |= mask_range(cur, j);
+                const uint32_t lj = __shfl_sync(FULL, len, j);
+                const uint32_t ln = __shfl_sync(FULL, len, (j + 1) & 31);
+                if (j + 1 < valid && ln > lj) { litmask |= 1u << j; cur = j + 1; continue; }   // lazy: defer
+                selmask |= 1u << j;
+                cur = j + lj;
+            }
+            const uint32_t sel = litmask | selmask;
+            if ((sel >> lane) & 1) {
+                const uint32_t rank = __popc(sel & ((1u << lane) - 1u));
+                if ((selmask >> lane) & 1) {
+                    mytok[nt + rank] = tok_match(len, dist);
+                    uint32_t idx, ne, ev, ds;
+                    len_symbol(len, idx, ne, ev);
+                    atomicAdd(&h[257 + idx], 1u);
+                    dist_symbol(dist, ds, ne, ev);
+                    atomicAdd(&h[NLIT + ds], 1u);
+                } else {
+                    mytok[nt + rank] = byte;
+                    atomicAdd(&h[byte], 1u);
+                }
+            }
+            nt += __popc(sel);
+            pos += cur;
+            __syncwarp();
+        }
+    }
+    __syncwarp();
+    if (lane == 0) ntok[chunk * NSEG + warp] = nt;
+    uint32_t* gh = hist + (chunk * NSEG + warp) * NSYM;
+    for (uint32_t i = lane; i < NSYM; i += 32) gh[i] = h[i];
+}
+
 }  // namespace b200
