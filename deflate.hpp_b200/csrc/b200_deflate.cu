@@ -238,7 +238,7 @@ const char* b200_kernel_name(int kernel_id) {
 
 size_t b200_deflate_bound(size_t n) {
     const size_t nchunks = (n + CHUNK - 1) / CHUNK;
-    return n + 15 * nchunks + 16;
+    return n + 20 * nchunks + 16;   // per chunk: two stored blocks (2 x 5) + separator (10)
 }
 
 void b200_free(void* p) { free(p); }

@@ -19,6 +19,12 @@ constexpr uint32_t HDR_WORDS = 160;        // >= 4498 bits worst-case dynamic he
 constexpr uint32_t MIN_MATCH = 3;
 constexpr uint32_t MAX_MATCH = 258;
 constexpr uint32_t MAX_DIST = 32768;
+// Chunk separator: TWO empty non-final stored blocks.  Byte-aligned it reads 00 | 00 00 FF FF | 00 | 00 00 FF FF
+// (after a Huffman block the first header's 3 bits share the block's last byte).  The 9-byte tail
+// "00 00 FF FF 00 00 00 FF FF" is what the chunk-parallel inflater scans for: a single sync marker
+// (4 bytes) shows up by chance about once per 4 GiB of compressed data, the doubled one never does.
+constexpr uint32_t SYNC_BYTES_ALIGNED = 10;   // bytes the separator takes when it starts byte-aligned
+constexpr uint32_t SYNC_PATTERN_BYTES = 9;
 
 // Token: literal -> byte value (dist field 0); match -> length in bits [0,9), distance in [16,32).
 __host__ __device__ __forceinline__ uint32_t tok_match(uint32_t len, uint32_t dist) { return len | (dist << 16); }

@@ -51,7 +51,7 @@ scan_sizes_kernel(const uint32_t* __restrict__ sizes, uint32_t n, const uint64_t
 
 // ---- K4: encode ------------------------------------------------------------------------------------
 constexpr uint32_t ENC_THREADS = NSEG * 32;
-constexpr uint32_t ENC_STAGE_BYTES = CHUNK + 64;       // block bytes (<= stored size) + phase + marker
+constexpr uint32_t ENC_STAGE_BYTES = CHUNK + 80;       // block bytes (<= stored size) + phase + marker
 constexpr size_t ENC_SMEM_BYTES = ENC_STAGE_BYTES + NSYM * 4;
 
 // OR `nbits` (<= 48) of v into the staging bit array at absolute bit position `bit`.
@@ -105,7 +105,10 @@ encode_kernel(const uint8_t* __restrict__ in, const uint32_t* __restrict__ tok, 
             for (uint32_t i = tid; i < bl; i += ENC_THREADS) sb[o + 5 + i] = src[done + i];
             o += 5 + bl; done += bl;
         }
-        if (!d.last && tid == 0) { sb[o] = 0; sb[o + 1] = 0; sb[o + 2] = 0; sb[o + 3] = 0xFF; sb[o + 4] = 0xFF; }
+        if (!d.last && tid == 0) {   // separator: two empty stored blocks
+            sb[o] = 0; sb[o + 1] = 0; sb[o + 2] = 0; sb[o + 3] = 0xFF; sb[o + 4] = 0xFF;
+            sb[o + 5] = 0; sb[o + 6] = 0; sb[o + 7] = 0; sb[o + 8] = 0xFF; sb[o + 9] = 0xFF;
+        }
     } else {
         const uint32_t bit0 = phase * 8;
         // header bits
@@ -155,9 +158,10 @@ encode_kernel(const uint8_t* __restrict__ in, const uint32_t* __restrict__ tok, 
             const uint32_t c = s_codes[256];
             const uint32_t eob_len = c & 0xFFu;
             stage_bits(stage, bit0 + d.total_bits - eob_len, c >> 8, eob_len);
-            if (!d.last) {   // empty stored block: 3 zero bits, pad, 00 00 FF FF
+            if (!d.last) {   // separator: 3 zero bits, pad, 00 00 FF FF, then 00 | 00 00 FF FF
                 const uint32_t mb = phase + (d.total_bits + 3 + 7) / 8;
                 stage_bits(stage, (mb + 2) * 8, 0xFFFFu, 16);   // atomic: may share a word with payload bits
+                stage_bits(stage, (mb + 7) * 8, 0xFFFFu, 16);
             }
         }
     }

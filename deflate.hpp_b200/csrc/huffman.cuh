@@ -234,7 +234,7 @@ huffman_kernel(const uint32_t* __restrict__ hist, uint64_t n, uint32_t nchunks, 
     BlockDesc* d = desc + chunk;
 
     const uint32_t nstored = (clen + 65534u) / 65535u;
-    const uint32_t stored_bytes = clen + 5u * nstored + (last ? 0u : 5u);
+    const uint32_t stored_bytes = clen + 5u * nstored + (last ? 0u : SYNC_BYTES_ALIGNED);
 
     if (level == 0) {
         if (lane == 0) {
@@ -327,7 +327,7 @@ huffman_kernel(const uint32_t* __restrict__ hist, uint64_t n, uint32_t nchunks, 
     const uint32_t fix_bits = 3 + fix;
     const uint32_t use_dyn = dyn_bits < fix_bits;
     const uint32_t bits = use_dyn ? dyn_bits : fix_bits;
-    const uint32_t huff_bytes = last ? (bits + 7) / 8 : (bits + 3 + 7) / 8 + 4;
+    const uint32_t huff_bytes = last ? (bits + 7) / 8 : (bits + 3 + 7) / 8 + (SYNC_BYTES_ALIGNED - 1);
     const uint32_t btype = huff_bytes < stored_bytes ? (use_dyn ? 2u : 1u) : 0u;
 
     // ---- emit codes, header, descriptor ---------------------------------------------------

@@ -329,6 +329,7 @@ __device__ int inflate_warp(InfWarp* S, const ModLut* ML, const uint8_t* in, uin
     const uint64_t in_bits = in_len * 8;
     const uint32_t wi_limit = (uint32_t)(br.limit >> 2) + 4;
     int st = ST_OK;
+    uint32_t empty_run = 0;
     end_flags = 0;
 
     // store the literals held in lane registers: positions [pend, op), position p lives in lane p & 31
@@ -362,10 +363,16 @@ __device__ int inflate_warp(InfWarp* S, const ModLut* ML, const uint8_t* in, uin
             op += len; pend = op;
             __syncwarp();
             br_seek(S, br, bpos + len, lane);
-            if (len == 0 && stop_at_sync && !bfinal) { end_flags |= END_SYNC; break; }
+            if (len == 0 && !bfinal) {
+                // chunk separator = two empty stored blocks in a row (common.cuh)
+                if (++empty_run == 2 && stop_at_sync) { end_flags |= END_SYNC; break; }
+            } else {
+                empty_run = 0;
+            }
         } else if (btype == 3) {
             if (strict) { st = ST_DATA; break; }           // the reference's switch has no case 3
         } else {
+            empty_run = 0;
             if (btype == 1) fixed_tables(S, lane);
             else { st = read_dynamic_header(S, br, lane); if (st) break; }
             // ---- symbol loop ----
@@ -513,8 +520,8 @@ inflate_batch_kernel(const uint8_t* __restrict__ in, const uint64_t* __restrict_
 }
 
 // ---- single stream, chunk-parallel ---------------------------------------------------------------
-// Pass 1/2: find every "00 00 FF FF" (the tail of an empty stored block); the byte after it is a
-// candidate chunk start.  One warp scans a contiguous 16 KiB region with coalesced 16-byte loads, so
+// Pass 1/2: find every chunk separator tail (00 00 FF FF 00 00 00 FF FF, see common.cuh); the byte after
+// it is a candidate chunk start.  One warp scans a contiguous 16 KiB region with coalesced 16-byte loads, so
 // candidates come out in stream order: pass A counts per warp, an exclusive scan gives each warp its
 // slot, pass B (WRITE) stores the candidate offsets.  cand[0] = 0 is written by the host side.
 constexpr uint32_t SYNC_REGION = 16384;
@@ -533,20 +540,26 @@ find_sync_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t* __restric
     uint32_t total = 0;
     for (uint64_t b = lo; b < hi; b += 512) {
         const uint64_t p = b + lane * 16;
-        uint32_t wd[5] = {0, 0, 0, 0, 0};
-        if (aligned && p + 20 <= n) {
+        uint32_t wd[7] = {0, 0, 0, 0, 0, 0, 0};
+        if (aligned && p + 28 <= n) {
             const uint4 v = *reinterpret_cast<const uint4*>(in + p);
             wd[0] = v.x; wd[1] = v.y; wd[2] = v.z; wd[3] = v.w;
             wd[4] = *reinterpret_cast<const uint32_t*>(in + p + 16);
+            wd[5] = *reinterpret_cast<const uint32_t*>(in + p + 20);
+            wd[6] = *reinterpret_cast<const uint32_t*>(in + p + 24);
         } else {
-            for (uint32_t j = 0; j < 20; j++)
+            for (uint32_t j = 0; j < 28; j++)
                 if (p + j < n) wd[j >> 2] |= (uint32_t)in[p + j] << (8 * (j & 3));
         }
-        uint32_t hits = 0;   // bit j: marker starts at byte p + j
+        uint32_t hits = 0;   // bit j: the 9-byte separator tail 00 00 FF FF 00 00 00 FF FF starts at byte p + j
         #pragma unroll
         for (uint32_t j = 0; j < 16; j++) {
-            const uint32_t x = __funnelshift_r(wd[j >> 2], wd[(j >> 2) + 1], (j & 3) * 8);
-            if (x == 0xFFFF0000u && p + j + 4 < n && p + j < hi) hits |= 1u << j;
+            const uint32_t sh = (j & 3) * 8;
+            const uint32_t x0 = __funnelshift_r(wd[j >> 2], wd[(j >> 2) + 1], sh);
+            const uint32_t x1 = __funnelshift_r(wd[(j >> 2) + 1], wd[(j >> 2) + 2], sh);
+            const uint32_t x2 = __funnelshift_r(wd[(j >> 2) + 2], wd[(j >> 2) + 3], sh);
+            if (x0 == 0xFFFF0000u && x1 == 0xFF000000u && (x2 & 0xFFu) == 0xFFu && p + j + SYNC_PATTERN_BYTES < n && p + j < hi)
+                hits |= 1u << j;
         }
         if (__ballot_sync(FULL, hits != 0)) {
             const uint32_t c = __popc(hits);
@@ -561,7 +574,7 @@ find_sync_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t* __restric
                 while (h) {
                     const uint32_t j = __ffs(h) - 1;
                     h &= h - 1;
-                    if (slot < cand_cap) cand[slot] = p + j + 4;
+                    if (slot < cand_cap) cand[slot] = p + j + SYNC_PATTERN_BYTES;
                     slot++;
                 }
             }

@@ -12,8 +12,10 @@
  * Stream format produced by the compressor (one valid RFC 1951 raw stream):
  *   input is cut into independent 64 KiB chunks; each chunk is ONE block (dynamic, fixed or stored,
  *   whichever is smallest by exact bit count) that starts byte-aligned; every chunk except the last
- *   is followed by an empty non-final stored block (pad bits, 00 00 FF FF) so that the next chunk is
- *   byte-aligned again; the last chunk's block carries BFINAL.  No match crosses a chunk boundary.
+ *   is followed by TWO empty non-final stored blocks (pad bits, 00 00 FF FF, 00, 00 00 FF FF) so
+ *   that the next chunk is byte-aligned again and its start can be found by scanning for the 9-byte
+ *   pattern 00 00 FF FF 00 00 00 FF FF (a single sync marker would turn up by chance in compressed
+ *   data); the last chunk's block carries BFINAL.  No match crosses a chunk boundary.
  */
 #ifndef B200_DEFLATE_H
 #define B200_DEFLATE_H

@@ -166,5 +166,12 @@ def test_false_sync_markers(b200):
     for level in (0, 2):
         c = b200.compress(data, level)
         assert b200.decompress(c) == data
+    # the full 9-byte chunk separator inside stored (incompressible) user data: candidates are found that
+    # are not chunk starts; validation must reject the optimistic layout and still decode correctly
+    sep = b"\x00\x00\xff\xff\x00\x00\x00\xff\xff"
+    noisy = b"".join(datagen.random_bytes(3000, seed=50 + i) + sep for i in range(60)) + datagen.text_like(100000)
+    for level in (0, 2, 3):
+        c = b200.compress(noisy, level)
+        assert b200.decompress(c) == noisy
     z = datagen.foreign_streams(datagen.random_bytes(200000) + b"\x00\x00\xff\xff" * 1000)["stored"]
     assert b200.decompress(z) == datagen.random_bytes(200000) + b"\x00\x00\xff\xff" * 1000
