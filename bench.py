@@ -250,28 +250,18 @@ def main():
     ctx.corpus_generate_dev(src.data_ptr(), SEED, rank * nchunks, nchunks, stream=st)
     cap = d.deflate_bound(n)
     dst = torch.empty(cap, dtype=torch.uint8, device=dev)
-    flags = d.F_NOT_LAST if rank != world - 1 else 0
+    import importlib
+    shard = importlib.import_module("deflate_hpp_b200.shard")
+    flags = shard.shard_flags(rank, world, d.F_NOT_LAST)
     gather_buf = None
     if world > 1 and rank == 0:
         gather_buf = torch.empty(cap * world, dtype=torch.uint8, device=dev)
-    sizes_t = torch.zeros(world, dtype=torch.int64, device=dev)
 
     def step():
         cn = ctx.compress_dev(src.data_ptr(), n, args.level, dst.data_ptr(), cap, flags=flags, stream=st)
         if world > 1:
-            mine = torch.tensor([cn], dtype=torch.int64, device=dev)
-            dist.all_gather_into_tensor(sizes_t, mine)
-            sz = sizes_t.tolist()
-            if rank == 0:
-                ops, off = [], sz[0]
-                for r in range(1, world):
-                    ops.append(dist.P2POp(dist.irecv, gather_buf[off:off + sz[r]], r))
-                    off += sz[r]
-                for w in dist.batch_isend_irecv(ops):
-                    w.wait()
-            else:
-                for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, dst[:cn], 0)]):
-                    w.wait()
+            # the one exchange step of this path: variable-size gather of compressed bytes to rank 0
+            shard.gather_bytes(dst, cn, dst=0, recv_buf=gather_buf)
         return cn
 
     def barrier():

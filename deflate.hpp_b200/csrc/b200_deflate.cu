@@ -113,6 +113,7 @@ struct b200_ctx {
     int device = 0;
     bool attrs_set = false;
     uint32_t batch_chunks = 4096;
+    bool fast_two_phase = false;     // B200_FAST_TWO_PHASE=1: chunk-wide-table matcher (better ratio, 2.5x slower K1)
     uint32_t better_depth = 128, better_nice = 258;   // "better" level: chain depth / good-enough length
     // compress scratch
     Buf tok, ntok, hist, codes, hdr, desc, sizes, offsets, total;
@@ -121,7 +122,12 @@ struct b200_ctx {
     uint32_t inf_grid = 148 * 7;     // persistent inflate grid: SMs x resident CTAs
     // host-API staging
     Buf d_in, d_out;
-    cudaStream_t stream = nullptr;   // used by the host-buffer API
+    cudaStream_t stream = nullptr;   // used by the host-buffer API (kernels)
+    cudaStream_t s_in = nullptr, s_out = nullptr;   // host-buffer API: H2D / D2H copy streams
+    std::vector<cudaEvent_t> events;
+    uint64_t* mailbox = nullptr;     // pinned: per-slice end offsets
+    size_t mailbox_cap = 0;
+    uint32_t host_slice_chunks = 2048;
     std::mutex mu;
     Prof prof;
 };
@@ -132,6 +138,7 @@ int set_attrs(b200_ctx* c) {
     if (c->attrs_set) return B200_OK;
     CK(cudaFuncSetAttribute(lz77_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LZ_SMEM_BYTES));
     CK(cudaFuncSetAttribute(lz77_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LZ_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(lz77_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LZF_SMEM_BYTES));
     CK(cudaFuncSetAttribute(lz77_better_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LZB_SMEM_BYTES));
     CK(cudaFuncSetAttribute(encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_SMEM_BYTES));
     c->attrs_set = true;
@@ -187,10 +194,14 @@ int b200_ctx_create(int device, b200_ctx** ctx) {
     if (!c) return B200_E_NOMEM;
     c->device = device;
     c->inf_grid = (uint32_t)prop.multiProcessorCount * INF_MAX_CTAS_PER_SM;
+    if (const char* e = getenv("B200_FAST_TWO_PHASE")) c->fast_two_phase = atoi(e) != 0;
     if (const char* e = getenv("B200_BETTER_DEPTH")) { int v = atoi(e); if (v > 0) c->better_depth = (uint32_t)v; }
     if (const char* e = getenv("B200_BETTER_NICE")) { int v = atoi(e); if (v >= 3) c->better_nice = (uint32_t)v; }
     if (const char* e = getenv("B200_BATCH_CHUNKS")) { int v = atoi(e); if (v > 0) c->batch_chunks = (uint32_t)v; }
-    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return B200_E_CUDA; }
+    if (const char* e = getenv("B200_HOST_SLICE_CHUNKS")) { int v = atoi(e); if (v > 0) c->host_slice_chunks = (uint32_t)v; }
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking) != cudaSuccess) { delete c; return B200_E_CUDA; }
     int rc = set_attrs(c);
     if (rc) { cudaStreamDestroy(c->stream); delete c; return rc; }
     *ctx = c;
@@ -204,6 +215,10 @@ void b200_ctx_destroy(b200_ctx* c) {
                   &c->counts, &c->woffs, &c->cand, &c->res, &c->result, &c->one_off, &c->counter, &c->d_in, &c->d_out};
     for (Buf* b : all) b->release();
     c->prof.destroy();
+    for (auto e : c->events) cudaEventDestroy(e);
+    if (c->mailbox) cudaFreeHost(c->mailbox);
+    if (c->s_in) cudaStreamDestroy(c->s_in);
+    if (c->s_out) cudaStreamDestroy(c->s_out);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -242,6 +257,45 @@ size_t b200_deflate_bound(size_t n) {
 }
 
 void b200_free(void* p) { free(p); }
+
+// One batch of chunks through K1..K4 on stream `st`.  bin/bn: this batch's first input byte and the
+// bytes from there to the end of the buffer; offs: the chunk-offset array (global chunk indexing).
+static int compress_batch(b200_ctx* c, const uint8_t* bin, uint64_t bn, uint32_t nb, uint64_t b0, bool final_batch,
+                          int level, uint64_t* offs, uint64_t* d_total, void* d_out, cudaStream_t st) {
+    if (level >= 1) {
+        PROF_BEGIN(c, K_LZ77, st);
+        if (level == 3)
+            lz77_better_kernel<<<nb, LZB_THREADS, LZB_SMEM_BYTES, st>>>(bin, bn, (uint32_t*)c->tok.p, (uint32_t*)c->ntok.p,
+                                                                     (uint32_t*)c->hist.p, c->better_depth, c->better_nice);
+        else if (level == 2 && c->fast_two_phase)
+            lz77_fast_kernel<<<nb, LZF_THREADS, LZF_SMEM_BYTES, st>>>(bin, bn, (uint32_t*)c->tok.p, (uint32_t*)c->ntok.p,
+                                                                   (uint32_t*)c->hist.p);
+        else if (level == 1)
+            lz77_kernel<1><<<nb, LZ_THREADS, LZ_SMEM_BYTES, st>>>(bin, bn, (uint32_t*)c->tok.p, (uint32_t*)c->ntok.p, (uint32_t*)c->hist.p);
+        else
+            lz77_kernel<0><<<nb, LZ_THREADS, LZ_SMEM_BYTES, st>>>(bin, bn, (uint32_t*)c->tok.p, (uint32_t*)c->ntok.p, (uint32_t*)c->hist.p);
+        LAUNCHED();
+        PROF_END(c, st);
+    }
+    PROF_BEGIN(c, K_HUFFMAN, st);
+    huffman_kernel<<<(nb + HUF_WARPS - 1) / HUF_WARPS, HUF_THREADS, 0, st>>>(
+        (const uint32_t*)c->hist.p, bn, nb, level, final_batch ? 1 : 0, (uint32_t*)c->codes.p,
+        (uint32_t*)c->hdr.p, (BlockDesc*)c->desc.p, (uint32_t*)c->sizes.p);
+    LAUNCHED();
+    PROF_END(c, st);
+    PROF_BEGIN(c, K_SCAN, st);
+    scan_sizes_kernel<<<1, SCAN_THREADS, 0, st>>>((const uint32_t*)c->sizes.p, nb, b0 ? offs + b0 : nullptr,
+                                                 offs + b0, d_total);
+    LAUNCHED();
+    PROF_END(c, st);
+    PROF_BEGIN(c, K_ENCODE, st);
+    encode_kernel<<<nb, ENC_THREADS, ENC_SMEM_BYTES, st>>>(bin, (const uint32_t*)c->tok.p, (const uint32_t*)c->ntok.p,
+                                                          (const uint32_t*)c->codes.p, (const uint32_t*)c->hdr.p,
+                                                          (const BlockDesc*)c->desc.p, offs + b0, (uint8_t*)d_out);
+    LAUNCHED();
+    PROF_END(c, st);
+    return B200_OK;
+}
 
 // ------------------------------------------------------------------------------------------------
 int b200_deflate_compress_dev(b200_ctx* c, const void* d_in, size_t n, int level, unsigned flags, void* d_out,
@@ -289,35 +343,7 @@ int b200_deflate_compress_dev(b200_ctx* c, const void* d_in, size_t n, int level
         const uint8_t* bin = in + b0 * CHUNK;
         const uint64_t bn = n - b0 * CHUNK;
         const bool last_batch = b0 + nb == nchunks;
-        if (level >= 1) {
-            PROF_BEGIN(c, K_LZ77, st);
-            if (level == 3)
-                lz77_better_kernel<<<nb, LZB_THREADS, LZB_SMEM_BYTES, st>>>(bin, bn, (uint32_t*)c->tok.p, (uint32_t*)c->ntok.p,
-                                                                         (uint32_t*)c->hist.p, c->better_depth, c->better_nice);
-            else if (level == 1)
-                lz77_kernel<1><<<nb, LZ_THREADS, LZ_SMEM_BYTES, st>>>(bin, bn, (uint32_t*)c->tok.p, (uint32_t*)c->ntok.p, (uint32_t*)c->hist.p);
-            else
-                lz77_kernel<0><<<nb, LZ_THREADS, LZ_SMEM_BYTES, st>>>(bin, bn, (uint32_t*)c->tok.p, (uint32_t*)c->ntok.p, (uint32_t*)c->hist.p);
-            LAUNCHED();
-            PROF_END(c, st);
-        }
-        PROF_BEGIN(c, K_HUFFMAN, st);
-        huffman_kernel<<<(nb + HUF_WARPS - 1) / HUF_WARPS, HUF_THREADS, 0, st>>>(
-            (const uint32_t*)c->hist.p, bn, nb, level, (last_batch && final_here) ? 1 : 0, (uint32_t*)c->codes.p,
-            (uint32_t*)c->hdr.p, (BlockDesc*)c->desc.p, (uint32_t*)c->sizes.p);
-        LAUNCHED();
-        PROF_END(c, st);
-        PROF_BEGIN(c, K_SCAN, st);
-        scan_sizes_kernel<<<1, SCAN_THREADS, 0, st>>>((const uint32_t*)c->sizes.p, nb, b0 ? offs + b0 : nullptr,
-                                                     offs + b0, d_total);
-        LAUNCHED();
-        PROF_END(c, st);
-        PROF_BEGIN(c, K_ENCODE, st);
-        encode_kernel<<<nb, ENC_THREADS, ENC_SMEM_BYTES, st>>>(bin, (const uint32_t*)c->tok.p, (const uint32_t*)c->ntok.p,
-                                                              (const uint32_t*)c->codes.p, (const uint32_t*)c->hdr.p,
-                                                              (const BlockDesc*)c->desc.p, offs + b0, (uint8_t*)d_out);
-        LAUNCHED();
-        PROF_END(c, st);
+        if ((rc = compress_batch(c, bin, bn, nb, b0, last_batch && final_here, level, offs, d_total, d_out, st))) return rc;
     }
     if (d_out_n) CK(cudaMemcpyAsync(d_out_n, d_total, 8, cudaMemcpyDeviceToDevice, st));
     if (h_out_n) {
@@ -458,49 +484,111 @@ int b200_corpus_generate_dev(void* d_out, uint64_t seed, uint64_t first_chunk, u
 
 // ------------------------------------------------------------------------------------------------
 // Host-buffer API
+//
+// Compress host memory into host memory.  The input is cut into slices (host_slice_chunks, 128 MiB by
+// default); slice k+1's host->device copy, slice k's kernels and slice k-1's device->host copy run on
+// three streams, chained by events, so with pinned host buffers the call is bound by the slower PCIe
+// direction instead of the sum of copy + compute + copy.  Output offsets chain on the device (K3's
+// carry), the host only learns each slice's end offset through a pinned mailbox.
+static int compress_host(b200_ctx* c, const uint8_t* in, size_t n, int level, uint8_t* out, size_t cap, size_t* out_n) {
+    CK(cudaSetDevice(c->device));
+    int rc;
+    const size_t bound = b200_deflate_bound(n);
+    if ((rc = c->d_in.ensure(n + 64))) return rc;
+    if ((rc = c->d_out.ensure(bound + 64))) return rc;
+    const uint64_t nchunks = (n + CHUNK - 1) / CHUNK;
+    if (nchunks == 0) {
+        size_t cn = 0;
+        rc = b200_deflate_compress_dev(c, c->d_in.p, 0, level, 0, c->d_out.p, c->d_out.cap, nullptr, &cn, nullptr, c->stream);
+        if (rc) return rc;
+        *out_n = cn;
+        if (cn > cap) return B200_E_OUTPUT;
+        CK(cudaMemcpyAsync(out, c->d_out.p, cn, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        return B200_OK;
+    }
+    const uint64_t B = nchunks < c->host_slice_chunks ? nchunks : c->host_slice_chunks;
+    const uint64_t nslices = (nchunks + B - 1) / B;
+    if ((rc = c->tok.ensure(B * CHUNK * 4))) return rc;
+    if ((rc = c->ntok.ensure(B * NSEG * 4))) return rc;
+    if ((rc = c->hist.ensure(B * NSEG * NSYM * 4))) return rc;
+    if ((rc = c->codes.ensure(B * NSYM * 4))) return rc;
+    if ((rc = c->hdr.ensure(B * HDR_WORDS * 4))) return rc;
+    if ((rc = c->desc.ensure(B * sizeof(BlockDesc)))) return rc;
+    if ((rc = c->sizes.ensure(B * 4))) return rc;
+    if ((rc = c->offsets.ensure((nchunks + 1) * 8))) return rc;
+    if ((rc = c->total.ensure(16))) return rc;
+    uint64_t* offs = (uint64_t*)c->offsets.p;
+    uint64_t* d_total = (uint64_t*)c->total.p;
+    if (c->mailbox_cap < nslices) {
+        if (c->mailbox) cudaFreeHost(c->mailbox);
+        c->mailbox = nullptr; c->mailbox_cap = 0;
+        CK(cudaHostAlloc((void**)&c->mailbox, (nslices + 16) * 8, cudaHostAllocDefault));
+        c->mailbox_cap = nslices + 16;
+    }
+    while (c->events.size() < 2 * nslices) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->events.push_back(e);
+    }
+    uint8_t* d_in = (uint8_t*)c->d_in.p;
+    uint8_t* d_out = (uint8_t*)c->d_out.p;
+    // enqueue every slice: H2D on s_in, kernels on stream (after the slice's H2D), mailbox write
+    for (uint64_t k = 0; k < nslices; k++) {
+        const uint64_t b0 = k * B;
+        const uint32_t nb = (uint32_t)((nchunks - b0 < B) ? nchunks - b0 : B);
+        const size_t off = (size_t)b0 * CHUNK;
+        const size_t len = (size_t)((b0 + nb == nchunks) ? n - off : (size_t)nb * CHUNK);
+        CK(cudaMemcpyAsync(d_in + off, in + off, len, cudaMemcpyHostToDevice, c->s_in));
+        CK(cudaEventRecord(c->events[2 * k], c->s_in));
+        CK(cudaStreamWaitEvent(c->stream, c->events[2 * k], 0));
+        if ((rc = compress_batch(c, d_in + off, n - off, nb, b0, b0 + nb == nchunks, level, offs, d_total, d_out, c->stream))) return rc;
+        CK(cudaMemcpyAsync(&c->mailbox[k], offs + b0 + nb, 8, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaEventRecord(c->events[2 * k + 1], c->stream));
+    }
+    // drain: as each slice finishes, copy its compressed bytes out on s_out
+    uint64_t begin = 0;
+    int result = B200_OK;
+    for (uint64_t k = 0; k < nslices; k++) {
+        CK(cudaEventSynchronize(c->events[2 * k + 1]));
+        const uint64_t endo = c->mailbox[k];
+        if (endo > cap) result = B200_E_OUTPUT;
+        if (result == B200_OK && endo > begin)
+            CK(cudaMemcpyAsync(out + begin, d_out + begin, endo - begin, cudaMemcpyDeviceToHost, c->s_out));
+        begin = endo;
+    }
+    CK(cudaStreamSynchronize(c->s_out));
+    CK(cudaStreamSynchronize(c->stream));
+    *out_n = (size_t)begin;
+    return result;
+}
+
 int b200_deflate_compress_into(const void* in, size_t n, int level, void* out, size_t cap, size_t* out_n) {
-    if ((!in && n) || !out_n || level < 0 || level > 3) return B200_E_ARG;
+    if ((!in && n) || !out_n || level < 0 || level > 3 || (!out && cap)) return B200_E_ARG;
     b200_ctx* c;
     int rc = default_ctx(&c);
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(c->mu);
-    CK(cudaSetDevice(c->device));
-    const size_t bound = b200_deflate_bound(n);
-    if ((rc = c->d_in.ensure(n + 64))) return rc;
-    if ((rc = c->d_out.ensure(bound + 64))) return rc;
-    if (n) CK(cudaMemcpyAsync(c->d_in.p, in, n, cudaMemcpyHostToDevice, c->stream));
-    size_t cn = 0;
-    rc = b200_deflate_compress_dev(c, c->d_in.p, n, level, 0, c->d_out.p, c->d_out.cap, nullptr, &cn, nullptr, c->stream);
-    if (rc) return rc;
-    *out_n = cn;
-    if (cn > cap || (!out && cn)) return B200_E_OUTPUT;
-    if (cn) CK(cudaMemcpyAsync(out, c->d_out.p, cn, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    return B200_OK;
+    return compress_host(c, (const uint8_t*)in, n, level, (uint8_t*)out, cap, out_n);
 }
 
 int b200_deflate_compress(const void* in, size_t n, int level, void** out, size_t* out_n) {
-    if (!out || !out_n) return B200_E_ARG;
+    if (!out || !out_n || (!in && n) || level < 0 || level > 3) return B200_E_ARG;
     *out = nullptr; *out_n = 0;
     b200_ctx* c;
     int rc = default_ctx(&c);
     if (rc) return rc;
+    const size_t bound = b200_deflate_bound(n);
+    uint8_t* buf = (uint8_t*)malloc(bound);          // untouched pages cost nothing; shrunk below
+    if (!buf) return B200_E_NOMEM;
     size_t cn = 0;
     {
         std::lock_guard<std::mutex> lk(c->mu);
-        CK(cudaSetDevice(c->device));
-        const size_t bound = b200_deflate_bound(n);
-        if ((rc = c->d_in.ensure(n + 64))) return rc;
-        if ((rc = c->d_out.ensure(bound + 64))) return rc;
-        if (n) CK(cudaMemcpyAsync(c->d_in.p, in, n, cudaMemcpyHostToDevice, c->stream));
-        rc = b200_deflate_compress_dev(c, c->d_in.p, n, level, 0, c->d_out.p, c->d_out.cap, nullptr, &cn, nullptr, c->stream);
-        if (rc) return rc;
-        void* buf = malloc(cn ? cn : 1);
-        if (!buf) return B200_E_NOMEM;
-        if (cn && cudaMemcpyAsync(buf, c->d_out.p, cn, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) { free(buf); return B200_E_CUDA; }
-        if (cudaStreamSynchronize(c->stream) != cudaSuccess) { free(buf); return B200_E_CUDA; }
-        *out = buf;
+        rc = compress_host(c, (const uint8_t*)in, n, level, buf, bound, &cn);
     }
+    if (rc) { free(buf); return rc; }
+    void* shrunk = realloc(buf, cn ? cn : 1);
+    *out = shrunk ? shrunk : buf;
     *out_n = cn;
     return B200_OK;
 }

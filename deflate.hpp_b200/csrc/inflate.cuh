@@ -447,24 +447,38 @@ __device__ int inflate_warp(InfWarp* S, const ModLut* ML, const uint8_t* in, uin
                     continue;                              // reference: copies nothing (inflate.hpp:268-270)
                 }
                 // ---- back-reference copy, all lanes ----
-                flush();
-                const uint32_t src = op - dist;
-                if (dist >= 32) {
-                    for (uint32_t b = 0; b < length; b += 32) {
-                        // a 32-byte step only reads bytes stored before the step began (dist >= 32)
-                        const uint32_t i = b + lane;
-                        if (i < length && op + i < cap) out[op + i] = out[src + i];
-                        if (dist < length) __syncwarp();
+                if (op > pend) {                           // pending literals first (same rule as flush())
+                    const uint32_t p = (op - 1) - ((op - 1 - lane) & 31);
+                    if (p >= pend && p < op && p < cap) out[p] = (uint8_t)lit;
+                }
+                __syncwarp();
+                const uint32_t room = op < cap ? cap - op : 0;          // bytes that may still be written
+                const uint32_t ncopy = min(length, room);
+                uint8_t* dp = out + op;
+                const uint8_t* sp = dp - dist;
+                if (dist >= length || dist >= 32) {
+                    if (length <= 32) {
+                        // the common case: one predicated load + store, nothing read that this step writes
+                        if (lane < ncopy) dp[lane] = sp[lane];
+                    } else {
+                        #pragma unroll 1
+                        for (uint32_t b = 0; b < length; b += 32) {
+                            // a 32-byte step only reads bytes stored before the step began (dist >= 32)
+                            const uint32_t i = b + lane;
+                            if (i < ncopy) dp[i] = sp[i];
+                            if (dist < length) __syncwarp();
+                        }
                     }
                 } else if (dist == 1) {
-                    const uint8_t v = src < cap ? out[src] : 0;
-                    for (uint32_t i = lane; i < length; i += 32)
-                        if (op + i < cap) out[op + i] = v;
+                    const uint8_t v = room ? sp[0] : 0;
+                    #pragma unroll 1
+                    for (uint32_t i = lane; i < ncopy; i += 32) dp[i] = v;
                 } else {
                     uint32_t r = ML->m[dist][lane];
                     const uint32_t step = ML->m[dist][32];
-                    for (uint32_t i = lane; i < length; i += 32) {
-                        if (op + i < cap) out[op + i] = out[src + r];
+                    #pragma unroll 1
+                    for (uint32_t i = lane; i < ncopy; i += 32) {
+                        dp[i] = sp[r];
                         r += step;
                         if (r >= dist) r -= dist;
                     }

@@ -1,0 +1,69 @@
+"""Multi-GPU sharding of the compress path: one process per GPU (torch.distributed), no data-path
+collective -- chunks are independent -- and ONE exchange step, the variable-size gather of the
+compressed bytes to a destination rank.
+
+    rank r owns the contiguous chunk range shard_range(n_chunks, r, world);
+    every rank but the last compresses with F_NOT_LAST, so the rank outputs concatenate, in rank
+    order, into one valid raw DEFLATE stream (see include/b200_deflate.h);
+    gather_bytes() = all_gather of the byte counts + point-to-point send/recv at the scanned offsets
+    (NCCL has no gatherv).
+
+Works with any torch.distributed backend: NCCL on GPUs, gloo on CPU tensors (tests/test_shard_gloo.py).
+"""
+from typing import List, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_chunks: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, balanced chunk range [lo, hi) of `rank`; ranges tile [0, n_chunks) in rank order."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    base, rem = divmod(n_chunks, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_flags(rank: int, world: int, not_last_flag: int) -> int:
+    """Compressor flags for this rank: only the last rank's last chunk carries BFINAL."""
+    return 0 if rank == world - 1 else not_last_flag
+
+
+def gather_plan(sizes: List[int]) -> List[int]:
+    """Exclusive scan of per-rank byte counts -> offset of each rank's bytes in the joined stream."""
+    out, acc = [], 0
+    for s in sizes:
+        out.append(acc)
+        acc += int(s)
+    return out
+
+
+def gather_bytes(local: torch.Tensor, n: int, dst: int = 0, recv_buf: torch.Tensor = None):
+    """Gather local[:n] (uint8) from every rank to `dst`, concatenated in rank order.
+
+    Returns (joined_view_or_None, sizes).  On `dst` the result lives in recv_buf (allocated if None)
+    and the local shard is copied into place; other ranks return None.
+    """
+    world, rank = dist.get_world_size(), dist.get_rank()
+    dev = local.device
+    mine = torch.tensor([n], dtype=torch.int64, device=dev)
+    allsz = torch.zeros(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(allsz, mine)
+    sizes = [int(x) for x in allsz.tolist()]
+    offs = gather_plan(sizes)
+    total = offs[-1] + sizes[-1]
+    if rank == dst:
+        if recv_buf is None or recv_buf.numel() < total:
+            recv_buf = torch.empty(total, dtype=torch.uint8, device=dev)
+        ops = [dist.P2POp(dist.irecv, recv_buf[offs[r]:offs[r] + sizes[r]], r)
+               for r in range(world) if r != dst and sizes[r]]
+        recv_buf[offs[dst]:offs[dst] + sizes[dst]].copy_(local[:n])
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        return recv_buf[:total], sizes
+    if n:
+        for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, local[:n], dst)]):
+            w.wait()
+    return None, sizes

@@ -1,0 +1,84 @@
+"""CPU tests of the multi-GPU host logic (gloo, world_size 2 and 3): chunk partition, flags and the
+variable-size gather used by bench.py --gpus N.  The byte payloads are real raw-deflate shards made
+with zlib full-flush framing, so the joined result can be checked as ONE valid stream."""
+import os
+import sys
+import zlib
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
+
+
+def _shard_mod():
+    import importlib.util
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    spec = importlib.util.spec_from_file_location("b200_shard", os.path.join(root, "deflate.hpp_b200", "shard.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def test_shard_range_tiles():
+    sh = _shard_mod()
+    for n in (0, 1, 7, 16, 16384, 262144 + 5):
+        for world in (1, 2, 3, 4, 8):
+            prev = 0
+            sizes = []
+            for r in range(world):
+                lo, hi = sh.shard_range(n, r, world)
+                assert lo == prev and hi >= lo
+                prev = hi
+                sizes.append(hi - lo)
+            assert prev == n and max(sizes) - min(sizes) <= 1
+    assert sh.gather_plan([5, 0, 7]) == [0, 5, 5]
+    assert [sh.shard_flags(r, 3, 1) for r in range(3)] == [1, 1, 0]
+
+
+def _payload(rank, world):
+    """Rank's shard of a 3-chunk-per-rank message, as a raw deflate fragment (non-final except last)."""
+    data = bytes([65 + rank]) * (1000 * (rank + 1)) + os.urandom(0)
+    co = zlib.compressobj(6, zlib.DEFLATED, -15)
+    frag = co.compress(data) + (co.flush(zlib.Z_FULL_FLUSH) if rank != world - 1 else co.flush())
+    return data, frag
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sh = _shard_mod()
+        data, frag = _payload(rank, world)
+        local = torch.frombuffer(bytearray(frag) + bytearray(64), dtype=torch.uint8)   # capacity > n on purpose
+        joined, sizes = sh.gather_bytes(local, len(frag), dst=0)
+        if rank == 0:
+            q.put((bytes(joined.numpy()), sizes))
+        else:
+            assert joined is None
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gather_bytes_gloo(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000 + world
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    joined, sizes = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    frags = [_payload(r, world) for r in range(world)]
+    assert sizes == [len(f[1]) for f in frags]
+    assert joined == b"".join(f[1] for f in frags)
+    # the rank-ordered concatenation is one valid raw deflate stream of the rank-ordered data
+    o = zlib.decompressobj(-15)
+    assert o.decompress(joined) == b"".join(f[0] for f in frags) and o.eof
