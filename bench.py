@@ -203,6 +203,15 @@ def ncu_traffic(kernel):
 
 def main():
     args = parse()
+    # stdout must carry exactly one JSON line: park the real stdout and point fd 1 at stderr so that
+    # library chatter (e.g. "NCCL version ...") cannot precede it
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -213,7 +222,7 @@ def main():
         try:
             r = cpu_reference_run(args.level, args.steps, args.warmup, budget_s=args.ref_budget_s)
         except FileNotFoundError as e:
-            print(json.dumps({"impl": "reference", "unavailable": f"oracle/_ref not built: {e}"}))
+            emit({"impl": "reference", "unavailable": f"oracle/_ref not built: {e}"})
             return 0
         line = {
             "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
@@ -226,7 +235,7 @@ def main():
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     import torch
@@ -246,23 +255,53 @@ def main():
 
     nchunks = args.mib * 16
     n = nchunks * CHUNK
-    src = torch.empty(n, dtype=torch.uint8, device=dev)
-    ctx.corpus_generate_dev(src.data_ptr(), SEED, rank * nchunks, nchunks, stream=st)
-    cap = d.deflate_bound(n)
-    dst = torch.empty(cap, dtype=torch.uint8, device=dev)
     import importlib
     shard = importlib.import_module("deflate_hpp_b200.shard")
-    flags = shard.shard_flags(rank, world, d.F_NOT_LAST)
-    gather_buf = None
-    if world > 1 and rank == 0:
-        gather_buf = torch.empty(cap * world, dtype=torch.uint8, device=dev)
+    src = torch.empty(n, dtype=torch.uint8, device=dev)
+    cap = d.deflate_bound(n)
+    dst = torch.empty(cap + 4096, dtype=torch.uint8, device=dev)
+    if world == 1:
+        ctx.corpus_generate_dev(src.data_ptr(), SEED, 0, nchunks, stream=st)
+        rounds = 1
+        slice_chunks = nchunks
+    else:
+        # block-cyclic shards of one (world x mib) MiB corpus: slice s (slice_chunks chunks) belongs to
+        # rank s % world, so compressed slices can be shipped to their final offset round by round
+        rounds = 4 if nchunks % 4 == 0 and nchunks >= 4096 else 1
+        slice_chunks = nchunks // rounds
+        for k in range(rounds):
+            ctx.corpus_generate_dev(src.data_ptr() + k * slice_chunks * CHUNK, SEED,
+                                    shard.slice_first_chunk(k, rank, world, slice_chunks), slice_chunks, stream=st)
+    gather_buf = torch.empty(cap * world, dtype=torch.uint8, device=dev) if (world > 1 and rank == 0) else None
+    pg = shard.PipelinedGather(gather_buf, dst=0) if world > 1 else None
+    if world > 1:
+        side = torch.cuda.Stream(device=dev)
+        sizes_dev = torch.zeros(rounds, dtype=torch.int64, device=dev)
+        round_done = [torch.cuda.Event() for _ in range(rounds)]
+    slice_bytes = slice_chunks * CHUNK
+    slice_cap = d.deflate_bound(slice_bytes)
 
     def step():
-        cn = ctx.compress_dev(src.data_ptr(), n, args.level, dst.data_ptr(), cap, flags=flags, stream=st)
-        if world > 1:
-            # the one exchange step of this path: variable-size gather of compressed bytes to rank 0
-            shard.gather_bytes(dst, cn, dst=0, recv_buf=gather_buf)
-        return cn
+        if world == 1:
+            return ctx.compress_dev(src.data_ptr(), n, args.level, dst.data_ptr(), cap, flags=0, stream=st)
+        # enqueue every round's kernels first (no host sync: sizes stay on the device) ...
+        main = torch.cuda.current_stream()
+        for k in range(rounds):
+            last = (k == rounds - 1) and (rank == world - 1)       # only the stream's very last chunk is final
+            ctx.compress_dev(src.data_ptr() + k * slice_bytes, slice_bytes, args.level, dst.data_ptr() + k * slice_cap,
+                             slice_cap, flags=0 if last else d.F_NOT_LAST, stream=st,
+                             d_out_n=sizes_dev[k:k + 1].data_ptr(), sync=False)
+            round_done[k].record(main)
+        # ... and trail them on a side stream: per round one sizes all_gather + sends/receives at final offsets
+        with torch.cuda.stream(side):
+            total = 0
+            for k in range(rounds):
+                side.wait_event(round_done[k])
+                sz = pg.post_round(dst[k * slice_cap:(k + 1) * slice_cap], sizes_dev[k:k + 1])
+                total += sz[rank]
+            step.joined = pg.finish()
+        main.wait_stream(side)
+        return total
 
     def barrier():
         if world > 1:
@@ -324,6 +363,19 @@ def main():
                "round_trip_bit_exact": ok,
                "kernels_ms_per_step": {k: v[0] / dsteps for k, v in dk.items()}}
     clocks = sampler.stop() if sampler else None
+
+    # ---- N > 1: the bytes gathered on rank 0 must be ONE valid stream of the whole corpus ----
+    gathered_ok = None
+    if world > 1 and rank == 0:
+        total_n = n * world
+        joined = step.joined
+        whole = torch.empty(total_n, dtype=torch.uint8, device=dev)
+        w, full = ctx.inflate_dev(gather_buf.data_ptr(), joined, whole.data_ptr(), total_n, stream=st)
+        expect = torch.empty(total_n, dtype=torch.uint8, device=dev)
+        ctx.corpus_generate_dev(expect.data_ptr(), SEED, 0, nchunks * world, stream=st)
+        torch.cuda.synchronize()
+        gathered_ok = bool(full == total_n and torch.equal(whole, expect))
+        del whole, expect
 
     # ---- roofline of the dominant kernel ----
     peak, peak_src = measured_peak()
@@ -395,10 +447,11 @@ def main():
                        "bytes_per_gpu": int(n), "chunks_per_gpu": nchunks, "l2_hygiene": "inputs (>= 1 GiB) larger than the 126 MB L2",
                        "seed": SEED},
             "ratio": {"b200": ratio, "reference_sample": cpu.get("ratio") if cpu else None},
+            "gathered_stream_bit_exact": gathered_ok,
             "decompress": dec, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             "gpu_launches": int(launches),
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

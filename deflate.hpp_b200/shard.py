@@ -67,3 +67,59 @@ def gather_bytes(local: torch.Tensor, n: int, dst: int = 0, recv_buf: torch.Tens
         for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, local[:n], dst)]):
             w.wait()
     return None, sizes
+
+
+# ---- block-cyclic sharding with a pipelined gather --------------------------------------------------
+# A contiguous partition forces the destination to wait for every rank's TOTAL size before it knows
+# where rank r's bytes go.  With a block-cyclic partition -- the corpus is cut into slices of
+# `slice_chunks` chunks, slice s belongs to rank s % world -- the final offset of a slice depends only
+# on slices that precede it in stream order, so after each round (one slice per rank) the ranks
+# all_gather that round's sizes and ship the compressed slice straight to its final place on the
+# destination while the next round is already being compressed.
+
+def slice_owner(s: int, world: int) -> int:
+    return s % world
+
+
+def slice_first_chunk(round_idx: int, rank: int, world: int, slice_chunks: int) -> int:
+    """Global index of the first chunk of the slice `rank` compresses in round `round_idx`."""
+    return (round_idx * world + rank) * slice_chunks
+
+
+class PipelinedGather:
+    """Per round: exchange sizes, post the sends/receives at final offsets, return without waiting."""
+
+    def __init__(self, recv_buf: torch.Tensor = None, dst: int = 0):
+        self.world, self.rank, self.dst = dist.get_world_size(), dist.get_rank(), dst
+        self.recv_buf = recv_buf
+        self.offset = 0          # bytes of the joined stream placed so far (all rounds before this one)
+        self.pending = []
+
+    def post_round(self, local: torch.Tensor, n):
+        """local[:n]: this rank's compressed slice of the current round.  `n` may be an int or a
+        one-element int64 tensor on the device (the compressor's d_out_n), in which case the only host
+        synchronisation of the round is reading back the gathered sizes."""
+        dev = local.device
+        mine = n if torch.is_tensor(n) else torch.tensor([n], dtype=torch.int64, device=dev)
+        allsz = torch.zeros(self.world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allsz, mine)
+        sizes = [int(x) for x in allsz.tolist()]
+        n = sizes[self.rank]
+        offs = [self.offset + o for o in gather_plan(sizes)]
+        if self.rank == self.dst:
+            ops = [dist.P2POp(dist.irecv, self.recv_buf[offs[r]:offs[r] + sizes[r]], r)
+                   for r in range(self.world) if r != self.dst and sizes[r]]
+            self.recv_buf[offs[self.dst]:offs[self.dst] + n].copy_(local[:n], non_blocking=True)
+            if ops:
+                self.pending += dist.batch_isend_irecv(ops)
+        elif n:
+            self.pending += dist.batch_isend_irecv([dist.P2POp(dist.isend, local[:n], self.dst)])
+        self.offset = offs[-1] + sizes[-1]
+        return sizes
+
+    def finish(self) -> int:
+        for w in self.pending:
+            w.wait()
+        self.pending = []
+        total, self.offset = self.offset, 0
+        return total
