@@ -429,9 +429,11 @@ int b200_inflate_dev(b200_ctx* c, const void* d_in, size_t n, void* d_out, size_
             PROF_BEGIN(c, K_INFLATE_CHUNKS, st);
             if ((rc = c->counter.ensure(64))) return rc;
             CK(cudaMemsetAsync(c->counter.p, 0, 8, st));
-            const uint64_t want = (ncand + INF_WARPS - 1) / INF_WARPS;
-            inflate_chunks_kernel<<<(uint32_t)(want < c->inf_grid ? want : c->inf_grid), INF_THREADS, 0, st>>>(
-                in, n, cand, ncand, (uint8_t*)d_out, cap, (ChunkResult*)c->res.p, flags, (unsigned long long*)c->counter.p);
+            {
+                const uint64_t want = (ncand + INF_WARPS - 1) / INF_WARPS;
+                inflate_chunks_kernel<<<(uint32_t)(want < c->inf_grid ? want : c->inf_grid), INF_THREADS, 0, st>>>(
+                    in, n, cand, ncand, (uint8_t*)d_out, cap, (ChunkResult*)c->res.p, flags, (unsigned long long*)c->counter.p);
+            }
             LAUNCHED();
             PROF_END(c, st);
             PROF_BEGIN(c, K_VALIDATE, st);

@@ -323,24 +323,22 @@ __device__ int inflate_warp(InfWarp* S, const ModLut* ML, const uint8_t* in, uin
     const uint32_t cap = (uint32_t)min(cap64, (uint64_t)0xFFFFFFF0u);
     const uint32_t max_out = (uint32_t)min(max_out64, (uint64_t)0xFFFFFF00u);
     uint32_t op = 0;        // bytes produced
-    uint32_t pend = 0;      // first position whose literal still sits in a lane register
-    uint32_t lit = 0;       // this lane's pending literal
     const bool strict = flags & 1u;
     const uint64_t in_bits = in_len * 8;
     const uint32_t wi_limit = (uint32_t)(br.limit >> 2) + 4;
+    // Literals are stored straight away: lane 0 writes an entry's first literal, lane 1 its second
+    // (entries carry one or two).  No pending state, nothing to flush before a back-reference.
+    // The per-lane constants are laundered through an empty asm so that the compiler keeps them in
+    // registers instead of re-deriving them from kernel parameters on every symbol (the integer ALU
+    // pipe is the bottleneck of this loop -- see profiles/).
+    uint8_t* outl = out + lane;                                  // this lane's byte column
+    uint8_t* outb = out;
+    uint32_t lit_shift = lane ? 16 : 8;
+    uint32_t capl = cap > lane ? cap - lane : 0;                 // op < capl  <=>  op + lane < cap
+    asm volatile("" : "+l"(outl), "+l"(outb), "+r"(lit_shift), "+r"(capl));
     int st = ST_OK;
     uint32_t empty_run = 0;
     end_flags = 0;
-
-    // store the literals held in lane registers: positions [pend, op), position p lives in lane p & 31
-    auto flush = [&]() {
-        if (op > pend) {
-            const uint32_t p = (op - 1) - ((op - 1 - lane) & 31);
-            if (p >= pend && p < op && p < cap) out[p] = (uint8_t)lit;
-            pend = op;
-        }
-        __syncwarp();
-    };
 
     for (;;) {
         if (br_bitpos(br) + 3 > in_bits) { st = ST_OVERRUN; break; }
@@ -356,11 +354,23 @@ __device__ int inflate_warp(InfWarp* S, const ModLut* ML, const uint8_t* in, uin
             if (strict && (len ^ nlen) != 0xFFFFu) { st = ST_DATA; break; }
             const uint64_t bpos = br_bitpos(br) >> 3;      // byte-aligned here
             if (bpos + len > in_len) { st = ST_OVERRUN; break; }
-            flush();
+            __syncwarp();
             const uint8_t* sp = in + bpos;
-            for (uint32_t i = lane; i < len; i += 32)
-                if (op + i < cap) out[op + i] = sp[i];
-            op += len; pend = op;
+            const uint32_t ncopy = op < cap ? min(len, cap - op) : 0;
+            uint8_t* dp = out + op;
+            if (((reinterpret_cast<uintptr_t>(sp) ^ reinterpret_cast<uintptr_t>(dp)) & 3) == 0) {
+                // source and destination agree modulo 4: bytes up to alignment, then one u32 per lane
+                const uint32_t head = min(ncopy, (uint32_t)((4 - (reinterpret_cast<uintptr_t>(dp) & 3)) & 3));
+                if (lane < head) dp[lane] = sp[lane];
+                const uint32_t words = (ncopy - head) >> 2;
+                for (uint32_t i = lane; i < words; i += 32)
+                    reinterpret_cast<uint32_t*>(dp + head)[i] = reinterpret_cast<const uint32_t*>(sp + head)[i];
+                const uint32_t done = head + words * 4;
+                if (done + lane < ncopy) dp[done + lane] = sp[done + lane];
+            } else {
+                for (uint32_t i = lane; i < ncopy; i += 32) dp[i] = sp[i];
+            }
+            op += len;
             __syncwarp();
             br_seek(S, br, bpos + len, lane);
             if (len == 0 && !bfinal) {
@@ -377,30 +387,21 @@ __device__ int inflate_warp(InfWarp* S, const ModLut* ML, const uint8_t* in, uin
             else { st = read_dynamic_header(S, br, lane); if (st) break; }
             // ---- symbol loop ----
             for (;;) {
-                br_need32(S, br, lane);
+                if (br.bc < 32) {
+                    br.bb |= (uint64_t)S->ring[br.wi & (RING_WORDS - 1)] << br.bc;
+                    br.bc += 32;
+                    br.wi++;
+                    if ((br.wi & 127) == 0) ring_fill(S, br, (br.wi >> 7) + 1, lane);
+                    if (br.wi > wi_limit || op > max_out) break;        // resolved after the loop
+                }
                 uint32_t e = S->lit[br_peek(br, LIT_BITS)];
                 if ((int32_t)e >= 0) {
-                    // one or two literals
                     br_drop(br, e & 31u);
-                    if ((op & 31) == lane) lit = (e >> 8) & 0xFFu;
-                    op++;
-                    if ((op & 31) == 0) {
-                        const uint32_t p = op - 32 + lane;
-                        if (p >= pend && p < cap) out[p] = (uint8_t)lit;
-                        pend = op;
-                        __syncwarp();
-                        if (op > max_out || br.wi > wi_limit) break;    // resolved after the loop
-                    }
-                    if (e & E_TWO) {
-                        if ((op & 31) == lane) lit = (e >> 16) & 0xFFu;
-                        op++;
-                        if ((op & 31) == 0) {
-                            const uint32_t p = op - 32 + lane;
-                            if (p >= pend && p < cap) out[p] = (uint8_t)lit;
-                            pend = op;
-                            __syncwarp();
-                        }
-                    }
+                    const uint32_t two = e >> 30;                       // E_TWO is bit 30, bit 31 is clear
+                    const uint8_t v = (uint8_t)(e >> lit_shift);
+                    uint8_t* a = outl + op;
+                    if (lane <= two && op < capl) *a = v;
+                    op += 1 + two;
                     continue;
                 }
                 uint32_t kind = (e >> 5) & 7u;
@@ -414,9 +415,8 @@ __device__ int inflate_warp(InfWarp* S, const ModLut* ML, const uint8_t* in, uin
                     if (e == LIT_INVALID) { st = ST_DATA; break; }
                     if ((int32_t)e >= 0) {
                         br_drop(br, sl);
-                        if ((op & 31) == lane) lit = (e >> 8) & 0xFFu;
+                        if (lane == 0 && op < cap) outb[op] = (uint8_t)(e >> 8);
                         op++;
-                        if ((op & 31) == 0) flush();
                         continue;
                     }
                     kind = (e >> 5) & 7u;
@@ -447,14 +447,10 @@ __device__ int inflate_warp(InfWarp* S, const ModLut* ML, const uint8_t* in, uin
                     continue;                              // reference: copies nothing (inflate.hpp:268-270)
                 }
                 // ---- back-reference copy, all lanes ----
-                if (op > pend) {                           // pending literals first (same rule as flush())
-                    const uint32_t p = (op - 1) - ((op - 1 - lane) & 31);
-                    if (p >= pend && p < op && p < cap) out[p] = (uint8_t)lit;
-                }
-                __syncwarp();
+                __syncwarp();                              // literal stores of lanes 0/1 are visible to every lane
                 const uint32_t room = op < cap ? cap - op : 0;          // bytes that may still be written
                 const uint32_t ncopy = min(length, room);
-                uint8_t* dp = out + op;
+                uint8_t* dp = outb + op;
                 const uint8_t* sp = dp - dist;
                 if (dist >= length || dist >= 32) {
                     if (length <= 32) {
@@ -484,9 +480,7 @@ __device__ int inflate_warp(InfWarp* S, const ModLut* ML, const uint8_t* in, uin
                     }
                 }
                 op += length;
-                pend = op;
                 __syncwarp();
-                if (op > max_out || br.wi > wi_limit) break;
             }
             if (st) break;
             if (br.wi > wi_limit || br_bitpos(br) > in_bits) { st = ST_OVERRUN; break; }
@@ -495,7 +489,7 @@ __device__ int inflate_warp(InfWarp* S, const ModLut* ML, const uint8_t* in, uin
         if (op > max_out) { end_flags |= END_TOO_BIG; st = ST_DATA; break; }
         if (bfinal) { end_flags |= END_FINAL; break; }
     }
-    flush();
+    __syncwarp();
     if (br_bitpos(br) > in_bits) st = ST_OVERRUN;   // whatever else went wrong, the reference would have thrown first
     out_len = op;
     in_used = (br_bitpos(br) + 7) >> 3;
