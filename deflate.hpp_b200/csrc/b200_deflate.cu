@@ -113,12 +113,13 @@ struct b200_ctx {
     int device = 0;
     bool attrs_set = false;
     uint32_t batch_chunks = 4096;
-    bool fast_two_phase = false;     // B200_FAST_TWO_PHASE=1: chunk-wide-table matcher (better ratio, 2.5x slower K1)
+    bool fast_two_phase = true;      // B200_FAST_TWO_PHASE=0: the single-phase segment-private matcher (A/B runs)
     uint32_t better_depth = 128, better_nice = 258;   // "better" level: chain depth / good-enough length
     // compress scratch
     Buf tok, ntok, hist, codes, hdr, desc, sizes, offsets, total;
     // inflate scratch
-    Buf counts, woffs, cand, res, result, one_off, counter;
+    Buf counts, woffs, cand, res, result, one_off, counter, cand16;
+    uint32_t lzf_grid = 148 * 2;     // persistent two-phase matcher: SMs x resident CTAs
     uint32_t inf_grid = 148 * 7;     // persistent inflate grid: SMs x resident CTAs
     // host-API staging
     Buf d_in, d_out;
@@ -194,6 +195,7 @@ int b200_ctx_create(int device, b200_ctx** ctx) {
     if (!c) return B200_E_NOMEM;
     c->device = device;
     c->inf_grid = (uint32_t)prop.multiProcessorCount * INF_MAX_CTAS_PER_SM;
+    c->lzf_grid = (uint32_t)prop.multiProcessorCount * 2;
     if (const char* e = getenv("B200_FAST_TWO_PHASE")) c->fast_two_phase = atoi(e) != 0;
     if (const char* e = getenv("B200_BETTER_DEPTH")) { int v = atoi(e); if (v > 0) c->better_depth = (uint32_t)v; }
     if (const char* e = getenv("B200_BETTER_NICE")) { int v = atoi(e); if (v >= 3) c->better_nice = (uint32_t)v; }
@@ -212,7 +214,7 @@ void b200_ctx_destroy(b200_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     Buf* all[] = {&c->tok, &c->ntok, &c->hist, &c->codes, &c->hdr, &c->desc, &c->sizes, &c->offsets, &c->total,
-                  &c->counts, &c->woffs, &c->cand, &c->res, &c->result, &c->one_off, &c->counter, &c->d_in, &c->d_out};
+                  &c->counts, &c->woffs, &c->cand, &c->res, &c->result, &c->one_off, &c->counter, &c->cand16, &c->d_in, &c->d_out};
     for (Buf* b : all) b->release();
     c->prof.destroy();
     for (auto e : c->events) cudaEventDestroy(e);
@@ -262,14 +264,23 @@ void b200_free(void* p) { free(p); }
 // bytes from there to the end of the buffer; offs: the chunk-offset array (global chunk indexing).
 static int compress_batch(b200_ctx* c, const uint8_t* bin, uint64_t bn, uint32_t nb, uint64_t b0, bool final_batch,
                           int level, uint64_t* offs, uint64_t* d_total, void* d_out, cudaStream_t st) {
+    if (level == 2 && c->fast_two_phase) {
+        int rc;
+        if ((rc = c->cand16.ensure((size_t)c->lzf_grid * CHUNK * 2))) return rc;
+        if ((rc = c->counter.ensure(64))) return rc;
+        CK(cudaMemsetAsync(c->counter.p, 0, 8, st));
+    }
     if (level >= 1) {
         PROF_BEGIN(c, K_LZ77, st);
         if (level == 3)
             lz77_better_kernel<<<nb, LZB_THREADS, LZB_SMEM_BYTES, st>>>(bin, bn, (uint32_t*)c->tok.p, (uint32_t*)c->ntok.p,
                                                                      (uint32_t*)c->hist.p, c->better_depth, c->better_nice);
-        else if (level == 2 && c->fast_two_phase)
-            lz77_fast_kernel<<<nb, LZF_THREADS, LZF_SMEM_BYTES, st>>>(bin, bn, (uint32_t*)c->tok.p, (uint32_t*)c->ntok.p,
-                                                                   (uint32_t*)c->hist.p);
+        else if (level == 2 && c->fast_two_phase) {
+            const uint32_t grid = nb < c->lzf_grid ? nb : c->lzf_grid;
+            lz77_fast_kernel<<<grid, LZF_THREADS, LZF_SMEM_BYTES, st>>>(bin, bn, nb, (uint32_t*)c->tok.p, (uint32_t*)c->ntok.p,
+                                                                     (uint32_t*)c->hist.p, (uint16_t*)c->cand16.p,
+                                                                     (unsigned int*)c->counter.p);
+        }
         else if (level == 1)
             lz77_kernel<1><<<nb, LZ_THREADS, LZ_SMEM_BYTES, st>>>(bin, bn, (uint32_t*)c->tok.p, (uint32_t*)c->ntok.p, (uint32_t*)c->hist.p);
         else

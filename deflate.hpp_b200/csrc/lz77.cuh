@@ -182,185 +182,207 @@ lz77_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t* __restrict__ t
 }
 
 // =====================================================================================================
-// "fast" level, two-phase (replaces lz77_kernel<0> as the default level-2 matcher).
+// "fast" level, two-phase matcher (level 2 default).
 //
-//   phase B  all 8 warps sweep the chunk in tiles of 256 positions against ONE chunk-wide hash table
-//            (8 K x u32 in shared memory, 4-byte hash).  Per tile: every thread looks its bucket up,
-//            __syncthreads, every thread inserts its position with atomicMax -- lookups therefore see
-//            exactly the positions before the tile, and the table content is deterministic (highest
-//            position wins).  Three candidates per position: the bucket, the nearest lower lane of the
-//            same warp with the same hash (__match_any_sync: matches closer than a tile), and p-1 (runs).
-//            The longest verified candidate, extended to at most LZF_CAP bytes, goes to the token
-//            scratch as (len | dist << 16).
-//   phase C  each warp parses one 8 KiB segment greedily over those candidates, 32 positions per step
-//            with ballot-mask selection; a selected match that hit the cap is extended to its full
-//            length (<= 258) by the whole warp, 128 bytes per step.
-// Against the single-phase kernel: the whole 32 KiB window is reachable from every position instead of
-// an 8 KiB segment-private table, ~40 % fewer tokens on the benchmark corpus (less work for K4 and for
-// the inflater), and no position is probed twice.
+// Persistent CTAs (grid = 2 x SMs) pull chunks from a global counter.  Per chunk:
+//   phase B  all 8 warps sweep the chunk in tiles of 1024 positions against ONE chunk-wide hash table
+//            (8 K x u32 in shared memory, 4-byte hash).  Per tile: every thread looks its buckets up,
+//            __syncthreads, every thread inserts its positions with atomicMax -- lookups therefore see
+//            exactly the positions before the tile and the table content is deterministic (highest
+//            position wins).  Four candidates per position: the bucket and the distances 1, 2, 3 (runs,
+//            short periods, RGB pixels -- what a tile-lagged table cannot see), the latter straight
+//            from registers.  Each is verified on 4 bytes and scored on the next 4 (no loops);
+//            the best score / nearest distance goes to a u16 candidate array in a per-CTA scratch
+//            slot (128 KB per CTA, 38 MB in total: it lives in L2 and is never meant to reach HBM).
+//   phase C  each warp parses one 8 KiB segment greedily: 32 positions per step, every lane extends
+//            its own candidate to full length (4 bytes per iteration), ballot-mask selection, tokens
+//            and shared-memory histograms exactly as in the single-phase kernel.
+// Against lz77_kernel<0>: the whole 32 KiB window is reachable from every position instead of an
+// 8 KiB segment-private table (large.bmp stand-in: 2x smaller output, corpus: 0.71 -> 0.62).
 // =====================================================================================================
 constexpr uint32_t LZF_THREADS = 256;
 constexpr uint32_t LZF_HASH_BITS = 13;
-constexpr uint32_t LZF_CAP = 36;                 // phase-B extension cap (multiple of 4)
-constexpr size_t LZF_SMEM_BYTES = CHUNK + LZ_DATA_PAD + (4u << LZF_HASH_BITS) + NSEG * NSYM * 4 + 16;
+constexpr uint32_t LZF_TILE = 4 * LZF_THREADS;     // positions between two table updates
+constexpr size_t LZF_SMEM_BYTES = CHUNK + LZ_DATA_PAD + (4u << LZF_HASH_BITS) + NSEG * NSYM * 4 + 32;
 
 __device__ __forceinline__ uint32_t lzf_hash(uint32_t w4) { return (w4 * 0x9E3779B1u) >> (32 - LZF_HASH_BITS); }
 
-// length of the common prefix of positions p and q (q < p), known to agree on 4 bytes, capped
-__device__ __forceinline__ uint32_t lzf_extend(const uint8_t* d, uint32_t p, uint32_t q, uint32_t maxl) {
-    uint32_t l = 4;
-    while (l < maxl) {
-        const uint32_t x = ld4_unaligned(d, p + l) ^ ld4_unaligned(d, q + l);
-        if (x) { l += (__ffs(x) - 1) >> 3; break; }
-        l += 4;
-    }
-    return min(l, maxl);
+// candidate q for position p: 0 if the first 4 bytes differ, else 4 + (matching bytes among the next 4)
+__device__ __forceinline__ uint32_t lzf_score(const uint8_t* d, uint32_t q, uint32_t w4, uint32_t w8) {
+    if (ld4_unaligned(d, q) != w4) return 0;
+    const uint32_t x = ld4_unaligned(d, q + 4) ^ w8;
+    return x ? 4 + ((__ffs(x) - 1) >> 3) : 8;
 }
 
 __global__ void __launch_bounds__(LZF_THREADS, 2)
-lz77_fast_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t* __restrict__ tok,
-                 uint32_t* __restrict__ ntok, uint32_t* __restrict__ hist) {
+lz77_fast_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t nchunks, uint32_t* __restrict__ tok,
+                 uint32_t* __restrict__ ntok, uint32_t* __restrict__ hist, uint16_t* __restrict__ cand_scratch,
+                 unsigned int* __restrict__ counter) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* s_data = smem;
     uint32_t* s_tab = reinterpret_cast<uint32_t*>(smem + CHUNK + LZ_DATA_PAD);
     uint32_t* s_hist = s_tab + (1u << LZF_HASH_BITS);
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_hist + NSEG * NSYM);
+    uint32_t* s_next = reinterpret_cast<uint32_t*>(s_bar + 1);
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint64_t chunk = blockIdx.x;
-    const uint64_t base = chunk * CHUNK;
-    const uint32_t clen = (uint32_t)min((uint64_t)CHUNK, n - base);
-    const uint8_t* src = in + base;
     const uint32_t FULL = 0xFFFFFFFFu;
-
-    const bool aligned = ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
-    const uint32_t bulk = aligned ? (clen & ~15u) : 0;
+    uint16_t* cand = cand_scratch + (size_t)blockIdx.x * CHUNK;
     if (tid == 0) mbar_init(s_bar, 1);
-    __syncthreads();
-    if (tid == 0 && bulk) tma_load_1d(s_data, src, bulk, s_bar);
-    for (uint32_t i = bulk + tid; i < clen; i += LZF_THREADS) s_data[i] = src[i];
-    for (uint32_t i = clen + tid; i < ((clen + 15u) & ~15u) + LZ_DATA_PAD && i < CHUNK + LZ_DATA_PAD; i += LZF_THREADS)
-        s_data[i] = 0;
-    for (uint32_t i = tid; i < (1u << LZF_HASH_BITS) + NSEG * NSYM; i += LZF_THREADS) s_tab[i] = 0;
-    if (bulk) mbar_wait(s_bar, 0);
-    __syncthreads();
+    uint32_t parity = 0;
 
-    // ---- phase B: candidates for every position ---------------------------------------------------
-    uint32_t* cand = tok + chunk * CHUNK;
-    for (uint32_t t0 = 0; t0 < clen; t0 += LZF_THREADS) {
-        const uint32_t p = t0 + tid;
-        const bool valid = p + 4 <= clen;
-        const uint32_t w4 = ld4_unaligned(s_data, p);
-        const uint32_t h = lzf_hash(w4);
-        const uint32_t q_tab = s_tab[h];
-        const uint32_t peers = __match_any_sync(FULL, valid ? h : (0x80000000u | lane));
-        const uint32_t lower = peers & ((1u << lane) - 1u);
-        __syncthreads();                                  // every lookup of this tile is done
-        if (valid) atomicMax(&s_tab[h], p);
-        uint32_t best = 0, bdist = 0;
-        if (valid) {
-            const uint32_t maxl = min(min(clen - p, MAX_MATCH), LZF_CAP);
-            if (q_tab < p && p - q_tab <= MAX_DIST && ld4_unaligned(s_data, q_tab) == w4) {
-                best = lzf_extend(s_data, p, q_tab, maxl);
-                bdist = p - q_tab;
-            }
-            if (lower && best < maxl) {
-                const uint32_t q = p - lane + (31 - __clz(lower));
-                if (ld4_unaligned(s_data, q) == w4) {
-                    const uint32_t l = lzf_extend(s_data, p, q, maxl);
-                    if (l >= best) { best = l; bdist = p - q; }           // ties: the nearer one
-                }
-            }
-            if (p > 0 && best < maxl && bdist != 1 && ld4_unaligned(s_data, p - 1) == w4) {
-                const uint32_t l = lzf_extend(s_data, p, p - 1, maxl);
-                if (l >= best) { best = l; bdist = 1; }
-            }
+    for (;;) {
+        __syncthreads();                                   // previous chunk fully done (s_next, smem reuse)
+        if (tid == 0) *s_next = atomicAdd(counter, 1u);
+        __syncthreads();
+        const uint64_t chunk = *s_next;
+        if (chunk >= nchunks) break;
+        const uint64_t base = chunk * CHUNK;
+        const uint32_t clen = (uint32_t)min((uint64_t)CHUNK, n - base);
+        const uint8_t* src = in + base;
+
+        const bool aligned = ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+        const uint32_t bulk = aligned ? (clen & ~15u) : 0;
+        if (tid == 0 && bulk) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of s_data are done
+            tma_load_1d(s_data, src, bulk, s_bar);
         }
-        if (p < clen) cand[p] = best | (bdist << 16);
-        __syncthreads();                                  // inserts land before the next tile looks up
-    }
-    // the block-wide barrier above also orders this CTA's cand[] stores before the loads below
+        for (uint32_t i = bulk + tid; i < clen; i += LZF_THREADS) s_data[i] = src[i];
+        for (uint32_t i = clen + tid; i < ((clen + 15u) & ~15u) + LZ_DATA_PAD && i < CHUNK + LZ_DATA_PAD; i += LZF_THREADS)
+            s_data[i] = 0;
+        for (uint32_t i = tid; i < (1u << LZF_HASH_BITS) + NSEG * NSYM; i += LZF_THREADS) s_tab[i] = 0;
+        if (bulk) { mbar_wait(s_bar, parity); parity ^= 1; }
+        __syncthreads();
 
-    // ---- phase C: greedy parse, one warp per segment ----------------------------------------------
-    const uint32_t seg_lo = warp * SEG;
-    const uint32_t seg_hi = min(clen, seg_lo + SEG);
-    uint32_t* hs = s_hist + warp * NSYM;
-    uint32_t* mytok = tok + chunk * CHUNK + seg_lo;
-    uint32_t nt = 0;
-    if (seg_lo < clen) {
-        uint32_t pos = seg_lo;
-        while (pos < seg_hi) {
-            const uint32_t p = pos + lane;
-            const uint32_t valid = min(32u, seg_hi - pos);
-            uint32_t len = 0, dist = 0;
-            if (lane < valid) {
-                const uint32_t c = cand[p];
-                len = min(c & 0xFFFFu, seg_hi - p);           // tokens never cross a segment
-                dist = c >> 16;
-                if (len < 4) len = 0;
+        // ---- phase B: one verified candidate distance per position ----------------------------------
+        // Tile = 1024 positions, 4 per thread (tid, tid+256, ...): each warp still holds 32 consecutive
+        // positions per sub-tile, so neighbours' words are a shuffle away.
+        for (uint32_t t0 = 0; t0 < clen; t0 += LZF_TILE) {
+            uint32_t w4[4], w8[4], hq[4];
+            #pragma unroll
+            for (uint32_t k = 0; k < 4; k++) {
+                const uint32_t p = t0 + k * LZF_THREADS + tid;
+                const uint32_t* w = reinterpret_cast<const uint32_t*>(s_data) + (p >> 2);
+                const uint32_t a = w[0], b = w[1], c = w[2], sh = (p & 3) * 8;
+                w4[k] = __funnelshift_r(a, b, sh);
+                w8[k] = __funnelshift_r(b, c, sh);
+                hq[k] = s_tab[lzf_hash(w4[k])];
             }
-            const uint32_t byte = s_data[p];
-            __syncwarp();                                     // candidate loads done before tokens overwrite them
-            const uint32_t mmask = __ballot_sync(FULL, len >= 4);
-            uint32_t litmask = 0, selmask = 0, cur = 0, advance = valid;
-            for (;;) {
-                const uint32_t m = cur < 32 ? (mmask & ~((1u << cur) - 1u)) : 0;
-                if (m == 0) {
-                    if (cur < valid) litmask |= mask_range(cur, valid);
-                    advance = max(valid, cur);
-                    break;
-                }
-                const uint32_t j = __ffs(m) - 1;
-                litmask |= mask_range(cur, j);
-                selmask |= 1u << j;
-                uint32_t lj = __shfl_sync(FULL, len, j);
-                if (lj == LZF_CAP) {
-                    // the candidate hit the phase-B cap: extend it, 128 bytes per warp step
-                    const uint32_t dj = __shfl_sync(FULL, dist, j);
-                    const uint32_t pj = pos + j;
-                    const uint32_t maxl = min(seg_hi - pj, MAX_MATCH);
-                    while (lj < maxl) {
-                        const uint32_t o = lj + 4 * lane;
-                        const uint32_t x = ld4_unaligned(s_data, pj + o) ^ ld4_unaligned(s_data, pj - dj + o);
-                        const uint32_t mm = __ballot_sync(FULL, x != 0);
-                        if (mm) {
-                            const uint32_t f = __ffs(mm) - 1;
-                            const uint32_t xb = __shfl_sync(FULL, x, f);
-                            lj += 4 * f + ((__ffs(xb) - 1) >> 3);
-                            break;
+            __syncthreads();                               // every lookup of this tile is done
+            #pragma unroll
+            for (uint32_t k = 0; k < 4; k++) {
+                const uint32_t p = t0 + k * LZF_THREADS + tid;
+                if (p + 4 <= clen) atomicMax(&s_tab[lzf_hash(w4[k])], p);
+            }
+            #pragma unroll
+            for (uint32_t k = 0; k < 4; k++) {
+                const uint32_t p = t0 + k * LZF_THREADS + tid;
+                // the 4 bytes before p: lane-4's word, or a shared-memory read at the warp's left edge
+                uint32_t prev4 = __shfl_up_sync(FULL, w4[k], 4);
+                if (lane < 4) prev4 = p >= 4 ? ld4_unaligned(s_data, p - 4)
+                                             : (p ? reinterpret_cast<const uint32_t*>(s_data)[0] << (8 * (4 - p)) : 0u);
+                uint32_t best = 0, bdist = 0;
+                if (p + 4 <= clen) {
+                    const uint32_t q = hq[k];
+                    if (q < p && p - q <= MAX_DIST) { best = lzf_score(s_data, q, w4[k], w8[k]); bdist = p - q; }
+                    // distances 1..3 (runs, 2- and 3-byte periods, RGB pixels) straight from registers:
+                    // bytes [p-d, p-d+4) = funnel(prev4, w4), bytes [p-d+4, p-d+8) = funnel(w4, w8)
+                    #pragma unroll
+                    for (uint32_t d = 3; d >= 1; d--) {
+                        if (p >= d && __funnelshift_r(prev4, w4[k], 8 * (4 - d)) == w4[k]) {
+                            const uint32_t x = __funnelshift_r(w4[k], w8[k], 8 * (4 - d)) ^ w8[k];
+                            const uint32_t sc = x ? 4 + ((__ffs(x) - 1) >> 3) : 8;
+                            if (sc >= best) { best = sc; bdist = d; }            // ties: the nearer one
                         }
-                        lj += 128;
                     }
-                    lj = min(lj, maxl);
-                    if (lane == j) len = lj;
+                    if (!best) bdist = 0;
                 }
-                cur = j + lj;
-                if (cur >= 32) { advance = cur; break; }
+                if (p < clen) cand[p] = (uint16_t)bdist;   // 32768 == 0x8000 still fits
             }
-            const uint32_t sel = litmask | selmask;
-            if ((sel >> lane) & 1) {
-                const uint32_t rank = __popc(sel & ((1u << lane) - 1u));
-                if ((selmask >> lane) & 1) {
-                    mytok[nt + rank] = tok_match(len, dist);
-                    uint32_t idx, ne, ev, ds;
-                    len_symbol(len, idx, ne, ev);
-                    atomicAdd(&hs[257 + idx], 1u);
-                    dist_symbol(dist, ds, ne, ev);
-                    atomicAdd(&hs[NLIT + ds], 1u);
-                } else {
-                    mytok[nt + rank] = byte;
-                    atomicAdd(&hs[byte], 1u);
-                }
-            }
-            nt += __popc(sel);
-            pos += advance;
-            __syncwarp();
+            __syncthreads();                               // inserts land before the next tile looks up
         }
+        // the block-wide barrier above also orders this CTA's cand[] stores before the loads below
+
+        // ---- phase C: greedy parse, one warp per segment ----------------------------------------------
+        const uint32_t seg_lo = warp * SEG;
+        const uint32_t seg_hi = min(clen, seg_lo + SEG);
+        uint32_t* hs = s_hist + warp * NSYM;
+        uint32_t* mytok = tok + chunk * CHUNK + seg_lo;
+        uint32_t nt = 0;
+        if (seg_lo < clen) {
+            uint32_t pos = seg_lo;
+            // candidates travel through two register blocks of 32 (aligned): the block after the one in
+            // use is already in flight, so the L2 latency of cand[] overlaps a whole parse step
+            // (L1 is bypassed: the slot is rewritten for every chunk this CTA processes)
+            uint32_t blk_base = pos & ~31u;
+            uint32_t blk0 = __ldcg(&cand[min(blk_base + lane, CHUNK - 1)]);
+            uint32_t blk1 = __ldcg(&cand[min(blk_base + 32 + lane, CHUNK - 1)]);
+            while (pos < seg_hi) {
+                if (pos >= blk_base + 32) {
+                    if (pos < blk_base + 64) { blk_base += 32; blk0 = blk1; }
+                    else { blk_base = pos & ~31u; blk0 = __ldcg(&cand[min(blk_base + lane, CHUNK - 1)]); }
+                    blk1 = __ldcg(&cand[min(blk_base + 32 + lane, CHUNK - 1)]);
+                }
+                const uint32_t p = pos + lane;
+                const uint32_t off = p - blk_base;                       // 0 .. 62
+                const uint32_t c0 = __shfl_sync(FULL, blk0, off & 31), c1 = __shfl_sync(FULL, blk1, off & 31);
+                const uint32_t avail = p < seg_hi ? seg_hi - p : 0;
+                uint32_t len = 0, dist = 0;
+                if (avail >= 4) {
+                    dist = off < 32 ? c0 : c1;
+                    if (dist) {
+                        const uint32_t q = p - dist;
+                        const uint32_t maxl = min(avail, MAX_MATCH);
+                        uint32_t l = 4;
+                        while (l < maxl) {
+                            const uint32_t x = ld4_unaligned(s_data, p + l) ^ ld4_unaligned(s_data, q + l);
+                            if (x) { l += (__ffs(x) - 1) >> 3; break; }
+                            l += 4;
+                        }
+                        len = min(l, maxl);
+                    }
+                }
+                const uint32_t byte = s_data[p];
+                const uint32_t valid = min(32u, seg_hi - pos);
+                const uint32_t mmask = __ballot_sync(FULL, len >= 4);
+                uint32_t litmask = 0, selmask = 0, cur = 0, advance = valid;
+                for (;;) {
+                    const uint32_t m = cur < 32 ? (mmask & ~((1u << cur) - 1u)) : 0;
+                    if (m == 0) {
+                        if (cur < valid) litmask |= mask_range(cur, valid);
+                        advance = max(valid, cur);
+                        break;
+                    }
+                    const uint32_t j = __ffs(m) - 1;
+                    litmask |= mask_range(cur, j);
+                    selmask |= 1u << j;
+                    cur = j + __shfl_sync(FULL, len, j);
+                    if (cur >= 32) { advance = cur; break; }
+                }
+                const uint32_t sel = litmask | selmask;
+                if ((sel >> lane) & 1) {
+                    const uint32_t rank = __popc(sel & ((1u << lane) - 1u));
+                    if ((selmask >> lane) & 1) {
+                        mytok[nt + rank] = tok_match(len, dist);
+                        uint32_t idx, ne, ev, ds;
+                        len_symbol(len, idx, ne, ev);
+                        atomicAdd(&hs[257 + idx], 1u);
+                        dist_symbol(dist, ds, ne, ev);
+                        atomicAdd(&hs[NLIT + ds], 1u);
+                    } else {
+                        mytok[nt + rank] = byte;
+                        atomicAdd(&hs[byte], 1u);
+                    }
+                }
+                nt += __popc(sel);
+                pos += advance;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) ntok[chunk * NSEG + warp] = nt;
+        uint32_t* gh = hist + (chunk * NSEG + warp) * NSYM;
+        for (uint32_t i = lane; i < NSYM; i += 32) gh[i] = hs[i];
     }
-    __syncwarp();
-    if (lane == 0) ntok[chunk * NSEG + warp] = nt;
-    uint32_t* gh = hist + (chunk * NSEG + warp) * NSYM;
-    for (uint32_t i = lane; i < NSYM; i += 32) gh[i] = hs[i];
 }
 
 // =====================================================================================================

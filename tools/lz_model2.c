@@ -29,23 +29,26 @@ int main(int argc, char** argv) {
                 clen_[p] = 0; cdist[p] = 0;
                 if (p + 4 > clen) continue;
                 uint32_t w4 = ld4(d, p), h = (w4 * 0x9E3779B1u) >> (32 - HB);
-                uint32_t cands[3]; int nc = 0;
+                uint32_t cands[8]; int nc = 0;
                 cands[nc++] = tab[h];
                 if (p > 0) cands[nc++] = p - 1;
-                if (PEER) { /* nearest earlier position in the same 32-lane group with the same hash */
+                if (PEER >= 2) { for (uint32_t k = 2; k <= (uint32_t)PEER + 1 && k <= p; k++) cands[nc++] = p - k; }
+                else if (PEER) { /* nearest earlier position in the same 32-lane group with the same hash */
                     for (uint32_t q = p; q-- > (p & ~31u);) { uint32_t h2 = (ld4(d, q) * 0x9E3779B1u) >> (32 - HB); if (h2 == h) { cands[nc++] = q; break; } }
                 }
                 uint32_t maxl = clen - p < 258 ? clen - p : 258;
+                uint32_t bscore = 0;
                 for (int k = 0; k < nc; k++) {
                     uint32_t q = cands[k]; if (q >= p || p - q > 32768) continue;
                     uint32_t l = 0; while (l < maxl && d[q + l] == d[p + l]) l++;
-                    if (l >= (uint32_t)MINM && l > clen_[p]) { clen_[p] = l; cdist[p] = p - q; }
+                    if (l < (uint32_t)MINM) continue;
+                    uint32_t score = CAP ? (l < (uint32_t)CAP ? l : (uint32_t)CAP) : l;   /* phase B only sees min(len, CAP) */
+                    if (score > bscore || (score == bscore && p - q < cdist[p])) { bscore = score; clen_[p] = l; cdist[p] = p - q; }
                     if (!ALL && k == 0 && clen_[p]) break;   /* table hit wins; others only as fallback */
                 }
             }
             for (uint32_t p = t0; p < t1; p++) if (p + 4 <= clen) { uint32_t h = (ld4(d, p) * 0x9E3779B1u) >> (32 - HB); if (tab[h] < p) tab[h] = p; }
         }
-        (void)CAP;
         uint32_t hl[288] = {0}, hd[32] = {0}; hl[256] = 1; double extra = 0;
         for (uint32_t s0 = 0; s0 < clen; s0 += SEG) {
             uint32_t s1 = s0 + SEG < clen ? s0 + SEG : clen, p = s0;
