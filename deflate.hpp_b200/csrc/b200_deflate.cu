@@ -113,7 +113,6 @@ struct b200_ctx {
     int device = 0;
     bool attrs_set = false;
     uint32_t batch_chunks = 4096;
-    bool fast_two_phase = true;      // B200_FAST_TWO_PHASE=0: the single-phase segment-private matcher (A/B runs)
     uint32_t better_depth = 128, better_nice = 258;   // "better" level: chain depth / good-enough length
     // compress scratch
     Buf tok, ntok, hist, codes, hdr, desc, sizes, offsets, total;
@@ -137,8 +136,6 @@ namespace {
 
 int set_attrs(b200_ctx* c) {
     if (c->attrs_set) return B200_OK;
-    CK(cudaFuncSetAttribute(lz77_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LZ_SMEM_BYTES));
-    CK(cudaFuncSetAttribute(lz77_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LZ_SMEM_BYTES));
     CK(cudaFuncSetAttribute(lz77_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LZF_SMEM_BYTES));
     CK(cudaFuncSetAttribute(lz77_better_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LZB_SMEM_BYTES));
     CK(cudaFuncSetAttribute(encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_SMEM_BYTES));
@@ -196,7 +193,6 @@ int b200_ctx_create(int device, b200_ctx** ctx) {
     c->device = device;
     c->inf_grid = (uint32_t)prop.multiProcessorCount * INF_MAX_CTAS_PER_SM;
     c->lzf_grid = (uint32_t)prop.multiProcessorCount * 2;
-    if (const char* e = getenv("B200_FAST_TWO_PHASE")) c->fast_two_phase = atoi(e) != 0;
     if (const char* e = getenv("B200_BETTER_DEPTH")) { int v = atoi(e); if (v > 0) c->better_depth = (uint32_t)v; }
     if (const char* e = getenv("B200_BETTER_NICE")) { int v = atoi(e); if (v >= 3) c->better_nice = (uint32_t)v; }
     if (const char* e = getenv("B200_BATCH_CHUNKS")) { int v = atoi(e); if (v > 0) c->batch_chunks = (uint32_t)v; }
@@ -264,7 +260,7 @@ void b200_free(void* p) { free(p); }
 // bytes from there to the end of the buffer; offs: the chunk-offset array (global chunk indexing).
 static int compress_batch(b200_ctx* c, const uint8_t* bin, uint64_t bn, uint32_t nb, uint64_t b0, bool final_batch,
                           int level, uint64_t* offs, uint64_t* d_total, void* d_out, cudaStream_t st) {
-    if (level == 2 && c->fast_two_phase) {
+    if (level == 2) {
         int rc;
         if ((rc = c->cand16.ensure((size_t)c->lzf_grid * CHUNK * 2))) return rc;
         if ((rc = c->counter.ensure(64))) return rc;
@@ -275,16 +271,14 @@ static int compress_batch(b200_ctx* c, const uint8_t* bin, uint64_t bn, uint32_t
         if (level == 3)
             lz77_better_kernel<<<nb, LZB_THREADS, LZB_SMEM_BYTES, st>>>(bin, bn, (uint32_t*)c->tok.p, (uint32_t*)c->ntok.p,
                                                                      (uint32_t*)c->hist.p, c->better_depth, c->better_nice);
-        else if (level == 2 && c->fast_two_phase) {
+        else if (level == 2) {
             const uint32_t grid = nb < c->lzf_grid ? nb : c->lzf_grid;
             lz77_fast_kernel<<<grid, LZF_THREADS, LZF_SMEM_BYTES, st>>>(bin, bn, nb, (uint32_t*)c->tok.p, (uint32_t*)c->ntok.p,
                                                                      (uint32_t*)c->hist.p, (uint16_t*)c->cand16.p,
                                                                      (unsigned int*)c->counter.p);
         }
-        else if (level == 1)
-            lz77_kernel<1><<<nb, LZ_THREADS, LZ_SMEM_BYTES, st>>>(bin, bn, (uint32_t*)c->tok.p, (uint32_t*)c->ntok.p, (uint32_t*)c->hist.p);
         else
-            lz77_kernel<0><<<nb, LZ_THREADS, LZ_SMEM_BYTES, st>>>(bin, bn, (uint32_t*)c->tok.p, (uint32_t*)c->ntok.p, (uint32_t*)c->hist.p);
+            lz77_literal_kernel<<<nb, LZL_THREADS, 0, st>>>(bin, bn, (uint32_t*)c->tok.p, (uint32_t*)c->ntok.p, (uint32_t*)c->hist.p);
         LAUNCHED();
         PROF_END(c, st);
     }

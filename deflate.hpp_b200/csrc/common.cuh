@@ -10,8 +10,8 @@
 namespace b200 {
 
 constexpr uint32_t CHUNK = 65536;          // independent unit: one DEFLATE block, one CTA
-constexpr uint32_t NSEG = 8;               // segments per chunk: one warp each
-constexpr uint32_t SEG = CHUNK / NSEG;     // 8192 bytes parsed by one warp
+constexpr uint32_t NSEG = 16;              // segments per chunk: one warp each (parse and encode)
+constexpr uint32_t SEG = CHUNK / NSEG;     // 4096 bytes parsed by one warp; tokens never cross a segment
 constexpr uint32_t NLIT = 288;             // literal/length alphabet slots (286 used)
 constexpr uint32_t NDIST = 32;             // distance alphabet slots (30 used)
 constexpr uint32_t NSYM = NLIT + NDIST;    // 320: [0,288) lit/len, [288,320) dist

@@ -1,26 +1,20 @@
-// lz77.cuh -- K1: per-chunk LZ77 tokeniser + histogram.
+// lz77.cuh -- K1: per-chunk LZ77 tokenisers + histograms.
 //
-// Replaces the reference's LZ77::getMatches (include/deflate.hpp:310-383, "fast") and the histogram
-// half of constructDynamicHuffmanTree (deflate.hpp:402-418).  Not a port: the reference probes only
-// 4-byte-aligned positions of a 32 KB chunk with one thread and a first-occurrence table
-// (deflate.hpp:373-376); here one CTA owns a 64 KiB chunk staged in shared memory by a TMA bulk copy,
-// each of its 8 warps parses an 8 KiB segment with its own shared-memory hash table, the 32 lanes of
-// a warp probe 32 consecutive positions at once, and the greedy selection is a warp-uniform loop
-// over ballot masks.  Tokens go to a global scratch buffer (one word per TOKEN, not per byte) and the
-// literal/length + distance histograms are accumulated with shared-memory atomics per warp.
+// Replaces the reference's LZ77::getMatches (include/deflate.hpp:310-383, "fast"), getMatchesSlow
+// (:268-304, "better") and the histogram half of constructDynamicHuffmanTree (:402-418).  Not a port:
+// the reference probes only 4-byte-aligned positions of a 32 KB chunk with one thread and a
+// first-occurrence table (:373-376), or scans all earlier positions for every position (:280-296).
+// Here one CTA owns a 64 KiB chunk staged in shared memory by a TMA bulk copy; candidates are found
+// for ALL positions in parallel against a chunk-wide structure (hash table for "fast", hash chains
+// for "better"), then each warp parses one 4 KiB segment greedily (or lazily), 32 positions per step
+// with ballot-mask selection.  Tokens go to a global scratch buffer (one word per TOKEN, not per
+// byte); literal/length + distance histograms are accumulated per segment with shared-memory atomics.
 #pragma once
 #include "common.cuh"
 
 namespace b200 {
 
-constexpr uint32_t LZ_THREADS = NSEG * 32;     // 256
-constexpr uint32_t LZ_HASH_BITS = 11;          // 2048 x u16 per warp
-constexpr uint32_t LZ_WARM = 4096;             // bytes of the previous segment pre-inserted into the table
 constexpr uint32_t LZ_DATA_PAD = 64;           // zeroed over-read slack after the chunk
-
-constexpr size_t LZ_SMEM_BYTES = CHUNK + LZ_DATA_PAD + NSEG * (2u << LZ_HASH_BITS) + NSEG * NSYM * 4 + 16;
-
-__device__ __forceinline__ uint32_t lz_hash(uint32_t w4) { return (w4 * 0x9E3779B1u) >> (32 - LZ_HASH_BITS); }
 
 __device__ __forceinline__ uint32_t mask_range(uint32_t a, uint32_t b) {   // bits [a, b), a <= b <= 32
     uint32_t hi = b >= 32 ? 0xFFFFFFFFu : ((1u << b) - 1u);
@@ -57,128 +51,40 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
-// MODE 0: greedy hash matcher (level 2 "fast").  MODE 1: literals only (level 1).
-// grid = chunks, block = 256.  first_chunk lets a batch address its slice of the scratch buffers.
-template <int MODE>
-__global__ void __launch_bounds__(LZ_THREADS, 2)
-lz77_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t* __restrict__ tok,
-            uint32_t* __restrict__ ntok, uint32_t* __restrict__ hist) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* s_data = smem;                                                  // CHUNK + pad
-    uint16_t* s_tab = reinterpret_cast<uint16_t*>(smem + CHUNK + LZ_DATA_PAD);
-    uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem + CHUNK + LZ_DATA_PAD + NSEG * (2u << LZ_HASH_BITS));
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_hist + NSEG * NSYM);
+// Per-segment histogram in shared memory, two 16-bit counters per word (a segment has at most
+// SEG = 4096 tokens, so a counter cannot carry into its neighbour).
+constexpr uint32_t HIST_WORDS = NSYM / 2;
+__device__ __forceinline__ void hist_add(uint32_t* h, uint32_t sym) { atomicAdd(&h[sym >> 1], 1u << ((sym & 1) * 16)); }
+__device__ __forceinline__ void hist_store(const uint32_t* h, uint32_t* gh, uint32_t lane) {
+    for (uint32_t i = lane; i < NSYM; i += 32) gh[i] = (h[i >> 1] >> ((i & 1) * 16)) & 0xFFFFu;
+}
 
+// =====================================================================================================
+// Level 1 (Huffman only, no matching -- reference deflate.hpp:706-708): every byte is a literal token.
+// grid = chunks, 512 threads, warp s handles segment s.  No shared-memory staging needed.
+// =====================================================================================================
+constexpr uint32_t LZL_THREADS = NSEG * 32;
+__global__ void __launch_bounds__(LZL_THREADS)
+lz77_literal_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t* __restrict__ tok,
+                    uint32_t* __restrict__ ntok, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t s_hist[NSEG * HIST_WORDS];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint64_t chunk = blockIdx.x;
     const uint64_t base = chunk * CHUNK;
     const uint32_t clen = (uint32_t)min((uint64_t)CHUNK, n - base);
-    const uint8_t* src = in + base;
-
-    // ---- stage the chunk in shared memory (TMA bulk copy for the 16-byte-aligned body) -------
-    const bool aligned = ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
-    const uint32_t bulk = aligned ? (clen & ~15u) : 0;
-    if (tid == 0) mbar_init(s_bar, 1);
+    for (uint32_t i = tid; i < NSEG * HIST_WORDS; i += LZL_THREADS) s_hist[i] = 0;
     __syncthreads();
-    if (tid == 0 && bulk) tma_load_1d(s_data, src, bulk, s_bar);
-    for (uint32_t i = bulk + tid; i < clen; i += LZ_THREADS) s_data[i] = src[i];
-    for (uint32_t i = clen + tid; i < ((clen + 15u) & ~15u) + LZ_DATA_PAD && i < CHUNK + LZ_DATA_PAD; i += LZ_THREADS)
-        s_data[i] = 0;
-    {   // zero hash tables + histograms while the copy is in flight
-        uint32_t* z = reinterpret_cast<uint32_t*>(s_tab);
-        const uint32_t nz = (NSEG * (2u << LZ_HASH_BITS) + NSEG * NSYM * 4) / 4;
-        for (uint32_t i = tid; i < nz; i += LZ_THREADS) z[i] = 0;
-    }
-    if (bulk) mbar_wait(s_bar, 0);
-    __syncthreads();
-
-    // ---- per-warp parse of one segment ----------------------------------------------------
-    const uint32_t seg_lo = warp * SEG;
-    const uint32_t seg_hi = min(clen, seg_lo + SEG);
-    uint16_t* tab = s_tab + warp * (1u << LZ_HASH_BITS);
-    uint32_t* h = s_hist + warp * NSYM;
+    const uint32_t seg_lo = warp * SEG, seg_hi = min(clen, seg_lo + SEG);
+    uint32_t* hs = s_hist + warp * HIST_WORDS;
     uint32_t* mytok = tok + chunk * CHUNK + seg_lo;
-    uint32_t nt = 0;
-    const uint32_t FULL = 0xFFFFFFFFu;
-
-    if (seg_lo < clen) {
-        if (MODE == 0) {
-            // warm start: pre-insert the tail of the previous segment so matches can reach into it
-            uint32_t ws = seg_lo > LZ_WARM ? seg_lo - LZ_WARM : 0;
-            for (uint32_t p = ws + lane; p < seg_lo; p += 32) tab[lz_hash(ld4_unaligned(s_data, p))] = (uint16_t)p;
-            __syncwarp();
-        }
-        uint32_t pos = seg_lo;
-        while (pos < seg_hi) {
-            const uint32_t p = pos + lane;
-            const uint32_t avail = p < seg_hi ? seg_hi - p : 0;
-            const uint32_t w4 = ld4_unaligned(s_data, p);
-            uint32_t len = 0, dist = 0;
-            if (MODE == 0) {
-                const uint32_t hsh = lz_hash(w4);
-                uint32_t q = tab[hsh];
-                __syncwarp();
-                if (avail >= 4) tab[hsh] = (uint16_t)p;
-                __syncwarp();
-                bool hit = avail >= 4 && q < p && (p - q) <= MAX_DIST && ld4_unaligned(s_data, q) == w4;
-                if (!hit && avail >= 4 && p > 0 && ld4_unaligned(s_data, p - 1) == w4) { q = p - 1; hit = true; }  // run
-                if (hit) {
-                    const uint32_t maxl = min(avail, MAX_MATCH);
-                    uint32_t l = 4;
-                    while (l < maxl) {
-                        uint32_t x = ld4_unaligned(s_data, p + l) ^ ld4_unaligned(s_data, q + l);
-                        if (x) { l += (__ffs(x) - 1) >> 3; break; }
-                        l += 4;
-                    }
-                    len = min(l, maxl);
-                    dist = p - q;
-                }
-            }
-            // greedy in-order selection over the 32 candidates: warp-uniform mask arithmetic
-            const uint32_t valid = min(32u, seg_hi - pos);
-            uint32_t litmask = 0, selmask = 0, advance = valid;
-            if (MODE == 0) {
-                const uint32_t mmask = __ballot_sync(FULL, len >= 4);
-                uint32_t cur = 0;
-                for (;;) {
-                    uint32_t m = cur < 32 ? (mmask & ~((1u << cur) - 1u)) : 0;
-                    if (m == 0) {
-                        if (cur < valid) litmask |= mask_range(cur, valid);
-                        advance = max(valid, cur);
-                        break;
-                    }
-                    uint32_t j = __ffs(m) - 1;
-                    litmask |= mask_range(cur, j);
-                    selmask |= 1u << j;
-                    cur = j + __shfl_sync(FULL, len, j);
-                    if (cur >= 32) { advance = cur; break; }
-                }
-            } else {
-                litmask = mask_range(0, valid);
-            }
-            const uint32_t sel = litmask | selmask;
-            if ((sel >> lane) & 1) {
-                const uint32_t rank = __popc(sel & ((1u << lane) - 1u));
-                if ((selmask >> lane) & 1) {
-                    mytok[nt + rank] = tok_match(len, dist);
-                    uint32_t idx, ne, ev, ds;
-                    len_symbol(len, idx, ne, ev);
-                    atomicAdd(&h[257 + idx], 1u);
-                    dist_symbol(dist, ds, ne, ev);
-                    atomicAdd(&h[NLIT + ds], 1u);
-                } else {
-                    mytok[nt + rank] = w4 & 0xFFu;
-                    atomicAdd(&h[w4 & 0xFFu], 1u);
-                }
-            }
-            nt += __popc(sel);
-            pos += advance;
-        }
+    for (uint32_t p = seg_lo + lane; p < seg_hi; p += 32) {
+        const uint32_t b = in[base + p];
+        mytok[p - seg_lo] = b;
+        hist_add(hs, b);
     }
     __syncwarp();
-    if (lane == 0) ntok[chunk * NSEG + warp] = nt;
-    uint32_t* gh = hist + (chunk * NSEG + warp) * NSYM;
-    for (uint32_t i = lane; i < NSYM; i += 32) gh[i] = h[i];
+    if (lane == 0) ntok[chunk * NSEG + warp] = seg_lo < clen ? seg_hi - seg_lo : 0;
+    hist_store(hs, hist + (chunk * NSEG + warp) * NSYM, lane);
 }
 
 // =====================================================================================================
@@ -194,16 +100,17 @@ lz77_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t* __restrict__ t
 //            from registers.  Each is verified on 4 bytes and scored on the next 4 (no loops);
 //            the best score / nearest distance goes to a u16 candidate array in a per-CTA scratch
 //            slot (128 KB per CTA, 38 MB in total: it lives in L2 and is never meant to reach HBM).
-//   phase C  each warp parses one 8 KiB segment greedily: 32 positions per step, every lane extends
+//   phase C  each warp parses one 4 KiB segment greedily: 32 positions per step, every lane extends
 //            its own candidate to full length (4 bytes per iteration), ballot-mask selection, tokens
 //            and shared-memory histograms exactly as in the single-phase kernel.
 // Against lz77_kernel<0>: the whole 32 KiB window is reachable from every position instead of an
 // 8 KiB segment-private table (large.bmp stand-in: 2x smaller output, corpus: 0.71 -> 0.62).
 // =====================================================================================================
-constexpr uint32_t LZF_THREADS = 256;
+constexpr uint32_t LZF_THREADS = NSEG * 32;          // 512
 constexpr uint32_t LZF_HASH_BITS = 13;
-constexpr uint32_t LZF_TILE = 4 * LZF_THREADS;     // positions between two table updates
-constexpr size_t LZF_SMEM_BYTES = CHUNK + LZ_DATA_PAD + (4u << LZF_HASH_BITS) + NSEG * NSYM * 4 + 32;
+constexpr uint32_t LZF_PER_THREAD = 2;
+constexpr uint32_t LZF_TILE = LZF_PER_THREAD * LZF_THREADS;     // 1024 positions between two table updates
+constexpr size_t LZF_SMEM_BYTES = CHUNK + LZ_DATA_PAD + (4u << LZF_HASH_BITS) + NSEG * HIST_WORDS * 4 + 32;
 
 __device__ __forceinline__ uint32_t lzf_hash(uint32_t w4) { return (w4 * 0x9E3779B1u) >> (32 - LZF_HASH_BITS); }
 
@@ -222,7 +129,7 @@ lz77_fast_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t nchunks, u
     uint8_t* s_data = smem;
     uint32_t* s_tab = reinterpret_cast<uint32_t*>(smem + CHUNK + LZ_DATA_PAD);
     uint32_t* s_hist = s_tab + (1u << LZF_HASH_BITS);
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_hist + NSEG * NSYM);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_hist + NSEG * HIST_WORDS);
     uint32_t* s_next = reinterpret_cast<uint32_t*>(s_bar + 1);
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -250,17 +157,17 @@ lz77_fast_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t nchunks, u
         for (uint32_t i = bulk + tid; i < clen; i += LZF_THREADS) s_data[i] = src[i];
         for (uint32_t i = clen + tid; i < ((clen + 15u) & ~15u) + LZ_DATA_PAD && i < CHUNK + LZ_DATA_PAD; i += LZF_THREADS)
             s_data[i] = 0;
-        for (uint32_t i = tid; i < (1u << LZF_HASH_BITS) + NSEG * NSYM; i += LZF_THREADS) s_tab[i] = 0;
+        for (uint32_t i = tid; i < (1u << LZF_HASH_BITS) + NSEG * HIST_WORDS; i += LZF_THREADS) s_tab[i] = 0;
         if (bulk) { mbar_wait(s_bar, parity); parity ^= 1; }
         __syncthreads();
 
         // ---- phase B: one verified candidate distance per position ----------------------------------
-        // Tile = 1024 positions, 4 per thread (tid, tid+256, ...): each warp still holds 32 consecutive
+        // Tile = 1024 positions, 2 per thread (tid, tid+512): each warp still holds 32 consecutive
         // positions per sub-tile, so neighbours' words are a shuffle away.
         for (uint32_t t0 = 0; t0 < clen; t0 += LZF_TILE) {
-            uint32_t w4[4], w8[4], hq[4];
+            uint32_t w4[LZF_PER_THREAD], w8[LZF_PER_THREAD], hq[LZF_PER_THREAD];
             #pragma unroll
-            for (uint32_t k = 0; k < 4; k++) {
+            for (uint32_t k = 0; k < LZF_PER_THREAD; k++) {
                 const uint32_t p = t0 + k * LZF_THREADS + tid;
                 const uint32_t* w = reinterpret_cast<const uint32_t*>(s_data) + (p >> 2);
                 const uint32_t a = w[0], b = w[1], c = w[2], sh = (p & 3) * 8;
@@ -270,12 +177,12 @@ lz77_fast_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t nchunks, u
             }
             __syncthreads();                               // every lookup of this tile is done
             #pragma unroll
-            for (uint32_t k = 0; k < 4; k++) {
+            for (uint32_t k = 0; k < LZF_PER_THREAD; k++) {
                 const uint32_t p = t0 + k * LZF_THREADS + tid;
                 if (p + 4 <= clen) atomicMax(&s_tab[lzf_hash(w4[k])], p);
             }
             #pragma unroll
-            for (uint32_t k = 0; k < 4; k++) {
+            for (uint32_t k = 0; k < LZF_PER_THREAD; k++) {
                 const uint32_t p = t0 + k * LZF_THREADS + tid;
                 // the 4 bytes before p: lane-4's word, or a shared-memory read at the warp's left edge
                 uint32_t prev4 = __shfl_up_sync(FULL, w4[k], 4);
@@ -306,7 +213,7 @@ lz77_fast_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t nchunks, u
         // ---- phase C: greedy parse, one warp per segment ----------------------------------------------
         const uint32_t seg_lo = warp * SEG;
         const uint32_t seg_hi = min(clen, seg_lo + SEG);
-        uint32_t* hs = s_hist + warp * NSYM;
+        uint32_t* hs = s_hist + warp * HIST_WORDS;
         uint32_t* mytok = tok + chunk * CHUNK + seg_lo;
         uint32_t nt = 0;
         if (seg_lo < clen) {
@@ -344,44 +251,46 @@ lz77_fast_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t nchunks, u
                 }
                 const uint32_t byte = s_data[p];
                 const uint32_t valid = min(32u, seg_hi - pos);
-                const uint32_t mmask = __ballot_sync(FULL, len >= 4);
-                uint32_t litmask = 0, selmask = 0, cur = 0, advance = valid;
-                for (;;) {
-                    const uint32_t m = cur < 32 ? (mmask & ~((1u << cur) - 1u)) : 0;
-                    if (m == 0) {
-                        if (cur < valid) litmask |= mask_range(cur, valid);
-                        advance = max(valid, cur);
-                        break;
-                    }
-                    const uint32_t j = __ffs(m) - 1;
-                    litmask |= mask_range(cur, j);
+                // greedy in-order selection: the serial part only walks from match to match
+                // (first match lane at or after the frontier, jump to its end) ...
+                uint32_t mm = __ballot_sync(FULL, len >= 4);
+                const uint32_t endl = lane + len;                        // where this lane's match would end
+                uint32_t selmask = 0, cur = 0;
+                while (mm) {
+                    const uint32_t j = __ffs(mm) - 1;
                     selmask |= 1u << j;
-                    cur = j + __shfl_sync(FULL, len, j);
-                    if (cur >= 32) { advance = cur; break; }
+                    cur = __shfl_sync(FULL, endl, j);
+                    mm = cur < 32 ? mm & (FULL << cur) : 0;
                 }
-                const uint32_t sel = litmask | selmask;
-                if ((sel >> lane) & 1) {
+                // ... and every lane then decides for itself whether a selected match covers it: the
+                // nearest selected lane at or below it is the only one that can (matches do not overlap)
+                const uint32_t below = selmask & (FULL >> (31 - lane));
+                const uint32_t owner = below ? 31 - __clz(below) : lane;
+                const uint32_t oend = __shfl_sync(FULL, endl, owner);
+                const bool is_sel = (selmask >> lane) & 1;
+                const bool is_lit = lane < valid && !(below && oend > lane);
+                const uint32_t sel = __ballot_sync(FULL, is_sel || is_lit);
+                if (is_sel || is_lit) {
                     const uint32_t rank = __popc(sel & ((1u << lane) - 1u));
-                    if ((selmask >> lane) & 1) {
+                    if (is_sel) {
                         mytok[nt + rank] = tok_match(len, dist);
                         uint32_t idx, ne, ev, ds;
                         len_symbol(len, idx, ne, ev);
-                        atomicAdd(&hs[257 + idx], 1u);
+                        hist_add(hs, 257 + idx);
                         dist_symbol(dist, ds, ne, ev);
-                        atomicAdd(&hs[NLIT + ds], 1u);
+                        hist_add(hs, NLIT + ds);
                     } else {
                         mytok[nt + rank] = byte;
-                        atomicAdd(&hs[byte], 1u);
+                        hist_add(hs, byte);
                     }
                 }
                 nt += __popc(sel);
-                pos += advance;
+                pos += max(valid, cur);
             }
         }
         __syncwarp();
         if (lane == 0) ntok[chunk * NSEG + warp] = nt;
-        uint32_t* gh = hist + (chunk * NSEG + warp) * NSYM;
-        for (uint32_t i = lane; i < NSYM; i += 32) gh[i] = hs[i];
+        hist_store(hs, hist + (chunk * NSEG + warp) * NSYM, lane);
     }
 }
 
@@ -397,7 +306,7 @@ lz77_fast_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t nchunks, u
 //   phase B  all 16 warps search: each lane walks the chain of its own position (nearest first, up to
 //            `depth` candidates, 32 KiB distance limit, 4-byte-stride extension) and stores its best
 //            (length, distance) in the chunk's token scratch
-//   phase C  warps 0..7 parse one 8 KiB segment each over those candidates with lazy evaluation
+//   phase C  every warp parses one 4 KiB segment over those candidates with lazy evaluation
 //            (a match is deferred when the next position has a longer one), emit tokens in place and
 //            build the histograms, exactly as the fast kernel does.
 // =====================================================================================================
@@ -493,13 +402,13 @@ lz77_better_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t* __restr
     }
     __syncthreads();   // also orders the global cand[] stores before phase C's loads (same CTA)
 
-    // ---- phase C: lazy parse per segment (warps 0..7) --------------------------------------------
-    for (uint32_t i = tid; i < NSEG * NSYM; i += LZB_THREADS) s_hist[i] = 0;
+    // ---- phase C: lazy parse, one warp per segment -----------------------------------------------
+    for (uint32_t i = tid; i < NSEG * HIST_WORDS; i += LZB_THREADS) s_hist[i] = 0;
     __syncthreads();
     if (warp >= NSEG) return;
     const uint32_t seg_lo = warp * SEG;
     const uint32_t seg_hi = min(clen, seg_lo + SEG);
-    uint32_t* h = s_hist + warp * NSYM;
+    uint32_t* h = s_hist + warp * HIST_WORDS;
     uint32_t* mytok = tok + chunk * CHUNK + seg_lo;
     uint32_t nt = 0;
     if (seg_lo < clen) {
@@ -538,12 +447,12 @@ lz77_better_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t* __restr
                     mytok[nt + rank] = tok_match(len, dist);
                     uint32_t idx, ne, ev, ds;
                     len_symbol(len, idx, ne, ev);
-                    atomicAdd(&h[257 + idx], 1u);
+                    hist_add(h, 257 + idx);
                     dist_symbol(dist, ds, ne, ev);
-                    atomicAdd(&h[NLIT + ds], 1u);
+                    hist_add(h, NLIT + ds);
                 } else {
                     mytok[nt + rank] = byte;
-                    atomicAdd(&h[byte], 1u);
+                    hist_add(h, byte);
                 }
             }
             nt += __popc(sel);
@@ -553,8 +462,7 @@ lz77_better_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t* __restr
     }
     __syncwarp();
     if (lane == 0) ntok[chunk * NSEG + warp] = nt;
-    uint32_t* gh = hist + (chunk * NSEG + warp) * NSYM;
-    for (uint32_t i = lane; i < NSYM; i += 32) gh[i] = h[i];
+    hist_store(h, hist + (chunk * NSEG + warp) * NSYM, lane);
 }
 
 }  // namespace b200
