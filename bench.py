@@ -272,8 +272,15 @@ def main():
         for k in range(rounds):
             ctx.corpus_generate_dev(src.data_ptr() + k * slice_chunks * CHUNK, SEED,
                                     shard.slice_first_chunk(k, rank, world, slice_chunks), slice_chunks, stream=st)
-    gather_buf = torch.empty(cap * world, dtype=torch.uint8, device=dev) if (world > 1 and rank == 0) else None
-    pg = shard.PipelinedGather(gather_buf, dst=0) if world > 1 else None
+    gather_buf, symm = None, None
+    transport = None
+    if world > 1:
+        if os.environ.get("B200_GATHER", "p2p_copy") == "p2p_copy":
+            gather_buf, symm = shard.symmetric_buffer(cap * world, dev)      # rank 0's instance receives
+        transport = "nvlink peer copy (symmetric memory, copy engines)" if symm is not None else "nccl send/recv"
+        if symm is None:
+            gather_buf = torch.empty(cap * world, dtype=torch.uint8, device=dev) if rank == 0 else None
+    pg = shard.PipelinedGather(gather_buf, dst=0, symm_handle=symm) if world > 1 else None
     if world > 1:
         side = torch.cuda.Stream(device=dev)
         sizes_dev = torch.zeros(rounds, dtype=torch.int64, device=dev)
@@ -447,7 +454,7 @@ def main():
                        "bytes_per_gpu": int(n), "chunks_per_gpu": nchunks, "l2_hygiene": "inputs (>= 1 GiB) larger than the 126 MB L2",
                        "seed": SEED},
             "ratio": {"b200": ratio, "reference_sample": cpu.get("ratio") if cpu else None},
-            "gathered_stream_bit_exact": gathered_ok,
+            "gathered_stream_bit_exact": gathered_ok, "gather_transport": transport,
             "decompress": dec, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             "gpu_launches": int(launches),
         }

@@ -193,6 +193,12 @@ int b200_ctx_create(int device, b200_ctx** ctx) {
     c->device = device;
     c->inf_grid = (uint32_t)prop.multiProcessorCount * INF_MAX_CTAS_PER_SM;
     c->lzf_grid = (uint32_t)prop.multiProcessorCount * 2;
+    // B200_RESERVE_SMS=k: leave k SMs out of the persistent matcher's grid so that concurrently running
+    // communication kernels (NCCL send/recv of the multi-GPU gather) can be scheduled while it runs
+    if (const char* e = getenv("B200_RESERVE_SMS")) {
+        int v = atoi(e);
+        if (v > 0 && v < prop.multiProcessorCount) c->lzf_grid = (uint32_t)(prop.multiProcessorCount - v) * 2;
+    }
     if (const char* e = getenv("B200_BETTER_DEPTH")) { int v = atoi(e); if (v > 0) c->better_depth = (uint32_t)v; }
     if (const char* e = getenv("B200_BETTER_NICE")) { int v = atoi(e); if (v >= 3) c->better_nice = (uint32_t)v; }
     if (const char* e = getenv("B200_BATCH_CHUNKS")) { int v = atoi(e); if (v > 0) c->batch_chunks = (uint32_t)v; }

@@ -86,14 +86,36 @@ def slice_first_chunk(round_idx: int, rank: int, world: int, slice_chunks: int) 
     return (round_idx * world + rank) * slice_chunks
 
 
-class PipelinedGather:
-    """Per round: exchange sizes, post the sends/receives at final offsets, return without waiting."""
+def symmetric_buffer(nbytes: int, device):
+    """A uint8 buffer of the same size on every rank whose rank-r instance every peer can address
+    (torch symmetric memory: CUDA VMM + NVLink peer mapping).  Returns (local tensor, handle) or
+    (None, None) when symmetric memory is not usable here (CPU/gloo, older drivers)."""
+    try:
+        import torch.distributed._symmetric_memory as symm_mem
+        buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=device)
+        hdl = symm_mem.rendezvous(buf, dist.group.WORLD)
+        return buf, hdl
+    except Exception:  # noqa: BLE001
+        return None, None
 
-    def __init__(self, recv_buf: torch.Tensor = None, dst: int = 0):
+
+class PipelinedGather:
+    """Per round: exchange sizes, ship the compressed slice to its final offset, return without waiting.
+
+    Two transports.  With a symmetric-memory handle every sender copies its slice straight into the
+    destination's buffer over NVLink with a peer cudaMemcpyAsync: copy engines, no SMs, so it overlaps
+    the next round's kernels even while the persistent matcher owns every SM.  Otherwise (gloo, or no
+    symmetric memory) NCCL/gloo point-to-point send/recv."""
+
+    def __init__(self, recv_buf: torch.Tensor = None, dst: int = 0, symm_handle=None):
         self.world, self.rank, self.dst = dist.get_world_size(), dist.get_rank(), dst
         self.recv_buf = recv_buf
         self.offset = 0          # bytes of the joined stream placed so far (all rounds before this one)
         self.pending = []
+        self.peer_dst = None
+        if symm_handle is not None:
+            n = recv_buf.numel()
+            self.peer_dst = symm_handle.get_buffer(dst, (n,), torch.uint8)   # the destination's buffer, peer-mapped
 
     def post_round(self, local: torch.Tensor, n):
         """local[:n]: this rank's compressed slice of the current round.  `n` may be an int or a
@@ -106,7 +128,11 @@ class PipelinedGather:
         sizes = [int(x) for x in allsz.tolist()]
         n = sizes[self.rank]
         offs = [self.offset + o for o in gather_plan(sizes)]
-        if self.rank == self.dst:
+        if self.peer_dst is not None:
+            # one-sided: every rank (the destination too) writes its slice at its final offset
+            if n:
+                self.peer_dst[offs[self.rank]:offs[self.rank] + n].copy_(local[:n], non_blocking=True)
+        elif self.rank == self.dst:
             ops = [dist.P2POp(dist.irecv, self.recv_buf[offs[r]:offs[r] + sizes[r]], r)
                    for r in range(self.world) if r != self.dst and sizes[r]]
             self.recv_buf[offs[self.dst]:offs[self.dst] + n].copy_(local[:n], non_blocking=True)
@@ -121,5 +147,9 @@ class PipelinedGather:
         for w in self.pending:
             w.wait()
         self.pending = []
+        if self.peer_dst is not None:
+            # one-sided writes: the destination may only read once every writer's copies have landed
+            torch.cuda.current_stream().synchronize()
+            dist.barrier()
         total, self.offset = self.offset, 0
         return total
