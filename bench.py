@@ -267,7 +267,9 @@ def main():
     else:
         # block-cyclic shards of one (world x mib) MiB corpus: slice s (slice_chunks chunks) belongs to
         # rank s % world, so compressed slices can be shipped to their final offset round by round
-        rounds = 4 if nchunks % 4 == 0 and nchunks >= 4096 else 1
+        rounds = int(os.environ.get("B200_GATHER_ROUNDS", "4"))
+        if nchunks % rounds or nchunks // rounds < 1024:
+            rounds = 1
         slice_chunks = nchunks // rounds
         for k in range(rounds):
             ctx.corpus_generate_dev(src.data_ptr() + k * slice_chunks * CHUNK, SEED,
@@ -275,9 +277,13 @@ def main():
     gather_buf, symm = None, None
     transport = None
     if world > 1:
-        if os.environ.get("B200_GATHER", "p2p_copy") == "p2p_copy":
+        gmode = os.environ.get("B200_GATHER", "fused")
+        if gmode in ("p2p_copy", "fused"):
             gather_buf, symm = shard.symmetric_buffer(cap * world, dev)      # rank 0's instance receives
-        transport = "nvlink peer copy (symmetric memory, copy engines)" if symm is not None else "nccl send/recv"
+        if symm is None:
+            gmode = "nccl"
+        transport = {"fused": "fused into the encode kernel: stores to rank 0's memory over NVLink (symmetric memory)",
+                     "p2p_copy": "nvlink peer copy (symmetric memory, copy engines)", "nccl": "nccl send/recv"}[gmode]
         if symm is None:
             gather_buf = torch.empty(cap * world, dtype=torch.uint8, device=dev) if rank == 0 else None
     pg = shard.PipelinedGather(gather_buf, dst=0, symm_handle=symm) if world > 1 else None
@@ -288,9 +294,38 @@ def main():
     slice_bytes = slice_chunks * CHUNK
     slice_cap = d.deflate_bound(slice_bytes)
 
+    if world > 1 and gmode == "fused":
+        peer0 = symm.get_buffer(0, (gather_buf.numel(),), torch.uint8)     # rank 0's buffer as seen from here
+        allsz = torch.zeros(rounds, world, dtype=torch.int64, device=dev)
+        zero = torch.zeros((), dtype=torch.int64, device=dev)
+        token = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def step_fused():
+        # per round: K1..K3, 8-byte all_gather of the shard sizes, K4 writes straight into rank 0's memory
+        # at the shard's final offset.  Everything is stream-ordered; the host never waits inside a step.
+        running = zero
+        keep = []
+        for k in range(rounds):
+            last = (k == rounds - 1) and (rank == world - 1)
+            ctx.compress_stage1_dev(src.data_ptr() + k * slice_bytes, slice_bytes, args.level,
+                                    sizes_dev[k:k + 1].data_ptr(), flags=0 if last else d.F_NOT_LAST, stream=st)
+            dist.all_gather_into_tensor(allsz[k], sizes_dev[k:k + 1])
+            base = running + allsz[k, :rank].sum()
+            running = running + allsz[k].sum()
+            keep.append(base)
+            ctx.compress_stage2_dev(src.data_ptr() + k * slice_bytes, slice_bytes, peer0.data_ptr(),
+                                    d_base=base.data_ptr(), stream=st)
+        dist.all_reduce(token)          # stream-ordered barrier: every rank's stores have been issued and retired
+        step.keep = keep
+        step.running = running
+        return sizes_dev
+
     def step():
         if world == 1:
             return ctx.compress_dev(src.data_ptr(), n, args.level, dst.data_ptr(), cap, flags=0, stream=st)
+        if gmode == "fused":
+            step_fused()
+            return None
         # enqueue every round's kernels first (no host sync: sizes stay on the device) ...
         main = torch.cuda.current_stream()
         for k in range(rounds):
@@ -334,6 +369,9 @@ def main():
     ctx.profile(False)
     kern = ctx.profile_read()
     ms = e0.elapsed_time(e1)
+    if world > 1 and gmode == "fused":
+        cn = int(sizes_dev.sum().item())
+        step.joined = int(step.running.item())
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

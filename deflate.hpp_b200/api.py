@@ -76,6 +76,10 @@ def lib():
     L.b200_free.argtypes = [c_void_p]
     L.b200_deflate_compress_dev.argtypes = [c_void_p, c_void_p, c_size_t, c_int, c_uint, c_void_p, c_size_t,
                                             c_void_p, P(c_size_t), c_void_p, c_void_p]
+    L.b200_deflate_compress_stage1_dev.argtypes = [c_void_p, c_void_p, c_size_t, c_int, c_uint, c_void_p, c_void_p]
+    L.b200_deflate_compress_stage1_dev.restype = c_int
+    L.b200_deflate_compress_stage2_dev.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]
+    L.b200_deflate_compress_stage2_dev.restype = c_int
     L.b200_inflate_dev.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p, P(c_size_t),
                                    P(c_size_t), c_void_p, c_uint, c_void_p]
     L.b200_inflate_batch_dev.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -223,6 +227,16 @@ class Context:
         if rc:
             raise B200Error(rc, "b200_deflate_compress_dev")
         return out_n.value if sync else None
+
+    def compress_stage1_dev(self, d_in, n, level, d_local_n, flags=0, stream=0):
+        rc = lib().b200_deflate_compress_stage1_dev(self._h, d_in, n, _level(level), flags, d_local_n, stream or None)
+        if rc:
+            raise B200Error(rc, "b200_deflate_compress_stage1_dev")
+
+    def compress_stage2_dev(self, d_in, n, d_out, d_base=0, stream=0):
+        rc = lib().b200_deflate_compress_stage2_dev(self._h, d_in, n, d_out, d_base or None, stream or None)
+        if rc:
+            raise B200Error(rc, "b200_deflate_compress_stage2_dev")
 
     def inflate_dev(self, d_in, n, d_out, cap, flags=0, stream=0):
         """Returns (written, full_size)."""

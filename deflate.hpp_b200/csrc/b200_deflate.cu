@@ -264,8 +264,11 @@ void b200_free(void* p) { free(p); }
 
 // One batch of chunks through K1..K4 on stream `st`.  bin/bn: this batch's first input byte and the
 // bytes from there to the end of the buffer; offs: the chunk-offset array (global chunk indexing).
+// stages: bit 0 = K1..K3 (tokenise, code, size, scan), bit 1 = K4 (encode + write)
 static int compress_batch(b200_ctx* c, const uint8_t* bin, uint64_t bn, uint32_t nb, uint64_t b0, bool final_batch,
-                          int level, uint64_t* offs, uint64_t* d_total, void* d_out, cudaStream_t st) {
+                          int level, uint64_t* offs, uint64_t* d_total, void* d_out, cudaStream_t st,
+                          int stages = 3, const uint64_t* d_extra_base = nullptr) {
+    if (stages & 1) {
     if (level == 2) {
         int rc;
         if ((rc = c->cand16.ensure((size_t)c->lzf_grid * CHUNK * 2))) return rc;
@@ -299,12 +302,15 @@ static int compress_batch(b200_ctx* c, const uint8_t* bin, uint64_t bn, uint32_t
                                                  offs + b0, d_total);
     LAUNCHED();
     PROF_END(c, st);
-    PROF_BEGIN(c, K_ENCODE, st);
-    encode_kernel<<<nb, ENC_THREADS, ENC_SMEM_BYTES, st>>>(bin, (const uint32_t*)c->tok.p, (const uint32_t*)c->ntok.p,
-                                                          (const uint32_t*)c->codes.p, (const uint32_t*)c->hdr.p,
-                                                          (const BlockDesc*)c->desc.p, offs + b0, (uint8_t*)d_out);
-    LAUNCHED();
-    PROF_END(c, st);
+    }   // stages & 1
+    if (stages & 2) {
+        PROF_BEGIN(c, K_ENCODE, st);
+        encode_kernel<<<nb, ENC_THREADS, ENC_SMEM_BYTES, st>>>(bin, (const uint32_t*)c->tok.p, (const uint32_t*)c->ntok.p,
+                                                              (const uint32_t*)c->codes.p, (const uint32_t*)c->hdr.p,
+                                                              (const BlockDesc*)c->desc.p, offs + b0, d_extra_base, (uint8_t*)d_out);
+        LAUNCHED();
+        PROF_END(c, st);
+    }
     return B200_OK;
 }
 
@@ -364,6 +370,46 @@ int b200_deflate_compress_dev(b200_ctx* c, const void* d_in, size_t n, int level
         *h_out_n = (size_t)tot;
     }
     return B200_OK;
+}
+
+// Staged variant for the multi-GPU gather fused into the encoder.  Stage 1 = K1..K3 for one batch
+// (n <= batch size), leaves this shard's compressed byte count in *d_local_n.  The caller exchanges the
+// counts (an 8-byte all_gather), computes where the shard starts in the joined stream, and stage 2 = K4
+// writes every chunk at d_out + *d_base + its local offset; d_out may be another GPU's memory.
+int b200_deflate_compress_stage1_dev(b200_ctx* c, const void* d_in, size_t n, int level, unsigned flags,
+                                     uint64_t* d_local_n, void* stream_) {
+    if (!c || !d_in || !n || level < 0 || level > 3 || !d_local_n) return B200_E_ARG;
+    const uint64_t nchunks = (n + CHUNK - 1) / CHUNK;
+    if (nchunks > c->batch_chunks) return B200_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream_;
+    CK(cudaSetDevice(c->device));
+    int rc;
+    const uint64_t B = nchunks;
+    if ((rc = c->total.ensure(16))) return rc;
+    if ((rc = c->tok.ensure(B * CHUNK * 4))) return rc;
+    if ((rc = c->ntok.ensure(B * NSEG * 4))) return rc;
+    if ((rc = c->hist.ensure(B * NSEG * NSYM * 4))) return rc;
+    if ((rc = c->codes.ensure(B * NSYM * 4))) return rc;
+    if ((rc = c->hdr.ensure(B * HDR_WORDS * 4))) return rc;
+    if ((rc = c->desc.ensure(B * sizeof(BlockDesc)))) return rc;
+    if ((rc = c->sizes.ensure(B * 4))) return rc;
+    if ((rc = c->offsets.ensure((nchunks + 1) * 8))) return rc;
+    if ((rc = compress_batch(c, (const uint8_t*)d_in, n, (uint32_t)nchunks, 0, !(flags & B200_F_NOT_LAST), level,
+                             (uint64_t*)c->offsets.p, (uint64_t*)c->total.p, nullptr, st, 1)))
+        return rc;
+    CK(cudaMemcpyAsync(d_local_n, c->total.p, 8, cudaMemcpyDeviceToDevice, st));
+    return B200_OK;
+}
+
+int b200_deflate_compress_stage2_dev(b200_ctx* c, const void* d_in, size_t n, void* d_out, const uint64_t* d_base,
+                                     void* stream_) {
+    if (!c || !d_in || !n || !d_out) return B200_E_ARG;
+    const uint64_t nchunks = (n + CHUNK - 1) / CHUNK;
+    if (nchunks > c->batch_chunks || !c->offsets.p) return B200_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream_;
+    CK(cudaSetDevice(c->device));
+    return compress_batch(c, (const uint8_t*)d_in, n, (uint32_t)nchunks, 0, false, 0, (uint64_t*)c->offsets.p,
+                          (uint64_t*)c->total.p, d_out, st, 2, d_base);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 3)
 encode_kernel(const uint8_t* __restrict__ in, const uint32_t* __restrict__ tok, const uint32_t* __restrict__ ntok,
               const uint32_t* __restrict__ codes, const uint32_t* __restrict__ hdr,
               const BlockDesc* __restrict__ desc, const uint64_t* __restrict__ offsets,
-              uint8_t* __restrict__ out) {
+              const uint64_t* __restrict__ extra_base, uint8_t* __restrict__ out) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint32_t* stage = reinterpret_cast<uint32_t*>(smem);
     uint32_t* s_codes = reinterpret_cast<uint32_t*>(smem + ENC_STAGE_BYTES);
@@ -79,7 +79,9 @@ encode_kernel(const uint8_t* __restrict__ in, const uint32_t* __restrict__ tok, 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint64_t chunk = blockIdx.x;
     const BlockDesc& d = desc[chunk];
-    const uint64_t dst = offsets[chunk];
+    // extra_base: where this shard starts inside `out` when `out` is the stream being assembled from several
+    // GPUs (out may then be another GPU's memory, mapped over NVLink: the copy-out below IS the gather)
+    const uint64_t dst = offsets[chunk] + (extra_base ? *extra_base : 0);
     const uint32_t phase = (uint32_t)(dst & 15);          // staging byte k <-> out[(dst & ~15) + k]
     const uint32_t nbytes = d.nbytes;
     const uint32_t stage_bytes = phase + nbytes;

@@ -122,6 +122,18 @@ int b200_deflate_compress_dev(b200_ctx* ctx, const void* d_in, size_t n, int lev
                               void* d_out, size_t cap, uint64_t* d_out_n, size_t* h_out_n,
                               uint64_t* d_chunk_off, void* stream);
 
+/* Multi-GPU gather fused into the encoder.  Stage 1 runs tokenise / code construction / sizing for one
+ * batch (n <= 4096 chunks) and leaves this shard's compressed byte count in *d_local_n (device).  The
+ * caller exchanges the counts between ranks (an 8-byte all_gather) and computes *d_base, the offset of
+ * this shard inside the joined stream.  Stage 2 bit-packs and writes every chunk of the shard at
+ * d_out + *d_base + (offset inside the shard): d_out may be ANOTHER GPU's memory mapped over NVLink
+ * (symmetric memory / cudaIpc), so the encoder's stores are the gather.  Same ctx, same stream, stage 2
+ * directly after stage 1 of the same input. */
+int b200_deflate_compress_stage1_dev(b200_ctx* ctx, const void* d_in, size_t n, int level, unsigned flags,
+                                     uint64_t* d_local_n, void* stream);
+int b200_deflate_compress_stage2_dev(b200_ctx* ctx, const void* d_in, size_t n, void* d_out,
+                                     const uint64_t* d_base, void* stream);
+
 /* Inflate one raw stream.  Streams produced by this library (or any stream whose blocks are joined
  * by byte-aligning empty stored blocks and whose chunks do not reference earlier chunks) are decoded
  * chunk-parallel, one warp per chunk; anything else is decoded by a single warp.  Writes at most cap
