@@ -277,7 +277,7 @@ def main():
     gather_buf, symm = None, None
     transport = None
     if world > 1:
-        gmode = os.environ.get("B200_GATHER", "fused")
+        gmode = os.environ.get("B200_GATHER", "p2p_copy")
         if gmode in ("p2p_copy", "fused"):
             gather_buf, symm = shard.symmetric_buffer(cap * world, dev)      # rank 0's instance receives
         if symm is None:
