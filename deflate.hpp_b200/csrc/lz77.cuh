@@ -300,9 +300,10 @@ lz77_fast_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t nchunks, u
 // The reference scans ALL earlier positions of a 32 KB chunk for every position (O(n^2), ~1.1 s per
 // chunk) and takes the longest match greedily.  Here one CTA owns a 64 KiB chunk for its whole
 // lifetime in ~224 KB of shared memory:
-//   phase A  warp 0 threads the chunk into hash chains (3-byte hash, 16 K heads + a 64 K-entry `prev`
-//            array, both u16 in shared memory); 32 positions per step, intra-step collisions resolved
-//            with __match_any_sync so the chains are strictly ordered by position
+//   phase A  warp 0 threads the chunk into hash chains (3-byte hash, 8 K u32 heads + a 64 K-entry u16
+//            `prev` array in shared memory); 32 positions per step push themselves onto their bucket
+//            with atomicExch (__match_any_sync, the first version, costs ~700 cycles per step when the
+//            32 hashes are distinct -- which they normally are)
 //   phase B  all 16 warps search: each lane walks the chain of its own position (nearest first, up to
 //            `depth` candidates, 32 KiB distance limit, 4-byte-stride extension) and stores its best
 //            (length, distance) in the chunk's token scratch
@@ -311,10 +312,10 @@ lz77_fast_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t nchunks, u
 //            build the histograms, exactly as the fast kernel does.
 // =====================================================================================================
 constexpr uint32_t LZB_THREADS = 512;
-constexpr uint32_t LZB_HASH_BITS = 14;
+constexpr uint32_t LZB_HASH_BITS = 13;          // 8 K heads x u32 (atomicExch needs 32-bit words)
 constexpr uint32_t LZB_NIL = 0xFFFFu;           // position 65535 can never be anybody's predecessor
 constexpr uint32_t LZB_TOO_FAR = 4096;          // a 3-byte match farther than this costs more than literals
-constexpr size_t LZB_SMEM_BYTES = CHUNK + LZ_DATA_PAD + CHUNK * 2 + (2u << LZB_HASH_BITS) + 16;
+constexpr size_t LZB_SMEM_BYTES = CHUNK + LZ_DATA_PAD + CHUNK * 2 + (4u << LZB_HASH_BITS) + 16;
 
 __device__ __forceinline__ uint32_t lzb_hash(uint32_t w4) { return ((w4 & 0xFFFFFFu) * 0x9E3779B1u) >> (32 - LZB_HASH_BITS); }
 
@@ -324,9 +325,9 @@ lz77_better_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t* __restr
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* s_data = smem;
     uint16_t* s_prev = reinterpret_cast<uint16_t*>(smem + CHUNK + LZ_DATA_PAD);
-    uint16_t* s_head = s_prev + CHUNK;
-    uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_head);          // phase C reuses the head table
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + CHUNK + LZ_DATA_PAD + CHUNK * 2 + (2u << LZB_HASH_BITS));
+    uint32_t* s_head = reinterpret_cast<uint32_t*>(s_prev + CHUNK);
+    uint32_t* s_hist = s_head;                                       // phase C reuses the head table
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + CHUNK + LZ_DATA_PAD + CHUNK * 2 + (4u << LZB_HASH_BITS));
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint64_t chunk = blockIdx.x;
@@ -343,28 +344,24 @@ lz77_better_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t* __restr
     for (uint32_t i = bulk + tid; i < clen; i += LZB_THREADS) s_data[i] = src[i];
     for (uint32_t i = clen + tid; i < ((clen + 15u) & ~15u) + LZ_DATA_PAD && i < CHUNK + LZ_DATA_PAD; i += LZB_THREADS)
         s_data[i] = 0;
-    for (uint32_t i = tid; i < (1u << LZB_HASH_BITS) / 2; i += LZB_THREADS) reinterpret_cast<uint32_t*>(s_head)[i] = 0xFFFFFFFFu;
+    for (uint32_t i = tid; i < (1u << LZB_HASH_BITS); i += LZB_THREADS) s_head[i] = LZB_NIL;
     if (bulk) mbar_wait(s_bar, 0);
     __syncthreads();
 
-    // ---- phase A: ordered hash chains (one warp) -------------------------------------------------
+    // ---- phase A: hash chains (one warp) -----------------------------------------------------------
+    // 32 positions per step push themselves onto their bucket with atomicExch: every position gets the
+    // previous head as its predecessor, so a bucket is one linked list through all its positions,
+    // newest first.  Steps are ordered; inside a step the hardware serialises lanes that hit the same
+    // bucket (the search below tolerates either order by skipping predecessors that are not earlier).
     if (warp == 0) {
         for (uint32_t t0 = 0; t0 < clen; t0 += 32) {
             const uint32_t p = t0 + lane;
-            const bool valid = p + 3 <= clen;
-            const uint32_t h = lzb_hash(ld4_unaligned(s_data, p));
-            const uint32_t key = valid ? h : (0x80000000u | lane);       // invalid lanes match nobody
-            const uint32_t peers = __match_any_sync(FULL, key);
-            const uint32_t lower = peers & ((1u << lane) - 1u);
-            if (valid) {
-                const uint32_t old = s_head[h];
-                s_prev[p] = (uint16_t)(lower ? t0 + (31 - __clz(lower)) : old);
+            if (p + 3 <= clen) {
+                const uint32_t h = lzb_hash(ld4_unaligned(s_data, p));
+                s_prev[p] = (uint16_t)atomicExch(&s_head[h], p);
             } else if (p < clen) {
                 s_prev[p] = (uint16_t)LZB_NIL;
             }
-            __syncwarp();
-            if (valid && (peers >> lane) == 1u) s_head[h] = (uint16_t)p;  // highest lane of its group
-            __syncwarp();
         }
     }
     __syncthreads();
@@ -381,7 +378,9 @@ lz77_better_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t* __restr
             uint32_t q = s_prev[p];
             uint32_t budget = depth;
             best = 2;
-            while (q != LZB_NIL && budget-- && p - q <= MAX_DIST) {
+            while (q != LZB_NIL && budget--) {
+                if (q >= p) { q = s_prev[q]; continue; }              // same-step neighbour linked the other way round
+                if (p - q > MAX_DIST) break;
                 // cheap reject: to beat `best` a candidate must agree on bytes [best-3, best] and at the head
                 if ((best < 3 || ld4_unaligned(s_data, q + best - 3) == ld4_unaligned(s_data, p + best - 3)) &&
                     ((ld4_unaligned(s_data, q) ^ w4) & 0xFFFFFFu) == 0) {
