@@ -434,7 +434,9 @@ def main():
         avg_launch_ms = dom_ms / max(1, dom_launches)
         achieved = alg_per_launch / (avg_launch_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "peak_source": peak_src, "traffic": ncu_traffic(dom),
+                "frac": achieved / peak, "peak_source": peak_src,
+                "traffic": ncu_traffic({1: "lz77_literal_kernel", 2: "lz77_fast_kernel", 3: "lz77_better_kernel"}.get(args.level, dom)
+                                       if dom == "lz77_kernel" else dom),
                 "algorithmic_bytes_per_launch": alg_per_launch, "avg_launch_ms": avg_launch_ms,
                 "launches_per_step": dom_launches,
                 "kernel_share_of_step": dom_ms / ms_per_step,

@@ -480,7 +480,8 @@ __device__ int inflate_warp(InfWarp* S, const ModLut* ML, const uint8_t* in, uin
                     }
                 }
                 op += length;
-                __syncwarp();
+                // no barrier here: the next reader of these bytes is a later back-reference, and every
+                // back-reference starts with the __syncwarp() above
             }
             if (st) break;
             if (br.wi > wi_limit || br_bitpos(br) > in_bits) { st = ST_OVERRUN; break; }

@@ -314,6 +314,7 @@ lz77_fast_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t nchunks, u
 constexpr uint32_t LZB_THREADS = 512;
 constexpr uint32_t LZB_HASH_BITS = 13;          // 8 K heads x u32 (atomicExch needs 32-bit words)
 constexpr uint32_t LZB_NIL = 0xFFFFu;           // position 65535 can never be anybody's predecessor
+constexpr uint32_t LZB_GOOD = 32;               // once a match this long is in hand, cut the remaining search to a quarter
 constexpr uint32_t LZB_TOO_FAR = 4096;          // a 3-byte match farther than this costs more than literals
 constexpr size_t LZB_SMEM_BYTES = CHUNK + LZ_DATA_PAD + CHUNK * 2 + (4u << LZB_HASH_BITS) + 16;
 
@@ -391,7 +392,11 @@ lz77_better_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t* __restr
                         l += 4;
                     }
                     l = min(l, maxl);
-                    if (l > best) { best = l; bdist = p - q; if (l >= stop) break; }
+                    if (l > best) {
+                        best = l; bdist = p - q;
+                        if (l >= stop) break;
+                        if (l >= LZB_GOOD && budget > depth / 4) budget = depth / 4;   // good enough: search less (zlib's good_length)
+                    }
                 }
                 q = s_prev[q];
             }
