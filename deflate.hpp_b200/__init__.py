@@ -19,6 +19,7 @@ from .api import (  # noqa: F401
     LEVEL_HUFFMAN,
     LEVEL_STORED,
     F_NOT_LAST,
+    F_NO_INDEX,
     F_STRICT,
     compress,
     decompress,

@@ -21,6 +21,7 @@ _LIB_NAME = "libb200deflate.so"
 CHUNK = 65536
 LEVEL_STORED, LEVEL_HUFFMAN, LEVEL_FAST, LEVEL_BETTER = 0, 1, 2, 3
 F_NOT_LAST = 1
+F_NO_INDEX = 2
 F_STRICT = 1
 E_OVERRUN, E_DATA, E_OUTPUT, E_CUDA, E_ARG, E_NOMEM = 1, 2, 3, 4, 5, 6
 

@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -23,6 +24,7 @@
 #include "encode.cuh"
 #include "huffman.cuh"
 #include "inflate.cuh"
+#include "inflate_tp.cuh"
 #include "lz77.cuh"
 
 using namespace b200;
@@ -51,10 +53,12 @@ std::atomic<uint64_t> g_launches{0};
 #define PROF_BEGIN(c, id, st) (c)->prof.begin((id), (st))
 #define PROF_END(c, st) (c)->prof.end((st))
 
-enum KernelId { K_LZ77 = 0, K_HUFFMAN, K_SCAN, K_ENCODE, K_FIND_SYNC, K_INFLATE_CHUNKS, K_VALIDATE, K_INFLATE_BATCH, K_CORPUS, K_COUNT };
+enum KernelId { K_LZ77 = 0, K_HUFFMAN, K_SCAN, K_ENCODE, K_FIND_SYNC, K_INFLATE_CHUNKS, K_VALIDATE, K_INFLATE_BATCH, K_CORPUS,
+                K_INFLATE_SYMBOLS, K_INFLATE_FALLBACK, K_INFLATE_COPY, K_COUNT };
 const char* const kKernelNames[K_COUNT] = {"lz77_kernel", "huffman_kernel", "scan_sizes_kernel", "encode_kernel",
                                            "find_sync_kernel", "inflate_chunks_kernel", "validate_chunks_kernel",
-                                           "inflate_batch_kernel", "corpus_kernels"};
+                                           "inflate_batch_kernel", "corpus_kernels", "inflate_symbols_kernel",
+                                           "inflate_fallback_kernel", "inflate_copy_kernel"};
 
 // Optional per-kernel timing: CUDA events recorded on the launching stream around every launch.
 struct Prof {
@@ -117,7 +121,9 @@ struct b200_ctx {
     // compress scratch
     Buf tok, ntok, hist, codes, hdr, desc, sizes, offsets, total;
     // inflate scratch
-    Buf counts, woffs, cand, res, result, one_off, counter, cand16;
+    Buf counts, woffs, cand, res, result, one_off, counter, cand16, ops, tpres, segnops;
+    bool with_index = true;          // B200_NO_INDEX=1 / B200_F_NO_INDEX: no segment index in front of full chunks
+    bool inflate_warp_path = false;  // B200_INFLATE_WARP=1: the one-warp-per-unit decoder only (A/B comparisons)
     uint32_t lzf_grid = 148 * 2;     // persistent two-phase matcher: SMs x resident CTAs
     uint32_t inf_grid = 148 * 7;     // persistent inflate grid: SMs x resident CTAs
     // host-API staging
@@ -139,9 +145,18 @@ int set_attrs(b200_ctx* c) {
     CK(cudaFuncSetAttribute(lz77_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LZF_SMEM_BYTES));
     CK(cudaFuncSetAttribute(lz77_better_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LZB_SMEM_BYTES));
     CK(cudaFuncSetAttribute(encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(inflate_segments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(inflate_symbols_kernel<BatchUnits>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM_BYTES));
     c->attrs_set = true;
     return B200_OK;
 }
+
+// per-call override of the context's segment-index switch (B200_F_NO_INDEX)
+struct IndexGuard {
+    b200_ctx* c; bool saved;
+    IndexGuard(b200_ctx* c_, unsigned flags) : c(c_), saved(c_->with_index) { if (flags & B200_F_NO_INDEX) c->with_index = false; }
+    ~IndexGuard() { c->with_index = saved; }
+};
 
 b200_ctx* g_default = nullptr;
 std::mutex g_default_mu;
@@ -158,6 +173,40 @@ int default_ctx(b200_ctx** out) {
     *out = g_default;
     return B200_OK;
 }
+
+
+// Two-pass fast path (inflate_tp.cuh) for a set of units: pass A (one thread per unit: symbols, literals,
+// op lists), the one-warp decoder for the units pass A gave up on, pass B (one warp per unit: copies).
+// c->tpres holds one TpResult per unit afterwards.  counter words: [1] fallback queue, [2] copy queue, [3] flag.
+template <class Units>
+static int inflate_two_pass(b200_ctx* c, const Units& U, uint64_t nunits, unsigned flags, cudaStream_t st) {
+    int rc;
+    if ((rc = c->counter.ensure(64))) return rc;
+    if ((rc = c->tpres.ensure(nunits * sizeof(TpResult)))) return rc;
+    unsigned long long* cnt = (unsigned long long*)c->counter.p;
+    CK(cudaMemsetAsync(cnt, 0, 32, st));
+    TpResult* res = (TpResult*)c->tpres.p;
+    PROF_BEGIN(c, K_INFLATE_SYMBOLS, st);
+    if constexpr (std::is_same<Units, ChunkUnits>::value)
+        inflate_segments_kernel<<<(uint32_t)((nunits + SG_CHUNKS - 1) / SG_CHUNKS), SG_THREADS, SG_SMEM_BYTES, st>>>(
+            U, res, (uint16_t*)c->segnops.p, flags, cnt + 3);
+    else
+        inflate_symbols_kernel<Units><<<(uint32_t)((nunits + TP_THREADS - 1) / TP_THREADS), TP_THREADS, TP_SMEM_BYTES, st>>>(U, res, flags, cnt + 3);
+    LAUNCHED();
+    PROF_END(c, st);
+    const uint64_t want = (nunits + INF_WARPS - 1) / INF_WARPS;
+    const uint32_t grid = (uint32_t)(want < c->inf_grid ? want : c->inf_grid);
+    PROF_BEGIN(c, K_INFLATE_FALLBACK, st);
+    inflate_fallback_kernel<Units><<<grid, INF_THREADS, 0, st>>>(U, res, flags, cnt + 3, cnt + 1);
+    LAUNCHED();
+    PROF_END(c, st);
+    PROF_BEGIN(c, K_INFLATE_COPY, st);
+    inflate_copy_kernel<Units><<<grid, INF_THREADS, 0, st>>>(U, res, cnt + 2);
+    LAUNCHED();
+    PROF_END(c, st);
+    return B200_OK;
+}
+
 
 }  // namespace
 
@@ -201,6 +250,8 @@ int b200_ctx_create(int device, b200_ctx** ctx) {
     }
     if (const char* e = getenv("B200_BETTER_DEPTH")) { int v = atoi(e); if (v > 0) c->better_depth = (uint32_t)v; }
     if (const char* e = getenv("B200_BETTER_NICE")) { int v = atoi(e); if (v >= 3) c->better_nice = (uint32_t)v; }
+    if (const char* e = getenv("B200_NO_INDEX")) c->with_index = atoi(e) == 0;
+    if (const char* e = getenv("B200_INFLATE_WARP")) c->inflate_warp_path = atoi(e) != 0;
     if (const char* e = getenv("B200_BATCH_CHUNKS")) { int v = atoi(e); if (v > 0) c->batch_chunks = (uint32_t)v; }
     if (const char* e = getenv("B200_HOST_SLICE_CHUNKS")) { int v = atoi(e); if (v > 0) c->host_slice_chunks = (uint32_t)v; }
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -216,7 +267,8 @@ void b200_ctx_destroy(b200_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     Buf* all[] = {&c->tok, &c->ntok, &c->hist, &c->codes, &c->hdr, &c->desc, &c->sizes, &c->offsets, &c->total,
-                  &c->counts, &c->woffs, &c->cand, &c->res, &c->result, &c->one_off, &c->counter, &c->cand16, &c->d_in, &c->d_out};
+                  &c->counts, &c->woffs, &c->cand, &c->res, &c->result, &c->one_off, &c->counter, &c->cand16, &c->ops, &c->tpres, &c->segnops,
+                  &c->d_in, &c->d_out};
     for (Buf* b : all) b->release();
     c->prof.destroy();
     for (auto e : c->events) cudaEventDestroy(e);
@@ -293,7 +345,7 @@ static int compress_batch(b200_ctx* c, const uint8_t* bin, uint64_t bn, uint32_t
     }
     PROF_BEGIN(c, K_HUFFMAN, st);
     huffman_kernel<<<(nb + HUF_WARPS - 1) / HUF_WARPS, HUF_THREADS, 0, st>>>(
-        (const uint32_t*)c->hist.p, bn, nb, level, final_batch ? 1 : 0, (uint32_t*)c->codes.p,
+        (const uint32_t*)c->hist.p, bn, nb, level, final_batch ? 1 : 0, c->with_index ? 1 : 0, (uint32_t*)c->codes.p,
         (uint32_t*)c->hdr.p, (BlockDesc*)c->desc.p, (uint32_t*)c->sizes.p);
     LAUNCHED();
     PROF_END(c, st);
@@ -324,6 +376,7 @@ int b200_deflate_compress_dev(b200_ctx* c, const void* d_in, size_t n, int level
     CK(cudaSetDevice(c->device));
     const bool final_here = !(flags & B200_F_NOT_LAST);
     const uint64_t nchunks = (n + CHUNK - 1) / CHUNK;
+    IndexGuard guard(c, flags);
     int rc;
     if ((rc = c->total.ensure(16))) return rc;
     uint64_t* d_total = (uint64_t*)c->total.p;
@@ -383,6 +436,7 @@ int b200_deflate_compress_stage1_dev(b200_ctx* c, const void* d_in, size_t n, in
     if (nchunks > c->batch_chunks) return B200_E_ARG;
     cudaStream_t st = (cudaStream_t)stream_;
     CK(cudaSetDevice(c->device));
+    IndexGuard guard(c, flags);
     int rc;
     const uint64_t B = nchunks;
     if ((rc = c->total.ensure(16))) return rc;
@@ -422,6 +476,25 @@ int b200_inflate_batch_dev(b200_ctx* c, const void* d_in, const uint64_t* d_in_o
     CK(cudaSetDevice(c->device));
     int rc;
     if ((rc = c->counter.ensure(64))) return rc;
+    if (!c->inflate_warp_path) {
+        // op-list scratch is addressed by output offset (2 bytes of scratch per output byte): its size is
+        // the span of the output regions, known only on the device -> one 8-byte readback
+        if ((rc = c->result.ensure(64))) return rc;
+        unsigned long long* d_span = (unsigned long long*)c->result.p + 4;
+        CK(cudaMemsetAsync(d_span, 0, 8, st));
+        batch_span_kernel<<<(uint32_t)((n_streams + 255) / 256), 256, 0, st>>>(d_out_off, d_out_cap, n_streams, d_span);
+        LAUNCHED();
+        unsigned long long span = 0;
+        CK(cudaMemcpyAsync(&span, d_span, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if ((rc = c->ops.ensure((span / 4 + 2) * 8))) return rc;
+        BatchUnits U{(const uint8_t*)d_in, d_in_off, d_in_len, (uint8_t*)d_out, d_out_off, d_out_cap, (uint64_t)n_streams,
+                     (uint64_t*)c->ops.p};
+        if ((rc = inflate_two_pass(c, U, n_streams, flags, st))) return rc;
+        batch_results_kernel<<<(uint32_t)((n_streams + 255) / 256), 256, 0, st>>>((const TpResult*)c->tpres.p, n_streams, d_out_len, d_status);
+        LAUNCHED();
+        return B200_OK;
+    }
     CK(cudaMemsetAsync(c->counter.p, 0, 8, st));
     const uint64_t want = (n_streams + INF_WARPS - 1) / INF_WARPS;
     const uint64_t grid = want < c->inf_grid ? want : c->inf_grid;
@@ -480,23 +553,35 @@ int b200_inflate_dev(b200_ctx* c, const void* d_in, size_t n, void* d_out, size_
                 LAUNCHED();
                 PROF_END(c, st);
             }
-            if ((rc = c->res.ensure(ncand * sizeof(ChunkResult)))) return rc;
             const unsigned long long init[2] = {1ull, 0ull};
             CK(cudaMemcpyAsync(d_result, init, 16, cudaMemcpyHostToDevice, st));
-            PROF_BEGIN(c, K_INFLATE_CHUNKS, st);
-            if ((rc = c->counter.ensure(64))) return rc;
-            CK(cudaMemsetAsync(c->counter.p, 0, 8, st));
-            {
-                const uint64_t want = (ncand + INF_WARPS - 1) / INF_WARPS;
-                inflate_chunks_kernel<<<(uint32_t)(want < c->inf_grid ? want : c->inf_grid), INF_THREADS, 0, st>>>(
-                    in, n, cand, ncand, (uint8_t*)d_out, cap, (ChunkResult*)c->res.p, flags, (unsigned long long*)c->counter.p);
+            if (c->inflate_warp_path) {
+                if ((rc = c->res.ensure(ncand * sizeof(ChunkResult)))) return rc;
+                PROF_BEGIN(c, K_INFLATE_CHUNKS, st);
+                if ((rc = c->counter.ensure(64))) return rc;
+                CK(cudaMemsetAsync(c->counter.p, 0, 8, st));
+                {
+                    const uint64_t want = (ncand + INF_WARPS - 1) / INF_WARPS;
+                    inflate_chunks_kernel<<<(uint32_t)(want < c->inf_grid ? want : c->inf_grid), INF_THREADS, 0, st>>>(
+                        in, n, cand, ncand, (uint8_t*)d_out, cap, (ChunkResult*)c->res.p, flags, (unsigned long long*)c->counter.p);
+                }
+                LAUNCHED();
+                PROF_END(c, st);
+                PROF_BEGIN(c, K_VALIDATE, st);
+                validate_chunks_kernel<<<(uint32_t)((ncand + 255) / 256), 256, 0, st>>>(cand, ncand, (const ChunkResult*)c->res.p, d_result);
+                LAUNCHED();
+                PROF_END(c, st);
+            } else {
+                if ((rc = c->ops.ensure(ncand * OPS_PER_CHUNK * 8))) return rc;
+                if ((rc = c->segnops.ensure(ncand * NSEG * 2))) return rc;
+                ChunkUnits U{in, (uint64_t)n, cand, ncand, (uint8_t*)d_out, (uint64_t)cap, (uint64_t*)c->ops.p,
+                             (const uint16_t*)c->segnops.p};
+                if ((rc = inflate_two_pass(c, U, ncand, flags, st))) return rc;
+                PROF_BEGIN(c, K_VALIDATE, st);
+                validate_units_kernel<<<(uint32_t)((ncand + 255) / 256), 256, 0, st>>>(cand, ncand, (uint64_t)n, (const TpResult*)c->tpres.p, d_result);
+                LAUNCHED();
+                PROF_END(c, st);
             }
-            LAUNCHED();
-            PROF_END(c, st);
-            PROF_BEGIN(c, K_VALIDATE, st);
-            validate_chunks_kernel<<<(uint32_t)((ncand + 255) / 256), 256, 0, st>>>(cand, ncand, (const ChunkResult*)c->res.p, d_result);
-            LAUNCHED();
-            PROF_END(c, st);
             unsigned long long verdict[2] = {0, 0};
             CK(cudaMemcpyAsync(verdict, d_result, 16, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));

@@ -26,6 +26,17 @@ constexpr uint32_t MAX_DIST = 32768;
 constexpr uint32_t SYNC_BYTES_ALIGNED = 10;   // bytes the separator takes when it starts byte-aligned
 constexpr uint32_t SYNC_PATTERN_BYTES = 9;
 
+// Segment index (parallel inflate inside a chunk).  A full 64 KiB chunk that is Huffman-coded is preceded by
+// INDEX_GROUPS empty non-final stored blocks, each starting byte-aligned: byte 0 = 1pppp000 (BFINAL 0,
+// BTYPE 00, then five "ignored up to the byte boundary" bits, RFC 1951 3.2.4), then 00 00 FF FF.  The four p
+// bits of the 64 groups spell 16 little-endian u16 words: word 0 = INDEX_MAGIC | (segments - 1) << 10,
+// word s (1..15) = the number of bits segment s-1's symbols take.  Every inflater skips these blocks; this
+// one reads them and starts one thread per 4 KiB segment.  Bit 7 of byte 0 is always set so that a group can
+// never look like a chunk separator (below) -- the separator's stored blocks have all-zero padding.
+constexpr uint32_t INDEX_GROUPS = 64;
+constexpr uint32_t INDEX_BYTES = INDEX_GROUPS * 5;          // 320
+constexpr uint32_t INDEX_MAGIC = 0x2B5;                     // 10 bits
+
 // Token: literal -> byte value (dist field 0); match -> length in bits [0,9), distance in [16,32).
 __host__ __device__ __forceinline__ uint32_t tok_match(uint32_t len, uint32_t dist) { return len | (dist << 16); }
 __host__ __device__ __forceinline__ uint32_t tok_dist(uint32_t t) { return t >> 16; }
@@ -40,7 +51,7 @@ struct BlockDesc {
     uint32_t clen;           // uncompressed bytes in this chunk
     uint32_t last;           // 1 = carries BFINAL, no sync marker
     uint32_t eob;            // bit-reversed EOB code | len << 16
-    uint32_t pad;
+    uint32_t index_bytes;    // 0, or INDEX_BYTES when the chunk is preceded by the segment index
     uint32_t seg_bitoff[NSEG];  // bit offset of each segment's first token, relative to block start
 };
 

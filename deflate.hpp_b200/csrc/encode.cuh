@@ -112,7 +112,14 @@ encode_kernel(const uint8_t* __restrict__ in, const uint32_t* __restrict__ tok, 
             sb[o + 5] = 0; sb[o + 6] = 0; sb[o + 7] = 0; sb[o + 8] = 0xFF; sb[o + 9] = 0xFF;
         }
     } else {
-        const uint32_t bit0 = phase * 8;
+        // segment index: 64 empty stored blocks whose padding bits carry the segments' bit lengths
+        if (d.index_bytes && tid < INDEX_GROUPS) {
+            const uint32_t w = tid >> 2;
+            const uint32_t word = w == 0 ? (INDEX_MAGIC | ((NSEG - 1) << 10)) : d.seg_bitoff[w] - d.seg_bitoff[w - 1];
+            const uint32_t nib = (word >> (4 * (tid & 3))) & 15u;
+            stage_bits(stage, (phase + 5 * tid) * 8, (uint64_t)(0x80u | (nib << 3)) | (0xFFFFull << 24), 40);
+        }
+        const uint32_t bit0 = (phase + d.index_bytes) * 8;
         // header bits
         const uint32_t hw = (d.hdr_bits + 31) / 32;
         for (uint32_t i = tid; i < hw; i += ENC_THREADS) {
@@ -161,7 +168,7 @@ encode_kernel(const uint8_t* __restrict__ in, const uint32_t* __restrict__ tok, 
             const uint32_t eob_len = c & 0xFFu;
             stage_bits(stage, bit0 + d.total_bits - eob_len, c >> 8, eob_len);
             if (!d.last) {   // separator: 3 zero bits, pad, 00 00 FF FF, then 00 | 00 00 FF FF
-                const uint32_t mb = phase + (d.total_bits + 3 + 7) / 8;
+                const uint32_t mb = phase + d.index_bytes + (d.total_bits + 3 + 7) / 8;
                 stage_bits(stage, (mb + 2) * 8, 0xFFFFu, 16);   // atomic: may share a word with payload bits
                 stage_bits(stage, (mb + 7) * 8, 0xFFFFu, 16);
             }

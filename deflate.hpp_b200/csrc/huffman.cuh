@@ -219,7 +219,7 @@ __device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
 // level 0 forces stored blocks.  last_is_final: the final chunk of this buffer carries BFINAL.
 __global__ void __launch_bounds__(HUF_THREADS)
 huffman_kernel(const uint32_t* __restrict__ hist, uint64_t n, uint32_t nchunks, int level, int last_is_final,
-               uint32_t* __restrict__ codes, uint32_t* __restrict__ hdr, BlockDesc* __restrict__ desc,
+               int with_index, uint32_t* __restrict__ codes, uint32_t* __restrict__ hdr, BlockDesc* __restrict__ desc,
                uint32_t* __restrict__ sizes) {
     __shared__ HufScratch scratch[HUF_WARPS];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -239,7 +239,7 @@ huffman_kernel(const uint32_t* __restrict__ hist, uint64_t n, uint32_t nchunks, 
     if (level == 0) {
         if (lane == 0) {
             d->btype = 0; d->hdr_bits = 0; d->total_bits = 0; d->nbytes = stored_bytes; d->clen = clen;
-            d->last = last; d->eob = 0;
+            d->last = last; d->eob = 0; d->index_bytes = 0;
             sizes[chunk] = stored_bytes;
         }
         return;
@@ -327,7 +327,11 @@ huffman_kernel(const uint32_t* __restrict__ hist, uint64_t n, uint32_t nchunks, 
     const uint32_t fix_bits = 3 + fix;
     const uint32_t use_dyn = dyn_bits < fix_bits;
     const uint32_t bits = use_dyn ? dyn_bits : fix_bits;
-    const uint32_t huff_bytes = last ? (bits + 7) / 8 : (bits + 3 + 7) / 8 + (SYNC_BYTES_ALIGNED - 1);
+    // full chunks carry the segment index (common.cuh) so that they can be inflated by 16 threads
+    // (only where it costs little: the chunk must save at least four times the index's size)
+    const uint32_t huff_plain = last ? (bits + 7) / 8 : (bits + 3 + 7) / 8 + (SYNC_BYTES_ALIGNED - 1);
+    const uint32_t index_bytes = (with_index && clen == CHUNK && huff_plain + 4 * INDEX_BYTES <= stored_bytes) ? INDEX_BYTES : 0u;
+    const uint32_t huff_bytes = index_bytes + huff_plain;
     const uint32_t btype = huff_bytes < stored_bytes ? (use_dyn ? 2u : 1u) : 0u;
 
     // ---- emit codes, header, descriptor ---------------------------------------------------
@@ -394,6 +398,7 @@ huffman_kernel(const uint32_t* __restrict__ hist, uint64_t n, uint32_t nchunks, 
         d->nbytes = btype ? huff_bytes : stored_bytes;
         d->clen = clen;
         d->last = last;
+        d->index_bytes = btype ? index_bytes : 0;
         d->eob = btype ? mycodes[256] : 0;   // written above by this warp (same-thread visibility not needed: recomputed by encoder)
         sizes[chunk] = d->nbytes;
     }

@@ -345,6 +345,7 @@ __device__ int inflate_warp(InfWarp* S, const ModLut* ML, const uint8_t* in, uin
         const uint32_t hdr = br_get(S, br, 3, lane);
         const uint32_t bfinal = hdr & 1, btype = hdr >> 1;
         if (btype == 0) {
+            const uint32_t padbits = br_peek(br, br.bc & 7);   // only an all-zero padding counts towards a separator
             br_drop(br, br.bc & 7);                       // to the byte boundary (bc == 0 mod 8 <=> aligned)
             br_need32(S, br, lane);
             const uint32_t len = br_peek(br, 16);
@@ -373,8 +374,9 @@ __device__ int inflate_warp(InfWarp* S, const ModLut* ML, const uint8_t* in, uin
             op += len;
             __syncwarp();
             br_seek(S, br, bpos + len, lane);
-            if (len == 0 && !bfinal) {
-                // chunk separator = two empty stored blocks in a row (common.cuh)
+            if (len == 0 && !bfinal && padbits == 0) {
+                // chunk separator = two empty stored blocks in a row (common.cuh); the segment index's
+                // stored blocks have a non-zero padding and never count
                 if (++empty_run == 2 && stop_at_sync) { end_flags |= END_SYNC; break; }
             } else {
                 empty_run = 0;

@@ -48,6 +48,9 @@ extern "C" {
 /* Flags for the compressor. */
 #define B200_F_NOT_LAST 1u /* this buffer is a shard that is NOT the end of the stream: its last chunk \
                               is closed with the byte-aligning empty stored block instead of BFINAL */
+#define B200_F_NO_INDEX 2u /* do not put the segment index (320 bytes of empty stored blocks whose padding bits \
+                              hold the bit length of every 4 KiB segment) in front of full 64 KiB chunks: the   \
+                              stream is 0.3-0.5 % smaller and inflates one warp per chunk instead of 16 threads */
 /* Flags for the inflater. */
 #define B200_F_STRICT 1u   /* reject what the reference silently accepts: distance beyond the output \
                               produced so far, NLEN != ~LEN, BTYPE 3 (default: behave like the reference) */

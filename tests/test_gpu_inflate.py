@@ -6,7 +6,7 @@ import zlib
 import numpy as np
 import pytest
 
-from conftest import gold
+from conftest import gold, zlib_raw_inflate
 import datagen
 
 pytestmark = pytest.mark.gpu
@@ -175,3 +175,72 @@ def test_false_sync_markers(b200):
         assert b200.decompress(c) == noisy
     z = datagen.foreign_streams(datagen.random_bytes(200000) + b"\x00\x00\xff\xff" * 1000)["stored"]
     assert b200.decompress(z) == datagen.random_bytes(200000) + b"\x00\x00\xff\xff" * 1000
+
+
+# ---- segment index (include/b200_deflate.h, csrc/common.cuh) -------------------------------------------
+INDEX_GROUPS, INDEX_BYTES = 64, 320
+
+
+def _index_at(c, off):
+    """Parses the 64 index groups at c[off:]; returns the 16 words or None."""
+    words = [0] * 16
+    for g in range(INDEX_GROUPS):
+        b = c[off + 5 * g: off + 5 * g + 5]
+        if len(b) < 5 or (b[0] & 0x87) != 0x80 or b[1:] != b"\x00\x00\xff\xff":
+            return None
+        words[g >> 2] |= ((b[0] >> 3) & 15) << (4 * (g & 3))
+    return words
+
+
+def _compress_dev(b200, data, level, flags=0):
+    import torch
+    ctx = b200.Context(0)
+    src = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
+    cap = b200.deflate_bound(len(data))
+    dst = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+    n = ctx.compress_dev(src.data_ptr(), len(data), level, dst.data_ptr(), cap, flags=flags)
+    torch.cuda.synchronize()
+    return bytes(dst[:n].cpu().numpy())
+
+
+@pytest.mark.parametrize("level", [1, 2, 3])
+def test_segment_index_streams(b200, oracle, level):
+    """Full Huffman-coded chunks start with the segment index: 64 empty stored blocks that zlib, the
+    reference inflater and its restatement skip, and that this inflater uses to decode 16 segments in
+    parallel.  Without it (B200_F_NO_INDEX) the stream is exactly 320 bytes per indexed chunk smaller and
+    decodes to the same bytes."""
+    data = datagen.text_like(5 * 65536 + 1234, seed=3)
+    c = _compress_dev(b200, data, level)
+    plain = _compress_dev(b200, data, level, flags=b200.F_NO_INDEX)
+    words = _index_at(c, 0)
+    assert words is not None and (words[0] & 0x3FF) == 0x2B5 and (words[0] >> 10) == 15
+    assert all(0 < w < 65536 for w in words[1:])
+    assert _index_at(plain, 0) is None
+    assert len(c) - len(plain) == 5 * INDEX_BYTES          # five full chunks, the partial one has none
+    for s in (c, plain):
+        out, unused = zlib_raw_inflate(s)
+        assert out == data and unused == b""
+        rc, o = oracle.inflate(s)
+        assert rc == 0 and o == data
+        assert b200.decompress(s) == data
+        assert b200.decompress(s, out_size=100000) == data[:100000]     # truncating overload
+
+
+def test_segment_index_not_trusted(b200):
+    """The index lives in bits every DEFLATE decoder must ignore, so a stream with a wrong index is
+    still a valid stream with the same content: the decoder has to notice and fall back."""
+    data = datagen.text_like(3 * 65536, seed=4) + datagen.image_like(2 * 65536)
+    c = bytearray(_compress_dev(b200, data, 2))
+    assert _index_at(c, 0) is not None
+    for g, flip in ((7, 0x08), (20, 0x40), (63, 0x10)):    # segment lengths of chunk 0
+        bad = bytearray(c)
+        bad[5 * g] ^= flip
+        assert zlib_raw_inflate(bytes(bad))[0] == data
+        assert b200.decompress(bytes(bad)) == data
+    bad = bytearray(c)
+    bad[0] ^= 0x08                                          # magic gone: chunk 0 is simply not indexed
+    assert b200.decompress(bytes(bad)) == data
+    # small inputs and chunks that barely compress carry no index
+    assert _index_at(_compress_dev(b200, gold("test.bmp"), 2), 0) is None
+    noisy = datagen.random_bytes(65536 * 2, seed=8)
+    assert _index_at(_compress_dev(b200, noisy, 1), 0) is None
