@@ -54,11 +54,11 @@ std::atomic<uint64_t> g_launches{0};
 #define PROF_END(c, st) (c)->prof.end((st))
 
 enum KernelId { K_LZ77 = 0, K_HUFFMAN, K_SCAN, K_ENCODE, K_FIND_SYNC, K_INFLATE_CHUNKS, K_VALIDATE, K_INFLATE_BATCH, K_CORPUS,
-                K_INFLATE_SYMBOLS, K_INFLATE_FALLBACK, K_INFLATE_COPY, K_COUNT };
+                K_INFLATE_SYMBOLS, K_INFLATE_FALLBACK, K_INFLATE_COPY, K_INFLATE_CLASSIFY, K_COUNT };
 const char* const kKernelNames[K_COUNT] = {"lz77_kernel", "huffman_kernel", "scan_sizes_kernel", "encode_kernel",
                                            "find_sync_kernel", "inflate_chunks_kernel", "validate_chunks_kernel",
                                            "inflate_batch_kernel", "corpus_kernels", "inflate_symbols_kernel",
-                                           "inflate_fallback_kernel", "inflate_copy_kernel"};
+                                           "inflate_fallback_kernel", "inflate_copy_kernel", "inflate_classify_kernel"};
 
 // Optional per-kernel timing: CUDA events recorded on the launching stream around every launch.
 struct Prof {
@@ -121,8 +121,10 @@ struct b200_ctx {
     // compress scratch
     Buf tok, ntok, hist, codes, hdr, desc, sizes, offsets, total;
     // inflate scratch
-    Buf counts, woffs, cand, res, result, one_off, counter, cand16, ops, tpres, segnops;
+    Buf counts, woffs, cand, res, result, one_off, counter, cand16, ops, tpres, segnops, chunk_list;
     bool with_index = true;          // B200_NO_INDEX=1 / B200_F_NO_INDEX: no segment index in front of full chunks
+    int sg_occ = 12, copy_occ = 12;  // resident CTAs per SM the two inflate passes are compiled for (tuning knobs)
+    unsigned copy_tune = 1;          // bit 0: prefetch the next step's sources into L2
     bool inflate_warp_path = false;  // B200_INFLATE_WARP=1: the one-warp-per-unit decoder only (A/B comparisons)
     uint32_t lzf_grid = 148 * 2;     // persistent two-phase matcher: SMs x resident CTAs
     uint32_t inf_grid = 148 * 7;     // persistent inflate grid: SMs x resident CTAs
@@ -145,7 +147,8 @@ int set_attrs(b200_ctx* c) {
     CK(cudaFuncSetAttribute(lz77_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LZF_SMEM_BYTES));
     CK(cudaFuncSetAttribute(lz77_better_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LZB_SMEM_BYTES));
     CK(cudaFuncSetAttribute(encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_SMEM_BYTES));
-    CK(cudaFuncSetAttribute(inflate_segments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(inflate_segments_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(inflate_segments_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM_BYTES));
     CK(cudaFuncSetAttribute(inflate_symbols_kernel<BatchUnits>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM_BYTES));
     c->attrs_set = true;
     return B200_OK;
@@ -184,13 +187,25 @@ static int inflate_two_pass(b200_ctx* c, const Units& U, uint64_t nunits, unsign
     if ((rc = c->counter.ensure(64))) return rc;
     if ((rc = c->tpres.ensure(nunits * sizeof(TpResult)))) return rc;
     unsigned long long* cnt = (unsigned long long*)c->counter.p;
-    CK(cudaMemsetAsync(cnt, 0, 32, st));
+    CK(cudaMemsetAsync(cnt, 0, 40, st));
     TpResult* res = (TpResult*)c->tpres.p;
+    if constexpr (std::is_same<Units, ChunkUnits>::value) {
+        // counter word [4] = number of indexed chunks, c->chunk_list = their indices
+        if ((rc = c->chunk_list.ensure(nunits * 4))) return rc;
+        PROF_BEGIN(c, K_INFLATE_CLASSIFY, st);
+        inflate_classify_kernel<<<(uint32_t)((nunits + 255) / 256), 256, 0, st>>>(U, res, (uint32_t*)c->chunk_list.p, cnt + 4, flags, cnt + 3);
+        LAUNCHED();
+        PROF_END(c, st);
+    }
     PROF_BEGIN(c, K_INFLATE_SYMBOLS, st);
-    if constexpr (std::is_same<Units, ChunkUnits>::value)
-        inflate_segments_kernel<<<(uint32_t)((nunits + SG_CHUNKS - 1) / SG_CHUNKS), SG_THREADS, SG_SMEM_BYTES, st>>>(
-            U, res, (uint16_t*)c->segnops.p, flags, cnt + 3);
-    else
+    if constexpr (std::is_same<Units, ChunkUnits>::value) {
+        if (c->sg_occ >= 16)
+            inflate_segments_kernel<16><<<(uint32_t)((nunits + SG_CHUNKS - 1) / SG_CHUNKS), SG_THREADS, SG_SMEM_BYTES, st>>>(
+                U, (const uint32_t*)c->chunk_list.p, cnt + 4, res, (uint16_t*)c->segnops.p, flags, cnt + 3);
+        else
+            inflate_segments_kernel<12><<<(uint32_t)((nunits + SG_CHUNKS - 1) / SG_CHUNKS), SG_THREADS, SG_SMEM_BYTES, st>>>(
+                U, (const uint32_t*)c->chunk_list.p, cnt + 4, res, (uint16_t*)c->segnops.p, flags, cnt + 3);
+    } else
         inflate_symbols_kernel<Units><<<(uint32_t)((nunits + TP_THREADS - 1) / TP_THREADS), TP_THREADS, TP_SMEM_BYTES, st>>>(U, res, flags, cnt + 3);
     LAUNCHED();
     PROF_END(c, st);
@@ -201,7 +216,12 @@ static int inflate_two_pass(b200_ctx* c, const Units& U, uint64_t nunits, unsign
     LAUNCHED();
     PROF_END(c, st);
     PROF_BEGIN(c, K_INFLATE_COPY, st);
-    inflate_copy_kernel<Units><<<grid, INF_THREADS, 0, st>>>(U, res, cnt + 2);
+    if (c->copy_occ >= 12) {
+        const uint64_t g12 = (uint64_t)(c->inf_grid / INF_MAX_CTAS_PER_SM) * 12;
+        inflate_copy_kernel<Units, 12><<<(uint32_t)(want < g12 ? want : g12), INF_THREADS, 0, st>>>(U, res, cnt + 2, c->copy_tune);
+    } else {
+        inflate_copy_kernel<Units, 6><<<grid, INF_THREADS, 0, st>>>(U, res, cnt + 2, c->copy_tune);
+    }
     LAUNCHED();
     PROF_END(c, st);
     return B200_OK;
@@ -251,6 +271,9 @@ int b200_ctx_create(int device, b200_ctx** ctx) {
     if (const char* e = getenv("B200_BETTER_DEPTH")) { int v = atoi(e); if (v > 0) c->better_depth = (uint32_t)v; }
     if (const char* e = getenv("B200_BETTER_NICE")) { int v = atoi(e); if (v >= 3) c->better_nice = (uint32_t)v; }
     if (const char* e = getenv("B200_NO_INDEX")) c->with_index = atoi(e) == 0;
+    if (const char* e = getenv("B200_SG_OCC")) c->sg_occ = atoi(e);
+    if (const char* e = getenv("B200_COPY_OCC")) c->copy_occ = atoi(e);
+    if (const char* e = getenv("B200_COPY_TUNE")) c->copy_tune = (unsigned)atoi(e);
     if (const char* e = getenv("B200_INFLATE_WARP")) c->inflate_warp_path = atoi(e) != 0;
     if (const char* e = getenv("B200_BATCH_CHUNKS")) { int v = atoi(e); if (v > 0) c->batch_chunks = (uint32_t)v; }
     if (const char* e = getenv("B200_HOST_SLICE_CHUNKS")) { int v = atoi(e); if (v > 0) c->host_slice_chunks = (uint32_t)v; }
@@ -267,7 +290,7 @@ void b200_ctx_destroy(b200_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     Buf* all[] = {&c->tok, &c->ntok, &c->hist, &c->codes, &c->hdr, &c->desc, &c->sizes, &c->offsets, &c->total,
-                  &c->counts, &c->woffs, &c->cand, &c->res, &c->result, &c->one_off, &c->counter, &c->cand16, &c->ops, &c->tpres, &c->segnops,
+                  &c->counts, &c->woffs, &c->cand, &c->res, &c->result, &c->one_off, &c->counter, &c->cand16, &c->ops, &c->tpres, &c->segnops, &c->chunk_list,
                   &c->d_in, &c->d_out};
     for (Buf* b : all) b->release();
     c->prof.destroy();

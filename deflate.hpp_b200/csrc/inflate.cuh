@@ -299,11 +299,16 @@ __device__ void fixed_tables(InfWarp* S, uint32_t lane) {
 
 // ---- one stream ------------------------------------------------------------------------------------
 // s_mod[d][c] = c % d for d in 1..31, c in 0..32 (period-aware copies without integer division)
-struct ModLut { uint8_t m[32][36]; };
+struct ModLut { uint8_t m[32][36]; uint64_t nib[9]; };   // nib[d]: nibble i = i % d (d = 1..8)
 __device__ __forceinline__ void modlut_init(ModLut* L, uint32_t tid, uint32_t nthreads) {
     for (uint32_t i = tid; i < 32 * 33; i += nthreads) {
         const uint32_t d = i / 33, c = i % 33;
         L->m[d][c] = (uint8_t)(d ? c % d : 0);
+    }
+    if (tid < 9) {
+        uint64_t v = 0;
+        for (uint32_t i = 0; i < 16; i++) v |= (uint64_t)(tid ? i % tid : 0) << (4 * i);
+        L->nib[tid] = v;
     }
 }
 

@@ -30,10 +30,12 @@ namespace b200 {
 
 constexpr uint32_t TP_LIT_BITS = 9;
 constexpr uint32_t TP_DST_BITS = 8;
+constexpr uint32_t SG_LIT_BITS = 10;                                       // segment kernel: one table per chunk, shared by 16 threads
 constexpr uint32_t TP_THREADS = 128;                                       // units per CTA in pass A
 constexpr uint32_t TP_ENTRIES = (1u << TP_LIT_BITS) + (1u << TP_DST_BITS); // u16 entries per thread
 constexpr uint32_t TP_LUT_WORDS = 64;                                      // [0,32) length base|extra, [32,64) distance
 constexpr uint32_t TP_SMEM_BYTES = TP_ENTRIES * 2 * TP_THREADS + TP_LUT_WORDS * 4;
+constexpr uint32_t TP_LIT_RUN = 3;             // extra literals a thread may take per trip of the hot loop
 constexpr int ST_FALLBACK = 3;                 // internal: unit must be redone by the one-warp decoder
 constexpr uint32_t OPS_PER_CHUNK = CHUNK / 4;  // op-list capacity of one chunk (u64 each)
 
@@ -125,7 +127,7 @@ struct TBits {
     const uint32_t* wp;   // 4-byte aligned address at or below the stream start
     uint32_t nw;          // words from wp that cover the stream
     uint32_t wi;          // next word to fetch
-    uint32_t w0, w1;      // fetched, not yet in bb
+    uint32_t w0, w1, w2;  // fetched, not yet in bb (w2 may still be in flight)
     uint32_t skip;        // bytes between wp and the stream start
     uint64_t bb;
     uint32_t bc;
@@ -139,14 +141,16 @@ __device__ __forceinline__ void tb_seek(TBits& r, uint64_t stream_byte) {
     r.bc = 32 - sh;
     r.w0 = tb_word(r, w + 1);
     r.w1 = tb_word(r, w + 2);
-    r.wi = w + 3;
+    r.w2 = tb_word(r, w + 3);
+    r.wi = w + 4;
 }
 __device__ __forceinline__ void tb_refill(TBits& r) {      // afterwards bc >= 33
     if (r.bc < 33) {
         r.bb |= (uint64_t)r.w0 << r.bc;
         r.bc += 32;
         r.w0 = r.w1;
-        r.w1 = tb_word(r, r.wi);
+        r.w1 = r.w2;
+        r.w2 = tb_word(r, r.wi);
         r.wi++;
     }
 }
@@ -154,7 +158,7 @@ __device__ __forceinline__ uint32_t tb_peek(const TBits& r, uint32_t n) { return
 __device__ __forceinline__ void tb_drop(TBits& r, uint32_t n) { r.bb >>= n; r.bc -= n; }
 __device__ __forceinline__ uint32_t tb_get(TBits& r, uint32_t n) { const uint32_t v = tb_peek(r, n); tb_drop(r, n); return v; }
 __device__ __forceinline__ uint64_t tb_bitpos(const TBits& r) {
-    return (uint64_t)(r.wi - 2) * 32 - r.bc - (uint64_t)r.skip * 8;
+    return (uint64_t)(r.wi - 3) * 32 - r.bc - (uint64_t)r.skip * 8;
 }
 
 // ---- literal output: bytes are merged into aligned 32-bit words ---------------------------------------
@@ -234,6 +238,7 @@ constexpr uint32_t TS_BLOCK = 0, TS_SYM = 1, TS_DONE = 2;
 struct TpCtx {
     uint16_t* lit; uint16_t* dst; uint32_t NT;      // tables: entry i at [i * NT]
     uint32_t lit_sa, dst_sa, ntb, lut_sa;           // the same as shared-memory addresses (ntb = bytes between entries)
+    uint32_t lit_bits;                              // index width of the literal/length table
     TpTables* T;
     uint64_t in_len, in_bits;
     uint64_t* ops;
@@ -248,8 +253,9 @@ struct TpState {
 };
 #define TP_FAIL(code) do { s.st = (code); s.state = TS_DONE; } while (0)
 
-__device__ __forceinline__ void tp_ctx_tables(TpCtx& c, uint16_t* lit, uint16_t* dst, uint32_t NT, const uint32_t* s_lut, TpTables* T) {
-    c.lit = lit; c.dst = dst; c.NT = NT; c.T = T;
+__device__ __forceinline__ void tp_ctx_tables(TpCtx& c, uint16_t* lit, uint16_t* dst, uint32_t NT, const uint32_t* s_lut, TpTables* T,
+                                              uint32_t lit_bits) {
+    c.lit = lit; c.dst = dst; c.NT = NT; c.T = T; c.lit_bits = lit_bits;
     c.lit_sa = (uint32_t)__cvta_generic_to_shared(lit);
     c.dst_sa = (uint32_t)__cvta_generic_to_shared(dst);
     c.lut_sa = (uint32_t)__cvta_generic_to_shared(s_lut);
@@ -269,11 +275,16 @@ __device__ __forceinline__ void tp_end_block(const TpCtx& c, TpState& s, uint32_
 // for decision (error classes, reference quirks, truncation at cap); only the data movement differs.
 // Written for a warp whose lanes decode different units: the refill is branch-free, the three outcomes
 // (literal / back-reference / rare) are one if-else chain that reconverges before the next trip.
+template <bool SEGM>
 __device__ __forceinline__ void tp_step_symbol(const TpCtx& c, TpState& s) {
+    // SEGM: tables are the chunk's SgChunk (entries contiguous, distance table right behind the literal table)
+    const uint32_t ntb = SEGM ? 2u : c.ntb;
+    const uint32_t dst_sa = SEGM ? c.lit_sa + (2u << SG_LIT_BITS) : c.dst_sa;
+    constexpr uint32_t LB = SEGM ? SG_LIT_BITS : TP_LIT_BITS;
     TBits& br = s.br;
     TOut& o = s.o;
     const uint32_t produced = o.v - o.al;
-    const uint32_t wi_lim = br.nw + 6;
+    const uint32_t wi_lim = br.nw + 7;
     if (produced >= c.stop_at || br.wi > wi_lim) {
         // rare: end of the segment, output limit, or far past the end of the input
         if (br.wi <= wi_lim && produced <= c.max_out && produced >= c.seg_stop) {
@@ -283,20 +294,21 @@ __device__ __forceinline__ void tp_step_symbol(const TpCtx& c, TpState& s) {
             tp_end_block(c, s, wi_lim);
         }
     } else {
-        {   // refill, branch-free
-            const bool need = br.bc < 33;
-            const uint64_t add = (uint64_t)br.w0 << (br.bc & 63);
-            br.bb |= need ? add : 0ull;
-            br.bc += need ? 32u : 0u;
-            const uint32_t nxt = (need && br.wi < br.nw) ? __ldg(br.wp + br.wi) : 0u;
-            br.w0 = need ? br.w1 : br.w0;
-            br.w1 = need ? nxt : br.w1;
-            br.wi += need ? 1u : 0u;
+        // refill: a plain (reconverging) branch.  The word fetched here is first touched at the NEXT refill,
+        // about three symbols later, so its latency is off the critical path (a branch-free version has to
+        // route it through a select and stalls on it at once)
+        if (br.bc < 33) {
+            br.bb |= (uint64_t)br.w0 << br.bc;
+            br.bc += 32;
+            br.w0 = br.w1;
+            br.w1 = br.w2;
+            br.w2 = tb_word(br, br.wi);
+            br.wi++;
         }
-        uint32_t e = lds_u16(c.lit_sa + tb_peek(br, TP_LIT_BITS) * c.ntb);
+        uint32_t e = lds_u16(c.lit_sa + tb_peek(br, LB) * ntb);
         bool ok = true;
         if ((e & 15u) == 0) {
-            const int r = tp_slow_symbol(*c.T, 0, (uint32_t)br.bb, TP_LIT_BITS + 1);
+            const int r = tp_slow_symbol(*c.T, 0, (uint32_t)br.bb, LB + 1);
             if (r < 0) { TP_FAIL(ST_OVERRUN); ok = false; }
             else e = tp_lit_entry((uint32_t)r & 0xFFFFu, (uint32_t)r >> 16);
         }
@@ -304,12 +316,24 @@ __device__ __forceinline__ void tp_step_symbol(const TpCtx& c, TpState& s) {
         if (ok && p < 256) {
             tb_drop(br, l);
             to_literal(o, p);
+            if (SEGM) {
+                // literals come in runs: take up to TP_LIT_RUN more in the same trip while the table has them
+                #pragma unroll
+                for (uint32_t k = 0; k < TP_LIT_RUN; k++) {
+                    if (k) tb_refill(br);        // after the first two literals fewer than LB bits may be left
+                    const uint32_t e2 = lds_u16(c.lit_sa + tb_peek(br, LB) * ntb);
+                    const uint32_t l2 = e2 & 15u, p2 = e2 >> 4;
+                    if (l2 == 0 || p2 >= 256 || o.v - o.al >= c.stop_at) break;
+                    tb_drop(br, l2);
+                    to_literal(o, p2);
+                }
+            }
         } else if (ok && !(p & 0x100u)) {
             tb_drop(br, l);
             const uint32_t lt = lds_u32(c.lut_sa + (p & 31u) * 4);
             const uint32_t length = (lt & 0xFFFFu) + tb_get(br, lt >> 16);
             tb_refill(br);
-            const uint32_t de = lds_u16(c.dst_sa + tb_peek(br, TP_DST_BITS) * c.ntb);
+            const uint32_t de = lds_u16(dst_sa + tb_peek(br, TP_DST_BITS) * ntb);
             uint32_t dl = de & 15u, dsym = de >> 4;
             if (dl == 0) {
                 const int r = tp_slow_symbol(*c.T, 1, (uint32_t)br.bb, TP_DST_BITS + 1);
@@ -423,7 +447,7 @@ __device__ __noinline__ TpState tp_step_block(const TpCtx c, TpState s) {
             }
             if (T.lens[256] == 0) { TP_FAIL(ST_DATA); return s; }
         }
-        if (!tp_build(c.lit, c.NT, T, T.lens, hlit, 0, TP_LIT_BITS, true)) { TP_FAIL(ST_DATA); return s; }
+        if (!tp_build(c.lit, c.NT, T, T.lens, hlit, 0, c.lit_bits, true)) { TP_FAIL(ST_DATA); return s; }
         if (!tp_build(c.dst, c.NT, T, T.lens + NLIT, hdist, 1, TP_DST_BITS, false)) { TP_FAIL(ST_DATA); return s; }
         s.state = TS_SYM;
         return s;
@@ -532,11 +556,11 @@ inflate_symbols_kernel(Units U, TpResult* __restrict__ res, unsigned flags, unsi
     TpTables T;
     TpCtx c;
     tp_ctx_init(c, u, flags);
-    tp_ctx_tables(c, tabs + threadIdx.x, tabs + threadIdx.x + (size_t)(1u << TP_LIT_BITS) * blockDim.x, blockDim.x, s_lut, &T);
+    tp_ctx_tables(c, tabs + threadIdx.x, tabs + threadIdx.x + (size_t)(1u << TP_LIT_BITS) * blockDim.x, blockDim.x, s_lut, &T, TP_LIT_BITS);
     TpState s;
     tp_state_init(s, c, u, live);
     while (__any_sync(0xFFFFFFFFu, s.state != TS_DONE)) {
-        if (s.state == TS_SYM) tp_step_symbol(c, s);
+        if (s.state == TS_SYM) tp_step_symbol<false>(c, s);
         else if (s.state == TS_BLOCK) s = tp_step_block(c, s);
     }
     if (!live) return;
@@ -546,22 +570,28 @@ inflate_symbols_kernel(Units U, TpResult* __restrict__ res, unsigned flags, unsi
     if (r.status == ST_FALLBACK) atomicOr(any_fallback, 1ull);
 }
 
-// ---- pass A, segmented: 16 threads per chunk, one per 4 KiB segment, tables shared by the chunk ----------
-constexpr uint32_t SG_CHUNKS = 16;                      // chunks per CTA
-constexpr uint32_t SG_THREADS = SG_CHUNKS * NSEG;       // 256
+// ---- pass A, segmented: a CTA takes SG_CHUNKS indexed chunks, builds their tables, then its threads pull
+// (chunk, segment) pairs from a shared queue until none is left -- segments differ a lot in symbol count
+// (text vs image chunks), a fixed thread <-> segment mapping left half of the lanes idle on average.
+constexpr uint32_t SG_CHUNKS = 4;                       // chunks per CTA
+constexpr uint32_t SG_THREADS = 64;                     // one segment per thread (more chunks per CTA cost more in occupancy
+                                                        // than the better balance wins back: measured)
 constexpr uint32_t OPS_PER_SEG = OPS_PER_CHUNK / NSEG;  // 1024
 struct __align__(16) SgChunk {
-    uint16_t lit[1u << TP_LIT_BITS];
+    uint16_t lit[1u << SG_LIT_BITS];
     uint16_t dst[1u << TP_DST_BITS];
     TpTables T;
+    TpUnit u;
+    TpResult r;                    // of the chunk's last segment (which also reads what follows the block)
     uint32_t seg_start[NSEG];      // bit offset of each segment's first symbol, from the chunk's first byte
     uint32_t seg_end[NSEG];        // where each segment's thread stopped
     uint16_t seg_nops[NSEG];
     uint8_t seg_ok[NSEG];
-    uint32_t nseg;                 // 0: not indexed
+    uint32_t nseg;                 // 0: not indexed / not ours
     uint32_t bfinal;
+    uint64_t unit;                 // global chunk index
 };
-constexpr uint32_t SG_SMEM_BYTES = SG_CHUNKS * sizeof(SgChunk) + TP_LUT_WORDS * 4;
+constexpr uint32_t SG_SMEM_BYTES = SG_CHUNKS * sizeof(SgChunk) + TP_LUT_WORDS * 4 + 16;
 
 // reads the segment index at the start of a chunk (common.cuh); returns the number of segments or 0
 __device__ uint32_t sg_read_index(const uint8_t* in, uint64_t in_len, uint32_t* words /* [NSEG] */) {
@@ -577,107 +607,161 @@ __device__ uint32_t sg_read_index(const uint8_t* in, uint64_t in_len, uint32_t* 
     return ((words[0] >> 10) & 15u) + 1;
 }
 
-__global__ void __launch_bounds__(SG_THREADS, 4)
-inflate_segments_kernel(ChunkUnits U, TpResult* __restrict__ res, uint16_t* __restrict__ segnops, unsigned flags,
-                        unsigned long long* __restrict__ any_fallback) {
-    extern __shared__ __align__(16) uint8_t tp_smem[];
-    uint32_t* s_lut = reinterpret_cast<uint32_t*>(tp_smem);
-    SgChunk* SC = reinterpret_cast<SgChunk*>(tp_smem + TP_LUT_WORDS * 4) + (threadIdx.x >> 4);
-    tp_lut_init(s_lut, threadIdx.x);
-    __syncthreads();
-    const uint32_t gl = threadIdx.x & 15;
-    const uint64_t i = (uint64_t)blockIdx.x * SG_CHUNKS + (threadIdx.x >> 4);
-    const bool live = i < U.count();
-    TpUnit u = {};
-    if (live) u = U.get(i);
+// Pass A0: one thread per chunk.  Indexed chunks are appended to `list` (the segment kernel then works on a
+// dense list: no lanes wasted on stored chunks); a chunk without index is finished here if it consists of
+// stored blocks (a few ops), and handed to the one-warp decoder if it is Huffman-coded.
+__global__ void __launch_bounds__(256)
+inflate_classify_kernel(ChunkUnits U, TpResult* __restrict__ res, uint32_t* __restrict__ list,
+                        unsigned long long* __restrict__ nlist, unsigned flags, unsigned long long* __restrict__ any_fallback) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= U.count()) return;
+    const TpUnit u = U.get(i);
+    uint32_t words[NSEG];
+    if (sg_read_index(u.in, u.in_len, words) >= 2) {
+        list[atomicAdd(nlist, 1ull)] = (uint32_t)i;
+        return;
+    }
     TpCtx c;
     tp_ctx_init(c, u, flags);
-    tp_ctx_tables(c, SC->lit, SC->dst, 1, s_lut, &SC->T);
+    c.lit = c.dst = nullptr; c.T = nullptr; c.NT = 1; c.lit_sa = c.dst_sa = c.lut_sa = 0; c.ntb = 2; c.lit_bits = TP_LIT_BITS;
+    c.allow_huffman = false;
     TpState s;
+    tp_state_init(s, c, u, true);
+    while (s.state != TS_DONE) s = tp_step_block(c, s);
     TpResult r;
-    bool solo_done = false;
+    tp_finish(c, s, r);
+    res[i] = r;
+    if (r.status == ST_FALLBACK) atomicOr(any_fallback, 1ull);
+}
 
-    // ---- phase 1 (first lane of the group): index + block header + tables, or the whole chunk if it is stored
-    if (gl == 0) {
+template <int OCC>
+__global__ void __launch_bounds__(SG_THREADS, OCC)
+inflate_segments_kernel(ChunkUnits U, const uint32_t* __restrict__ list, const unsigned long long* __restrict__ nlist,
+                        TpResult* __restrict__ res, uint16_t* __restrict__ segnops, unsigned flags,
+                        unsigned long long* __restrict__ any_fallback) {
+    const uint64_t nl = *nlist;
+    if ((uint64_t)blockIdx.x * SG_CHUNKS >= nl) return;
+    extern __shared__ __align__(16) uint8_t tp_smem[];
+    uint32_t* s_lut = reinterpret_cast<uint32_t*>(tp_smem);
+    uint32_t* s_queue = s_lut + TP_LUT_WORDS;
+    SgChunk* SCs = reinterpret_cast<SgChunk*>(tp_smem + TP_LUT_WORDS * 4 + 16);
+    tp_lut_init(s_lut, threadIdx.x);
+    if (threadIdx.x == 0) *s_queue = 0;
+    __syncthreads();
+    TpCtx c;
+    TpState s;
+
+    // ---- phase 1: every (SG_THREADS / SG_CHUNKS)-th thread prepares one chunk: index, block header, tables
+    constexpr uint32_t BUILD_STRIDE = SG_THREADS / SG_CHUNKS;
+    if (threadIdx.x % BUILD_STRIDE == 0) {
+        SgChunk* SC = SCs + threadIdx.x / BUILD_STRIDE;
+        const uint64_t li = (uint64_t)blockIdx.x * SG_CHUNKS + threadIdx.x / BUILD_STRIDE;
         SC->nseg = 0;
-        if (live) {
+        if (li < nl) {
+            const uint64_t i = list[li];
+            const TpUnit u = U.get(i);
+            SC->u = u; SC->unit = i;
+            tp_ctx_init(c, u, flags);
+            tp_ctx_tables(c, SC->lit, SC->dst, 1, s_lut, &SC->T, SG_LIT_BITS);
             uint32_t words[NSEG];
             const uint32_t nseg = sg_read_index(u.in, u.in_len, words);
             tp_state_init(s, c, u, true);
             if (nseg >= 2) {
                 tb_seek(s.br, INDEX_BYTES);
                 s = tp_step_block(c, s);
-                if (s.state == TS_SYM) {
-                    uint32_t bit = (uint32_t)tb_bitpos(s.br);
-                    SC->seg_start[0] = bit;
-                    for (uint32_t k = 1; k < nseg; k++) { bit += words[k]; SC->seg_start[k] = bit; }
-                    SC->nseg = nseg;
-                    SC->bfinal = s.bfinal;
-                } else {
-                    // not a Huffman block after the index: let the one-warp decoder sort it out
-                    s.st = ST_FALLBACK; s.state = TS_DONE;
-                    tp_finish(c, s, r);
-                    solo_done = true;
-                }
+            }
+            if (nseg >= 2 && s.state == TS_SYM) {
+                uint32_t bit = (uint32_t)tb_bitpos(s.br);
+                SC->seg_start[0] = bit;
+                for (uint32_t k = 1; k < nseg; k++) { bit += words[k]; SC->seg_start[k] = bit; }
+                SC->nseg = nseg;
+                SC->bfinal = s.bfinal;
             } else {
-                // no index: stored chunks are a few ops; anything Huffman-coded goes to the one-warp decoder
-                c.allow_huffman = false;
-                while (s.state != TS_DONE) s = tp_step_block(c, s);
+                // not a Huffman block after the index: let the one-warp decoder sort it out
+                TpResult r;
+                s.st = ST_FALLBACK; s.state = TS_DONE;
                 tp_finish(c, s, r);
-                solo_done = true;
+                res[i] = r;
+                atomicOr(any_fallback, 1ull);
             }
         }
     }
-    __syncwarp();
-    // ---- phase 2: one thread per segment
-    const uint32_t nseg = SC->nseg;
-    const bool mine = live && gl < nseg;
-    if (mine) {
-        tp_state_init(s, c, u, true);
-        const uint32_t bit = SC->seg_start[gl];
-        tb_seek(s.br, bit >> 3);
-        tb_drop(s.br, bit & 7);
-        s.o.v = s.o.vlo = s.o.al + gl * SEG;
-        to_window(s.o);
-        s.state = TS_SYM;
-        s.bfinal = SC->bfinal;
-        c.ops = u.ops + gl * OPS_PER_SEG;
-        c.ops_cap = OPS_PER_SEG;
-        c.seg_stop = gl + 1 < nseg ? (gl + 1) * SEG : 0xFFFFFFFFu;
-        c.stop_at = min(c.seg_stop, c.max_out + 1);
-        c.allow_huffman = false;              // one Huffman block per indexed chunk
-    } else {
-        s.state = TS_DONE;
-    }
-    while (__any_sync(0xFFFFFFFFu, s.state != TS_DONE)) {
-        if (s.state == TS_SYM) tp_step_symbol(c, s);
-        else if (s.state == TS_BLOCK) s = tp_step_block(c, s);
-    }
-    if (mine) {
-        if (gl + 1 < nseg) {
-            to_flush(s.o);
-            SC->seg_end[gl] = (uint32_t)tb_bitpos(s.br);
-            SC->seg_ok[gl] = s.st == ST_OK && (s.end_flags & END_SEG);
-        } else {
-            tp_finish(c, s, r);
+    __syncthreads();
+
+    // ---- phase 2: threads pull segments from the queue; every trip of the loop all lanes of a warp meet at
+    // the vote, lanes with a segment decode one symbol, lanes without one fetch the next
+    SgChunk* SC = SCs;
+    uint32_t seg = 0;
+    bool have = false, more = true;
+    s.state = TS_DONE;
+    while (__any_sync(0xFFFFFFFFu, more)) {
+        if (s.state == TS_SYM) {
+            tp_step_symbol<true>(c, s);
+        } else if (more) {
+            if (have) {
+                // finish the segment: the chunk's last one also consumes what follows the block (the chunk
+                // separator, or nothing after a final block; a second Huffman block -> one-warp decoder)
+                while (s.state == TS_BLOCK) s = tp_step_block(c, s);
+                if (seg + 1 < SC->nseg) {
+                    to_flush(s.o);
+                    SC->seg_end[seg] = (uint32_t)tb_bitpos(s.br);
+                    SC->seg_ok[seg] = s.st == ST_OK && (s.end_flags & END_SEG);
+                } else {
+                    TpResult r;
+                    tp_finish(c, s, r);
+                    SC->r = r;
+                }
+                SC->seg_nops[seg] = (uint16_t)s.nops;
+                have = false;
+            }
+            const uint32_t q = atomicAdd(s_queue, 1u);
+            if (q >= SG_CHUNKS * NSEG) {
+                more = false;
+            } else {
+                SC = SCs + q / NSEG;
+                seg = q % NSEG;
+                const uint32_t nseg = SC->nseg;
+                if (seg < nseg) {
+                    const TpUnit u = SC->u;
+                    tp_ctx_init(c, u, flags);
+                    tp_ctx_tables(c, SC->lit, SC->dst, 1, s_lut, &SC->T, SG_LIT_BITS);
+                    tp_state_init(s, c, u, true);
+                    const uint32_t bit = SC->seg_start[seg];
+                    tb_seek(s.br, bit >> 3);
+                    tb_drop(s.br, bit & 7);
+                    s.o.v = s.o.vlo = s.o.al + seg * SEG;
+                    to_window(s.o);
+                    s.state = TS_SYM;
+                    s.bfinal = SC->bfinal;
+                    c.ops = u.ops + seg * OPS_PER_SEG;
+                    c.ops_cap = OPS_PER_SEG;
+                    c.seg_stop = seg + 1 < nseg ? (seg + 1) * SEG : 0xFFFFFFFFu;
+                    c.stop_at = min(c.seg_stop, c.max_out + 1);
+                    c.allow_huffman = false;              // one Huffman block per indexed chunk
+                    have = true;
+                }
+            }
         }
-        SC->seg_nops[gl] = (uint16_t)s.nops;
     }
-    __syncwarp();
-    // ---- phase 3: the segments must chain exactly, else the index was not ours
-    if (live && nseg && gl == nseg - 1) {
-        bool ok = true;
-        for (uint32_t k = 0; k + 1 < nseg; k++) ok = ok && SC->seg_ok[k] && SC->seg_end[k] == SC->seg_start[k + 1];
-        if (!ok) { r.status = ST_FALLBACK; r.nops = 0; }
-        else if (r.status != ST_FALLBACK) {
-            r.nops = TP_SEGMENTED | nseg;
-            for (uint32_t k = 0; k < nseg; k++) segnops[i * NSEG + k] = SC->seg_nops[k];
+    __syncthreads();
+
+    // ---- phase 3: the segments of a chunk must chain exactly, else the index was not ours
+    if (threadIdx.x % BUILD_STRIDE == 0) {
+        SgChunk* SK = SCs + threadIdx.x / BUILD_STRIDE;
+        const uint32_t nseg = SK->nseg;
+        if (nseg) {
+            const uint64_t i = SK->unit;
+            TpResult r = SK->r;
+            bool ok = true;
+            for (uint32_t k = 0; k + 1 < nseg; k++) ok = ok && SK->seg_ok[k] && SK->seg_end[k] == SK->seg_start[k + 1];
+            if (!ok) { r.status = ST_FALLBACK; r.nops = 0; }
+            else if (r.status != ST_FALLBACK) {
+                r.nops = TP_SEGMENTED | nseg;
+                for (uint32_t k = 0; k < nseg; k++) segnops[i * NSEG + k] = SK->seg_nops[k];
+            }
+            res[i] = r;
+            if (r.status == ST_FALLBACK) atomicOr(any_fallback, 1ull);
         }
-        res[i] = r;
-        if (r.status == ST_FALLBACK) atomicOr(any_fallback, 1ull);
-    } else if (live && solo_done && gl == 0) {
-        res[i] = r;
-        if (r.status == ST_FALLBACK) atomicOr(any_fallback, 1ull);
     }
 }
 #undef TP_FAIL
@@ -748,33 +832,83 @@ __device__ __forceinline__ void tp_warp_match(uint8_t* dp, uint32_t dist, uint32
         }
     }
 }
-// stored block: input bytes -> output, 4 bytes per lane per step with the source realigned by a funnel shift
+// stored block: input bytes -> output.  Destination-aligned 16-byte stores; the source is read as aligned
+// 32-bit words and realigned with funnel shifts (five words give one 16-byte vector).
 __device__ __forceinline__ void tp_warp_stored(uint8_t* dp, const uint8_t* sp, uint32_t n, uint32_t lane) {
-    const uint32_t head = min(n, (uint32_t)((4 - (reinterpret_cast<uintptr_t>(dp) & 3)) & 3));
+    const uint32_t head = min(n, (uint32_t)((16 - (reinterpret_cast<uintptr_t>(dp) & 15)) & 15));
     if (lane < head) dp[lane] = sp[lane];
-    const uint32_t words = (n - head) >> 2;
+    const uint32_t vecs = (n - head) >> 4;
     const uint8_t* s = sp + head;
     const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(s) & 3) * 8;
     const uint32_t* sw = reinterpret_cast<const uint32_t*>(s - (sh >> 3));
-    uint32_t* dw = reinterpret_cast<uint32_t*>(dp + head);
-    if (sh == 0) {
-        for (uint32_t i = lane; i < words; i += 32) dw[i] = sw[i];
-    } else {
-        // sw[i + 1] of the last word stays inside the block's own bytes or the 4 that follow (never past
-        // the aligned word that holds the block's last byte)
-        for (uint32_t i = lane; i < words; i += 32) dw[i] = __funnelshift_r(sw[i], sw[i + 1], sh);
+    uint4* dv = reinterpret_cast<uint4*>(dp + head);
+    // sw[4 i + 4] of the last vector stays inside the aligned word that holds the block's last byte (sh != 0)
+    #pragma unroll 2
+    for (uint32_t i = lane; i < vecs; i += 32) {
+        const uint32_t* w = sw + 4 * i;
+        const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3);
+        uint4 v;
+        if (sh == 0) { v = make_uint4(w0, w1, w2, w3); }
+        else {
+            const uint32_t w4 = __ldg(w + 4);
+            v = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+        }
+        dv[i] = v;
     }
-    const uint32_t done = head + words * 4;
+    const uint32_t done = head + vecs * 16;
     if (done + lane < n) dp[done + lane] = sp[done + lane];
 }
 
 constexpr uint32_t TP_FREE_MAX = 16;     // longest op a single lane copies on its own
 
+// Lane-local copy of n <= 16 bytes that do not overlap (dist >= n): 16 predicated byte loads with immediate
+// offsets, then 16 predicated byte stores -- one memory round trip, no address arithmetic per byte.
+#define TP_R16(M) M(0) M(1) M(2) M(3) M(4) M(5) M(6) M(7) M(8) M(9) M(10) M(11) M(12) M(13) M(14) M(15)
+#define TP_SETP(i) "setp.gt.u32 p" #i ", %2, " #i ";\n"
+#define TP_LD(i) "@p" #i " ld.global.u8 t" #i ", [%0+" #i "];\n"
+#define TP_ST(i) "@p" #i " st.global.u8 [%1+" #i "], t" #i ";\n"
+__device__ __forceinline__ void tp_lane_copy16(uint8_t* dp, const uint8_t* sp, uint32_t n) {
+    asm volatile("{\n.reg .pred p<16>;\n.reg .b32 t<16>;\n" TP_R16(TP_SETP) TP_R16(TP_LD) TP_R16(TP_ST) "}\n"
+                 :: "l"(sp), "l"(dp), "r"(n) : "memory");
+}
+// Lane-local copy of n <= 16 bytes of a pattern of period dist <= 8 that starts at sp (= dp - dist): the 8
+// pattern bytes are packed into two registers, output byte i = pattern byte i % dist (byte permute with the
+// selector nibbles of ML->nib[dist]).
+#define TP_LDP(i) "@p" #i " ld.global.u8 t" #i ", [%2+" #i "];\n"
+__device__ __forceinline__ void tp_lane_pattern16(uint8_t* dp, const uint8_t* sp, uint32_t dist, uint32_t n, uint64_t nib) {
+    uint32_t lo, hi;
+    asm volatile("{\n.reg .pred p<8>;\n.reg .b32 t<8>;\n"
+                 "mov.b32 t0, 0; mov.b32 t1, 0; mov.b32 t2, 0; mov.b32 t3, 0; mov.b32 t4, 0; mov.b32 t5, 0; mov.b32 t6, 0; mov.b32 t7, 0;\n"
+                 "setp.gt.u32 p0, %3, 0; setp.gt.u32 p1, %3, 1; setp.gt.u32 p2, %3, 2; setp.gt.u32 p3, %3, 3;\n"
+                 "setp.gt.u32 p4, %3, 4; setp.gt.u32 p5, %3, 5; setp.gt.u32 p6, %3, 6; setp.gt.u32 p7, %3, 7;\n"
+                 TP_LDP(0) TP_LDP(1) TP_LDP(2) TP_LDP(3) TP_LDP(4) TP_LDP(5) TP_LDP(6) TP_LDP(7)
+                 "prmt.b32 t0, t0, t1, 0x0040; prmt.b32 t2, t2, t3, 0x0040; prmt.b32 %0, t0, t2, 0x5410;\n"
+                 "prmt.b32 t4, t4, t5, 0x0040; prmt.b32 t6, t6, t7, 0x0040; prmt.b32 %1, t4, t6, 0x5410;\n"
+                 "}\n" : "=r"(lo), "=r"(hi) : "l"(sp), "r"(dist) : "memory");
+    #pragma unroll
+    for (uint32_t i = 0; i < TP_FREE_MAX; i++) {
+        const uint32_t v = __byte_perm(lo, hi, (uint32_t)(nib >> (4 * i)) & 7u);
+        if (i < n) dp[i] = (uint8_t)v;
+    }
+}
+
+// Applies one op list in order.  32 ops per step.  An op is READY when every byte it reads is final before
+// the step starts: its source ends at or below the step's first destination, or begins at or after the end
+// of the previous op (then it only reads literals, which pass A wrote), or it is the step's first op.  Ready
+// ops of at most TP_FREE_MAX bytes are copied one per lane, all at once (one memory round trip for the
+// whole step); the others go through the cooperative copy in order.
 __device__ void tp_apply_ops(const uint64_t* __restrict__ ops, uint32_t nops, uint8_t* out, uint32_t cap,
-                             const uint8_t* in, const ModLut* ML, uint32_t lane) {
+                             const uint8_t* in, const ModLut* ML, uint32_t lane, unsigned tune) {
     const uint32_t FULL = 0xFFFFFFFFu;
+    uint64_t o_next = lane < nops ? ops[lane] : 0ull;
     for (uint32_t b = 0; b < nops; b += 32) {
-        const uint64_t o = b + lane < nops ? ops[b + lane] : 0ull;
+        const uint64_t o = o_next;
+        if (b + 32 < nops) o_next = b + 32 + lane < nops ? ops[b + 32 + lane] : 0ull;      // in flight during this step
+        if (tune & 1u) {
+            // the step after this one will read around these addresses: start pulling the lines in now
+            const uint32_t npos = (uint32_t)o_next, ndist = (uint32_t)(o_next >> 48);
+            if (ndist) asm volatile("prefetch.global.L2 [%0];" :: "l"(out + (npos - ndist)));
+        }
         const uint32_t pos = (uint32_t)o, len = (uint32_t)(o >> 32) & 0xFFFFu, dist = (uint32_t)(o >> 48);
         // stored pairs: a header slot (dist 0, len > 0) is followed by a raw data slot whose bits mean nothing
         uint32_t hdrs = __ballot_sync(FULL, len != 0 && dist == 0), data = 0;
@@ -786,23 +920,27 @@ __device__ void tp_apply_ops(const uint64_t* __restrict__ ops, uint32_t nops, ui
         hdrs &= ~data;
         const bool is_data = (data >> lane) & 1u;
         const bool is_match = !is_data && len != 0 && dist != 0;
-        const uint32_t live = __ballot_sync(FULL, is_match) | hdrs;
+        const uint32_t matches = __ballot_sync(FULL, is_match);
+        const uint32_t live = matches | hdrs;
         if (!live) continue;
-        const uint32_t p0 = __shfl_sync(FULL, pos, __ffs(live) - 1);
+        const uint32_t first = __ffs(live) - 1;
+        const uint32_t p0 = __shfl_sync(FULL, pos, first);
         const uint32_t ncopy = pos < cap ? min(len, cap - pos) : 0;
-        const bool fre = is_match && len <= TP_FREE_MAX && pos - dist + len <= p0;
-        if (fre) {
-            // all loads first (one memory round trip), then all stores; the ranges cannot overlap (dist >= len)
-            uint8_t* dp = out + pos;
-            const uint8_t* sp = dp - dist;
-            uint8_t t[TP_FREE_MAX];
-            #pragma unroll
-            for (uint32_t i = 0; i < TP_FREE_MAX; i++) if (i < ncopy) t[i] = sp[i];
-            #pragma unroll
-            for (uint32_t i = 0; i < TP_FREE_MAX; i++) if (i < ncopy) dp[i] = t[i];
+        const uint32_t prev_end = __shfl_up_sync(FULL, pos + len, 1);
+        const bool prev_live = lane != 0 && ((live >> (lane - 1)) & 1u);
+        const uint32_t a = pos - dist, m = min(len, dist);    // the op reads [a, a + m)
+        const bool local = is_match && len <= TP_FREE_MAX && (dist >= len || dist <= 8);
+        const bool ready = local && (a + m <= p0 || lane == first || (prev_live && a >= prev_end));
+        const bool plain = ready && dist >= len;
+        if (__any_sync(FULL, plain)) {
+            if (plain) tp_lane_copy16(out + pos, out + a, ncopy);
+        }
+        if (__any_sync(FULL, ready && !plain)) {
+            // overlapping (dist < len): the dist bytes below the destination repeat; they are final as well
+            if (ready && !plain) tp_lane_pattern16(out + pos, out + a, dist, ncopy, ML->nib[dist]);
         }
         __syncwarp();
-        uint32_t seq = live & ~__ballot_sync(FULL, fre);
+        uint32_t seq = live & ~__ballot_sync(FULL, ready);
         while (seq) {
             const uint32_t j = __ffs(seq) - 1;
             seq &= seq - 1;
@@ -821,9 +959,9 @@ __device__ void tp_apply_ops(const uint64_t* __restrict__ ops, uint32_t nops, ui
     }
 }
 
-template <class Units>
-__global__ void __launch_bounds__(INF_THREADS)
-inflate_copy_kernel(Units U, const TpResult* __restrict__ res, unsigned long long* __restrict__ counter) {
+template <class Units, int OCC>
+__global__ void __launch_bounds__(INF_THREADS, OCC)
+inflate_copy_kernel(Units U, const TpResult* __restrict__ res, unsigned long long* __restrict__ counter, unsigned tune) {
     __shared__ ModLut ML;
     modlut_init(&ML, threadIdx.x, INF_THREADS);
     __syncthreads();
@@ -841,9 +979,9 @@ inflate_copy_kernel(Units U, const TpResult* __restrict__ res, unsigned long lon
         if (nops & TP_SEGMENTED) {
             const uint16_t* sn = U.seg_counts(i);
             const uint32_t nseg = nops & 0xFFu;
-            for (uint32_t k = 0; k < nseg; k++) tp_apply_ops(u.ops + k * OPS_PER_SEG, sn[k], u.out, cap, u.in, &ML, lane);
+            for (uint32_t k = 0; k < nseg; k++) tp_apply_ops(u.ops + k * OPS_PER_SEG, sn[k], u.out, cap, u.in, &ML, lane, tune);
         } else {
-            tp_apply_ops(u.ops, nops, u.out, cap, u.in, &ML, lane);
+            tp_apply_ops(u.ops, nops, u.out, cap, u.in, &ML, lane, tune);
         }
     }
 }
