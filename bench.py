@@ -407,6 +407,19 @@ def main():
         dec = {"value": n / (dms * 1e-3) / 1e9, "unit": "GB/s (output bytes)", "ms_per_step": dms, "steps": dsteps,
                "round_trip_bit_exact": ok,
                "kernels_ms_per_step": {k: v[0] / dsteps for k, v in dk.items()}}
+        if dk:
+            # roofline of the inflater's dominant kernel: algorithmic bytes = N_comp + N_out
+            ddom = max(dk, key=lambda k: dk[k][0])
+            dl = max(1, dk[ddom][1] // dsteps)
+            d_alg = float(cn + n) / dl
+            d_avg_ms = dk[ddom][0] / dk[ddom][1]
+            dpeak, dpeak_src = measured_peak()
+            dec["roofline"] = {"bound": "hbm", "kernel": ddom, "achieved": d_alg / (d_avg_ms * 1e-3) / 1e9, "peak": dpeak,
+                               "unit": "GB/s", "frac": d_alg / (d_avg_ms * 1e-3) / 1e9 / dpeak, "peak_source": dpeak_src,
+                               "traffic": ncu_traffic(ddom), "algorithmic_bytes_per_launch": d_alg,
+                               "avg_launch_ms": d_avg_ms, "launches_per_step": dl,
+                               "kernel_share_of_step": dk[ddom][0] / dsteps / dms,
+                               "whole_path_frac": float(cn + n) / (dms * 1e-3) / 1e9 / dpeak}
     clocks = sampler.stop() if sampler else None
 
     # ---- N > 1: the bytes gathered on rank 0 must be ONE valid stream of the whole corpus ----

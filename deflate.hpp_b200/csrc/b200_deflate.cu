@@ -57,7 +57,7 @@ enum KernelId { K_LZ77 = 0, K_HUFFMAN, K_SCAN, K_ENCODE, K_FIND_SYNC, K_INFLATE_
                 K_INFLATE_SYMBOLS, K_INFLATE_FALLBACK, K_INFLATE_COPY, K_INFLATE_CLASSIFY, K_COUNT };
 const char* const kKernelNames[K_COUNT] = {"lz77_kernel", "huffman_kernel", "scan_sizes_kernel", "encode_kernel",
                                            "find_sync_kernel", "inflate_chunks_kernel", "validate_chunks_kernel",
-                                           "inflate_batch_kernel", "corpus_kernels", "inflate_symbols_kernel",
+                                           "inflate_batch_kernel", "corpus_kernels", "inflate_segments_kernel",
                                            "inflate_fallback_kernel", "inflate_copy_kernel", "inflate_classify_kernel"};
 
 // Optional per-kernel timing: CUDA events recorded on the launching stream around every launch.
@@ -125,6 +125,9 @@ struct b200_ctx {
     bool with_index = true;          // B200_NO_INDEX=1 / B200_F_NO_INDEX: no segment index in front of full chunks
     int sg_occ = 12, copy_occ = 12;  // resident CTAs per SM the two inflate passes are compiled for (tuning knobs)
     unsigned copy_tune = 1;          // bit 0: prefetch the next step's sources into L2
+    bool batch_two_pass = false;     // B200_BATCH_TP=1: batch inflate through the two-pass path, one THREAD per stream (measured
+                                     // slower than one warp per stream on 1-64 KiB zlib streams: 15 vs 75 GB/s; kept for
+                                     // workloads with very many tiny streams)
     bool inflate_warp_path = false;  // B200_INFLATE_WARP=1: the one-warp-per-unit decoder only (A/B comparisons)
     uint32_t lzf_grid = 148 * 2;     // persistent two-phase matcher: SMs x resident CTAs
     uint32_t inf_grid = 148 * 7;     // persistent inflate grid: SMs x resident CTAs
@@ -274,6 +277,7 @@ int b200_ctx_create(int device, b200_ctx** ctx) {
     if (const char* e = getenv("B200_SG_OCC")) c->sg_occ = atoi(e);
     if (const char* e = getenv("B200_COPY_OCC")) c->copy_occ = atoi(e);
     if (const char* e = getenv("B200_COPY_TUNE")) c->copy_tune = (unsigned)atoi(e);
+    if (const char* e = getenv("B200_BATCH_TP")) c->batch_two_pass = atoi(e) != 0;
     if (const char* e = getenv("B200_INFLATE_WARP")) c->inflate_warp_path = atoi(e) != 0;
     if (const char* e = getenv("B200_BATCH_CHUNKS")) { int v = atoi(e); if (v > 0) c->batch_chunks = (uint32_t)v; }
     if (const char* e = getenv("B200_HOST_SLICE_CHUNKS")) { int v = atoi(e); if (v > 0) c->host_slice_chunks = (uint32_t)v; }
@@ -499,7 +503,7 @@ int b200_inflate_batch_dev(b200_ctx* c, const void* d_in, const uint64_t* d_in_o
     CK(cudaSetDevice(c->device));
     int rc;
     if ((rc = c->counter.ensure(64))) return rc;
-    if (!c->inflate_warp_path) {
+    if (c->batch_two_pass && !c->inflate_warp_path) {
         // op-list scratch is addressed by output offset (2 bytes of scratch per output byte): its size is
         // the span of the output regions, known only on the device -> one 8-byte readback
         if ((rc = c->result.ensure(64))) return rc;

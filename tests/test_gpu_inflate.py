@@ -104,9 +104,13 @@ def test_reference_quirks_and_strict(b200, oracle):
         b200.decompress(bt3, flags=b200.F_STRICT)
 
 
-def test_batch_mixed(b200, oracle):
-    """BASELINE config 4 at reduced count: many independent small streams, one warp each."""
+@pytest.mark.parametrize("two_pass", [False, True])
+def test_batch_mixed(b200, oracle, monkeypatch, two_pass):
+    """BASELINE config 4 at reduced count: many independent small streams, one warp each (default) or one
+    thread each through the two-pass path (B200_BATCH_TP=1)."""
     import torch
+    if two_pass:
+        monkeypatch.setenv("B200_BATCH_TP", "1")
     rng = np.random.default_rng(5)
     kinds = sorted(datagen.KINDS)
     streams, expect = [], []

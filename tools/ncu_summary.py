@@ -51,7 +51,7 @@ def main():
     traffic = {}
     seen = {}
     for r in rows[2:]:
-        name = r[col["Kernel Name"]].split("(")[0].replace("void ", "").replace("b200::", "")
+        name = r[col["Kernel Name"]].split("(")[0].replace("void ", "").replace("b200::", "").split("<")[0]
         k = seen.get(name, 0)
         seen[name] = k + 1
         cells = []
