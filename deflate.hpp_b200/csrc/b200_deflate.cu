@@ -121,7 +121,12 @@ struct b200_ctx {
     // compress scratch
     Buf tok, ntok, hist, codes, hdr, desc, sizes, offsets, total;
     // inflate scratch
-    Buf counts, woffs, cand, res, result, one_off, counter, cand16, ops, tpres, segnops, chunk_list;
+    Buf counts, woffs, cand, res, result, one_off, counter, cand16, ops, tpres, segnops, chunk_list, group_cnt;
+    std::vector<cudaEvent_t> group_events;
+    cudaStream_t s_side = nullptr;   // inflate: copy pass of group g while group g + 1 is in pass A
+    uint64_t inflate_group_chunks = 0;   // 0 = auto (32768 chunks); B200_INFLATE_GROUP
+    bool inflate_overlap = false;        // B200_INFLATE_OVERLAP=1: copy pass of group g on a side stream while group g + 1 is in
+                                         // pass A (measured: +1 % on a 4 GiB stream, so off by default)
     bool with_index = true;          // B200_NO_INDEX=1 / B200_F_NO_INDEX: no segment index in front of full chunks
     int sg_occ = 12, copy_occ = 12;  // resident CTAs per SM the two inflate passes are compiled for (tuning knobs)
     unsigned copy_tune = 1;          // bit 0: prefetch the next step's sources into L2
@@ -138,7 +143,7 @@ struct b200_ctx {
     std::vector<cudaEvent_t> events;
     uint64_t* mailbox = nullptr;     // pinned: per-slice end offsets
     size_t mailbox_cap = 0;
-    uint32_t host_slice_chunks = 2048;
+    uint32_t host_slice_chunks = 1024;   // 64 MiB: measured best (smaller slices starve the persistent matcher)
     std::mutex mu;
     Prof prof;
 };
@@ -183,20 +188,16 @@ int default_ctx(b200_ctx** out) {
 
 // Two-pass fast path (inflate_tp.cuh) for a set of units: pass A (one thread per unit: symbols, literals,
 // op lists), the one-warp decoder for the units pass A gave up on, pass B (one warp per unit: copies).
-// c->tpres holds one TpResult per unit afterwards.  counter words: [1] fallback queue, [2] copy queue, [3] flag.
+// `res` receives one TpResult per unit.  cnt: 8 zeroed counter words ([1] fallback queue, [2] copy queue,
+// [3] fallback flag, [4] number of indexed chunks).  Pass B is enqueued on `st_copy` after pass A's kernels on
+// `st` (event ev_a); with st_copy != st it overlaps whatever follows on `st`.
 template <class Units>
-static int inflate_two_pass(b200_ctx* c, const Units& U, uint64_t nunits, unsigned flags, cudaStream_t st) {
-    int rc;
-    if ((rc = c->counter.ensure(64))) return rc;
-    if ((rc = c->tpres.ensure(nunits * sizeof(TpResult)))) return rc;
-    unsigned long long* cnt = (unsigned long long*)c->counter.p;
-    CK(cudaMemsetAsync(cnt, 0, 40, st));
-    TpResult* res = (TpResult*)c->tpres.p;
+static int inflate_two_pass(b200_ctx* c, const Units& U, uint64_t nunits, unsigned flags, TpResult* res,
+                            unsigned long long* cnt, uint32_t* chunk_list, uint16_t* segnops, cudaStream_t st,
+                            cudaStream_t st_copy, cudaEvent_t ev_a) {
     if constexpr (std::is_same<Units, ChunkUnits>::value) {
-        // counter word [4] = number of indexed chunks, c->chunk_list = their indices
-        if ((rc = c->chunk_list.ensure(nunits * 4))) return rc;
         PROF_BEGIN(c, K_INFLATE_CLASSIFY, st);
-        inflate_classify_kernel<<<(uint32_t)((nunits + 255) / 256), 256, 0, st>>>(U, res, (uint32_t*)c->chunk_list.p, cnt + 4, flags, cnt + 3);
+        inflate_classify_kernel<<<(uint32_t)((nunits + 255) / 256), 256, 0, st>>>(U, res, chunk_list, cnt + 4, flags, cnt + 3);
         LAUNCHED();
         PROF_END(c, st);
     }
@@ -204,10 +205,10 @@ static int inflate_two_pass(b200_ctx* c, const Units& U, uint64_t nunits, unsign
     if constexpr (std::is_same<Units, ChunkUnits>::value) {
         if (c->sg_occ >= 16)
             inflate_segments_kernel<16><<<(uint32_t)((nunits + SG_CHUNKS - 1) / SG_CHUNKS), SG_THREADS, SG_SMEM_BYTES, st>>>(
-                U, (const uint32_t*)c->chunk_list.p, cnt + 4, res, (uint16_t*)c->segnops.p, flags, cnt + 3);
+                U, chunk_list, cnt + 4, res, segnops, flags, cnt + 3);
         else
             inflate_segments_kernel<12><<<(uint32_t)((nunits + SG_CHUNKS - 1) / SG_CHUNKS), SG_THREADS, SG_SMEM_BYTES, st>>>(
-                U, (const uint32_t*)c->chunk_list.p, cnt + 4, res, (uint16_t*)c->segnops.p, flags, cnt + 3);
+                U, chunk_list, cnt + 4, res, segnops, flags, cnt + 3);
     } else
         inflate_symbols_kernel<Units><<<(uint32_t)((nunits + TP_THREADS - 1) / TP_THREADS), TP_THREADS, TP_SMEM_BYTES, st>>>(U, res, flags, cnt + 3);
     LAUNCHED();
@@ -218,18 +219,64 @@ static int inflate_two_pass(b200_ctx* c, const Units& U, uint64_t nunits, unsign
     inflate_fallback_kernel<Units><<<grid, INF_THREADS, 0, st>>>(U, res, flags, cnt + 3, cnt + 1);
     LAUNCHED();
     PROF_END(c, st);
-    PROF_BEGIN(c, K_INFLATE_COPY, st);
+    if (st_copy != st) {
+        CK(cudaEventRecord(ev_a, st));
+        CK(cudaStreamWaitEvent(st_copy, ev_a, 0));
+    }
+    PROF_BEGIN(c, K_INFLATE_COPY, st_copy);
     if (c->copy_occ >= 12) {
         const uint64_t g12 = (uint64_t)(c->inf_grid / INF_MAX_CTAS_PER_SM) * 12;
-        inflate_copy_kernel<Units, 12><<<(uint32_t)(want < g12 ? want : g12), INF_THREADS, 0, st>>>(U, res, cnt + 2, c->copy_tune);
+        inflate_copy_kernel<Units, 12><<<(uint32_t)(want < g12 ? want : g12), INF_THREADS, 0, st_copy>>>(U, res, cnt + 2, c->copy_tune);
     } else {
-        inflate_copy_kernel<Units, 6><<<grid, INF_THREADS, 0, st>>>(U, res, cnt + 2, c->copy_tune);
+        inflate_copy_kernel<Units, 6><<<grid, INF_THREADS, 0, st_copy>>>(U, res, cnt + 2, c->copy_tune);
     }
     LAUNCHED();
-    PROF_END(c, st);
+    PROF_END(c, st_copy);
     return B200_OK;
 }
 
+// Chunk mode: the candidate chunks are cut into groups of 32768 (2 GiB of output) so that op-list scratch is
+// bounded (2 bytes per output byte of a GROUP, not of the stream; a ring of two slots).  Optionally group g's
+// copy pass runs on a side stream while group g + 1 is in pass A.  cand[ncand] must hold n (sentinel).
+static int inflate_chunks_two_pass(b200_ctx* c, const uint8_t* in, uint64_t n, const uint64_t* cand, uint64_t ncand,
+                                   uint8_t* out, uint64_t cap, unsigned flags, cudaStream_t st) {
+    int rc;
+    uint64_t G = c->inflate_group_chunks;
+    if (G == 0) G = 32768;     // 2 GiB of output, 4 GiB of op-list scratch per slot; smaller groups run as partial waves (measured)
+    if (G > ncand) G = ncand;
+    const uint64_t ngroups = (ncand + G - 1) / G;
+    const uint64_t nslots = ngroups < 2 ? ngroups : 2;
+    if ((rc = c->tpres.ensure(ncand * sizeof(TpResult)))) return rc;
+    if ((rc = c->chunk_list.ensure(ncand * 4))) return rc;
+    if ((rc = c->segnops.ensure(ncand * NSEG * 2))) return rc;
+    if ((rc = c->ops.ensure(nslots * G * OPS_PER_CHUNK * 8))) return rc;
+    if ((rc = c->group_cnt.ensure(ngroups * 64))) return rc;
+    CK(cudaMemsetAsync(c->group_cnt.p, 0, ngroups * 64, st));
+    while (c->group_events.size() < 2 * ngroups) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->group_events.push_back(e);
+    }
+    const bool overlap = ngroups > 1 && c->inflate_overlap;
+    cudaStream_t side = overlap ? c->s_side : st;
+    for (uint64_t g = 0; g < ngroups; g++) {
+        const uint64_t g0 = g * G;
+        const uint64_t ng = ncand - g0 < G ? ncand - g0 : G;
+        if (overlap && g >= nslots) CK(cudaStreamWaitEvent(st, c->group_events[2 * (g - nslots) + 1], 0));   // slot's ops consumed
+        const uint64_t o0 = g0 * CHUNK;
+        ChunkUnits U{in, n, cand + g0, ng, out + o0, cap > o0 ? cap - o0 : 0, (uint64_t*)c->ops.p + (g % nslots) * G * OPS_PER_CHUNK,
+                     (const uint16_t*)c->segnops.p + g0 * NSEG};
+        if ((rc = inflate_two_pass(c, U, ng, flags, (TpResult*)c->tpres.p + g0, (unsigned long long*)c->group_cnt.p + g * 8,
+                                   (uint32_t*)c->chunk_list.p + g0, (uint16_t*)c->segnops.p + g0 * NSEG, st, side,
+                                   c->group_events[2 * g])))
+            return rc;
+        if (overlap) CK(cudaEventRecord(c->group_events[2 * g + 1], side));
+    }
+    if (overlap)
+        for (uint64_t g = ngroups >= nslots ? ngroups - nslots : 0; g < ngroups; g++)
+            CK(cudaStreamWaitEvent(st, c->group_events[2 * g + 1], 0));
+    return B200_OK;
+}
 
 }  // namespace
 
@@ -274,6 +321,8 @@ int b200_ctx_create(int device, b200_ctx** ctx) {
     if (const char* e = getenv("B200_BETTER_DEPTH")) { int v = atoi(e); if (v > 0) c->better_depth = (uint32_t)v; }
     if (const char* e = getenv("B200_BETTER_NICE")) { int v = atoi(e); if (v >= 3) c->better_nice = (uint32_t)v; }
     if (const char* e = getenv("B200_NO_INDEX")) c->with_index = atoi(e) == 0;
+    if (const char* e = getenv("B200_INFLATE_GROUP")) { long v = atol(e); if (v > 0) c->inflate_group_chunks = (uint64_t)v; }
+    if (const char* e = getenv("B200_INFLATE_OVERLAP")) c->inflate_overlap = atoi(e) != 0;
     if (const char* e = getenv("B200_SG_OCC")) c->sg_occ = atoi(e);
     if (const char* e = getenv("B200_COPY_OCC")) c->copy_occ = atoi(e);
     if (const char* e = getenv("B200_COPY_TUNE")) c->copy_tune = (unsigned)atoi(e);
@@ -283,7 +332,8 @@ int b200_ctx_create(int device, b200_ctx** ctx) {
     if (const char* e = getenv("B200_HOST_SLICE_CHUNKS")) { int v = atoi(e); if (v > 0) c->host_slice_chunks = (uint32_t)v; }
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking) != cudaSuccess) { delete c; return B200_E_CUDA; }
+        cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->s_side, cudaStreamNonBlocking) != cudaSuccess) { delete c; return B200_E_CUDA; }
     int rc = set_attrs(c);
     if (rc) { cudaStreamDestroy(c->stream); delete c; return rc; }
     *ctx = c;
@@ -294,11 +344,13 @@ void b200_ctx_destroy(b200_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     Buf* all[] = {&c->tok, &c->ntok, &c->hist, &c->codes, &c->hdr, &c->desc, &c->sizes, &c->offsets, &c->total,
-                  &c->counts, &c->woffs, &c->cand, &c->res, &c->result, &c->one_off, &c->counter, &c->cand16, &c->ops, &c->tpres, &c->segnops, &c->chunk_list,
+                  &c->counts, &c->woffs, &c->cand, &c->res, &c->result, &c->one_off, &c->counter, &c->cand16, &c->ops, &c->tpres, &c->segnops, &c->chunk_list, &c->group_cnt,
                   &c->d_in, &c->d_out};
     for (Buf* b : all) b->release();
     c->prof.destroy();
     for (auto e : c->events) cudaEventDestroy(e);
+    for (auto e : c->group_events) cudaEventDestroy(e);
+    if (c->s_side) cudaStreamDestroy(c->s_side);
     if (c->mailbox) cudaFreeHost(c->mailbox);
     if (c->s_in) cudaStreamDestroy(c->s_in);
     if (c->s_out) cudaStreamDestroy(c->s_out);
@@ -517,7 +569,11 @@ int b200_inflate_batch_dev(b200_ctx* c, const void* d_in, const uint64_t* d_in_o
         if ((rc = c->ops.ensure((span / 4 + 2) * 8))) return rc;
         BatchUnits U{(const uint8_t*)d_in, d_in_off, d_in_len, (uint8_t*)d_out, d_out_off, d_out_cap, (uint64_t)n_streams,
                      (uint64_t*)c->ops.p};
-        if ((rc = inflate_two_pass(c, U, n_streams, flags, st))) return rc;
+        if ((rc = c->tpres.ensure(n_streams * sizeof(TpResult)))) return rc;
+        CK(cudaMemsetAsync(c->counter.p, 0, 64, st));
+        if ((rc = inflate_two_pass(c, U, n_streams, flags, (TpResult*)c->tpres.p, (unsigned long long*)c->counter.p, nullptr,
+                                   nullptr, st, st, nullptr)))
+            return rc;
         batch_results_kernel<<<(uint32_t)((n_streams + 255) / 256), 256, 0, st>>>((const TpResult*)c->tpres.p, n_streams, d_out_len, d_status);
         LAUNCHED();
         return B200_OK;
@@ -599,11 +655,9 @@ int b200_inflate_dev(b200_ctx* c, const void* d_in, size_t n, void* d_out, size_
                 LAUNCHED();
                 PROF_END(c, st);
             } else {
-                if ((rc = c->ops.ensure(ncand * OPS_PER_CHUNK * 8))) return rc;
-                if ((rc = c->segnops.ensure(ncand * NSEG * 2))) return rc;
-                ChunkUnits U{in, (uint64_t)n, cand, ncand, (uint8_t*)d_out, (uint64_t)cap, (uint64_t*)c->ops.p,
-                             (const uint16_t*)c->segnops.p};
-                if ((rc = inflate_two_pass(c, U, ncand, flags, st))) return rc;
+                const uint64_t n64 = n;
+                CK(cudaMemcpyAsync(cand + ncand, &n64, 8, cudaMemcpyHostToDevice, st));      // sentinel: the last chunk ends at n
+                if ((rc = inflate_chunks_two_pass(c, in, n, cand, ncand, (uint8_t*)d_out, cap, flags, st))) return rc;
                 PROF_BEGIN(c, K_VALIDATE, st);
                 validate_units_kernel<<<(uint32_t)((ncand + 255) / 256), 256, 0, st>>>(cand, ncand, (uint64_t)n, (const TpResult*)c->tpres.p, d_result);
                 LAUNCHED();
@@ -656,7 +710,7 @@ int b200_corpus_generate_dev(void* d_out, uint64_t seed, uint64_t first_chunk, u
 // ------------------------------------------------------------------------------------------------
 // Host-buffer API
 //
-// Compress host memory into host memory.  The input is cut into slices (host_slice_chunks, 128 MiB by
+// Compress host memory into host memory.  The input is cut into slices (host_slice_chunks, 64 MiB by
 // default); slice k+1's host->device copy, slice k's kernels and slice k-1's device->host copy run on
 // three streams, chained by events, so with pinned host buffers the call is bound by the slower PCIe
 // direction instead of the sum of copy + compute + copy.  Output offsets chain on the device (K3's

@@ -508,7 +508,7 @@ struct ChunkUnits {
     __device__ __forceinline__ TpUnit get(uint64_t i) const {
         TpUnit u;
         const uint64_t start = cand[i];
-        const uint64_t end = i + 1 < ncand ? cand[i + 1] : n;       // a well-formed chunk ends exactly there
+        const uint64_t end = cand[i + 1];                           // a well-formed chunk ends exactly there (cand[last + 1] = n)
         u.in = in + start; u.in_len = end - start;
         const uint64_t o0 = i * CHUNK;
         u.out = out + o0; u.cap = o0 >= cap ? 0 : min((uint64_t)CHUNK, cap - o0); u.max_out = CHUNK;

@@ -248,3 +248,23 @@ def test_segment_index_not_trusted(b200):
     assert _index_at(_compress_dev(b200, gold("test.bmp"), 2), 0) is None
     noisy = datagen.random_bytes(65536 * 2, seed=8)
     assert _index_at(_compress_dev(b200, noisy, 1), 0) is None
+
+
+@pytest.mark.parametrize("overlap", ["0", "1"])
+def test_chunk_groups(b200, monkeypatch, overlap):
+    """Long streams are inflated in groups of chunks (bounded scratch, optionally the copy pass of one group
+    overlapping pass A of the next): force tiny groups so that an 11-chunk stream takes six of them."""
+    import torch
+    monkeypatch.setenv("B200_INFLATE_GROUP", "2")
+    monkeypatch.setenv("B200_INFLATE_OVERLAP", overlap)
+    data = datagen.text_like(4 * 65536, seed=21) + datagen.random_bytes(2 * 65536, seed=22) + datagen.image_like(4 * 65536 + 777)
+    c = _compress_dev(b200, data, 2)
+    ctx = b200.Context(0)
+    src = torch.frombuffer(bytearray(c), dtype=torch.uint8).cuda()
+    for cap in (len(data), len(data) + 5000, 3 * 65536 + 11):
+        dst = torch.zeros(cap + 16, dtype=torch.uint8, device="cuda")
+        w, full = ctx.inflate_dev(src.data_ptr(), len(c), dst.data_ptr(), cap)
+        torch.cuda.synchronize()
+        assert full == len(data) and w == min(cap, len(data))
+        assert bytes(dst[:w].cpu().numpy()) == data[:w]
+        assert int(dst[cap:].sum()) == 0                     # nothing written past the caller's capacity
