@@ -188,8 +188,8 @@ int default_ctx(b200_ctx** out) {
 
 // Two-pass fast path (inflate_tp.cuh) for a set of units: pass A (one thread per unit: symbols, literals,
 // op lists), the one-warp decoder for the units pass A gave up on, pass B (one warp per unit: copies).
-// `res` receives one TpResult per unit.  cnt: 8 zeroed counter words ([1] fallback queue, [2] copy queue,
-// [3] fallback flag, [4] number of indexed chunks).  Pass B is enqueued on `st_copy` after pass A's kernels on
+// `res` receives one TpResult per unit.  cnt: 32 zeroed u64 counter words ([1] fallback queue, [2] copy queue,
+// [3] fallback flag, [4] number of indexed chunks, [8..23] = 32 u32 bucket counts); chunk_list: 32 x nunits u32.  Pass B is enqueued on `st_copy` after pass A's kernels on
 // `st` (event ev_a); with st_copy != st it overlaps whatever follows on `st`.
 template <class Units>
 static int inflate_two_pass(b200_ctx* c, const Units& U, uint64_t nunits, unsigned flags, TpResult* res,
@@ -197,7 +197,7 @@ static int inflate_two_pass(b200_ctx* c, const Units& U, uint64_t nunits, unsign
                             cudaStream_t st_copy, cudaEvent_t ev_a) {
     if constexpr (std::is_same<Units, ChunkUnits>::value) {
         PROF_BEGIN(c, K_INFLATE_CLASSIFY, st);
-        inflate_classify_kernel<<<(uint32_t)((nunits + 255) / 256), 256, 0, st>>>(U, res, chunk_list, cnt + 4, flags, cnt + 3);
+        inflate_classify_kernel<<<(uint32_t)((nunits + 255) / 256), 256, 0, st>>>(U, res, chunk_list, (uint32_t*)(cnt + 8), cnt + 4, flags, cnt + 3);
         LAUNCHED();
         PROF_END(c, st);
     }
@@ -205,10 +205,10 @@ static int inflate_two_pass(b200_ctx* c, const Units& U, uint64_t nunits, unsign
     if constexpr (std::is_same<Units, ChunkUnits>::value) {
         if (c->sg_occ >= 16)
             inflate_segments_kernel<16><<<(uint32_t)((nunits + SG_CHUNKS - 1) / SG_CHUNKS), SG_THREADS, SG_SMEM_BYTES, st>>>(
-                U, chunk_list, cnt + 4, res, segnops, flags, cnt + 3);
+                U, chunk_list, (const uint32_t*)(cnt + 8), cnt + 4, res, segnops, flags, cnt + 3);
         else
             inflate_segments_kernel<12><<<(uint32_t)((nunits + SG_CHUNKS - 1) / SG_CHUNKS), SG_THREADS, SG_SMEM_BYTES, st>>>(
-                U, chunk_list, cnt + 4, res, segnops, flags, cnt + 3);
+                U, chunk_list, (const uint32_t*)(cnt + 8), cnt + 4, res, segnops, flags, cnt + 3);
     } else
         inflate_symbols_kernel<Units><<<(uint32_t)((nunits + TP_THREADS - 1) / TP_THREADS), TP_THREADS, TP_SMEM_BYTES, st>>>(U, res, flags, cnt + 3);
     LAUNCHED();
@@ -247,11 +247,11 @@ static int inflate_chunks_two_pass(b200_ctx* c, const uint8_t* in, uint64_t n, c
     const uint64_t ngroups = (ncand + G - 1) / G;
     const uint64_t nslots = ngroups < 2 ? ngroups : 2;
     if ((rc = c->tpres.ensure(ncand * sizeof(TpResult)))) return rc;
-    if ((rc = c->chunk_list.ensure(ncand * 4))) return rc;
+    if ((rc = c->chunk_list.ensure(G * SG_BUCKETS * 4))) return rc;
     if ((rc = c->segnops.ensure(ncand * NSEG * 2))) return rc;
     if ((rc = c->ops.ensure(nslots * G * OPS_PER_CHUNK * 8))) return rc;
-    if ((rc = c->group_cnt.ensure(ngroups * 64))) return rc;
-    CK(cudaMemsetAsync(c->group_cnt.p, 0, ngroups * 64, st));
+    if ((rc = c->group_cnt.ensure(ngroups * 256))) return rc;
+    CK(cudaMemsetAsync(c->group_cnt.p, 0, ngroups * 256, st));
     while (c->group_events.size() < 2 * ngroups) {
         cudaEvent_t e;
         CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -266,8 +266,8 @@ static int inflate_chunks_two_pass(b200_ctx* c, const uint8_t* in, uint64_t n, c
         const uint64_t o0 = g0 * CHUNK;
         ChunkUnits U{in, n, cand + g0, ng, out + o0, cap > o0 ? cap - o0 : 0, (uint64_t*)c->ops.p + (g % nslots) * G * OPS_PER_CHUNK,
                      (const uint16_t*)c->segnops.p + g0 * NSEG};
-        if ((rc = inflate_two_pass(c, U, ng, flags, (TpResult*)c->tpres.p + g0, (unsigned long long*)c->group_cnt.p + g * 8,
-                                   (uint32_t*)c->chunk_list.p + g0, (uint16_t*)c->segnops.p + g0 * NSEG, st, side,
+        if ((rc = inflate_two_pass(c, U, ng, flags, (TpResult*)c->tpres.p + g0, (unsigned long long*)c->group_cnt.p + g * 32,
+                                   (uint32_t*)c->chunk_list.p, (uint16_t*)c->segnops.p + g0 * NSEG, st, side,
                                    c->group_events[2 * g])))
             return rc;
         if (overlap) CK(cudaEventRecord(c->group_events[2 * g + 1], side));
@@ -570,7 +570,8 @@ int b200_inflate_batch_dev(b200_ctx* c, const void* d_in, const uint64_t* d_in_o
         BatchUnits U{(const uint8_t*)d_in, d_in_off, d_in_len, (uint8_t*)d_out, d_out_off, d_out_cap, (uint64_t)n_streams,
                      (uint64_t*)c->ops.p};
         if ((rc = c->tpres.ensure(n_streams * sizeof(TpResult)))) return rc;
-        CK(cudaMemsetAsync(c->counter.p, 0, 64, st));
+        if ((rc = c->counter.ensure(256))) return rc;
+        CK(cudaMemsetAsync(c->counter.p, 0, 256, st));
         if ((rc = inflate_two_pass(c, U, n_streams, flags, (TpResult*)c->tpres.p, (unsigned long long*)c->counter.p, nullptr,
                                    nullptr, st, st, nullptr)))
             return rc;

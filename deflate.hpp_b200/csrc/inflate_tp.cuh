@@ -122,43 +122,68 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
     return v;
 }
 
-// ---- per-thread bit reader: two prefetched words between memory and the 64-bit buffer --------------
+// ---- per-thread bit reader: a small ring in shared memory, filled by cp.async, between HBM and the 64-bit buffer --
+// ~800 streams per SM are read 4 bytes at a time: the L1 cannot hold a line per stream, 4 of 10 words come from
+// DRAM.  A register queue between the load and its use does not help enough -- shifting the queue touches the
+// register a load is still writing one refill after it was issued, and refills come in bursts (literal runs).
+// cp.async has no destination register: word i + TB_RING is requested when word i is consumed, sits in the
+// thread's ring slots in shared memory ([slot][thread]: conflict-free) and is waited for TB_RING - 1 refills later.
+constexpr uint32_t TB_RING = 4;
 struct TBits {
     const uint32_t* wp;   // 4-byte aligned address at or below the stream start
     uint32_t nw;          // words from wp that cover the stream
-    uint32_t wi;          // next word to fetch
-    uint32_t w0, w1, w2;  // fetched, not yet in bb (w2 may still be in flight)
+    uint32_t wi;          // words merged into bb so far == index of the word held in w0
+    uint32_t w0;          // next word to merge
+    uint32_t ring_sa;     // shared-memory address of this thread's slot 0
+    uint32_t ring_stride; // bytes between slots (4 x threads sharing the ring array)
     uint32_t skip;        // bytes between wp and the stream start
     uint64_t bb;
     uint32_t bc;
 };
-__device__ __forceinline__ uint32_t tb_word(const TBits& r, uint32_t i) { return i < r.nw ? __ldg(r.wp + i) : 0u; }
+// request word i into its ring slot (zero-filled past the end of the stream); one cp.async group per word
+__device__ __forceinline__ void tb_request(const TBits& r, uint32_t i) {
+    const uint32_t dst = r.ring_sa + (i % TB_RING) * r.ring_stride;
+    const bool in_range = i < r.nw;
+    const uint32_t* src = r.wp + (in_range ? i : 0u);
+    const uint32_t nbytes = in_range ? 4u : 0u;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\ncp.async.commit_group;" :: "r"(dst), "l"(src), "r"(nbytes) : "memory");
+}
+__device__ __forceinline__ uint32_t tb_slot(const TBits& r, uint32_t i) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(r.ring_sa + (i % TB_RING) * r.ring_stride) : "memory");
+    return v;
+}
+// merge w0 into the bit buffer (bc <= 32 on entry), request the word TB_RING ahead, fetch the next w0
+__device__ __forceinline__ void tb_take(TBits& r) {
+    r.bb |= (uint64_t)r.w0 << r.bc;
+    r.bc += 32;
+    tb_request(r, r.wi + TB_RING);                 // into the slot of word wi, which w0 has left
+    asm volatile("cp.async.wait_group %0;" :: "n"(TB_RING - 1) : "memory");     // word wi + 1 has landed
+    r.wi++;
+    r.w0 = tb_slot(r, r.wi);
+}
 __device__ __forceinline__ void tb_seek(TBits& r, uint64_t stream_byte) {
     const uint64_t b = r.skip + stream_byte;
     const uint32_t w = (uint32_t)(b >> 2);
     const uint32_t sh = (uint32_t)(b & 3) * 8;
-    r.bb = (uint64_t)(tb_word(r, w) >> sh);
-    r.bc = 32 - sh;
-    r.w0 = tb_word(r, w + 1);
-    r.w1 = tb_word(r, w + 2);
-    r.w2 = tb_word(r, w + 3);
-    r.wi = w + 4;
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    #pragma unroll
+    for (uint32_t k = 0; k < TB_RING; k++) tb_request(r, w + k);
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    r.wi = w;
+    r.w0 = tb_slot(r, w);
+    r.bb = 0; r.bc = 0;
+    tb_take(r);
+    r.bb >>= sh; r.bc -= sh;
 }
 __device__ __forceinline__ void tb_refill(TBits& r) {      // afterwards bc >= 33
-    if (r.bc < 33) {
-        r.bb |= (uint64_t)r.w0 << r.bc;
-        r.bc += 32;
-        r.w0 = r.w1;
-        r.w1 = r.w2;
-        r.w2 = tb_word(r, r.wi);
-        r.wi++;
-    }
+    if (r.bc < 33) tb_take(r);
 }
 __device__ __forceinline__ uint32_t tb_peek(const TBits& r, uint32_t n) { return (uint32_t)r.bb & ((1u << n) - 1u); }
 __device__ __forceinline__ void tb_drop(TBits& r, uint32_t n) { r.bb >>= n; r.bc -= n; }
 __device__ __forceinline__ uint32_t tb_get(TBits& r, uint32_t n) { const uint32_t v = tb_peek(r, n); tb_drop(r, n); return v; }
 __device__ __forceinline__ uint64_t tb_bitpos(const TBits& r) {
-    return (uint64_t)(r.wi - 3) * 32 - r.bc - (uint64_t)r.skip * 8;
+    return (uint64_t)r.wi * 32 - r.bc - (uint64_t)r.skip * 8;
 }
 
 // ---- literal output: bytes are merged into aligned 32-bit words ---------------------------------------
@@ -284,7 +309,7 @@ __device__ __forceinline__ void tp_step_symbol(const TpCtx& c, TpState& s) {
     TBits& br = s.br;
     TOut& o = s.o;
     const uint32_t produced = o.v - o.al;
-    const uint32_t wi_lim = br.nw + 7;
+    const uint32_t wi_lim = br.nw + 4;
     if (produced >= c.stop_at || br.wi > wi_lim) {
         // rare: end of the segment, output limit, or far past the end of the input
         if (br.wi <= wi_lim && produced <= c.max_out && produced >= c.seg_stop) {
@@ -294,17 +319,8 @@ __device__ __forceinline__ void tp_step_symbol(const TpCtx& c, TpState& s) {
             tp_end_block(c, s, wi_lim);
         }
     } else {
-        // refill: a plain (reconverging) branch.  The word fetched here is first touched at the NEXT refill,
-        // about three symbols later, so its latency is off the critical path (a branch-free version has to
-        // route it through a select and stalls on it at once)
-        if (br.bc < 33) {
-            br.bb |= (uint64_t)br.w0 << br.bc;
-            br.bc += 32;
-            br.w0 = br.w1;
-            br.w1 = br.w2;
-            br.w2 = tb_word(br, br.wi);
-            br.wi++;
-        }
+        // refill: a plain (reconverging) branch; the word requested here is waited for TB_RING - 1 refills later
+        if (br.bc < 33) tb_take(br);
         uint32_t e = lds_u16(c.lit_sa + tb_peek(br, LB) * ntb);
         bool ok = true;
         if ((e & 15u) == 0) {
@@ -467,7 +483,10 @@ __device__ __forceinline__ void tp_ctx_init(TpCtx& c, const TpUnit& u, unsigned 
     c.stop_at = c.max_out + 1;
     c.stop_at_sync = u.stop_at_sync; c.strict = flags & 1u; c.allow_huffman = true;
 }
-__device__ __forceinline__ void tp_state_init(TpState& s, const TpCtx& c, const TpUnit& u, bool live) {
+__device__ __forceinline__ void tp_state_init(TpState& s, const TpCtx& c, const TpUnit& u, bool live, uint32_t* ring, uint32_t nthreads) {
+    // ring: the CTA's [TB_RING][nthreads] word array in shared memory; this thread owns column threadIdx.x
+    s.br.ring_sa = (uint32_t)__cvta_generic_to_shared(ring + threadIdx.x);
+    s.br.ring_stride = nthreads * 4;
     s.st = ST_OK;
     s.state = live ? TS_BLOCK : TS_DONE;
     if (live && u.in_len >= (1ull << 33)) { s.st = ST_FALLBACK; s.state = TS_DONE; }     // word indices are 32-bit here
@@ -545,6 +564,7 @@ template <class Units>
 __global__ void __launch_bounds__(TP_THREADS)
 inflate_symbols_kernel(Units U, TpResult* __restrict__ res, unsigned flags, unsigned long long* __restrict__ any_fallback) {
     extern __shared__ __align__(16) uint8_t tp_smem[];
+    __shared__ uint32_t s_ring[TB_RING * TP_THREADS];
     uint32_t* s_lut = reinterpret_cast<uint32_t*>(tp_smem);
     uint16_t* tabs = reinterpret_cast<uint16_t*>(tp_smem + TP_LUT_WORDS * 4);
     tp_lut_init(s_lut, threadIdx.x);
@@ -558,7 +578,7 @@ inflate_symbols_kernel(Units U, TpResult* __restrict__ res, unsigned flags, unsi
     tp_ctx_init(c, u, flags);
     tp_ctx_tables(c, tabs + threadIdx.x, tabs + threadIdx.x + (size_t)(1u << TP_LIT_BITS) * blockDim.x, blockDim.x, s_lut, &T, TP_LIT_BITS);
     TpState s;
-    tp_state_init(s, c, u, live);
+    tp_state_init(s, c, u, live, s_ring, blockDim.x);
     while (__any_sync(0xFFFFFFFFu, s.state != TS_DONE)) {
         if (s.state == TS_SYM) tp_step_symbol<false>(c, s);
         else if (s.state == TS_BLOCK) s = tp_step_block(c, s);
@@ -610,15 +630,21 @@ __device__ uint32_t sg_read_index(const uint8_t* in, uint64_t in_len, uint32_t* 
 // Pass A0: one thread per chunk.  Indexed chunks are appended to `list` (the segment kernel then works on a
 // dense list: no lanes wasted on stored chunks); a chunk without index is finished here if it consists of
 // stored blocks (a few ops), and handed to the one-warp decoder if it is Huffman-coded.
+constexpr uint32_t SG_BUCKETS = 32;      // indexed chunks are bucketed by compressed size (2 KiB steps)
 __global__ void __launch_bounds__(256)
-inflate_classify_kernel(ChunkUnits U, TpResult* __restrict__ res, uint32_t* __restrict__ list,
+inflate_classify_kernel(ChunkUnits U, TpResult* __restrict__ res, uint32_t* __restrict__ blist, uint32_t* __restrict__ bcnt,
                         unsigned long long* __restrict__ nlist, unsigned flags, unsigned long long* __restrict__ any_fallback) {
+    __shared__ uint32_t s_ring[TB_RING * 256];
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= U.count()) return;
     const TpUnit u = U.get(i);
     uint32_t words[NSEG];
     if (sg_read_index(u.in, u.in_len, words) >= 2) {
-        list[atomicAdd(nlist, 1ull)] = (uint32_t)i;
+        // chunks of similar compressed size have similar symbol counts: the segment kernel takes them bucket by
+        // bucket, largest first, so that the threads of a warp finish together and the longest chains start first
+        const uint32_t b = (uint32_t)min(u.in_len >> 11, (uint64_t)SG_BUCKETS - 1);
+        blist[(uint64_t)b * U.count() + atomicAdd(&bcnt[b], 1u)] = (uint32_t)i;
+        atomicAdd(nlist, 1ull);
         return;
     }
     TpCtx c;
@@ -626,7 +652,7 @@ inflate_classify_kernel(ChunkUnits U, TpResult* __restrict__ res, uint32_t* __re
     c.lit = c.dst = nullptr; c.T = nullptr; c.NT = 1; c.lit_sa = c.dst_sa = c.lut_sa = 0; c.ntb = 2; c.lit_bits = TP_LIT_BITS;
     c.allow_huffman = false;
     TpState s;
-    tp_state_init(s, c, u, true);
+    tp_state_init(s, c, u, true, s_ring, 256);
     while (s.state != TS_DONE) s = tp_step_block(c, s);
     TpResult r;
     tp_finish(c, s, r);
@@ -636,12 +662,13 @@ inflate_classify_kernel(ChunkUnits U, TpResult* __restrict__ res, uint32_t* __re
 
 template <int OCC>
 __global__ void __launch_bounds__(SG_THREADS, OCC)
-inflate_segments_kernel(ChunkUnits U, const uint32_t* __restrict__ list, const unsigned long long* __restrict__ nlist,
-                        TpResult* __restrict__ res, uint16_t* __restrict__ segnops, unsigned flags,
+inflate_segments_kernel(ChunkUnits U, const uint32_t* __restrict__ blist, const uint32_t* __restrict__ bcnt,
+                        const unsigned long long* __restrict__ nlist, TpResult* __restrict__ res, uint16_t* __restrict__ segnops, unsigned flags,
                         unsigned long long* __restrict__ any_fallback) {
     const uint64_t nl = *nlist;
     if ((uint64_t)blockIdx.x * SG_CHUNKS >= nl) return;
     extern __shared__ __align__(16) uint8_t tp_smem[];
+    __shared__ uint32_t s_ring[TB_RING * SG_THREADS];
     uint32_t* s_lut = reinterpret_cast<uint32_t*>(tp_smem);
     uint32_t* s_queue = s_lut + TP_LUT_WORDS;
     SgChunk* SCs = reinterpret_cast<SgChunk*>(tp_smem + TP_LUT_WORDS * 4 + 16);
@@ -658,14 +685,20 @@ inflate_segments_kernel(ChunkUnits U, const uint32_t* __restrict__ list, const u
         const uint64_t li = (uint64_t)blockIdx.x * SG_CHUNKS + threadIdx.x / BUILD_STRIDE;
         SC->nseg = 0;
         if (li < nl) {
-            const uint64_t i = list[li];
+            // position li of the bucket-ordered list (largest bucket first)
+            uint64_t i = 0, off = 0;
+            for (int b = SG_BUCKETS - 1; b >= 0; b--) {
+                const uint32_t nb = bcnt[b];
+                if (li < off + nb) { i = blist[(uint64_t)b * U.count() + (li - off)]; break; }
+                off += nb;
+            }
             const TpUnit u = U.get(i);
             SC->u = u; SC->unit = i;
             tp_ctx_init(c, u, flags);
             tp_ctx_tables(c, SC->lit, SC->dst, 1, s_lut, &SC->T, SG_LIT_BITS);
             uint32_t words[NSEG];
             const uint32_t nseg = sg_read_index(u.in, u.in_len, words);
-            tp_state_init(s, c, u, true);
+            tp_state_init(s, c, u, true, s_ring, SG_THREADS);
             if (nseg >= 2) {
                 tb_seek(s.br, INDEX_BYTES);
                 s = tp_step_block(c, s);
@@ -725,7 +758,7 @@ inflate_segments_kernel(ChunkUnits U, const uint32_t* __restrict__ list, const u
                     const TpUnit u = SC->u;
                     tp_ctx_init(c, u, flags);
                     tp_ctx_tables(c, SC->lit, SC->dst, 1, s_lut, &SC->T, SG_LIT_BITS);
-                    tp_state_init(s, c, u, true);
+                    tp_state_init(s, c, u, true, s_ring, SG_THREADS);
                     const uint32_t bit = SC->seg_start[seg];
                     tb_seek(s.br, bit >> 3);
                     tb_drop(s.br, bit & 7);
