@@ -121,7 +121,7 @@ struct b200_ctx {
     // compress scratch
     Buf tok, ntok, hist, codes, hdr, desc, sizes, offsets, total;
     // inflate scratch
-    Buf counts, woffs, cand, res, result, one_off, counter, cand16, ops, tpres, segnops, chunk_list, group_cnt;
+    Buf counts, woffs, cand, res, result, one_off, counter, cand16, ops, tpres, segnops, chunk_list, group_cnt, sync_cache;
     std::vector<cudaEvent_t> group_events;
     cudaStream_t s_side = nullptr;   // inflate: copy pass of group g while group g + 1 is in pass A
     uint64_t inflate_group_chunks = 0;   // 0 = auto (32768 chunks); B200_INFLATE_GROUP
@@ -344,7 +344,7 @@ void b200_ctx_destroy(b200_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     Buf* all[] = {&c->tok, &c->ntok, &c->hist, &c->codes, &c->hdr, &c->desc, &c->sizes, &c->offsets, &c->total,
-                  &c->counts, &c->woffs, &c->cand, &c->res, &c->result, &c->one_off, &c->counter, &c->cand16, &c->ops, &c->tpres, &c->segnops, &c->chunk_list, &c->group_cnt,
+                  &c->counts, &c->woffs, &c->cand, &c->res, &c->result, &c->one_off, &c->counter, &c->cand16, &c->ops, &c->tpres, &c->segnops, &c->chunk_list, &c->group_cnt, &c->sync_cache,
                   &c->d_in, &c->d_out};
     for (Buf* b : all) b->release();
     c->prof.destroy();
@@ -617,7 +617,8 @@ int b200_inflate_dev(b200_ctx* c, const void* d_in, size_t n, void* d_out, size_
         uint64_t* cand = (uint64_t*)c->cand.p;
         const uint32_t g = (uint32_t)((nwarps * 32 + 255) / 256);
         PROF_BEGIN(c, K_FIND_SYNC, st);
-        find_sync_kernel<false><<<g, 256, 0, st>>>(in, n, (uint32_t*)c->counts.p, nullptr, nullptr, 0);
+        if ((rc = c->sync_cache.ensure(nwarps * SYNC_CACHE * 4))) return rc;
+        find_sync_kernel<false><<<g, 256, 0, st>>>(in, n, (uint32_t*)c->counts.p, (uint32_t*)c->sync_cache.p, nullptr, nullptr, 0);
         LAUNCHED();
         PROF_END(c, st);
         PROF_BEGIN(c, K_SCAN, st);
@@ -633,7 +634,8 @@ int b200_inflate_dev(b200_ctx* c, const void* d_in, size_t n, void* d_out, size_
             CK(cudaMemsetAsync(cand, 0, 8, st));   // cand[0] = 0
             if (nmark) {
                 PROF_BEGIN(c, K_FIND_SYNC, st);
-                find_sync_kernel<true><<<g, 256, 0, st>>>(in, n, nullptr, (const uint64_t*)c->woffs.p, cand + 1, nmark);
+                find_sync_kernel<true><<<g, 256, 0, st>>>(in, n, (uint32_t*)c->counts.p, (uint32_t*)c->sync_cache.p,
+                                                          (const uint64_t*)c->woffs.p, cand + 1, nmark);
                 LAUNCHED();
                 PROF_END(c, st);
             }

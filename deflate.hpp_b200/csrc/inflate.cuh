@@ -541,9 +541,12 @@ inflate_batch_kernel(const uint8_t* __restrict__ in, const uint64_t* __restrict_
 // candidates come out in stream order: pass A counts per warp, an exclusive scan gives each warp its
 // slot, pass B (WRITE) stores the candidate offsets.  cand[0] = 0 is written by the host side.
 constexpr uint32_t SYNC_REGION = 16384;
+constexpr uint32_t SYNC_CACHE = 4;          // candidates per region the count pass remembers (a region holds one on average
+                                            // at most: chunks compress to >= 20 KB or are stored); the write pass re-reads
+                                            // the input only for regions with more
 template <bool WRITE>
 __global__ void __launch_bounds__(256)
-find_sync_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t* __restrict__ counts,
+find_sync_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t* __restrict__ counts, uint32_t* __restrict__ cache,
                  const uint64_t* __restrict__ offsets, uint64_t* __restrict__ cand, uint64_t cand_cap) {
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -553,16 +556,31 @@ find_sync_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t* __restric
     const uint32_t FULL = 0xFFFFFFFFu;
     const bool aligned = (reinterpret_cast<uintptr_t>(in) & 15) == 0;
     uint64_t run = WRITE ? offsets[w] : 0;
+    if (WRITE) {
+        const uint32_t c = counts[w];
+        if (c <= SYNC_CACHE) {
+            if (lane < c && run + lane < cand_cap) cand[run + lane] = lo + cache[w * SYNC_CACHE + lane] + SYNC_PATTERN_BYTES;
+            return;
+        }
+    }
     uint32_t total = 0;
+    #pragma unroll 2
     for (uint64_t b = lo; b < hi; b += 512) {
         const uint64_t p = b + lane * 16;
         uint32_t wd[7] = {0, 0, 0, 0, 0, 0, 0};
-        if (aligned && p + 28 <= n) {
-            const uint4 v = *reinterpret_cast<const uint4*>(in + p);
+        const bool fast = aligned && p + 28 <= n;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (fast) v = *reinterpret_cast<const uint4*>(in + p);
+        // the 12 bytes after a lane's 16 are the next lane's first three words: one load per lane, not four
+        const uint32_t nx = __shfl_down_sync(FULL, v.x, 1), ny = __shfl_down_sync(FULL, v.y, 1), nz = __shfl_down_sync(FULL, v.z, 1);
+        if (fast) {
             wd[0] = v.x; wd[1] = v.y; wd[2] = v.z; wd[3] = v.w;
-            wd[4] = *reinterpret_cast<const uint32_t*>(in + p + 16);
-            wd[5] = *reinterpret_cast<const uint32_t*>(in + p + 20);
-            wd[6] = *reinterpret_cast<const uint32_t*>(in + p + 24);
+            if (lane < 31 && p + 44 <= n) { wd[4] = nx; wd[5] = ny; wd[6] = nz; }
+            else {
+                wd[4] = *reinterpret_cast<const uint32_t*>(in + p + 16);
+                wd[5] = *reinterpret_cast<const uint32_t*>(in + p + 20);
+                wd[6] = *reinterpret_cast<const uint32_t*>(in + p + 24);
+            }
         } else {
             for (uint32_t j = 0; j < 28; j++)
                 if (p + j < n) wd[j >> 2] |= (uint32_t)in[p + j] << (8 * (j & 3));
@@ -584,15 +602,14 @@ find_sync_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t* __restric
                 const uint32_t u = __shfl_up_sync(FULL, incl, o);
                 if ((int)lane >= o) incl += u;
             }
-            if (WRITE) {
-                uint64_t slot = run + (incl - c);
-                uint32_t h = hits;
-                while (h) {
-                    const uint32_t j = __ffs(h) - 1;
-                    h &= h - 1;
-                    if (slot < cand_cap) cand[slot] = p + j + SYNC_PATTERN_BYTES;
-                    slot++;
-                }
+            uint64_t slot = (WRITE ? run : (uint64_t)total) + (incl - c);
+            uint32_t h = hits;
+            while (h) {
+                const uint32_t j = __ffs(h) - 1;
+                h &= h - 1;
+                if (WRITE) { if (slot < cand_cap) cand[slot] = p + j + SYNC_PATTERN_BYTES; }
+                else if (slot < SYNC_CACHE) cache[w * SYNC_CACHE + slot] = (uint32_t)(p + j - lo);
+                slot++;
             }
             const uint32_t tot = __shfl_sync(FULL, incl, 31);
             run += tot; total += tot;
