@@ -86,6 +86,8 @@ def lib():
     L.b200_inflate_batch_dev.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                          c_void_p, c_void_p, c_size_t, c_uint, c_void_p]
     L.b200_corpus_generate_dev.argtypes = [c_void_p, c_u64, c_u64, c_u64, c_void_p]
+    L.b200_adler32_dev.argtypes = [c_void_p, c_void_p, c_size_t, P(ctypes.c_uint32), c_void_p, c_void_p]
+    L.b200_adler32_dev.restype = c_int
     for f in ("b200_ctx_create", "b200_deflate_compress", "b200_deflate_compress_into", "b200_inflate",
               "b200_inflate_alloc", "b200_inflate_zlib", "b200_inflate_zlib_alloc", "b200_deflate_compress_dev",
               "b200_inflate_dev", "b200_inflate_batch_dev", "b200_corpus_generate_dev"):
@@ -255,6 +257,14 @@ class Context:
                                           d_out_len, d_status, n_streams, flags, stream or None)
         if rc:
             raise B200Error(rc, "b200_inflate_batch_dev")
+
+    def adler32_dev(self, d_data, n, stream=0):
+        """Adler-32 of n device bytes, computed on the GPU."""
+        out = ctypes.c_uint32()
+        rc = lib().b200_adler32_dev(self._h, d_data or None, n, ctypes.byref(out), None, stream or None)
+        if rc:
+            raise B200Error(rc, "b200_adler32_dev")
+        return out.value
 
     @staticmethod
     def corpus_generate_dev(d_out, seed, first_chunk, n_chunks, stream=0):

@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "checksum.cuh"
 #include "corpus.cuh"
 #include "encode.cuh"
 #include "huffman.cuh"
@@ -121,7 +122,7 @@ struct b200_ctx {
     // compress scratch
     Buf tok, ntok, hist, codes, hdr, desc, sizes, offsets, total;
     // inflate scratch
-    Buf counts, woffs, cand, res, result, one_off, counter, cand16, ops, tpres, segnops, chunk_list, group_cnt, sync_cache;
+    Buf counts, woffs, cand, res, result, one_off, counter, cand16, ops, tpres, segnops, chunk_list, group_cnt, sync_cache, adler_parts;
     std::vector<cudaEvent_t> group_events;
     cudaStream_t s_side = nullptr;   // inflate: copy pass of group g while group g + 1 is in pass A
     uint64_t inflate_group_chunks = 0;   // 0 = auto (32768 chunks); B200_INFLATE_GROUP
@@ -344,7 +345,7 @@ void b200_ctx_destroy(b200_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     Buf* all[] = {&c->tok, &c->ntok, &c->hist, &c->codes, &c->hdr, &c->desc, &c->sizes, &c->offsets, &c->total,
-                  &c->counts, &c->woffs, &c->cand, &c->res, &c->result, &c->one_off, &c->counter, &c->cand16, &c->ops, &c->tpres, &c->segnops, &c->chunk_list, &c->group_cnt, &c->sync_cache,
+                  &c->counts, &c->woffs, &c->cand, &c->res, &c->result, &c->one_off, &c->counter, &c->cand16, &c->ops, &c->tpres, &c->segnops, &c->chunk_list, &c->group_cnt, &c->sync_cache, &c->adler_parts,
                   &c->d_in, &c->d_out};
     for (Buf* b : all) b->release();
     c->prof.destroy();
@@ -698,6 +699,28 @@ int b200_inflate_dev(b200_ctx* c, const void* d_in, size_t n, void* d_out, size_
     return status;
 }
 
+int b200_adler32_dev(b200_ctx* c, const void* d_data, size_t n, uint32_t* h_out, uint32_t* d_out, void* stream_) {
+    if (!c || (!d_data && n) || (!h_out && !d_out)) return B200_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream_;
+    CK(cudaSetDevice(c->device));
+    int rc;
+    const uint64_t nblocks = (n + CHUNK - 1) / CHUNK;
+    if ((rc = c->adler_parts.ensure((nblocks + 1) * sizeof(AdlerPart) + 16))) return rc;
+    AdlerPart* parts = (AdlerPart*)c->adler_parts.p;
+    uint32_t* d_res = d_out ? d_out : (uint32_t*)(parts + nblocks + 1);
+    if (nblocks) {
+        adler_partial_kernel<<<(uint32_t)nblocks, ADLER_THREADS, 0, st>>>((const uint8_t*)d_data, n, parts);
+        LAUNCHED();
+    }
+    adler_fold_kernel<<<1, 32, 0, st>>>(parts, nblocks, n, d_res);
+    LAUNCHED();
+    if (h_out) {
+        CK(cudaMemcpyAsync(h_out, d_res, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    return B200_OK;
+}
+
 int b200_corpus_generate_dev(void* d_out, uint64_t seed, uint64_t first_chunk, uint64_t n_chunks, void* stream_) {
     if (!d_out && n_chunks) return B200_E_ARG;
     if (!n_chunks) return B200_OK;
@@ -821,8 +844,9 @@ int b200_deflate_compress(const void* in, size_t n, int level, void** out, size_
     return B200_OK;
 }
 
+// adler_expect: if non-NULL, the 4-byte big-endian Adler-32 trailer the decoded bytes must match (strict zlib)
 static int inflate_host(const uint8_t* in, size_t n, void* out, size_t cap, void** out_alloc, size_t* out_n,
-                        size_t* full_n, unsigned flags) {
+                        size_t* full_n, unsigned flags, const uint8_t* adler_expect = nullptr) {
     b200_ctx* c;
     int rc = default_ctx(&c);
     if (rc) return rc;
@@ -838,6 +862,15 @@ static int inflate_host(const uint8_t* in, size_t n, void* out, size_t cap, void
         rc = b200_inflate_dev(c, c->d_in.p, n, c->d_out.p, dcap, nullptr, &written, &full, nullptr, flags, c->stream);
         if (!out_alloc || full <= dcap) break;
         dcap = full;                       // decoded size is now known exactly: one more pass
+    }
+    if (rc == B200_OK && adler_expect && full <= dcap) {
+        // the whole decoded stream sits in d_out: check it there
+        uint32_t got = 0;
+        const int rc2 = b200_adler32_dev(c, c->d_out.p, full, &got, nullptr, c->stream);
+        if (rc2) return rc2;
+        const uint32_t want = ((uint32_t)adler_expect[0] << 24) | ((uint32_t)adler_expect[1] << 16) |
+                              ((uint32_t)adler_expect[2] << 8) | adler_expect[3];
+        if (got != want) rc = B200_E_DATA;
     }
     if (out_alloc) {
         void* buf = malloc(written ? written : 1);
@@ -874,16 +907,38 @@ static size_t zlib_header_skip(const uint8_t* in, size_t n) {
     return skip < n ? skip : n;
 }
 
+// strict mode: CM must be 8 (deflate), the header check bits must hold, and there must be room for the trailer
+static int zlib_strict_check(const uint8_t* in, size_t n, size_t skip) {
+    if (n < skip + 4) return B200_E_OVERRUN;
+    if ((in[0] & 15) != 8 || (((uint32_t)in[0] << 8) | in[1]) % 31 != 0) return B200_E_DATA;
+    return B200_OK;
+}
+
 int b200_inflate_zlib(const void* in, size_t n, void* out, size_t cap, size_t* out_n, size_t* full_n, unsigned flags) {
     if (!in || n < 2) return B200_E_OVERRUN;
-    const size_t s = zlib_header_skip((const uint8_t*)in, n);
-    return b200_inflate((const uint8_t*)in + s, n - s, out, cap, out_n, full_n, flags);
+    if ((!out && cap)) return B200_E_ARG;
+    const uint8_t* p = (const uint8_t*)in;
+    const size_t s = zlib_header_skip(p, n);
+    if (flags & B200_F_STRICT) {
+        const int rc = zlib_strict_check(p, n, s);
+        if (rc) return rc;
+        return inflate_host(p + s, n - s - 4, out, cap, nullptr, out_n, full_n, flags, p + n - 4);
+    }
+    return b200_inflate(p + s, n - s, out, cap, out_n, full_n, flags);
 }
 
 int b200_inflate_zlib_alloc(const void* in, size_t n, void** out, size_t* out_n, unsigned flags) {
     if (!in || n < 2) { if (out) *out = nullptr; if (out_n) *out_n = 0; return B200_E_OVERRUN; }
-    const size_t s = zlib_header_skip((const uint8_t*)in, n);
-    return b200_inflate_alloc((const uint8_t*)in + s, n - s, out, out_n, flags);
+    if (!out || !out_n) return B200_E_ARG;
+    const uint8_t* p = (const uint8_t*)in;
+    const size_t s = zlib_header_skip(p, n);
+    if (flags & B200_F_STRICT) {
+        *out = nullptr; *out_n = 0;
+        const int rc = zlib_strict_check(p, n, s);
+        if (rc) return rc;
+        return inflate_host(p + s, n - s - 4, nullptr, 0, out, out_n, nullptr, flags, p + n - 4);
+    }
+    return b200_inflate_alloc(p + s, n - s, out, out_n, flags);
 }
 
 }  // extern "C"

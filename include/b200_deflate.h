@@ -53,7 +53,8 @@ extern "C" {
                               stream is 0.3-0.5 % smaller and inflates one warp per chunk instead of 16 threads */
 /* Flags for the inflater. */
 #define B200_F_STRICT 1u   /* reject what the reference silently accepts: distance beyond the output \
-                              produced so far, NLEN != ~LEN, BTYPE 3 (default: behave like the reference) */
+                              produced so far, NLEN != ~LEN, BTYPE 3, and for zlib streams a bad header or   \
+                              Adler-32 trailer (default: behave like the reference) */
 
 #define B200_CHUNK_BYTES 65536u
 
@@ -105,7 +106,9 @@ int b200_inflate_alloc(const void* in, size_t n, void** out, size_t* out_n, unsi
 
 /* Replaces inflate::decompressZlib (inflate.hpp:326,352): skips the 2-byte zlib header (and, unlike
  * the reference whose FDICT test at :329/:355 can never fire, the 4-byte DICTID when FDICT is set);
- * the Adler-32 trailer is ignored like the reference does. */
+ * the Adler-32 trailer is ignored like the reference does.  With B200_F_STRICT the header (CM = 8, check
+ * bits) and the trailer are verified -- the Adler-32 is computed on the GPU over the decoded bytes -- and a
+ * mismatch is B200_E_DATA (the output has been written all the same). */
 int b200_inflate_zlib(const void* in, size_t n, void* out, size_t cap, size_t* out_n, size_t* full_n,
                       unsigned flags);
 int b200_inflate_zlib_alloc(const void* in, size_t n, void** out, size_t* out_n, unsigned flags);
@@ -153,6 +156,10 @@ int b200_inflate_batch_dev(b200_ctx* ctx, const void* d_in, const uint64_t* d_in
                            const uint64_t* d_in_len, void* d_out, const uint64_t* d_out_off,
                            const uint64_t* d_out_cap, uint64_t* d_out_len, int32_t* d_status,
                            size_t n_streams, unsigned flags, void* stream);
+
+/* Adler-32 (RFC 1950) of d_data[0..n) computed on the device; the result goes to *h_out (synchronizes the
+ * stream) and / or *d_out (device, no sync).  What B200_F_STRICT uses to check a zlib stream's trailer. */
+int b200_adler32_dev(b200_ctx* ctx, const void* d_data, size_t n, uint32_t* h_out, uint32_t* d_out, void* stream);
 
 /* Synthetic corpus of BASELINE config 3/5 (definition: oracle/corpus_oracle.c):
  * chunks first_chunk .. first_chunk+n_chunks-1 of 64 KiB each, written to d_out. */

@@ -268,3 +268,43 @@ def test_chunk_groups(b200, monkeypatch, overlap):
         assert full == len(data) and w == min(cap, len(data))
         assert bytes(dst[:w].cpu().numpy()) == data[:w]
         assert int(dst[cap:].sum()) == 0                     # nothing written past the caller's capacity
+
+
+# ---- zlib framing: Adler-32 on the device, strict header / trailer checks ------------
+def test_adler32_device(b200):
+    import torch
+    ctx = b200.Context(0)
+    src = datagen.text_like(3 * 65536 + 999, seed=31) + datagen.random_bytes(2 * 65536 + 1, seed=32) + b"\xff" * 70000
+    buf = torch.frombuffer(bytearray(b"\x00" + src), dtype=torch.uint8).cuda()      # +1: an unaligned view below
+    for n in (0, 1, 15, 16, 17, 255, 65535, 65536, 65537, 200000, len(src)):
+        assert ctx.adler32_dev(buf.data_ptr() + 1, n) == zlib.adler32(src[:n]), n
+    aligned = torch.frombuffer(bytearray(src), dtype=torch.uint8).cuda()
+    for n in (16, 4096, 65536, 65536 * 2 + 48, len(src)):
+        assert ctx.adler32_dev(aligned.data_ptr(), n) == zlib.adler32(src[:n]), n
+
+
+def test_zlib_strict_checks_header_and_trailer(b200):
+    """The reference skips two bytes and ignores the Adler-32 trailer (inflate.hpp:326-361); so does this library
+    unless B200_F_STRICT is set, in which case header check bits and the trailer (computed on the GPU over the
+    decoded bytes) must hold."""
+    data = datagen.text_like(300000, seed=33)
+    z = zlib.compress(data, 6)
+    assert b200.decompress_zlib(z) == data
+    assert b200.decompress_zlib(z, flags=b200.F_STRICT) == data
+    assert b200.decompress_zlib(z, out_size=len(data), flags=b200.F_STRICT) == data
+    for name in ("zlib.dat", "weird.dat"):                     # the reference's own fixtures carry valid trailers
+        assert b200.decompress_zlib(gold(name), flags=b200.F_STRICT) == zlib.decompress(gold(name))
+    bad_trailer = z[:-1] + bytes([z[-1] ^ 1])
+    assert b200.decompress_zlib(bad_trailer) == data             # like the reference: not looked at
+    with pytest.raises(b200.B200Error) as e:
+        b200.decompress_zlib(bad_trailer, flags=b200.F_STRICT)
+    assert e.value.code == 2
+    bad_header = bytes([z[0], z[1] ^ 1]) + z[2:]
+    assert b200.decompress_zlib(bad_header) == data
+    with pytest.raises(b200.B200Error):
+        b200.decompress_zlib(bad_header, flags=b200.F_STRICT)
+    # a GPU-compressed raw stream wrapped as zlib by hand
+    raw = b200.compress(data, 2)
+    wrapped = b"\x78\x9c" + raw + zlib.adler32(data).to_bytes(4, "big")
+    assert b200.decompress_zlib(wrapped, flags=b200.F_STRICT) == data
+    assert zlib.decompress(wrapped) == data
