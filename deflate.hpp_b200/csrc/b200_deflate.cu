@@ -129,7 +129,8 @@ struct b200_ctx {
     bool inflate_overlap = false;        // B200_INFLATE_OVERLAP=1: copy pass of group g on a side stream while group g + 1 is in
                                          // pass A (measured: +1 % on a 4 GiB stream, so off by default)
     bool with_index = true;          // B200_NO_INDEX=1 / B200_F_NO_INDEX: no segment index in front of full chunks
-    int sg_occ = 12, copy_occ = 12;  // resident CTAs per SM the two inflate passes are compiled for (tuning knobs)
+    int sg_occ = 12, copy_occ = 8;   // resident CTAs per SM the two inflate passes are compiled for (tuning knobs; 8 x 4 warps at
+                                     // 64 registers: no spills in the lane-local copies, measured best of 6 / 8 / 12)
     unsigned copy_tune = 1;          // bit 0: prefetch the next step's sources into L2
     bool batch_two_pass = false;     // B200_BATCH_TP=1: batch inflate through the two-pass path, one THREAD per stream (measured
                                      // slower than one warp per stream on 1-64 KiB zlib streams: 15 vs 75 GB/s; kept for
@@ -228,6 +229,9 @@ static int inflate_two_pass(b200_ctx* c, const Units& U, uint64_t nunits, unsign
     if (c->copy_occ >= 12) {
         const uint64_t g12 = (uint64_t)(c->inf_grid / INF_MAX_CTAS_PER_SM) * 12;
         inflate_copy_kernel<Units, 12><<<(uint32_t)(want < g12 ? want : g12), INF_THREADS, 0, st_copy>>>(U, res, cnt + 2, c->copy_tune);
+    } else if (c->copy_occ >= 8) {
+        const uint64_t g8 = (uint64_t)(c->inf_grid / INF_MAX_CTAS_PER_SM) * 8;
+        inflate_copy_kernel<Units, 8><<<(uint32_t)(want < g8 ? want : g8), INF_THREADS, 0, st_copy>>>(U, res, cnt + 2, c->copy_tune);
     } else {
         inflate_copy_kernel<Units, 6><<<grid, INF_THREADS, 0, st_copy>>>(U, res, cnt + 2, c->copy_tune);
     }

@@ -933,10 +933,13 @@ __device__ __forceinline__ void tp_lane_pattern16(uint8_t* dp, const uint8_t* sp
 __device__ void tp_apply_ops(const uint64_t* __restrict__ ops, uint32_t nops, uint8_t* out, uint32_t cap,
                              const uint8_t* in, const ModLut* ML, uint32_t lane, unsigned tune) {
     const uint32_t FULL = 0xFFFFFFFFu;
+    // the op words of the next two steps are always in flight (a step can be shorter than a DRAM round trip)
     uint64_t o_next = lane < nops ? ops[lane] : 0ull;
+    uint64_t o_next2 = 32 + lane < nops ? ops[32 + lane] : 0ull;
     for (uint32_t b = 0; b < nops; b += 32) {
         const uint64_t o = o_next;
-        if (b + 32 < nops) o_next = b + 32 + lane < nops ? ops[b + 32 + lane] : 0ull;      // in flight during this step
+        o_next = o_next2;
+        if (b + 64 < nops) o_next2 = b + 64 + lane < nops ? ops[b + 64 + lane] : 0ull;
         if (tune & 1u) {
             // the step after this one will read around these addresses: start pulling the lines in now
             const uint32_t npos = (uint32_t)o_next, ndist = (uint32_t)(o_next >> 48);
