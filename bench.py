@@ -291,6 +291,9 @@ def main():
         side = torch.cuda.Stream(device=dev)
         sizes_dev = torch.zeros(rounds, dtype=torch.int64, device=dev)
         round_done = [torch.cuda.Event() for _ in range(rounds)]
+        inline_sizes = os.environ.get("B200_GATHER_INLINE_SIZES", "1") != "0"
+        allsz_dev = torch.zeros(rounds, world, dtype=torch.int64, device=dev)
+        allsz_host = torch.zeros(rounds, world, dtype=torch.int64).pin_memory()
     slice_bytes = slice_chunks * CHUNK
     slice_cap = d.deflate_bound(slice_bytes)
 
@@ -326,20 +329,30 @@ def main():
         if gmode == "fused":
             step_fused()
             return None
-        # enqueue every round's kernels first (no host sync: sizes stay on the device) ...
+        # enqueue every round's kernels first (no host sync: sizes stay on the device).  The 8-byte all_gather of
+        # a round's sizes is enqueued on the SAME stream, between two rounds: the persistent matcher owns every SM
+        # while it runs, and a collective posted on a side stream waits for an SM until that kernel ends
         main = torch.cuda.current_stream()
         for k in range(rounds):
             last = (k == rounds - 1) and (rank == world - 1)       # only the stream's very last chunk is final
             ctx.compress_dev(src.data_ptr() + k * slice_bytes, slice_bytes, args.level, dst.data_ptr() + k * slice_cap,
                              slice_cap, flags=0 if last else d.F_NOT_LAST, stream=st,
                              d_out_n=sizes_dev[k:k + 1].data_ptr(), sync=False)
+            if inline_sizes:
+                dist.all_gather_into_tensor(allsz_dev[k], sizes_dev[k:k + 1])
+                allsz_host[k].copy_(allsz_dev[k], non_blocking=True)
             round_done[k].record(main)
-        # ... and trail them on a side stream: per round one sizes all_gather + sends/receives at final offsets
+        # ... and trail them on a side stream: per round the sends/receives (peer copies) at final offsets
         with torch.cuda.stream(side):
             total = 0
             for k in range(rounds):
-                side.wait_event(round_done[k])
-                sz = pg.post_round(dst[k * slice_cap:(k + 1) * slice_cap], sizes_dev[k:k + 1])
+                if inline_sizes:
+                    round_done[k].synchronize()                    # host: this round's sizes are in pinned memory
+                    side.wait_event(round_done[k])
+                    sz = pg.post_round(dst[k * slice_cap:(k + 1) * slice_cap], None, sizes=[int(x) for x in allsz_host[k].tolist()])
+                else:
+                    side.wait_event(round_done[k])
+                    sz = pg.post_round(dst[k * slice_cap:(k + 1) * slice_cap], sizes_dev[k:k + 1])
                 total += sz[rank]
             step.joined = pg.finish()
         main.wait_stream(side)

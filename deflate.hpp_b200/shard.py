@@ -117,15 +117,17 @@ class PipelinedGather:
             n = recv_buf.numel()
             self.peer_dst = symm_handle.get_buffer(dst, (n,), torch.uint8)   # the destination's buffer, peer-mapped
 
-    def post_round(self, local: torch.Tensor, n):
+    def post_round(self, local: torch.Tensor, n, sizes=None):
         """local[:n]: this rank's compressed slice of the current round.  `n` may be an int or a
         one-element int64 tensor on the device (the compressor's d_out_n), in which case the only host
-        synchronisation of the round is reading back the gathered sizes."""
+        synchronisation of the round is reading back the gathered sizes.  `sizes`: every rank's byte count of
+        this round if the caller has exchanged them already (then no collective is issued here)."""
         dev = local.device
-        mine = n if torch.is_tensor(n) else torch.tensor([n], dtype=torch.int64, device=dev)
-        allsz = torch.zeros(self.world, dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(allsz, mine)
-        sizes = [int(x) for x in allsz.tolist()]
+        if sizes is None:
+            mine = n if torch.is_tensor(n) else torch.tensor([n], dtype=torch.int64, device=dev)
+            allsz = torch.zeros(self.world, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(allsz, mine)
+            sizes = [int(x) for x in allsz.tolist()]
         n = sizes[self.rank]
         offs = [self.offset + o for o in gather_plan(sizes)]
         if self.peer_dst is not None:

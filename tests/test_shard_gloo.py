@@ -82,3 +82,50 @@ def test_gather_bytes_gloo(world):
     # the rank-ordered concatenation is one valid raw deflate stream of the rank-ordered data
     o = zlib.decompressobj(-15)
     assert o.decompress(joined) == b"".join(f[0] for f in frags) and o.eof
+
+
+def _pipelined_worker(rank, world, port, q, pre_exchanged):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sh = _shard_mod()
+        rounds = 3
+        recv = torch.zeros(1 << 16, dtype=torch.uint8) if rank == 0 else None
+        pg = sh.PipelinedGather(recv, dst=0)
+        for k in range(rounds):
+            frag = bytes([97 + rank + 3 * k]) * (50 * (rank + 1) + 7 * k)
+            local = torch.frombuffer(bytearray(frag) + bytearray(16), dtype=torch.uint8)
+            if pre_exchanged:
+                # what bench.py does: the sizes travel through an all_gather the caller issued itself
+                mine = torch.tensor([len(frag)], dtype=torch.int64)
+                allsz = torch.zeros(world, dtype=torch.int64)
+                dist.all_gather_into_tensor(allsz, mine)
+                pg.post_round(local, None, sizes=[int(x) for x in allsz.tolist()])
+            else:
+                pg.post_round(local, len(frag))
+        total = pg.finish()
+        if rank == 0:
+            q.put(bytes(recv[:total].numpy()))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("pre_exchanged", [False, True])
+def test_pipelined_gather_gloo(pre_exchanged):
+    """Block-cyclic rounds: after every round each rank's slice lands at its final offset on rank 0, round by
+    round and rank by rank, with the sizes exchanged by the gatherer or by the caller."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000 + int(pre_exchanged)
+    procs = [ctx.Process(target=_pipelined_worker, args=(r, world, port, q, pre_exchanged)) for r in range(world)]
+    for p in procs:
+        p.start()
+    joined = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    expect = b"".join(bytes([97 + r + 3 * k]) * (50 * (r + 1) + 7 * k) for k in range(3) for r in range(world))
+    assert joined == expect
