@@ -500,6 +500,28 @@ def main():
                "ms_per_step": et * 1e3, "steps": esteps,
                "api": "b200_deflate_compress_into(host in, host out) -- pinned host buffers, per rank"}
 
+    # inflate through the host-buffer C-ABI call as well (not pipelined: H2D of the stream, kernels, D2H of the output)
+    if dec is not None and not args.no_e2e:
+        L = d.lib()
+        h_comp = torch.empty(cn, dtype=torch.uint8).pin_memory()
+        h_comp.copy_(dst[:cn])
+        h_back = torch.empty(n, dtype=torch.uint8).pin_memory()
+        got, full_n = ctypes.c_size_t(), ctypes.c_size_t()
+        times = []
+        for i in range(3):
+            t0 = time.perf_counter()
+            rc = L.b200_inflate(h_comp.data_ptr(), cn, h_back.data_ptr(), n, ctypes.byref(got), ctypes.byref(full_n), 0)
+            t1 = time.perf_counter()
+            if rc:
+                raise d.B200Error(rc, "b200_inflate")
+            if i:
+                times.append(t1 - t0)
+        et = sum(times) / len(times)
+        dec["e2e"] = {"value": n / et / 1e9, "unit": "GB/s (output bytes)", "h2d_bytes_per_step": int(cn), "d2h_bytes_per_step": int(n),
+                      "ms_per_step": et * 1e3, "bit_exact": bool(got.value == n and torch.equal(h_back, src.cpu())),
+                      "api": "b200_inflate(host in, host out) -- pinned host buffers"}
+        del h_comp, h_back
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
