@@ -145,6 +145,8 @@ struct b200_ctx {
     std::vector<cudaEvent_t> events;
     uint64_t* mailbox = nullptr;     // pinned: per-slice end offsets
     size_t mailbox_cap = 0;
+    size_t host_inflate_slice = (size_t)256 << 20;  // host-buffer inflate: bytes of input per pipeline slice (0 = off; measured best of
+                                                    // 64..384 MiB: smaller groups of chunks run as partial waves); B200_HOST_INFLATE_SLICE
     uint32_t host_slice_chunks = 1024;   // 64 MiB: measured best (smaller slices starve the persistent matcher)
     std::mutex mu;
     Prof prof;
@@ -334,6 +336,7 @@ int b200_ctx_create(int device, b200_ctx** ctx) {
     if (const char* e = getenv("B200_BATCH_TP")) c->batch_two_pass = atoi(e) != 0;
     if (const char* e = getenv("B200_INFLATE_WARP")) c->inflate_warp_path = atoi(e) != 0;
     if (const char* e = getenv("B200_BATCH_CHUNKS")) { int v = atoi(e); if (v > 0) c->batch_chunks = (uint32_t)v; }
+    if (const char* e = getenv("B200_HOST_INFLATE_SLICE")) { long long v = atoll(e); if (v >= 0) c->host_inflate_slice = (size_t)v; }
     if (const char* e = getenv("B200_HOST_SLICE_CHUNKS")) { int v = atoi(e); if (v > 0) c->host_slice_chunks = (uint32_t)v; }
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking) != cudaSuccess ||
@@ -623,7 +626,7 @@ int b200_inflate_dev(b200_ctx* c, const void* d_in, size_t n, void* d_out, size_
         const uint32_t g = (uint32_t)((nwarps * 32 + 255) / 256);
         PROF_BEGIN(c, K_FIND_SYNC, st);
         if ((rc = c->sync_cache.ensure(nwarps * SYNC_CACHE * 4))) return rc;
-        find_sync_kernel<false><<<g, 256, 0, st>>>(in, n, (uint32_t*)c->counts.p, (uint32_t*)c->sync_cache.p, nullptr, nullptr, 0);
+        find_sync_kernel<false><<<g, 256, 0, st>>>(in, n, (uint32_t*)c->counts.p, (uint32_t*)c->sync_cache.p, nullptr, nullptr, 0, 0);
         LAUNCHED();
         PROF_END(c, st);
         PROF_BEGIN(c, K_SCAN, st);
@@ -640,7 +643,7 @@ int b200_inflate_dev(b200_ctx* c, const void* d_in, size_t n, void* d_out, size_
             if (nmark) {
                 PROF_BEGIN(c, K_FIND_SYNC, st);
                 find_sync_kernel<true><<<g, 256, 0, st>>>(in, n, (uint32_t*)c->counts.p, (uint32_t*)c->sync_cache.p,
-                                                          (const uint64_t*)c->woffs.p, cand + 1, nmark);
+                                                          (const uint64_t*)c->woffs.p, cand + 1, nmark, 0);
                 LAUNCHED();
                 PROF_END(c, st);
             }
@@ -667,7 +670,7 @@ int b200_inflate_dev(b200_ctx* c, const void* d_in, size_t n, void* d_out, size_
                 CK(cudaMemcpyAsync(cand + ncand, &n64, 8, cudaMemcpyHostToDevice, st));      // sentinel: the last chunk ends at n
                 if ((rc = inflate_chunks_two_pass(c, in, n, cand, ncand, (uint8_t*)d_out, cap, flags, st))) return rc;
                 PROF_BEGIN(c, K_VALIDATE, st);
-                validate_units_kernel<<<(uint32_t)((ncand + 255) / 256), 256, 0, st>>>(cand, ncand, (uint64_t)n, (const TpResult*)c->tpres.p, d_result);
+                validate_units_kernel<<<(uint32_t)((ncand + 255) / 256), 256, 0, st>>>(cand, ncand, (uint64_t)n, (const TpResult*)c->tpres.p, d_result, 1);
                 LAUNCHED();
                 PROF_END(c, st);
             }
@@ -848,6 +851,105 @@ int b200_deflate_compress(const void* in, size_t n, int level, void** out, size_
     return B200_OK;
 }
 
+// Host buffers, long streams of this library's own format: the input travels in slices; as soon as a slice has
+// landed, the chunks that are complete so far are found (find_sync from the last known chunk start), decoded and
+// validated as a group, and their output starts its way back on a third stream -- H2D of slice k + 1, kernels of
+// slice k and D2H of slice k - 1 overlap (PCIe is full duplex), instead of H2D, then kernels, then D2H.
+// *handled = false: the stream did not validate (foreign, damaged, ...): nothing is reported, the caller takes the
+// plain path, which also produces the proper error code.  The decoded bytes stay in c->d_out.
+static int inflate_host_pipelined(b200_ctx* c, const uint8_t* in, size_t n, uint8_t* out, size_t cap, size_t* out_n,
+                                  size_t* full_n, unsigned flags, bool* handled) {
+    *handled = false;
+    const size_t S = c->host_inflate_slice & ~(size_t)15;
+    if (!S || n < 2 * S || !cap || c->inflate_warp_path) return B200_OK;
+    int rc;
+    const size_t nsl = (n + S - 1) / S;
+    if ((rc = c->d_in.ensure(n + 64))) return rc;
+    if ((rc = c->d_out.ensure(cap + 64))) return rc;
+    if ((rc = c->result.ensure(64))) return rc;
+    while (c->events.size() < nsl) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->events.push_back(e);
+    }
+    uint8_t* d_in = (uint8_t*)c->d_in.p;
+    uint8_t* d_out = (uint8_t*)c->d_out.p;
+    unsigned long long* d_result = (unsigned long long*)c->result.p;
+    cudaStream_t st = c->stream;
+    for (size_t k = 0; k < nsl; k++) {
+        const size_t off = k * S, len = off + S < n ? S : n - off;
+        CK(cudaMemcpyAsync(d_in + off, in + off, len, cudaMemcpyHostToDevice, c->s_in));
+        CK(cudaEventRecord(c->events[k], c->s_in));
+    }
+    uint64_t start = 0, chunk0 = 0, total = 0;
+    bool ok = true;
+    for (size_t k = 0; k < nsl && ok; k++) {
+        CK(cudaStreamWaitEvent(st, c->events[k], 0));
+        const bool last = k + 1 == nsl;
+        const uint64_t avail = last ? n : (k + 1) * S;
+        const uint64_t base = start & ~15ull, rel0 = start - base, region = avail - base;
+        const uint8_t* rin = d_in + base;
+        const uint64_t nwarps = (region + SYNC_REGION - 1) / SYNC_REGION;
+        const uint64_t cand_cap = region / 64 + 1024;
+        if ((rc = c->counts.ensure(nwarps * 4))) return rc;
+        if ((rc = c->woffs.ensure((nwarps + 1) * 8))) return rc;
+        if ((rc = c->sync_cache.ensure(nwarps * SYNC_CACHE * 4))) return rc;
+        if ((rc = c->cand.ensure((cand_cap + 2) * 8))) return rc;
+        uint64_t* cand = (uint64_t*)c->cand.p;
+        const uint32_t g = (uint32_t)((nwarps * 32 + 255) / 256);
+        PROF_BEGIN(c, K_FIND_SYNC, st);
+        find_sync_kernel<false><<<g, 256, 0, st>>>(rin, region, (uint32_t*)c->counts.p, (uint32_t*)c->sync_cache.p, nullptr, nullptr, 0, rel0);
+        LAUNCHED();
+        PROF_END(c, st);
+        scan_sizes_kernel<<<1, SCAN_THREADS, 0, st>>>((const uint32_t*)c->counts.p, (uint32_t)nwarps, nullptr, (uint64_t*)c->woffs.p,
+                                                     (uint64_t*)d_result + 2);
+        LAUNCHED();
+        uint64_t nmark = 0;
+        CK(cudaMemcpyAsync(&nmark, d_result + 2, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (nmark + 2 > cand_cap) { ok = false; break; }
+        const uint64_t ncand = nmark + 1;
+        const uint64_t units = last ? ncand : ncand - 1;      // the last candidate of a slice starts a chunk that is still arriving
+        if (units == 0) continue;
+        CK(cudaMemcpyAsync(cand, &rel0, 8, cudaMemcpyHostToDevice, st));
+        if (nmark) {
+            PROF_BEGIN(c, K_FIND_SYNC, st);
+            find_sync_kernel<true><<<g, 256, 0, st>>>(rin, region, (uint32_t*)c->counts.p, (uint32_t*)c->sync_cache.p,
+                                                      (const uint64_t*)c->woffs.p, cand + 1, nmark, rel0);
+            LAUNCHED();
+            PROF_END(c, st);
+        }
+        if (last) CK(cudaMemcpyAsync(cand + ncand, &region, 8, cudaMemcpyHostToDevice, st));     // sentinel: the last chunk ends at n
+        const unsigned long long init[2] = {1ull, 0ull};
+        CK(cudaMemcpyAsync(d_result, init, 16, cudaMemcpyHostToDevice, st));
+        const uint64_t o0 = chunk0 * CHUNK;
+        if ((rc = inflate_chunks_two_pass(c, rin, region, cand, units, d_out + o0, cap > o0 ? cap - o0 : 0, flags, st))) return rc;
+        PROF_BEGIN(c, K_VALIDATE, st);
+        validate_units_kernel<<<(uint32_t)((units + 255) / 256), 256, 0, st>>>(cand, units, region, (const TpResult*)c->tpres.p, d_result,
+                                                                              last ? 1 : 0);
+        LAUNCHED();
+        PROF_END(c, st);
+        unsigned long long verdict[2] = {0, 0};
+        uint64_t next_rel = 0;
+        CK(cudaMemcpyAsync(verdict, d_result, 16, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&next_rel, cand + units, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (verdict[0] != 1) { ok = false; break; }
+        const uint64_t lo = o0 < cap ? o0 : cap, hi = o0 + verdict[1] < cap ? o0 + verdict[1] : cap;
+        if (hi > lo) CK(cudaMemcpyAsync(out + lo, d_out + lo, hi - lo, cudaMemcpyDeviceToHost, c->s_out));
+        total = o0 + verdict[1];
+        chunk0 += units;
+        start = base + next_rel;
+    }
+    CK(cudaStreamSynchronize(c->s_in));
+    CK(cudaStreamSynchronize(c->s_out));
+    if (!ok) return B200_OK;
+    *handled = true;
+    if (out_n) *out_n = (size_t)(total < cap ? total : cap);
+    if (full_n) *full_n = (size_t)total;
+    return B200_OK;
+}
+
 // adler_expect: if non-NULL, the 4-byte big-endian Adler-32 trailer the decoded bytes must match (strict zlib)
 static int inflate_host(const uint8_t* in, size_t n, void* out, size_t cap, void** out_alloc, size_t* out_n,
                         size_t* full_n, unsigned flags, const uint8_t* adler_expect = nullptr) {
@@ -856,17 +958,23 @@ static int inflate_host(const uint8_t* in, size_t n, void* out, size_t cap, void
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(c->mu);
     CK(cudaSetDevice(c->device));
+    size_t written = 0, full = 0;
+    size_t dcap = cap;
+    bool piped = false;
+    if (!out_alloc) {
+        if ((rc = inflate_host_pipelined(c, in, n, (uint8_t*)out, cap, &written, &full, flags, &piped))) return rc;
+    }
+    if (!piped) {
     if ((rc = c->d_in.ensure(n + 64))) return rc;
     if (n) CK(cudaMemcpyAsync(c->d_in.p, in, n, cudaMemcpyHostToDevice, c->stream));
-    size_t dcap = cap;
     if (out_alloc) dcap = n * 4 + 65536 > (size_t)1 << 20 ? n * 4 + 65536 : (size_t)1 << 20;   // first guess
-    size_t written = 0, full = 0;
     for (int attempt = 0; attempt < 3; attempt++) {
         if ((rc = c->d_out.ensure(dcap + 64))) return rc;
         rc = b200_inflate_dev(c, c->d_in.p, n, c->d_out.p, dcap, nullptr, &written, &full, nullptr, flags, c->stream);
         if (!out_alloc || full <= dcap) break;
         dcap = full;                       // decoded size is now known exactly: one more pass
     }
+    }   // !piped
     if (rc == B200_OK && adler_expect && full <= dcap) {
         // the whole decoded stream sits in d_out: check it there
         uint32_t got = 0;
@@ -882,7 +990,7 @@ static int inflate_host(const uint8_t* in, size_t n, void* out, size_t cap, void
         if (written && cudaMemcpyAsync(buf, c->d_out.p, written, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) { free(buf); return B200_E_CUDA; }
         if (cudaStreamSynchronize(c->stream) != cudaSuccess) { free(buf); return B200_E_CUDA; }
         *out_alloc = buf;
-    } else if (written) {
+    } else if (written && !piped) {
         CK(cudaMemcpyAsync(out, c->d_out.p, written, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
     }

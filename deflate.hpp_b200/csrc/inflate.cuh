@@ -547,7 +547,8 @@ constexpr uint32_t SYNC_CACHE = 4;          // candidates per region the count p
 template <bool WRITE>
 __global__ void __launch_bounds__(256)
 find_sync_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t* __restrict__ counts, uint32_t* __restrict__ cache,
-                 const uint64_t* __restrict__ offsets, uint64_t* __restrict__ cand, uint64_t cand_cap) {
+                 const uint64_t* __restrict__ offsets, uint64_t* __restrict__ cand, uint64_t cand_cap, uint64_t min_cand) {
+    // min_cand: candidates at or below this offset are not reported (a scan that restarts at a known chunk start)
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t lo = w * SYNC_REGION;
@@ -592,7 +593,8 @@ find_sync_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t* __restric
             const uint32_t x0 = __funnelshift_r(wd[j >> 2], wd[(j >> 2) + 1], sh);
             const uint32_t x1 = __funnelshift_r(wd[(j >> 2) + 1], wd[(j >> 2) + 2], sh);
             const uint32_t x2 = __funnelshift_r(wd[(j >> 2) + 2], wd[(j >> 2) + 3], sh);
-            if (x0 == 0xFFFF0000u && x1 == 0xFF000000u && (x2 & 0xFFu) == 0xFFu && p + j + SYNC_PATTERN_BYTES < n && p + j < hi)
+            if (x0 == 0xFFFF0000u && x1 == 0xFF000000u && (x2 & 0xFFu) == 0xFFu && p + j + SYNC_PATTERN_BYTES < n && p + j < hi &&
+                p + j + SYNC_PATTERN_BYTES > min_cand)
                 hits |= 1u << j;
         }
         if (__ballot_sync(FULL, hits != 0)) {

@@ -1023,15 +1023,22 @@ inflate_copy_kernel(Units U, const TpResult* __restrict__ res, unsigned long lon
 }
 
 // chunk mode verdict (same rule as validate_chunks_kernel): result[0] = 1 if the optimistic layout is right,
-// result[1] = total decoded bytes
+// result[1] = total decoded bytes.  last_is_final = 0: these chunks are a prefix of a longer stream, every one of
+// them must be a full chunk that ends at the next candidate (cand[ncand] is valid).
 __global__ void validate_units_kernel(const uint64_t* __restrict__ cand, uint64_t ncand, uint64_t n,
-                                      const TpResult* __restrict__ res, unsigned long long* __restrict__ result) {
+                                      const TpResult* __restrict__ res, unsigned long long* __restrict__ result,
+                                      int last_is_final) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ncand) return;
     const TpResult r = res[i];
     bool ok = r.status == ST_OK;
-    if (i + 1 < ncand) ok = ok && cand[i] + r.in_end == cand[i + 1] && r.out_len == CHUNK && (r.end_flags & END_SYNC);
-    else { ok = ok && (r.end_flags & END_FINAL); if (ok) result[1] = i * CHUNK + r.out_len; }
+    if (i + 1 < ncand || !last_is_final) {
+        ok = ok && cand[i] + r.in_end == cand[i + 1] && r.out_len == CHUNK && (r.end_flags & END_SYNC);
+        if (ok && i + 1 == ncand) result[1] = ncand * CHUNK;
+    } else {
+        ok = ok && (r.end_flags & END_FINAL);
+        if (ok) result[1] = i * CHUNK + r.out_len;
+    }
     if (!ok) atomicAnd(&result[0], 0ull);
 }
 

@@ -308,3 +308,41 @@ def test_zlib_strict_checks_header_and_trailer(b200):
     wrapped = b"\x78\x9c" + raw + zlib.adler32(data).to_bytes(4, "big")
     assert b200.decompress_zlib(wrapped, flags=b200.F_STRICT) == data
     assert zlib.decompress(wrapped) == data
+
+
+def test_host_inflate_pipelined():
+    """The host-buffer inflate call streams long inputs in slices (H2D of slice k + 1, kernels of slice k, D2H of
+    slice k - 1 overlap).  The default slice is 256 MiB; run a child process with 1 MiB slices so that a 20 MB
+    input takes the pipelined path, including truncation and streams it has to hand back to the plain path."""
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    script = r"""
+import sys, zlib
+sys.path.insert(0, %r)
+sys.path.insert(0, %r)
+import deflate_hpp_b200 as b200
+import datagen
+data = datagen.text_like(7 * 1024 * 1024, seed=41) + datagen.random_bytes(3 * 1024 * 1024 + 17, seed=42) + datagen.image_like(9 * 1024 * 1024 + 5)
+for level in (2, 0):
+    c = b200.compress(data, level)
+    assert len(c) > 4 * 1024 * 1024 or level == 2
+    assert b200.decompress(c, out_size=len(data)) == data
+    assert b200.decompress(c, out_size=len(data) + 12345) == data
+    assert b200.decompress(c, out_size=5 * 1024 * 1024 + 3) == data[:5 * 1024 * 1024 + 3]
+    assert b200.decompress(c) == data
+z = zlib.compressobj(1, zlib.DEFLATED, -15)
+foreign = z.compress(data) + z.flush()
+assert b200.decompress(foreign, out_size=len(data)) == data          # no chunk structure: plain path
+cut = b200.compress(data, 2)[:6 * 1024 * 1024]
+try:
+    b200.decompress(cut, out_size=len(data))
+    raise SystemExit("truncated stream did not raise")
+except b200.B200Error as e:
+    assert e.code in (1, 2)
+print("ok", b200.launch_count())
+""" % (ROOT, os.path.join(ROOT, "tests"))
+    env = dict(os.environ, B200_HOST_INFLATE_SLICE=str(1 << 20))
+    r = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout[-2000:] + r.stderr[-4000:]
