@@ -1,28 +1,34 @@
-// inflate_tp.cuh -- K6 (fast path): two-pass INFLATE for many independent units (chunks of one stream,
+// inflate_tp.cuh -- K6 (fast path): two-pass INFLATE for many independent units (the chunks of one stream,
 // or the streams of a batch).
 //
 // The one-warp-per-unit decoder in inflate.cuh runs the bit-serial symbol decode redundantly on all 32
-// lanes: ncu shows it issue-bound at ~50 warp-instructions per symbol (profiles/r01b).  Here the two
+// lanes: ncu shows it issue-bound at ~50 warp-instructions per symbol (profiles/, r01b rows).  Here the two
 // halves of INFLATE are separated by what they parallelise over:
 //
-//   pass A  inflate_symbols_kernel   ONE THREAD per unit.  Huffman decode only (reference:
-//           decompressHuffmanBlock / decodeTree, include/inflate.hpp:136-275).  Each thread owns a 9-bit
-//           literal/length and an 8-bit distance lookup table in shared memory (u16 entries, interleaved
-//           [index][thread] so that a warp's 32 private lookups hit 32 different words), reads its
-//           stream through two prefetched 32-bit words, writes literals straight to the output as merged
-//           aligned 32-bit words, and appends every back-reference (and stored block) to the unit's op
-//           list in HBM as one u64 {pos, len, dist}.  A warp instruction decodes up to 32 symbols of 32
-//           different units instead of one symbol 32 times.
-//   pass B  inflate_copy_kernel      ONE WARP per unit.  Applies the unit's ops in order (reference: the
+//   pass A  Huffman decode only (reference: decompressHuffmanBlock / decodeTree, include/inflate.hpp:136-275),
+//           ONE THREAD per piece of the stream.  A thread reads its input through a 4-word cp.async ring in
+//           shared memory, looks symbols up in u16 direct tables in shared memory, writes literals straight to
+//           the output as merged aligned 32-bit words, and appends every back-reference (and stored block) to
+//           an op list in HBM as one u64 {pos, len, dist}.  A warp instruction decodes up to 32 symbols of 32
+//           different pieces instead of one symbol 32 times.
+//             inflate_classify_kernel + inflate_segments_kernel  (chunks of one stream)  the piece is a 4 KiB
+//               SEGMENT of a chunk: this library's compressor writes the bit length of every segment into the
+//               stream (segment index, common.cuh), so 16 threads share one chunk and its tables.  Chunks
+//               without index go to the one-warp decoder (or are finished at once if they are stored blocks).
+//             inflate_symbols_kernel  (generic: the piece is a whole unit, each thread owns interleaved private
+//               tables)  batch inflate with B200_BATCH_TP=1; on 1-64 KiB zlib streams one warp per stream is
+//               faster, so this is opt-in.
+//   pass B  inflate_copy_kernel, ONE WARP per unit.  Applies the unit's ops in order (reference: the
 //           back-reference loop inflate.hpp:262-272 and the stored-block copy :294-303).  32 ops are loaded
-//           per step; short ops whose source lies entirely below the step's first destination are
-//           independent of one another and are copied one per lane, the rest go through the cooperative
-//           (all lanes, period-aware) copy in order.
+//           per step; short ops whose source is final before the step starts are independent of one another
+//           and are copied one per lane, the rest go through the cooperative (all lanes, period-aware) copy
+//           in order.
 //
 // Pass A may leave garbage in bytes that pass B owns (it stores whole words); pass B runs after pass A
 // (stream order) and only ever reads bytes below its current position, so every byte a copy reads is final.
-// Units the fast path cannot take (op list full, > 4 GiB) are marked ST_FALLBACK and decoded by the
-// one-warp decoder (inflate_fallback kernels in inflate.cuh); results are identical either way.
+// Units the fast path cannot take (no index, index that does not chain, op list full, > 4 GiB) are marked
+// ST_FALLBACK and decoded by inflate_fallback_kernel = the one-warp decoder of inflate.cuh; results are
+// identical either way (every GPU test stream goes through both).
 #pragma once
 #include "inflate.cuh"
 
