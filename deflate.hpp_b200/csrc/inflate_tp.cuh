@@ -499,7 +499,8 @@ __device__ __forceinline__ void tp_state_init(TpState& s, const TpCtx& c, const 
     s.br.skip = (uint32_t)(reinterpret_cast<uintptr_t>(u.in) & 3);
     s.br.wp = reinterpret_cast<const uint32_t*>(u.in - s.br.skip);
     s.br.nw = s.state == TS_DONE ? 0 : (uint32_t)((s.br.skip + u.in_len + 3) >> 2);
-    tb_seek(s.br, 0);
+    if (s.state != TS_DONE) tb_seek(s.br, 0);                 // a thread without a unit never touches memory
+    else { s.br.wi = 0; s.br.w0 = 0; s.br.bb = 0; s.br.bc = 0; }
     s.o.al = (uint32_t)(reinterpret_cast<uintptr_t>(u.out) & 3);
     s.o.ob = u.out - s.o.al;
     s.o.v = s.o.vlo = s.o.al;
@@ -509,6 +510,7 @@ __device__ __forceinline__ void tp_state_init(TpState& s, const TpCtx& c, const 
     s.nops = 0; s.empty_run = 0; s.end_flags = 0; s.bfinal = 0;
 }
 __device__ __forceinline__ void tp_finish(const TpCtx& c, TpState& s, TpResult& res) {
+    asm volatile("cp.async.wait_all;" ::: "memory");        // nothing of this thread's ring traffic outlives its unit
     to_flush(s.o);
     if (s.st != ST_FALLBACK && tb_bitpos(s.br) > c.in_bits) s.st = ST_OVERRUN;
     res.in_end = (tb_bitpos(s.br) + 7) >> 3;
@@ -742,6 +744,7 @@ inflate_segments_kernel(ChunkUnits U, const uint32_t* __restrict__ blist, const 
                 // separator, or nothing after a final block; a second Huffman block -> one-warp decoder)
                 while (s.state == TS_BLOCK) s = tp_step_block(c, s);
                 if (seg + 1 < SC->nseg) {
+                    asm volatile("cp.async.wait_all;" ::: "memory");
                     to_flush(s.o);
                     SC->seg_end[seg] = (uint32_t)tb_bitpos(s.br);
                     SC->seg_ok[seg] = s.st == ST_OK && (s.end_flags & END_SEG);
