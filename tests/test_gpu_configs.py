@@ -163,3 +163,24 @@ def test_config3_full_size(b200, monkeypatch):
     back.zero_()
     w, full = ctx.inflate_dev(plain.data_ptr(), pn, back.data_ptr(), n)
     assert w == full == n and torch.equal(back, src)
+
+
+def test_beyond_4gib_device_resident(b200):
+    """Offsets are 64-bit end to end: 4.5 GiB of the corpus (73 728 chunks, three inflate groups) compressed and
+    inflated on the device, inflate(compress(x)) == x.  (BASELINE config 5 puts 16 GiB on one GPU at N = 1.)"""
+    import torch
+    nchunks = 73728
+    n = nchunks * b200.CHUNK
+    assert n > 1 << 32
+    ctx = b200.Context(0)
+    src = torch.empty(n, dtype=torch.uint8, device="cuda")
+    ctx.corpus_generate_dev(src.data_ptr(), 20261018, 0, nchunks)
+    cap = b200.deflate_bound(n)
+    dst = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    cn = ctx.compress_dev(src.data_ptr(), n, 2, dst.data_ptr(), cap)
+    assert cn < 0.65 * n
+    back = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    w, full = ctx.inflate_dev(dst.data_ptr(), cn, back.data_ptr(), n)
+    assert w == full == n
+    for lo in range(0, n, 1 << 30):                        # compare in 1 GiB pieces (bounded temporaries)
+        assert torch.equal(back[lo:lo + (1 << 30)], src[lo:lo + (1 << 30)]), lo
