@@ -3,9 +3,12 @@
 // Pipeline (compress):  K1 lz77_kernel -> K2 huffman_kernel -> K3 scan_sizes_kernel -> K4 encode_kernel,
 // per batch of chunks, all on one stream; chunk sizes are exact after K2 so K4 writes every chunk at
 // its final byte offset (no compaction pass).
-// Pipeline (inflate, single stream): find_sync (count, scan, write) -> inflate_chunks (one warp per
-// candidate chunk, optimistic layout) -> validate; a stream that does not have this library's chunk
-// structure falls back to one warp decoding it sequentially (inflate_batch_kernel with one stream).
+// Pipeline (inflate, single stream): find_sync (count, scan, write) -> per group of <= 32768 candidate chunks:
+// classify -> segments (pass A: one thread per 4 KiB segment of every indexed chunk) -> fallback (one warp per
+// chunk pass A could not take) -> copy (pass B: one warp per chunk applies the op lists) -> validate (optimistic
+// layout chunk i -> out + i * 64 KiB); a stream that does not have this library's chunk structure falls back to
+// one warp decoding it sequentially (inflate_batch_kernel with one stream).  Host buffers: slices of the input
+// are decoded as they arrive while earlier output is on its way back (inflate_host_pipelined).
 // There is no CPU fallback anywhere in this file.
 #include "../../include/b200_deflate.h"
 

@@ -141,10 +141,12 @@ int b200_deflate_compress_stage2_dev(b200_ctx* ctx, const void* d_in, size_t n, 
                                      const uint64_t* d_base, void* stream);
 
 /* Inflate one raw stream.  Streams produced by this library (or any stream whose blocks are joined
- * by byte-aligning empty stored blocks and whose chunks do not reference earlier chunks) are decoded
- * chunk-parallel, one warp per chunk; anything else is decoded by a single warp.  Writes at most cap
- * bytes; *h_out_n / *d_out_n = min(decoded, cap); status (B200_*) is the return value when h_out_n is
- * given, else it is left in d_status (int32, may be NULL). */
+ * by byte-aligning pairs of empty stored blocks and whose chunks do not reference earlier chunks) are
+ * decoded chunk-parallel: chunks that carry the segment index by one thread per 4 KiB segment plus a copy
+ * pass (csrc/inflate_tp.cuh), chunks without it by one warp each; anything else is decoded by a single
+ * warp.  Scratch: 128 KiB per chunk, at most 2 x 32768 chunks.  Writes at most cap bytes; *h_out_n /
+ * *d_out_n = min(decoded, cap); status (B200_*) is the return value when h_out_n is given, else it is
+ * left in d_status (int32, may be NULL).  Synchronizes `stream` internally. */
 int b200_inflate_dev(b200_ctx* ctx, const void* d_in, size_t n, void* d_out, size_t cap,
                      uint64_t* d_out_n, size_t* h_out_n, size_t* h_full_n, int32_t* d_status,
                      unsigned flags, void* stream);
