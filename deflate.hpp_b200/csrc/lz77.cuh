@@ -110,7 +110,9 @@ constexpr uint32_t LZF_THREADS = NSEG * 32;          // 512
 constexpr uint32_t LZF_HASH_BITS = 13;
 constexpr uint32_t LZF_PER_THREAD = 2;
 constexpr uint32_t LZF_TILE = LZF_PER_THREAD * LZF_THREADS;     // 1024 positions between two table updates
-constexpr size_t LZF_SMEM_BYTES = CHUNK + LZ_DATA_PAD + (4u << LZF_HASH_BITS) + NSEG * HIST_WORDS * 4 + 32;
+constexpr uint32_t LZF_RING_BLOCKS = 4;                 // per-warp ring of candidate blocks (32 x u16 each) in shared memory
+constexpr size_t LZF_SMEM_BYTES = CHUNK + LZ_DATA_PAD + (4u << LZF_HASH_BITS) + NSEG * HIST_WORDS * 4 + 32 +
+                                  NSEG * LZF_RING_BLOCKS * 64;
 
 __device__ __forceinline__ uint32_t lzf_hash(uint32_t w4) { return (w4 * 0x9E3779B1u) >> (32 - LZF_HASH_BITS); }
 
@@ -131,6 +133,7 @@ lz77_fast_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t nchunks, u
     uint32_t* s_hist = s_tab + (1u << LZF_HASH_BITS);
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_hist + NSEG * HIST_WORDS);
     uint32_t* s_next = reinterpret_cast<uint32_t*>(s_bar + 1);
+    uint16_t* s_ring = reinterpret_cast<uint16_t*>(smem + CHUNK + LZ_DATA_PAD + (4u << LZF_HASH_BITS) + NSEG * HIST_WORDS * 4 + 32);
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t FULL = 0xFFFFFFFFu;
@@ -218,25 +221,32 @@ lz77_fast_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t nchunks, u
         uint32_t nt = 0;
         if (seg_lo < clen) {
             uint32_t pos = seg_lo;
-            // candidates travel through two register blocks of 32 (aligned): the block after the one in
-            // use is already in flight, so the L2 latency of cand[] overlaps a whole parse step
-            // (L1 is bypassed: the slot is rewritten for every chunk this CTA processes)
-            uint32_t blk_base = pos & ~31u;
-            uint32_t blk0 = __ldcg(&cand[min(blk_base + lane, CHUNK - 1)]);
-            uint32_t blk1 = __ldcg(&cand[min(blk_base + 32 + lane, CHUNK - 1)]);
+            // candidates travel through a per-warp ring of four 32-entry blocks in shared memory, filled by
+            // cp.async (no destination register: a register queue has to be shifted one step after the load
+            // was issued and stalls on it -- 10 % of this kernel's stall samples).  Blocks b0 .. b0+3 of the
+            // current position are always requested; b0 and b0+1 are waited for.  (L1 is bypassed: the slot
+            // is rewritten for every chunk this CTA processes.)
+            uint16_t* ring = s_ring + warp * (LZF_RING_BLOCKS * 32);
+            const uint32_t ring_sa = (uint32_t)__cvta_generic_to_shared(ring);
+            uint32_t req_next = pos >> 5;                  // first block not requested yet
             while (pos < seg_hi) {
-                if (pos >= blk_base + 32) {
-                    if (pos < blk_base + 64) { blk_base += 32; blk0 = blk1; }
-                    else { blk_base = pos & ~31u; blk0 = __ldcg(&cand[min(blk_base + lane, CHUNK - 1)]); }
-                    blk1 = __ldcg(&cand[min(blk_base + 32 + lane, CHUNK - 1)]);
+                const uint32_t b0 = pos >> 5;
+                if (req_next < b0) req_next = b0;          // a long match jumped over blocks nobody needs
+                #pragma unroll 1
+                while (req_next < b0 + LZF_RING_BLOCKS) {
+                    if (lane < 4 && req_next < CHUNK / 32)         // 64 bytes per block: four 16-byte copies, L2 only (.cg)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::
+                                     "r"(ring_sa + (req_next % LZF_RING_BLOCKS) * 64 + lane * 16), "l"(cand + req_next * 32 + lane * 8) : "memory");
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                    req_next++;
                 }
+                asm volatile("cp.async.wait_group 2;" ::: "memory");        // all but the two newest blocks: b0, b0+1 are in
+                __syncwarp();
                 const uint32_t p = pos + lane;
-                const uint32_t off = p - blk_base;                       // 0 .. 62
-                const uint32_t c0 = __shfl_sync(FULL, blk0, off & 31), c1 = __shfl_sync(FULL, blk1, off & 31);
                 const uint32_t avail = p < seg_hi ? seg_hi - p : 0;
                 uint32_t len = 0, dist = 0;
                 if (avail >= 4) {
-                    dist = off < 32 ? c0 : c1;
+                    dist = ring[((p >> 5) % LZF_RING_BLOCKS) * 32 + (p & 31)];
                     if (dist) {
                         const uint32_t q = p - dist;
                         const uint32_t maxl = min(avail, MAX_MATCH);
