@@ -334,23 +334,29 @@ __device__ __forceinline__ void tp_step_symbol(const TpCtx& c, TpState& s) {
             if (r < 0) { TP_FAIL(ST_OVERRUN); ok = false; }
             else e = tp_lit_entry((uint32_t)r & 0xFFFFu, (uint32_t)r >> 16);
         }
-        const uint32_t l = e & 15u, p = e >> 4;
+        uint32_t l = e & 15u, p = e >> 4;
+        bool is_match = ok && p >= 0x200u && !(p & 0x100u);
         if (ok && p < 256) {
             tb_drop(br, l);
             to_literal(o, p);
             if (SEGM) {
-                // literals come in runs: take up to TP_LIT_RUN more in the same trip while the table has them
+                // literals come in runs: take up to TP_LIT_RUN more in the same trip while the table has them, and
+                // if the run ends at a back-reference, take that too -- every lane then does "literals, match" per
+                // trip, the two halves of the trip are executed once for the whole warp
                 #pragma unroll
                 for (uint32_t k = 0; k < TP_LIT_RUN; k++) {
                     if (k) tb_refill(br);        // after the first two literals fewer than LB bits may be left
                     const uint32_t e2 = lds_u16(c.lit_sa + tb_peek(br, LB) * ntb);
                     const uint32_t l2 = e2 & 15u, p2 = e2 >> 4;
-                    if (l2 == 0 || p2 >= 256 || o.v - o.al >= c.stop_at) break;
-                    tb_drop(br, l2);
-                    to_literal(o, p2);
+                    if (l2 == 0 || o.v - o.al >= c.stop_at) break;
+                    if (p2 < 256) { tb_drop(br, l2); to_literal(o, p2); continue; }
+                    if (p2 >= 0x200u && !(p2 & 0x100u)) { l = l2; p = p2; is_match = true; }
+                    break;
                 }
             }
-        } else if (ok && !(p & 0x100u)) {
+        }
+        if (is_match) {
+            const uint32_t pos = o.v - o.al;
             tb_drop(br, l);
             const uint32_t lt = lds_u32(c.lut_sa + (p & 31u) * 4);
             const uint32_t length = (lt & 0xFFFFu) + tb_get(br, lt >> 16);
@@ -368,18 +374,18 @@ __device__ __forceinline__ void tp_step_symbol(const TpCtx& c, TpState& s) {
                 tb_drop(br, dl);
                 const uint32_t dt = lds_u32(c.lut_sa + (32 + dsym) * 4);
                 const uint32_t dist = (dt & 0xFFFFu) + tb_get(br, dt >> 16);
-                if (dist > produced) {
+                if (dist > pos) {
                     if (c.stop_at_sync) { s.end_flags |= END_NEEDS_HISTORY; TP_FAIL(ST_DATA); }
                     else if (c.strict) TP_FAIL(ST_DATA);
                     // else reference: copies nothing (inflate.hpp:268-270)
-                } else if (produced < c.cap && s.nops >= c.ops_cap) {
+                } else if (pos < c.cap && s.nops >= c.ops_cap) {
                     TP_FAIL(ST_FALLBACK);
                 } else {
-                    if (produced < c.cap) c.ops[s.nops++] = tp_op(produced, length, dist);
+                    if (pos < c.cap) c.ops[s.nops++] = tp_op(pos, length, dist);
                     to_skip_match(o, length);
                 }
             }
-        } else if (ok) {
+        } else if (ok && p >= 256) {
             if (p == 0x100u) { tb_drop(br, l); tp_end_block(c, s, wi_lim); }    // end of block
             else TP_FAIL(ST_DATA);                                              // 286 / 287
         }
