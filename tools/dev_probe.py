@@ -1,6 +1,6 @@
 """Development probe (not a pytest): quick end-to-end check + rough timings on a GPU box.
 
-    gpurun -- 'python tests/dev_probe.py [MiB]'
+    gpurun -- 'python tools/dev_probe.py [MiB]'
 """
 import ctypes
 import hashlib
