@@ -271,9 +271,19 @@ def main():
         if nchunks % rounds or nchunks // rounds < 1024:
             rounds = 1
         slice_chunks = nchunks // rounds
+        # B200_GATHER_SPLIT="5,5,4,2": uneven rounds (weights) -- the copy of the LAST round is what the step cannot
+        # hide, so it should be small; round k then covers chunks [world * P_k + rank * S_k, + S_k) of the corpus
+        round_chunks = [slice_chunks] * rounds
+        split = os.environ.get("B200_GATHER_SPLIT", "")
+        if split and os.environ.get("B200_GATHER", "p2p_copy") != "fused":
+            w = [int(x) for x in split.split(",") if x.strip()]
+            if w and all(x > 0 for x in w) and (nchunks % sum(w)) == 0 and min(w) * (nchunks // sum(w)) >= 1024:
+                round_chunks = [x * (nchunks // sum(w)) for x in w]
+                rounds = len(round_chunks)
+        round_first = [sum(round_chunks[:k]) for k in range(rounds)]          # P_k, in chunks (also the offset inside src)
         for k in range(rounds):
-            ctx.corpus_generate_dev(src.data_ptr() + k * slice_chunks * CHUNK, SEED,
-                                    shard.slice_first_chunk(k, rank, world, slice_chunks), slice_chunks, stream=st)
+            ctx.corpus_generate_dev(src.data_ptr() + round_first[k] * CHUNK, SEED,
+                                    world * round_first[k] + rank * round_chunks[k], round_chunks[k], stream=st)
     gather_buf, symm = None, None
     transport = None
     if world > 1:
@@ -296,6 +306,9 @@ def main():
         allsz_host = torch.zeros(rounds, world, dtype=torch.int64).pin_memory()
     slice_bytes = slice_chunks * CHUNK
     slice_cap = d.deflate_bound(slice_bytes)
+    if world > 1:
+        dst_cap = [d.deflate_bound(c * CHUNK) for c in round_chunks]
+        dst_off = [sum(dst_cap[:k]) for k in range(rounds)]
 
     if world > 1 and gmode == "fused":
         peer0 = symm.get_buffer(0, (gather_buf.numel(),), torch.uint8)     # rank 0's buffer as seen from here
@@ -335,8 +348,8 @@ def main():
         main = torch.cuda.current_stream()
         for k in range(rounds):
             last = (k == rounds - 1) and (rank == world - 1)       # only the stream's very last chunk is final
-            ctx.compress_dev(src.data_ptr() + k * slice_bytes, slice_bytes, args.level, dst.data_ptr() + k * slice_cap,
-                             slice_cap, flags=0 if last else d.F_NOT_LAST, stream=st,
+            ctx.compress_dev(src.data_ptr() + round_first[k] * CHUNK, round_chunks[k] * CHUNK, args.level,
+                             dst.data_ptr() + dst_off[k], dst_cap[k], flags=0 if last else d.F_NOT_LAST, stream=st,
                              d_out_n=sizes_dev[k:k + 1].data_ptr(), sync=False)
             if inline_sizes:
                 dist.all_gather_into_tensor(allsz_dev[k], sizes_dev[k:k + 1])
@@ -349,10 +362,10 @@ def main():
                 if inline_sizes:
                     round_done[k].synchronize()                    # host: this round's sizes are in pinned memory
                     side.wait_event(round_done[k])
-                    sz = pg.post_round(dst[k * slice_cap:(k + 1) * slice_cap], None, sizes=[int(x) for x in allsz_host[k].tolist()])
+                    sz = pg.post_round(dst[dst_off[k]:dst_off[k] + dst_cap[k]], None, sizes=[int(x) for x in allsz_host[k].tolist()])
                 else:
                     side.wait_event(round_done[k])
-                    sz = pg.post_round(dst[k * slice_cap:(k + 1) * slice_cap], sizes_dev[k:k + 1])
+                    sz = pg.post_round(dst[dst_off[k]:dst_off[k] + dst_cap[k]], sizes_dev[k:k + 1])
                 total += sz[rank]
             step.joined = pg.finish()
         main.wait_stream(side)
