@@ -528,8 +528,10 @@ __device__ __forceinline__ void tp_finish(const TpCtx& c, TpState& s, TpResult& 
 }
 
 __device__ __forceinline__ void tp_lut_init(uint32_t* s_lut, uint32_t tid) {
-    if (tid < 32) s_lut[tid] = tid < 29 ? ((uint32_t)C_LEN_BASE[tid] | (len_extra_bits(tid) << 16)) : 0;
-    else if (tid < 64) { const uint32_t k = tid - 32; s_lut[tid] = k < 30 ? ((uint32_t)C_DIST_BASE[k] | (dist_extra_bits(k) << 16)) : 0; }
+    for (uint32_t t = tid; t < TP_LUT_WORDS; t += blockDim.x) {
+        if (t < 32) s_lut[t] = t < 29 ? ((uint32_t)C_LEN_BASE[t] | (len_extra_bits(t) << 16)) : 0;
+        else { const uint32_t k = t - 32; s_lut[t] = k < 30 ? ((uint32_t)C_DIST_BASE[k] | (dist_extra_bits(k) << 16)) : 0; }
+    }
 }
 
 // ---- unit descriptors -------------------------------------------------------------------------------
