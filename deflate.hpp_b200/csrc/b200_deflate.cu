@@ -134,6 +134,7 @@ struct b200_ctx {
     bool with_index = true;          // B200_NO_INDEX=1 / B200_F_NO_INDEX: no segment index in front of full chunks
     int sg_occ = 12, copy_occ = 8;   // resident CTAs per SM the two inflate passes are compiled for (tuning knobs; 8 x 4 warps at
                                      // 64 registers: no spills in the lane-local copies, measured best of 6 / 8 / 12)
+    uint32_t sg_pad = 0;             // B200_SG_PAD: extra dynamic shared memory per pass-A CTA (occupancy experiments)
     unsigned copy_tune = 1;          // bit 0: prefetch the next step's sources into L2
     bool batch_two_pass = false;     // B200_BATCH_TP=1: batch inflate through the two-pass path, one THREAD per stream (measured
                                      // slower than one warp per stream on 1-64 KiB zlib streams: 15 vs 75 GB/s; kept for
@@ -162,7 +163,7 @@ int set_attrs(b200_ctx* c) {
     CK(cudaFuncSetAttribute(lz77_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LZF_SMEM_BYTES));
     CK(cudaFuncSetAttribute(lz77_better_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LZB_SMEM_BYTES));
     CK(cudaFuncSetAttribute(encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_SMEM_BYTES));
-    CK(cudaFuncSetAttribute(inflate_segments_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(inflate_segments_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM_BYTES + 65536));
     CK(cudaFuncSetAttribute(inflate_segments_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM_BYTES));
     CK(cudaFuncSetAttribute(inflate_symbols_kernel<BatchUnits>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM_BYTES));
     c->attrs_set = true;
@@ -214,7 +215,7 @@ static int inflate_two_pass(b200_ctx* c, const Units& U, uint64_t nunits, unsign
             inflate_segments_kernel<16><<<(uint32_t)((nunits + SG_CHUNKS - 1) / SG_CHUNKS), SG_THREADS, SG_SMEM_BYTES, st>>>(
                 U, chunk_list, (const uint32_t*)(cnt + 8), cnt + 4, res, segnops, flags, cnt + 3);
         else
-            inflate_segments_kernel<12><<<(uint32_t)((nunits + SG_CHUNKS - 1) / SG_CHUNKS), SG_THREADS, SG_SMEM_BYTES, st>>>(
+            inflate_segments_kernel<12><<<(uint32_t)((nunits + SG_CHUNKS - 1) / SG_CHUNKS), SG_THREADS, SG_SMEM_BYTES + c->sg_pad, st>>>(
                 U, chunk_list, (const uint32_t*)(cnt + 8), cnt + 4, res, segnops, flags, cnt + 3);
     } else
         inflate_symbols_kernel<Units><<<(uint32_t)((nunits + TP_THREADS - 1) / TP_THREADS), TP_THREADS, TP_SMEM_BYTES, st>>>(U, res, flags, cnt + 3);
@@ -333,6 +334,7 @@ int b200_ctx_create(int device, b200_ctx** ctx) {
     if (const char* e = getenv("B200_NO_INDEX")) c->with_index = atoi(e) == 0;
     if (const char* e = getenv("B200_INFLATE_GROUP")) { long v = atol(e); if (v > 0) c->inflate_group_chunks = (uint64_t)v; }
     if (const char* e = getenv("B200_INFLATE_OVERLAP")) c->inflate_overlap = atoi(e) != 0;
+    if (const char* e = getenv("B200_SG_PAD")) c->sg_pad = (uint32_t)atoi(e);
     if (const char* e = getenv("B200_SG_OCC")) c->sg_occ = atoi(e);
     if (const char* e = getenv("B200_COPY_OCC")) c->copy_occ = atoi(e);
     if (const char* e = getenv("B200_COPY_TUNE")) c->copy_tune = (unsigned)atoi(e);
