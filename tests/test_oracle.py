@@ -192,7 +192,7 @@ def _dynamic_block_boundaries(data, bitpos, seg=4096):
     return marks, out, br.pos
 
 
-def test_segment_index_fixture(oracle):
+def test_segment_index_fixture(oracle, ref):
     """tests/golden/b200_indexed.deflate was compressed on a B200 (tools/make_index_fixture.py).  The index in
     front of each full chunk -- 64 empty stored blocks whose padding bits spell 16 words (csrc/common.cuh) -- must
     state exactly the bit lengths an independent bit-by-bit decoder sees between 4 KiB output boundaries, every
@@ -202,6 +202,8 @@ def test_segment_index_fixture(oracle):
     data = datagen.text_like(65536, seed=51) + datagen.image_like(65536, seed=52) + datagen.text_like(65536 + 3000, seed=53)
     rc, out = oracle.inflate(c)
     assert rc == 0 and out == data
+    n, r_out = ref.inflate(c)                    # the unmodified reference inflater skips the index as well
+    assert n == len(data) and r_out == data
     assert zlib.decompressobj(-15).decompress(c) == data
     pos = 0                                     # byte offset of the current chunk
     for chunk in range(3):
