@@ -86,6 +86,9 @@ def lib():
     L.b200_inflate_batch_dev.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                          c_void_p, c_void_p, c_size_t, c_uint, c_void_p]
     L.b200_corpus_generate_dev.argtypes = [c_void_p, c_u64, c_u64, c_u64, c_void_p]
+    L.b200_deflate_compress_batch_dev.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_uint, c_void_p,
+                                                  c_size_t, c_void_p, P(c_size_t), c_void_p]
+    L.b200_deflate_compress_batch_dev.restype = c_int
     L.b200_adler32_dev.argtypes = [c_void_p, c_void_p, c_size_t, P(ctypes.c_uint32), c_void_p, c_void_p]
     L.b200_adler32_dev.restype = c_int
     for f in ("b200_ctx_create", "b200_deflate_compress", "b200_deflate_compress_into", "b200_inflate",
@@ -257,6 +260,15 @@ class Context:
                                           d_out_len, d_status, n_streams, flags, stream or None)
         if rc:
             raise B200Error(rc, "b200_inflate_batch_dev")
+
+    def compress_batch_dev(self, d_in, d_in_off, d_in_len, n_files, level, d_out, cap, d_out_off, flags=0, stream=0):
+        """n_files independent inputs -> n_files independent streams; returns the total compressed size."""
+        total = ctypes.c_size_t()
+        rc = lib().b200_deflate_compress_batch_dev(self._h, d_in, d_in_off, d_in_len, n_files, _level(level), flags, d_out, cap,
+                                                   d_out_off, ctypes.byref(total), stream or None)
+        if rc:
+            raise B200Error(rc, "b200_deflate_compress_batch_dev")
+        return total.value
 
     def adler32_dev(self, d_data, n, stream=0):
         """Adler-32 of n device bytes, computed on the GPU."""

@@ -125,7 +125,7 @@ struct b200_ctx {
     // compress scratch
     Buf tok, ntok, hist, codes, hdr, desc, sizes, offsets, total;
     // inflate scratch
-    Buf counts, woffs, cand, res, result, one_off, counter, cand16, ops, tpres, segnops, chunk_list, group_cnt, sync_cache, adler_parts;
+    Buf counts, woffs, cand, res, result, one_off, counter, cand16, ops, tpres, segnops, chunk_list, group_cnt, sync_cache, adler_parts, batch_nch, batch_first, batch_srcs;
     std::vector<cudaEvent_t> group_events;
     cudaStream_t s_side = nullptr;   // inflate: copy pass of group g while group g + 1 is in pass A
     uint64_t inflate_group_chunks = 0;   // 0 = auto (32768 chunks); B200_INFLATE_GROUP
@@ -176,6 +176,37 @@ struct IndexGuard {
     IndexGuard(b200_ctx* c_, unsigned flags) : c(c_), saved(c_->with_index) { if (flags & B200_F_NO_INDEX) c->with_index = false; }
     ~IndexGuard() { c->with_index = saved; }
 };
+
+// ---- batch compression helpers ------------------------------------------------------------------------------
+// chunks per input (an empty input still gets one chunk: its stream is the two bytes 03 00) and the space the
+// batch needs in the worst case
+__global__ void batch_count_kernel(const uint64_t* __restrict__ in_len, uint64_t n, uint32_t* __restrict__ nch,
+                                   unsigned long long* __restrict__ need) {
+    const uint64_t f = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n) return;
+    const uint64_t len = in_len[f];
+    const uint64_t k = len ? (len + CHUNK - 1) / CHUNK : 1;
+    nch[f] = (uint32_t)k;
+    atomicAdd(need, (unsigned long long)(len + 20 * ((len + CHUNK - 1) / CHUNK) + 16));      // = b200_deflate_bound(len)
+}
+__global__ void batch_srcs_kernel(const uint64_t* __restrict__ in_off, const uint64_t* __restrict__ in_len,
+                                  const uint64_t* __restrict__ first, uint64_t n, ChunkSrc* __restrict__ srcs) {
+    const uint64_t f = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n) return;
+    const uint64_t len = in_len[f], off = in_off[f], c0 = first[f], k = first[f + 1] - c0;
+    for (uint64_t j = 0; j < k; j++) {
+        ChunkSrc s;
+        s.off = off + j * CHUNK;
+        s.clen = (uint32_t)(len - j * CHUNK < CHUNK ? len - j * CHUNK : CHUNK);
+        s.last = j + 1 == k;
+        srcs[c0 + j] = s;
+    }
+}
+__global__ void batch_offsets_kernel(const uint64_t* __restrict__ first, const uint64_t* __restrict__ chunk_off, uint64_t n,
+                                     uint64_t* __restrict__ out_off) {
+    const uint64_t f = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f <= n) out_off[f] = chunk_off[first[f]];
+}
 
 b200_ctx* g_default = nullptr;
 std::mutex g_default_mu;
@@ -357,7 +388,7 @@ void b200_ctx_destroy(b200_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     Buf* all[] = {&c->tok, &c->ntok, &c->hist, &c->codes, &c->hdr, &c->desc, &c->sizes, &c->offsets, &c->total,
-                  &c->counts, &c->woffs, &c->cand, &c->res, &c->result, &c->one_off, &c->counter, &c->cand16, &c->ops, &c->tpres, &c->segnops, &c->chunk_list, &c->group_cnt, &c->sync_cache, &c->adler_parts,
+                  &c->counts, &c->woffs, &c->cand, &c->res, &c->result, &c->one_off, &c->counter, &c->cand16, &c->ops, &c->tpres, &c->segnops, &c->chunk_list, &c->group_cnt, &c->sync_cache, &c->adler_parts, &c->batch_nch, &c->batch_first, &c->batch_srcs,
                   &c->d_in, &c->d_out};
     for (Buf* b : all) b->release();
     c->prof.destroy();
@@ -411,7 +442,8 @@ void b200_free(void* p) { free(p); }
 // stages: bit 0 = K1..K3 (tokenise, code, size, scan), bit 1 = K4 (encode + write)
 static int compress_batch(b200_ctx* c, const uint8_t* bin, uint64_t bn, uint32_t nb, uint64_t b0, bool final_batch,
                           int level, uint64_t* offs, uint64_t* d_total, void* d_out, cudaStream_t st,
-                          int stages = 3, const uint64_t* d_extra_base = nullptr) {
+                          int stages = 3, const uint64_t* d_extra_base = nullptr, const ChunkSrc* srcs = nullptr) {
+    // srcs: batch compression -- chunk k of this batch is described by srcs[k] (absolute offsets into bin)
     if (stages & 1) {
     if (level == 2) {
         int rc;
@@ -423,21 +455,21 @@ static int compress_batch(b200_ctx* c, const uint8_t* bin, uint64_t bn, uint32_t
         PROF_BEGIN(c, K_LZ77, st);
         if (level == 3)
             lz77_better_kernel<<<nb, LZB_THREADS, LZB_SMEM_BYTES, st>>>(bin, bn, (uint32_t*)c->tok.p, (uint32_t*)c->ntok.p,
-                                                                     (uint32_t*)c->hist.p, c->better_depth, c->better_nice);
+                                                                     (uint32_t*)c->hist.p, c->better_depth, c->better_nice, srcs);
         else if (level == 2) {
             const uint32_t grid = nb < c->lzf_grid ? nb : c->lzf_grid;
             lz77_fast_kernel<<<grid, LZF_THREADS, LZF_SMEM_BYTES, st>>>(bin, bn, nb, (uint32_t*)c->tok.p, (uint32_t*)c->ntok.p,
                                                                      (uint32_t*)c->hist.p, (uint16_t*)c->cand16.p,
-                                                                     (unsigned int*)c->counter.p);
+                                                                     (unsigned int*)c->counter.p, srcs);
         }
         else
-            lz77_literal_kernel<<<nb, LZL_THREADS, 0, st>>>(bin, bn, (uint32_t*)c->tok.p, (uint32_t*)c->ntok.p, (uint32_t*)c->hist.p);
+            lz77_literal_kernel<<<nb, LZL_THREADS, 0, st>>>(bin, bn, (uint32_t*)c->tok.p, (uint32_t*)c->ntok.p, (uint32_t*)c->hist.p, srcs);
         LAUNCHED();
         PROF_END(c, st);
     }
     PROF_BEGIN(c, K_HUFFMAN, st);
     huffman_kernel<<<(nb + HUF_WARPS - 1) / HUF_WARPS, HUF_THREADS, 0, st>>>(
-        (const uint32_t*)c->hist.p, bn, nb, level, final_batch ? 1 : 0, c->with_index ? 1 : 0, (uint32_t*)c->codes.p,
+        (const uint32_t*)c->hist.p, bn, nb, level, final_batch ? 1 : 0, c->with_index ? 1 : 0, srcs, (uint32_t*)c->codes.p,
         (uint32_t*)c->hdr.p, (BlockDesc*)c->desc.p, (uint32_t*)c->sizes.p);
     LAUNCHED();
     PROF_END(c, st);
@@ -451,7 +483,7 @@ static int compress_batch(b200_ctx* c, const uint8_t* bin, uint64_t bn, uint32_t
         PROF_BEGIN(c, K_ENCODE, st);
         encode_kernel<<<nb, ENC_THREADS, ENC_SMEM_BYTES, st>>>(bin, (const uint32_t*)c->tok.p, (const uint32_t*)c->ntok.p,
                                                               (const uint32_t*)c->codes.p, (const uint32_t*)c->hdr.p,
-                                                              (const BlockDesc*)c->desc.p, offs + b0, d_extra_base, (uint8_t*)d_out);
+                                                              (const BlockDesc*)c->desc.p, offs + b0, d_extra_base, (uint8_t*)d_out, srcs);
         LAUNCHED();
         PROF_END(c, st);
     }
@@ -513,6 +545,68 @@ int b200_deflate_compress_dev(b200_ctx* c, const void* d_in, size_t n, int level
         CK(cudaMemcpyAsync(&tot, d_total, 8, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         *h_out_n = (size_t)tot;
+    }
+    return B200_OK;
+}
+
+// Batch compression: n_files independent inputs -> n_files independent raw DEFLATE streams, one launch sequence.
+int b200_deflate_compress_batch_dev(b200_ctx* c, const void* d_in, const uint64_t* d_in_off, const uint64_t* d_in_len,
+                                    size_t n_files, int level, unsigned flags, void* d_out, size_t cap,
+                                    uint64_t* d_out_off, size_t* h_total, void* stream_) {
+    if (!c || !d_in_off || !d_in_len || !d_out || !d_out_off || level < 0 || level > 3) return B200_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream_;
+    CK(cudaSetDevice(c->device));
+    if (n_files == 0) {
+        CK(cudaMemsetAsync(d_out_off, 0, 8, st));
+        if (h_total) { CK(cudaStreamSynchronize(st)); *h_total = 0; }
+        return B200_OK;
+    }
+    IndexGuard guard(c, flags);
+    int rc;
+    if ((rc = c->batch_nch.ensure(n_files * 4))) return rc;
+    if ((rc = c->batch_first.ensure((n_files + 1) * 8))) return rc;
+    if ((rc = c->total.ensure(32))) return rc;
+    unsigned long long* d_tot = (unsigned long long*)c->total.p;        // [0] compressed total, [1] chunks, [2] bytes needed
+    CK(cudaMemsetAsync(d_tot, 0, 32, st));
+    const uint32_t g = (uint32_t)((n_files + 255) / 256);
+    batch_count_kernel<<<g, 256, 0, st>>>(d_in_len, n_files, (uint32_t*)c->batch_nch.p, d_tot + 2);
+    LAUNCHED();
+    // the scan kernel takes 32-bit counts: fine below 2^32 inputs
+    scan_sizes_kernel<<<1, SCAN_THREADS, 0, st>>>((const uint32_t*)c->batch_nch.p, (uint32_t)n_files, nullptr,
+                                                 (uint64_t*)c->batch_first.p, (uint64_t*)d_tot + 1);
+    LAUNCHED();
+    unsigned long long h[3] = {0, 0, 0};
+    CK(cudaMemcpyAsync(h, d_tot, 24, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const uint64_t nchunks = h[1];
+    if (h[2] > cap) return B200_E_ARG;                                  // cap must cover sum of b200_deflate_bound(len)
+    if ((rc = c->batch_srcs.ensure(nchunks * sizeof(ChunkSrc)))) return rc;
+    ChunkSrc* srcs = (ChunkSrc*)c->batch_srcs.p;
+    batch_srcs_kernel<<<g, 256, 0, st>>>(d_in_off, d_in_len, (const uint64_t*)c->batch_first.p, n_files, srcs);
+    LAUNCHED();
+    const uint64_t B = nchunks < c->batch_chunks ? nchunks : c->batch_chunks;
+    if ((rc = c->tok.ensure(B * CHUNK * 4))) return rc;
+    if ((rc = c->ntok.ensure(B * NSEG * 4))) return rc;
+    if ((rc = c->hist.ensure(B * NSEG * NSYM * 4))) return rc;
+    if ((rc = c->codes.ensure(B * NSYM * 4))) return rc;
+    if ((rc = c->hdr.ensure(B * HDR_WORDS * 4))) return rc;
+    if ((rc = c->desc.ensure(B * sizeof(BlockDesc)))) return rc;
+    if ((rc = c->sizes.ensure(B * 4))) return rc;
+    if ((rc = c->offsets.ensure((nchunks + 1) * 8))) return rc;
+    uint64_t* offs = (uint64_t*)c->offsets.p;
+    for (uint64_t b0 = 0; b0 < nchunks; b0 += B) {
+        const uint32_t nb = (uint32_t)((nchunks - b0 < B) ? nchunks - b0 : B);
+        if ((rc = compress_batch(c, (const uint8_t*)d_in, 0, nb, b0, false, level, offs, (uint64_t*)d_tot, d_out, st, 3, nullptr,
+                                 srcs + b0)))
+            return rc;
+    }
+    batch_offsets_kernel<<<(uint32_t)((n_files + 256) / 256), 256, 0, st>>>((const uint64_t*)c->batch_first.p, offs, n_files, d_out_off);
+    LAUNCHED();
+    if (h_total) {
+        uint64_t tot = 0;
+        CK(cudaMemcpyAsync(&tot, d_tot, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        *h_total = (size_t)tot;
     }
     return B200_OK;
 }

@@ -42,6 +42,11 @@ __host__ __device__ __forceinline__ uint32_t tok_match(uint32_t len, uint32_t di
 __host__ __device__ __forceinline__ uint32_t tok_dist(uint32_t t) { return t >> 16; }
 __host__ __device__ __forceinline__ uint32_t tok_len(uint32_t t) { return t & 0x1FFu; }
 
+// Batch compression (many independent inputs in one launch sequence): chunk c of the batch is bytes
+// [off, off + clen) of the input buffer; `last` = it closes its stream (BFINAL, no separator after it).
+// Kernels take a `const ChunkSrc*` that is NULL for one contiguous input (chunk c = bytes [c * CHUNK, ...)).
+struct ChunkSrc { uint64_t off; uint32_t clen; uint32_t last; };
+
 // Block descriptor written by the Huffman kernel, read by the encoder.
 struct BlockDesc {
     uint32_t btype;          // 0 stored, 1 fixed, 2 dynamic

@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 3)
 encode_kernel(const uint8_t* __restrict__ in, const uint32_t* __restrict__ tok, const uint32_t* __restrict__ ntok,
               const uint32_t* __restrict__ codes, const uint32_t* __restrict__ hdr,
               const BlockDesc* __restrict__ desc, const uint64_t* __restrict__ offsets,
-              const uint64_t* __restrict__ extra_base, uint8_t* __restrict__ out) {
+              const uint64_t* __restrict__ extra_base, uint8_t* __restrict__ out, const ChunkSrc* __restrict__ srcs) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint32_t* stage = reinterpret_cast<uint32_t*>(smem);
     uint32_t* s_codes = reinterpret_cast<uint32_t*>(smem + ENC_STAGE_BYTES);
@@ -94,7 +94,7 @@ encode_kernel(const uint8_t* __restrict__ in, const uint32_t* __restrict__ tok, 
     if (d.btype == 0) {
         // stored blocks: [hdr byte][LEN][NLEN][raw bytes], <= 65535 bytes each (deflate.hpp:387-399)
         uint8_t* sb = smem + phase;
-        const uint8_t* src = in + chunk * CHUNK;
+        const uint8_t* src = in + (srcs ? srcs[chunk].off : chunk * CHUNK);
         const uint32_t nblk = (d.clen + 65534u) / 65535u;
         uint32_t done = 0, o = 0;
         for (uint32_t b = 0; b < nblk; b++) {
@@ -129,7 +129,7 @@ encode_kernel(const uint8_t* __restrict__ in, const uint32_t* __restrict__ tok, 
             stage_bits(stage, bit0 + i * 32, v, 32);
         }
         // payload: warp = segment; 32 tokens per step, warp scan of bit lengths
-        const uint32_t nt = ntok[chunk * NSEG + warp];
+        const uint32_t nt = d.clen ? ntok[chunk * NSEG + warp] : 0u;      // an empty input: header + end of block only
         const uint32_t* mytok = tok + chunk * CHUNK + warp * SEG;
         uint32_t bit = bit0 + d.seg_bitoff[warp];
         for (uint32_t b = 0; b < nt; b += 32) {

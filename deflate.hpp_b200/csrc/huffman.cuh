@@ -219,24 +219,25 @@ __device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
 // level 0 forces stored blocks.  last_is_final: the final chunk of this buffer carries BFINAL.
 __global__ void __launch_bounds__(HUF_THREADS)
 huffman_kernel(const uint32_t* __restrict__ hist, uint64_t n, uint32_t nchunks, int level, int last_is_final,
-               int with_index, uint32_t* __restrict__ codes, uint32_t* __restrict__ hdr, BlockDesc* __restrict__ desc,
+               int with_index, const ChunkSrc* __restrict__ srcs, uint32_t* __restrict__ codes, uint32_t* __restrict__ hdr, BlockDesc* __restrict__ desc,
                uint32_t* __restrict__ sizes) {
     __shared__ HufScratch scratch[HUF_WARPS];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t chunk = blockIdx.x * HUF_WARPS + warp;
     if (chunk >= nchunks) return;
     HufScratch* s = &scratch[warp];
-    const uint32_t clen = (uint32_t)min((uint64_t)CHUNK, n - (uint64_t)chunk * CHUNK);
-    const bool last = last_is_final && chunk == nchunks - 1;
+    const uint32_t clen = srcs ? srcs[chunk].clen : (uint32_t)min((uint64_t)CHUNK, n - (uint64_t)chunk * CHUNK);
+    const bool last = srcs ? srcs[chunk].last != 0 : (last_is_final && chunk == nchunks - 1);
     const uint32_t* h = hist + (size_t)chunk * NSEG * NSYM;
     uint32_t* mycodes = codes + (size_t)chunk * NSYM;
     uint32_t* myhdr = hdr + (size_t)chunk * HDR_WORDS;
     BlockDesc* d = desc + chunk;
 
     const uint32_t nstored = (clen + 65534u) / 65535u;
-    const uint32_t stored_bytes = clen + 5u * nstored + (last ? 0u : SYNC_BYTES_ALIGNED);
+    // an empty input (batch compression only) still needs a block: stored is not an option, the fixed block wins (03 00)
+    const uint32_t stored_bytes = clen ? clen + 5u * nstored + (last ? 0u : SYNC_BYTES_ALIGNED) : 0xFFFFFFFFu;
 
-    if (level == 0) {
+    if (level == 0 && clen) {
         if (lane == 0) {
             d->btype = 0; d->hdr_bits = 0; d->total_bits = 0; d->nbytes = stored_bytes; d->clen = clen;
             d->last = last; d->eob = 0; d->index_bytes = 0;
@@ -248,7 +249,7 @@ huffman_kernel(const uint32_t* __restrict__ hist, uint64_t n, uint32_t nchunks, 
     // ---- reduce the per-segment histograms ------------------------------------------------
     for (uint32_t i = lane; i < NSYM; i += 32) {
         uint32_t f = 0;
-        for (uint32_t sgm = 0; sgm < NSEG; sgm++) f += h[sgm * NSYM + i];
+        if (clen) for (uint32_t sgm = 0; sgm < NSEG; sgm++) f += h[sgm * NSYM + i];     // (level 0 runs no tokeniser)
         s->freq[i] = f + (i == 256 ? 1u : 0u);
     }
     __syncwarp();
@@ -379,7 +380,7 @@ huffman_kernel(const uint32_t* __restrict__ hist, uint64_t n, uint32_t nchunks, 
         uint32_t sb = 0;
         if (btype) {
             for (uint32_t i = lane; i < NSYM; i += 32) {
-                const uint32_t f = h[sgm * NSYM + i];
+                const uint32_t f = clen ? h[sgm * NSYM + i] : 0u;
                 if (!f) continue;
                 const uint32_t cl = btype == 2 ? s->lens[i] : (i < NLIT ? fixed_lit_len(i) : 5u);
                 const uint32_t ex = i < NLIT ? (i > 256 ? len_extra_bits(i - 257) : 0u) : dist_extra_bits(i - NLIT);

@@ -66,12 +66,12 @@ __device__ __forceinline__ void hist_store(const uint32_t* h, uint32_t* gh, uint
 constexpr uint32_t LZL_THREADS = NSEG * 32;
 __global__ void __launch_bounds__(LZL_THREADS)
 lz77_literal_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t* __restrict__ tok,
-                    uint32_t* __restrict__ ntok, uint32_t* __restrict__ hist) {
+                    uint32_t* __restrict__ ntok, uint32_t* __restrict__ hist, const ChunkSrc* __restrict__ srcs) {
     __shared__ uint32_t s_hist[NSEG * HIST_WORDS];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint64_t chunk = blockIdx.x;
-    const uint64_t base = chunk * CHUNK;
-    const uint32_t clen = (uint32_t)min((uint64_t)CHUNK, n - base);
+    const uint64_t base = srcs ? srcs[chunk].off : chunk * CHUNK;
+    const uint32_t clen = srcs ? srcs[chunk].clen : (uint32_t)min((uint64_t)CHUNK, n - base);
     for (uint32_t i = tid; i < NSEG * HIST_WORDS; i += LZL_THREADS) s_hist[i] = 0;
     __syncthreads();
     const uint32_t seg_lo = warp * SEG, seg_hi = min(clen, seg_lo + SEG);
@@ -126,7 +126,7 @@ __device__ __forceinline__ uint32_t lzf_score(const uint8_t* d, uint32_t q, uint
 __global__ void __launch_bounds__(LZF_THREADS, 2)
 lz77_fast_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t nchunks, uint32_t* __restrict__ tok,
                  uint32_t* __restrict__ ntok, uint32_t* __restrict__ hist, uint16_t* __restrict__ cand_scratch,
-                 unsigned int* __restrict__ counter) {
+                 unsigned int* __restrict__ counter, const ChunkSrc* __restrict__ srcs) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* s_data = smem;
     uint32_t* s_tab = reinterpret_cast<uint32_t*>(smem + CHUNK + LZ_DATA_PAD);
@@ -147,8 +147,8 @@ lz77_fast_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t nchunks, u
         __syncthreads();
         const uint64_t chunk = *s_next;
         if (chunk >= nchunks) break;
-        const uint64_t base = chunk * CHUNK;
-        const uint32_t clen = (uint32_t)min((uint64_t)CHUNK, n - base);
+        const uint64_t base = srcs ? srcs[chunk].off : chunk * CHUNK;
+        const uint32_t clen = srcs ? srcs[chunk].clen : (uint32_t)min((uint64_t)CHUNK, n - base);
         const uint8_t* src = in + base;
 
         const bool aligned = ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
@@ -332,7 +332,8 @@ __device__ __forceinline__ uint32_t lzb_hash(uint32_t w4) { return ((w4 & 0xFFFF
 
 __global__ void __launch_bounds__(LZB_THREADS, 1)
 lz77_better_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t* __restrict__ tok,
-                   uint32_t* __restrict__ ntok, uint32_t* __restrict__ hist, uint32_t depth, uint32_t nice) {
+                   uint32_t* __restrict__ ntok, uint32_t* __restrict__ hist, uint32_t depth, uint32_t nice,
+                   const ChunkSrc* __restrict__ srcs) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* s_data = smem;
     uint16_t* s_prev = reinterpret_cast<uint16_t*>(smem + CHUNK + LZ_DATA_PAD);
@@ -342,8 +343,8 @@ lz77_better_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t* __restr
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint64_t chunk = blockIdx.x;
-    const uint64_t base = chunk * CHUNK;
-    const uint32_t clen = (uint32_t)min((uint64_t)CHUNK, n - base);
+    const uint64_t base = srcs ? srcs[chunk].off : chunk * CHUNK;
+    const uint32_t clen = srcs ? srcs[chunk].clen : (uint32_t)min((uint64_t)CHUNK, n - base);
     const uint8_t* src = in + base;
     const uint32_t FULL = 0xFFFFFFFFu;
 

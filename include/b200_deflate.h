@@ -128,6 +128,16 @@ int b200_deflate_compress_dev(b200_ctx* ctx, const void* d_in, size_t n, int lev
                               void* d_out, size_t cap, uint64_t* d_out_n, size_t* h_out_n,
                               uint64_t* d_chunk_off, void* stream);
 
+/* Batch compression: n_files independent inputs (input f = d_in + d_in_off[f], d_in_len[f] bytes; empty inputs
+ * allowed) become n_files independent raw DEFLATE streams in one launch sequence -- what calling
+ * deflate::compress (deflate.hpp:779) once per file produces, without the per-call launch latency.  Stream f is
+ * d_out[d_out_off[f] .. d_out_off[f + 1]) (d_out_off has n_files + 1 entries, device memory); every stream ends
+ * with its own BFINAL block.  cap must cover the sum of b200_deflate_bound(d_in_len[f]) (checked: B200_E_ARG).
+ * *h_total (may be NULL) receives the total compressed size.  Synchronizes `stream` once (chunk count). */
+int b200_deflate_compress_batch_dev(b200_ctx* ctx, const void* d_in, const uint64_t* d_in_off,
+                                    const uint64_t* d_in_len, size_t n_files, int level, unsigned flags,
+                                    void* d_out, size_t cap, uint64_t* d_out_off, size_t* h_total, void* stream);
+
 /* Multi-GPU gather fused into the encoder.  Stage 1 runs tokenise / code construction / sizing for one
  * batch (n <= 4096 chunks) and leaves this shard's compressed byte count in *d_local_n (device).  The
  * caller exchanges the counts between ranks (an 8-byte all_gather) and computes *d_base, the offset of

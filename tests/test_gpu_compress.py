@@ -159,3 +159,42 @@ def test_ratio_with_index_on_highly_compressible_data(b200, oracle, ref, level):
         assert b200.decompress(c) == data
         theirs = len(ref.compress(data, level))
         assert len(c) <= RATIO_TOL * theirs, (name, len(c), theirs)
+
+
+@pytest.mark.parametrize("level", LEVELS)
+def test_batch_compress(b200, oracle, level):
+    """A batch of files in one launch sequence (the north star's "batch of files"): every file becomes its own
+    raw DEFLATE stream, byte-identical to what a separate compress call produces, and decodes with zlib, the
+    oracle and the GPU inflater.  Sizes include empty, one byte, the chunk size +- 1 and several chunks."""
+    import numpy as np
+    import torch
+    sizes = [0, 1, 100, 65535, 65536, 65537, 200000, 3 * 65536, 0, 5000]
+    kinds = sorted(datagen.KINDS)
+    files = [datagen.KINDS[kinds[i % len(kinds)]](n, seed=60 + i) if n else b"" for i, n in enumerate(sizes)]
+    gap = 7                                                     # odd gaps: inputs need not be aligned
+    in_off = np.cumsum([0] + [len(f) + gap for f in files[:-1]]).astype(np.uint64)
+    in_len = np.array([len(f) for f in files], dtype=np.uint64)
+    blob = bytearray(int(in_off[-1] + in_len[-1]) + 64)
+    for o, f in zip(in_off, files):
+        blob[int(o):int(o) + len(f)] = f
+    cap = sum(b200.deflate_bound(len(f)) for f in files)
+    d_in = torch.frombuffer(blob, dtype=torch.uint8).cuda()
+    t = lambda a: torch.from_numpy(a.view(np.int64)).cuda()
+    d_off, d_len = t(in_off), t(in_len)
+    d_out = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+    d_out_off = torch.zeros(len(files) + 1, dtype=torch.int64, device="cuda")
+    ctx = b200.Context(0)
+    total = ctx.compress_batch_dev(d_in.data_ptr(), d_off.data_ptr(), d_len.data_ptr(), len(files), level, d_out.data_ptr(), cap,
+                                   d_out_off.data_ptr())
+    torch.cuda.synchronize()
+    offs = d_out_off.cpu().numpy()
+    assert offs[0] == 0 and offs[-1] == total and all(offs[i] <= offs[i + 1] for i in range(len(files)))
+    out = bytes(d_out[:total].cpu().numpy())
+    for i, f in enumerate(files):
+        stream = out[offs[i]:offs[i + 1]]
+        check_stream(stream, f, oracle)
+        assert b200.decompress(stream) == f, i
+        assert stream == b200.compress(f, level), i             # same bytes as a call of its own
+    with pytest.raises(b200.B200Error):                         # the capacity is checked against the worst case
+        ctx.compress_batch_dev(d_in.data_ptr(), d_off.data_ptr(), d_len.data_ptr(), len(files), level, d_out.data_ptr(), cap - 1,
+                               d_out_off.data_ptr())
