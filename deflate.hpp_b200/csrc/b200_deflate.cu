@@ -97,6 +97,21 @@ struct Prof {
     }
 };
 
+// Public entry points run on the context's device and leave the caller's current device as they found it.
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+        ok = (prev == dev) || cudaSetDevice(dev) == cudaSuccess;
+        if (prev == dev) prev = -1;             // nothing to restore
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define ON_DEVICE(c)                        \
+    DeviceGuard dev_guard__((c)->device);   \
+    if (!dev_guard__.ok) { cudaGetLastError(); return B200_E_CUDA; }
+
 struct Buf {
     void* p = nullptr;
     size_t cap = 0;
@@ -348,10 +363,11 @@ int b200_ctx_create(int device, b200_ctx** ctx) {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) return B200_E_CUDA;   // kernels are built for sm_100a only
-    CK(cudaSetDevice(device));
     b200_ctx* c = new (std::nothrow) b200_ctx();
     if (!c) return B200_E_NOMEM;
     c->device = device;
+    DeviceGuard dev_guard__(device);
+    if (!dev_guard__.ok) { cudaGetLastError(); delete c; return B200_E_CUDA; }
     c->inf_grid = (uint32_t)prop.multiProcessorCount * INF_MAX_CTAS_PER_SM;
     c->lzf_grid = (uint32_t)prop.multiProcessorCount * 2;
     // B200_RESERVE_SMS=k: leave k SMs out of the persistent matcher's grid so that concurrently running
@@ -377,16 +393,16 @@ int b200_ctx_create(int device, b200_ctx** ctx) {
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&c->s_side, cudaStreamNonBlocking) != cudaSuccess) { delete c; return B200_E_CUDA; }
+        cudaStreamCreateWithFlags(&c->s_side, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); b200_ctx_destroy(c); return B200_E_CUDA; }
     int rc = set_attrs(c);
-    if (rc) { cudaStreamDestroy(c->stream); delete c; return rc; }
+    if (rc) { b200_ctx_destroy(c); return rc; }
     *ctx = c;
     return B200_OK;
 }
 
 void b200_ctx_destroy(b200_ctx* c) {
     if (!c) return;
-    cudaSetDevice(c->device);
+    DeviceGuard dev_guard__(c->device);
     Buf* all[] = {&c->tok, &c->ntok, &c->hist, &c->codes, &c->hdr, &c->desc, &c->sizes, &c->offsets, &c->total,
                   &c->counts, &c->woffs, &c->cand, &c->res, &c->result, &c->one_off, &c->counter, &c->cand16, &c->ops, &c->tpres, &c->segnops, &c->chunk_list, &c->group_cnt, &c->sync_cache, &c->adler_parts, &c->batch_nch, &c->batch_first, &c->batch_srcs,
                   &c->d_in, &c->d_out};
@@ -411,7 +427,7 @@ int b200_ctx_profile(b200_ctx* c, int enable) {
 
 int b200_ctx_profile_read(b200_ctx* c, int kernel_id, double* total_ms, uint64_t* launches) {
     if (!c || kernel_id < 0 || kernel_id >= K_COUNT) return B200_E_ARG;
-    CK(cudaSetDevice(c->device));
+    ON_DEVICE(c);
     double ms = 0;
     uint64_t n = 0;
     for (auto& r : c->prof.recs) {
@@ -497,7 +513,7 @@ int b200_deflate_compress_dev(b200_ctx* c, const void* d_in, size_t n, int level
     if (!c || (!d_in && n) || !d_out || level < 0 || level > 3) return B200_E_ARG;
     if (cap < b200_deflate_bound(n)) return B200_E_ARG;
     cudaStream_t st = (cudaStream_t)stream_;
-    CK(cudaSetDevice(c->device));
+    ON_DEVICE(c);
     const bool final_here = !(flags & B200_F_NOT_LAST);
     const uint64_t nchunks = (n + CHUNK - 1) / CHUNK;
     IndexGuard guard(c, flags);
@@ -555,7 +571,7 @@ int b200_deflate_compress_batch_dev(b200_ctx* c, const void* d_in, const uint64_
                                     uint64_t* d_out_off, size_t* h_total, void* stream_) {
     if (!c || !d_in_off || !d_in_len || !d_out || !d_out_off || level < 0 || level > 3) return B200_E_ARG;
     cudaStream_t st = (cudaStream_t)stream_;
-    CK(cudaSetDevice(c->device));
+    ON_DEVICE(c);
     if (n_files == 0) {
         CK(cudaMemsetAsync(d_out_off, 0, 8, st));
         if (h_total) { CK(cudaStreamSynchronize(st)); *h_total = 0; }
@@ -621,7 +637,7 @@ int b200_deflate_compress_stage1_dev(b200_ctx* c, const void* d_in, size_t n, in
     const uint64_t nchunks = (n + CHUNK - 1) / CHUNK;
     if (nchunks > c->batch_chunks) return B200_E_ARG;
     cudaStream_t st = (cudaStream_t)stream_;
-    CK(cudaSetDevice(c->device));
+    ON_DEVICE(c);
     IndexGuard guard(c, flags);
     int rc;
     const uint64_t B = nchunks;
@@ -647,7 +663,7 @@ int b200_deflate_compress_stage2_dev(b200_ctx* c, const void* d_in, size_t n, vo
     const uint64_t nchunks = (n + CHUNK - 1) / CHUNK;
     if (nchunks > c->batch_chunks || !c->offsets.p) return B200_E_ARG;
     cudaStream_t st = (cudaStream_t)stream_;
-    CK(cudaSetDevice(c->device));
+    ON_DEVICE(c);
     return compress_batch(c, (const uint8_t*)d_in, n, (uint32_t)nchunks, 0, false, 0, (uint64_t*)c->offsets.p,
                           (uint64_t*)c->total.p, d_out, st, 2, d_base);
 }
@@ -659,7 +675,7 @@ int b200_inflate_batch_dev(b200_ctx* c, const void* d_in, const uint64_t* d_in_o
     if (!c || !d_in_off || !d_in_len || !d_out_off || !d_out_cap || !d_out_len || !d_status) return B200_E_ARG;
     if (n_streams == 0) return B200_OK;
     cudaStream_t st = (cudaStream_t)stream_;
-    CK(cudaSetDevice(c->device));
+    ON_DEVICE(c);
     int rc;
     if ((rc = c->counter.ensure(64))) return rc;
     if (c->batch_two_pass && !c->inflate_warp_path) {
@@ -704,7 +720,7 @@ int b200_inflate_dev(b200_ctx* c, const void* d_in, size_t n, void* d_out, size_
                      size_t* h_out_n, size_t* h_full_n, int32_t* d_status, unsigned flags, void* stream_) {
     if (!c || (!d_in && n) || (!d_out && cap)) return B200_E_ARG;
     cudaStream_t st = (cudaStream_t)stream_;
-    CK(cudaSetDevice(c->device));
+    ON_DEVICE(c);
     int rc;
     const uint8_t* in = (const uint8_t*)d_in;
     int status = B200_OK;
@@ -723,8 +739,8 @@ int b200_inflate_dev(b200_ctx* c, const void* d_in, size_t n, void* d_out, size_
         if ((rc = c->cand.ensure((cand_cap + 1) * 8))) return rc;
         uint64_t* cand = (uint64_t*)c->cand.p;
         const uint32_t g = (uint32_t)((nwarps * 32 + 255) / 256);
-        PROF_BEGIN(c, K_FIND_SYNC, st);
         if ((rc = c->sync_cache.ensure(nwarps * SYNC_CACHE * 4))) return rc;
+        PROF_BEGIN(c, K_FIND_SYNC, st);
         find_sync_kernel<false><<<g, 256, 0, st>>>(in, n, (uint32_t*)c->counts.p, (uint32_t*)c->sync_cache.p, nullptr, nullptr, 0, 0);
         LAUNCHED();
         PROF_END(c, st);
@@ -750,9 +766,9 @@ int b200_inflate_dev(b200_ctx* c, const void* d_in, size_t n, void* d_out, size_
             CK(cudaMemcpyAsync(d_result, init, 16, cudaMemcpyHostToDevice, st));
             if (c->inflate_warp_path) {
                 if ((rc = c->res.ensure(ncand * sizeof(ChunkResult)))) return rc;
-                PROF_BEGIN(c, K_INFLATE_CHUNKS, st);
                 if ((rc = c->counter.ensure(64))) return rc;
                 CK(cudaMemsetAsync(c->counter.p, 0, 8, st));
+                PROF_BEGIN(c, K_INFLATE_CHUNKS, st);
                 {
                     const uint64_t want = (ncand + INF_WARPS - 1) / INF_WARPS;
                     inflate_chunks_kernel<<<(uint32_t)(want < c->inf_grid ? want : c->inf_grid), INF_THREADS, 0, st>>>(
@@ -808,7 +824,7 @@ int b200_inflate_dev(b200_ctx* c, const void* d_in, size_t n, void* d_out, size_
 int b200_adler32_dev(b200_ctx* c, const void* d_data, size_t n, uint32_t* h_out, uint32_t* d_out, void* stream_) {
     if (!c || (!d_data && n) || (!h_out && !d_out)) return B200_E_ARG;
     cudaStream_t st = (cudaStream_t)stream_;
-    CK(cudaSetDevice(c->device));
+    ON_DEVICE(c);
     int rc;
     const uint64_t nblocks = (n + CHUNK - 1) / CHUNK;
     if ((rc = c->adler_parts.ensure((nblocks + 1) * sizeof(AdlerPart) + 16))) return rc;
@@ -848,7 +864,7 @@ int b200_corpus_generate_dev(void* d_out, uint64_t seed, uint64_t first_chunk, u
 // direction instead of the sum of copy + compute + copy.  Output offsets chain on the device (K3's
 // carry), the host only learns each slice's end offset through a pinned mailbox.
 static int compress_host(b200_ctx* c, const uint8_t* in, size_t n, int level, uint8_t* out, size_t cap, size_t* out_n) {
-    CK(cudaSetDevice(c->device));
+    ON_DEVICE(c);
     int rc;
     const size_t bound = b200_deflate_bound(n);
     if ((rc = c->d_in.ensure(n + 64))) return rc;
@@ -1056,23 +1072,27 @@ static int inflate_host(const uint8_t* in, size_t n, void* out, size_t cap, void
     int rc = default_ctx(&c);
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(c->mu);
-    CK(cudaSetDevice(c->device));
+    ON_DEVICE(c);
     size_t written = 0, full = 0;
     size_t dcap = cap;
     bool piped = false;
     if (!out_alloc) {
         if ((rc = inflate_host_pipelined(c, in, n, (uint8_t*)out, cap, &written, &full, flags, &piped))) return rc;
+        // strict zlib: the trailer covers the WHOLE decoded stream; a truncating caller buffer does not excuse it
+        if (piped && adler_expect && full > cap) piped = false;
     }
     if (!piped) {
     if ((rc = c->d_in.ensure(n + 64))) return rc;
     if (n) CK(cudaMemcpyAsync(c->d_in.p, in, n, cudaMemcpyHostToDevice, c->stream));
+    const bool need_full = out_alloc || adler_expect;      // the device buffer must hold every decoded byte
     if (out_alloc) dcap = n * 4 + 65536 > (size_t)1 << 20 ? n * 4 + 65536 : (size_t)1 << 20;   // first guess
     for (int attempt = 0; attempt < 3; attempt++) {
         if ((rc = c->d_out.ensure(dcap + 64))) return rc;
         rc = b200_inflate_dev(c, c->d_in.p, n, c->d_out.p, dcap, nullptr, &written, &full, nullptr, flags, c->stream);
-        if (!out_alloc || full <= dcap) break;
+        if (!need_full || full <= dcap) break;
         dcap = full;                       // decoded size is now known exactly: one more pass
     }
+    if (!out_alloc && written > cap) written = cap;        // the caller's buffer truncates (inflate.hpp:345)
     }   // !piped
     if (rc == B200_OK && adler_expect && full <= dcap) {
         // the whole decoded stream sits in d_out: check it there

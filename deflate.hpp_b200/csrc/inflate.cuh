@@ -314,7 +314,7 @@ __device__ __forceinline__ void modlut_init(ModLut* L, uint32_t tid, uint32_t nt
 
 // Decodes blocks until BFINAL (or, if stop_at_sync, until an empty stored block).  Warp-uniform: all
 // 32 lanes execute the same symbol decode; lanes differ only in which output bytes they store.
-// Output positions are 32-bit (one stream or chunk < 4 GiB).  `cap` bounds what may be written or read
+// `cap` bounds what may be written or read
 // back; decoding continues past it so the full size is still reported (the reference truncates the
 // same way, inflate.hpp:345).  max_out: stop (END_TOO_BIG) once more than this was produced.
 __device__ int inflate_warp(InfWarp* S, const ModLut* ML, const uint8_t* in, uint64_t in_len, uint8_t* out,
@@ -325,9 +325,15 @@ __device__ int inflate_warp(InfWarp* S, const ModLut* ML, const uint8_t* in, uin
     br.base16 = in - br.skip;
     br.limit = br.skip + in_len;
     br_seek(S, br, 0, lane);
-    const uint32_t cap = (uint32_t)min(cap64, (uint64_t)0xFFFFFFF0u);
-    const uint32_t max_out = (uint32_t)min(max_out64, (uint64_t)0xFFFFFF00u);
-    uint32_t op = 0;        // bytes produced
+    // Output positions are 64-bit end to end: `op` counts bytes since the last REBASE (the hot loop keeps 32-bit
+    // arithmetic); once op passes 2 GiB the output pointers move up by 2 GiB and `base` remembers it.  Between two
+    // rebase checks (every bit-buffer refill, every stored block) op grows by at most 32 symbols x 258 bytes or one
+    // stored block of 65535, so it cannot wrap.
+    constexpr uint32_t REBASE = 0x80000000u;
+    uint64_t base = 0;      // bytes rebased away so far
+    uint32_t cap = (uint32_t)min(cap64, (uint64_t)0xFFFFFFF0u);
+    uint32_t max_out = (uint32_t)min(max_out64, (uint64_t)0xFFFFFF00u);
+    uint32_t op = 0;        // bytes produced since `base`
     const bool strict = flags & 1u;
     const uint64_t in_bits = in_len * 8;
     const uint32_t wi_limit = (uint32_t)(br.limit >> 2) + 4;
@@ -341,6 +347,12 @@ __device__ int inflate_warp(InfWarp* S, const ModLut* ML, const uint8_t* in, uin
     uint32_t lit_shift = lane ? 16 : 8;
     uint32_t capl = cap > lane ? cap - lane : 0;                 // op < capl  <=>  op + lane < cap
     asm volatile("" : "+l"(outl), "+l"(outb), "+r"(lit_shift), "+r"(capl));
+    auto rebase = [&]() {
+        outl += REBASE; outb += REBASE; out += REBASE; op -= REBASE; base += REBASE;
+        cap = (uint32_t)min(cap64 > base ? cap64 - base : (uint64_t)0, (uint64_t)0xFFFFFFF0u);
+        max_out = (uint32_t)min(max_out64 > base ? max_out64 - base : (uint64_t)0, (uint64_t)0xFFFFFF00u);
+        capl = cap > lane ? cap - lane : 0;
+    };
     int st = ST_OK;
     uint32_t empty_run = 0;
     end_flags = 0;
@@ -377,6 +389,7 @@ __device__ int inflate_warp(InfWarp* S, const ModLut* ML, const uint8_t* in, uin
                 for (uint32_t i = lane; i < ncopy; i += 32) dp[i] = sp[i];
             }
             op += len;
+            if (op >= REBASE) rebase();
             __syncwarp();
             br_seek(S, br, bpos + len, lane);
             if (len == 0 && !bfinal && padbits == 0) {
@@ -400,6 +413,7 @@ __device__ int inflate_warp(InfWarp* S, const ModLut* ML, const uint8_t* in, uin
                     br.wi++;
                     if ((br.wi & 127) == 0) ring_fill(S, br, (br.wi >> 7) + 1, lane);
                     if (br.wi > wi_limit || op > max_out) break;        // resolved after the loop
+                    if (op >= REBASE) rebase();
                 }
                 uint32_t e = S->lit[br_peek(br, LIT_BITS)];
                 if ((int32_t)e >= 0) {
@@ -447,7 +461,7 @@ __device__ int inflate_warp(InfWarp* S, const ModLut* ML, const uint8_t* in, uin
                 const uint32_t dne = (de >> 8) & 15u;
                 const uint32_t dist = (de >> 16) + br_peek(br, dne);
                 br_drop(br, dne);
-                if (dist > op) {
+                if (dist > op && base == 0) {
                     // reaches before the first byte this warp produced
                     if (stop_at_sync) { end_flags |= END_NEEDS_HISTORY; st = ST_DATA; break; }
                     if (strict) { st = ST_DATA; break; }
@@ -499,7 +513,7 @@ __device__ int inflate_warp(InfWarp* S, const ModLut* ML, const uint8_t* in, uin
     }
     __syncwarp();
     if (br_bitpos(br) > in_bits) st = ST_OVERRUN;   // whatever else went wrong, the reference would have thrown first
-    out_len = op;
+    out_len = base + op;
     in_used = (br_bitpos(br) + 7) >> 3;
     return st;
 }

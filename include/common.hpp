@@ -19,6 +19,8 @@
 #include <fstream>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
+#include <utility>
 #include <vector>
 
 #include "b200_deflate.h"

@@ -37,14 +37,19 @@ public:
         return out.size();
     }
 
-    // README form: bool selects fast (false) or better (true).
-    static std::vector<uint8_t> compress(char* data, size_t data_size, bool better) {
+    // README form: bool selects fast (false) or better (true).  Templates constrained to exactly `bool`, so every
+    // other integral level type (unsigned, long, size_t, int64_t ...) still resolves to the int overloads above,
+    // as it does in the reference.
+    template <class B, typename std::enable_if<std::is_same<B, bool>::value, int>::type = 0>
+    static std::vector<uint8_t> compress(char* data, size_t data_size, B better) {
         return compress(data, data_size, better ? B200_LEVEL_BETTER : B200_LEVEL_FAST);
     }
-    static std::vector<uint8_t> compress(std::vector<uint8_t>& data, bool better) {
+    template <class B, typename std::enable_if<std::is_same<B, bool>::value, int>::type = 0>
+    static std::vector<uint8_t> compress(std::vector<uint8_t>& data, B better) {
         return compress(data, better ? B200_LEVEL_BETTER : B200_LEVEL_FAST);
     }
-    static size_t compress(std::string file_path, std::string new_file, bool better) {
+    template <class B, typename std::enable_if<std::is_same<B, bool>::value, int>::type = 0>
+    static size_t compress(std::string file_path, std::string new_file, B better) {
         return compress(std::move(file_path), std::move(new_file), better ? B200_LEVEL_BETTER : B200_LEVEL_FAST);
     }
 };

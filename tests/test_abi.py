@@ -82,6 +82,16 @@ int main() {
     std::vector<uint8_t> (*d4)(void*, size_t) = &inflate::decompressZlib;
     std::vector<uint8_t> (*d5)(std::vector<uint8_t>) = &inflate::decompress;
     size_t (*d6)(std::string, std::string) = &inflate::decompress;
+    // every integral level type the reference accepts must still resolve (ADVICE r1: the bool overloads made
+    // unsigned / long / size_t ambiguous); only an exact bool picks the README form
+    if (false) {
+        std::vector<uint8_t> v;
+        unsigned lu = 2; long ll = 2; size_t ls = 2; int64_t l64 = 2; short sh = 2; char ch = 2;
+        deflate::compress(v, lu); deflate::compress(v, ll); deflate::compress(v, ls); deflate::compress(v, l64);
+        deflate::compress(v, sh); deflate::compress(v, ch); deflate::compress(v, true);
+        deflate::compress((char*)nullptr, (size_t)0, lu); deflate::compress((char*)nullptr, (size_t)0, false);
+        deflate::compress("a", "b", ls); deflate::compress("a", "b", false);
+    }
     return !(c1 && c2 && c3 && d1 && d2 && d3 && d4 && d5 && d6);
 }
 ''' % (ROOT, ROOT))
