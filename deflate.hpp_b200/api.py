@@ -83,6 +83,9 @@ def lib():
     L.b200_deflate_compress_stage2_dev.restype = c_int
     L.b200_inflate_dev.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p, P(c_size_t),
                                    P(c_size_t), c_void_p, c_uint, c_void_p]
+    L.b200_inflate_shard_dev.argtypes = [c_void_p, c_void_p, c_size_t, c_size_t, c_size_t, c_int, c_int, c_void_p, c_size_t,
+                                         P(c_size_t), P(c_size_t), P(c_size_t), c_uint, c_void_p]
+    L.b200_inflate_shard_dev.restype = c_int
     L.b200_inflate_batch_dev.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                          c_void_p, c_void_p, c_size_t, c_uint, c_void_p]
     L.b200_corpus_generate_dev.argtypes = [c_void_p, c_u64, c_u64, c_u64, c_void_p]
@@ -253,6 +256,16 @@ class Context:
         if rc:
             raise B200Error(rc, "b200_inflate_dev")
         return out_n.value, full.value
+
+    def inflate_shard_dev(self, d_in, n, lo, hi, first_is_start, ends_stream, d_out, cap, flags=0, stream=0):
+        """A window of a longer stream (multi-GPU inflate).  Returns (decoded bytes, chunks, next_start)."""
+        out_n, nch, nxt = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()
+        rc = lib().b200_inflate_shard_dev(self._h, d_in, n, lo, hi, 1 if first_is_start else 0, 1 if ends_stream else 0,
+                                          d_out, cap, ctypes.byref(out_n), ctypes.byref(nch), ctypes.byref(nxt),
+                                          flags, stream or None)
+        if rc:
+            raise B200Error(rc, "b200_inflate_shard_dev")
+        return out_n.value, nch.value, nxt.value
 
     def inflate_batch_dev(self, d_in, d_in_off, d_in_len, d_out, d_out_off, d_out_cap, d_out_len, d_status,
                           n_streams, flags=0, stream=0):

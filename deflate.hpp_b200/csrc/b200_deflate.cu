@@ -714,6 +714,116 @@ int b200_inflate_batch_dev(b200_ctx* c, const void* d_in, const uint64_t* d_in_o
     return B200_OK;
 }
 
+// number of candidates below `hi` (candidates are sorted): one thread, binary search
+__global__ void count_below_kernel(const uint64_t* __restrict__ cand, uint64_t ncand, uint64_t hi, unsigned long long* __restrict__ out) {
+    uint64_t lo = 0, up = ncand;
+    while (lo < up) {
+        const uint64_t mid = (lo + up) >> 1;
+        if (cand[mid] < hi) lo = mid + 1; else up = mid;
+    }
+    *out = lo;
+}
+
+// Chunk-parallel decode of in[0..n) (the stream, or a window of it).  Chunk starts = byte 0 (if first_is_start) and the
+// byte after every separator tail; chunks that START in [lo, hi) are decoded to out + k * 64 KiB.  If the window ends
+// the stream (expect_final) the last chunk must carry BFINAL, otherwise every decoded chunk must be a full one that ends
+// at the next chunk start (or exactly at n).  *valid = the optimistic layout held; *total = decoded bytes; *nunits =
+// chunks decoded; *next_start = offset of the first chunk that was NOT decoded (n if none).  Synchronizes `st`.
+static int inflate_chunked(b200_ctx* c, const uint8_t* in, uint64_t n, uint64_t lo, uint64_t hi, bool first_is_start, bool expect_final,
+                           uint8_t* out, uint64_t cap, unsigned flags, cudaStream_t st, bool* valid, uint64_t* total,
+                           uint64_t* nunits, uint64_t* next_start) {
+    int rc;
+    *valid = false; *total = 0;
+    if (nunits) *nunits = 0;
+    if (next_start) *next_start = n;
+    if ((rc = c->result.ensure(64))) return rc;
+    unsigned long long* d_result = (unsigned long long*)c->result.p;   // [0] valid, [1] total, [2] marks, [3] units below hi
+    const uint64_t nwarps = (n + SYNC_REGION - 1) / SYNC_REGION;
+    const uint64_t cand_cap = n / 64 + 1024;
+    if ((rc = c->counts.ensure(nwarps * 4))) return rc;
+    if ((rc = c->woffs.ensure((nwarps + 1) * 8))) return rc;
+    if ((rc = c->cand.ensure((cand_cap + 2) * 8))) return rc;
+    if ((rc = c->sync_cache.ensure(nwarps * SYNC_CACHE * 4))) return rc;
+    uint64_t* cand0 = (uint64_t*)c->cand.p;
+    const uint32_t g = (uint32_t)((nwarps * 32 + 255) / 256);
+    PROF_BEGIN(c, K_FIND_SYNC, st);
+    const uint64_t min_cand = lo ? lo - 1 : 0;         // a chunk start s is reported iff s > min_cand
+    find_sync_kernel<false><<<g, 256, 0, st>>>(in, n, (uint32_t*)c->counts.p, (uint32_t*)c->sync_cache.p, nullptr, nullptr, 0, min_cand);
+    LAUNCHED();
+    PROF_END(c, st);
+    PROF_BEGIN(c, K_SCAN, st);
+    scan_sizes_kernel<<<1, SCAN_THREADS, 0, st>>>((const uint32_t*)c->counts.p, (uint32_t)nwarps, nullptr,
+                                                 (uint64_t*)c->woffs.p, (uint64_t*)d_result + 2);
+    LAUNCHED();
+    PROF_END(c, st);
+    uint64_t nmark = 0;
+    CK(cudaMemcpyAsync(&nmark, d_result + 2, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (nmark + 1 > cand_cap) return B200_OK;          // not ours: far too many separators
+    CK(cudaMemsetAsync(cand0, 0, 8, st));               // cand0[0] = 0
+    if (nmark) {
+        PROF_BEGIN(c, K_FIND_SYNC, st);
+        find_sync_kernel<true><<<g, 256, 0, st>>>(in, n, (uint32_t*)c->counts.p, (uint32_t*)c->sync_cache.p,
+                                                  (const uint64_t*)c->woffs.p, cand0 + 1, nmark, min_cand);
+        LAUNCHED();
+        PROF_END(c, st);
+    }
+    const uint64_t n64 = n;
+    CK(cudaMemcpyAsync(cand0 + nmark + 1, &n64, 8, cudaMemcpyHostToDevice, st));      // sentinel: the last chunk ends at n
+    uint64_t* cand = first_is_start ? cand0 : cand0 + 1;
+    const uint64_t ncand = first_is_start ? nmark + 1 : nmark;
+    uint64_t units = ncand;
+    if (hi < n && ncand) {
+        count_below_kernel<<<1, 1, 0, st>>>(cand, ncand, hi, d_result + 3);
+        LAUNCHED();
+        CK(cudaMemcpyAsync(&units, d_result + 3, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    if (units == 0) { *valid = true; return B200_OK; }
+    const bool ends_stream = expect_final && units == ncand;
+    const unsigned long long init[2] = {1ull, 0ull};
+    CK(cudaMemcpyAsync(d_result, init, 16, cudaMemcpyHostToDevice, st));
+    if (c->inflate_warp_path) {
+        if (!ends_stream || !first_is_start) return B200_OK;         // A/B path: whole streams only
+        if ((rc = c->res.ensure(ncand * sizeof(ChunkResult)))) return rc;
+        if ((rc = c->counter.ensure(64))) return rc;
+        CK(cudaMemsetAsync(c->counter.p, 0, 8, st));
+        PROF_BEGIN(c, K_INFLATE_CHUNKS, st);
+        {
+            const uint64_t want = (ncand + INF_WARPS - 1) / INF_WARPS;
+            inflate_chunks_kernel<<<(uint32_t)(want < c->inf_grid ? want : c->inf_grid), INF_THREADS, 0, st>>>(
+                in, n, cand, ncand, out, cap, (ChunkResult*)c->res.p, flags, (unsigned long long*)c->counter.p);
+        }
+        LAUNCHED();
+        PROF_END(c, st);
+        PROF_BEGIN(c, K_VALIDATE, st);
+        validate_chunks_kernel<<<(uint32_t)((ncand + 255) / 256), 256, 0, st>>>(cand, ncand, (const ChunkResult*)c->res.p, d_result);
+        LAUNCHED();
+        PROF_END(c, st);
+    } else {
+        if ((rc = inflate_chunks_two_pass(c, in, n, cand, units, out, cap, flags, st))) return rc;
+        PROF_BEGIN(c, K_VALIDATE, st);
+        validate_units_kernel<<<(uint32_t)((units + 255) / 256), 256, 0, st>>>(cand, units, (uint64_t)n, (const TpResult*)c->tpres.p, d_result,
+                                                                              ends_stream ? 1 : 0);
+        LAUNCHED();
+        PROF_END(c, st);
+    }
+    unsigned long long verdict[2] = {0, 0};
+    uint64_t nxt = n;
+    CK(cudaMemcpyAsync(verdict, d_result, 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&nxt, cand + units, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (verdict[0] == 1) {
+        *valid = true; *total = verdict[1];
+        if (nunits) *nunits = units;
+        if (next_start) *next_start = nxt;
+    }
+    return B200_OK;
+}
+
+static int inflate_foreign(b200_ctx* c, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t cap, unsigned flags, cudaStream_t st,
+                           bool* done, uint64_t* full);
+
 // Single stream.  Synchronizes `stream` internally (the candidate count and the validation verdict
 // steer the launches).
 int b200_inflate_dev(b200_ctx* c, const void* d_in, size_t n, void* d_out, size_t cap, uint64_t* d_out_n,
@@ -727,73 +837,12 @@ int b200_inflate_dev(b200_ctx* c, const void* d_in, size_t n, void* d_out, size_
     uint64_t full = 0;
     bool done = false;
 
-    if ((rc = c->result.ensure(64))) return rc;
-    unsigned long long* d_result = (unsigned long long*)c->result.p;   // [0] valid, [1] total, [2..] fallback scratch
-
     if (n >= 8 && !getenv("B200_INFLATE_SEQUENTIAL")) {
-        // ---- candidates ----
-        const uint64_t nwarps = (n + SYNC_REGION - 1) / SYNC_REGION;
-        const uint64_t cand_cap = n / 64 + 1024;
-        if ((rc = c->counts.ensure(nwarps * 4))) return rc;
-        if ((rc = c->woffs.ensure((nwarps + 1) * 8))) return rc;
-        if ((rc = c->cand.ensure((cand_cap + 1) * 8))) return rc;
-        uint64_t* cand = (uint64_t*)c->cand.p;
-        const uint32_t g = (uint32_t)((nwarps * 32 + 255) / 256);
-        if ((rc = c->sync_cache.ensure(nwarps * SYNC_CACHE * 4))) return rc;
-        PROF_BEGIN(c, K_FIND_SYNC, st);
-        find_sync_kernel<false><<<g, 256, 0, st>>>(in, n, (uint32_t*)c->counts.p, (uint32_t*)c->sync_cache.p, nullptr, nullptr, 0, 0);
-        LAUNCHED();
-        PROF_END(c, st);
-        PROF_BEGIN(c, K_SCAN, st);
-        scan_sizes_kernel<<<1, SCAN_THREADS, 0, st>>>((const uint32_t*)c->counts.p, (uint32_t)nwarps, nullptr,
-                                                     (uint64_t*)c->woffs.p, (uint64_t*)d_result + 2);
-        LAUNCHED();
-        PROF_END(c, st);
-        uint64_t nmark = 0;
-        CK(cudaMemcpyAsync(&nmark, d_result + 2, 8, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        if (nmark + 1 <= cand_cap) {
-            const uint64_t ncand = nmark + 1;
-            CK(cudaMemsetAsync(cand, 0, 8, st));   // cand[0] = 0
-            if (nmark) {
-                PROF_BEGIN(c, K_FIND_SYNC, st);
-                find_sync_kernel<true><<<g, 256, 0, st>>>(in, n, (uint32_t*)c->counts.p, (uint32_t*)c->sync_cache.p,
-                                                          (const uint64_t*)c->woffs.p, cand + 1, nmark, 0);
-                LAUNCHED();
-                PROF_END(c, st);
-            }
-            const unsigned long long init[2] = {1ull, 0ull};
-            CK(cudaMemcpyAsync(d_result, init, 16, cudaMemcpyHostToDevice, st));
-            if (c->inflate_warp_path) {
-                if ((rc = c->res.ensure(ncand * sizeof(ChunkResult)))) return rc;
-                if ((rc = c->counter.ensure(64))) return rc;
-                CK(cudaMemsetAsync(c->counter.p, 0, 8, st));
-                PROF_BEGIN(c, K_INFLATE_CHUNKS, st);
-                {
-                    const uint64_t want = (ncand + INF_WARPS - 1) / INF_WARPS;
-                    inflate_chunks_kernel<<<(uint32_t)(want < c->inf_grid ? want : c->inf_grid), INF_THREADS, 0, st>>>(
-                        in, n, cand, ncand, (uint8_t*)d_out, cap, (ChunkResult*)c->res.p, flags, (unsigned long long*)c->counter.p);
-                }
-                LAUNCHED();
-                PROF_END(c, st);
-                PROF_BEGIN(c, K_VALIDATE, st);
-                validate_chunks_kernel<<<(uint32_t)((ncand + 255) / 256), 256, 0, st>>>(cand, ncand, (const ChunkResult*)c->res.p, d_result);
-                LAUNCHED();
-                PROF_END(c, st);
-            } else {
-                const uint64_t n64 = n;
-                CK(cudaMemcpyAsync(cand + ncand, &n64, 8, cudaMemcpyHostToDevice, st));      // sentinel: the last chunk ends at n
-                if ((rc = inflate_chunks_two_pass(c, in, n, cand, ncand, (uint8_t*)d_out, cap, flags, st))) return rc;
-                PROF_BEGIN(c, K_VALIDATE, st);
-                validate_units_kernel<<<(uint32_t)((ncand + 255) / 256), 256, 0, st>>>(cand, ncand, (uint64_t)n, (const TpResult*)c->tpres.p, d_result, 1);
-                LAUNCHED();
-                PROF_END(c, st);
-            }
-            unsigned long long verdict[2] = {0, 0};
-            CK(cudaMemcpyAsync(verdict, d_result, 16, cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            if (verdict[0] == 1) { done = true; full = verdict[1]; }
-        }
+        // ---- this library's own chunked streams ----
+        if ((rc = inflate_chunked(c, in, n, 0, n, true, true, (uint8_t*)d_out, cap, flags, st, &done, &full, nullptr, nullptr))) return rc;
+        // ---- anything else that is big enough to be worth it: block-parallel (inflate_foreign.cuh) ----
+        if (!done && !c->inflate_warp_path && !getenv("B200_NO_FOREIGN_PARALLEL"))
+            if ((rc = inflate_foreign(c, in, n, (uint8_t*)d_out, cap, flags, st, &done, &full))) return rc;
     }
     if (!done) {
         // ---- sequential fallback: one warp, whole stream ----
@@ -819,6 +868,35 @@ int b200_inflate_dev(b200_ctx* c, const void* d_in, size_t n, void* d_out, size_
     if (h_out_n) *h_out_n = (size_t)written;
     if (h_full_n) *h_full_n = (size_t)full;
     return status;
+}
+
+// A window of a longer stream of this library's format (multi-GPU inflate: every rank takes a byte range of the joined
+// stream plus some slack and decodes the chunks that START inside its range).
+int b200_inflate_shard_dev(b200_ctx* c, const void* d_in, size_t n, size_t lo, size_t hi, int first_is_start, int ends_stream,
+                           void* d_out, size_t cap, size_t* h_out_n, size_t* h_nchunks, size_t* h_next_start,
+                           unsigned flags, void* stream_) {
+    if (!c || (!d_in && n) || (!d_out && cap) || !h_out_n) return B200_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream_;
+    ON_DEVICE(c);
+    bool valid = false;
+    uint64_t total = 0, units = 0, nxt = n;
+    if (hi > n) hi = n;
+    if (lo > hi) return B200_E_ARG;
+    const int rc = inflate_chunked(c, (const uint8_t*)d_in, n, first_is_start ? 0 : lo, hi, first_is_start != 0, ends_stream != 0, (uint8_t*)d_out, cap, flags, st,
+                                   &valid, &total, &units, &nxt);
+    if (rc) return rc;
+    if (!valid) return B200_E_DATA;                       // not a run of this library's chunks
+    if (total > cap) return B200_E_OUTPUT;
+    *h_out_n = (size_t)total;
+    if (h_nchunks) *h_nchunks = (size_t)units;
+    if (h_next_start) *h_next_start = (size_t)nxt;
+    return B200_OK;
+}
+
+// (stub until inflate_foreign.cuh lands)
+static int inflate_foreign(b200_ctx*, const uint8_t*, uint64_t, uint8_t*, uint64_t, unsigned, cudaStream_t, bool* done, uint64_t*) {
+    *done = false;
+    return B200_OK;
 }
 
 int b200_adler32_dev(b200_ctx* c, const void* d_data, size_t n, uint32_t* h_out, uint32_t* d_out, void* stream_) {

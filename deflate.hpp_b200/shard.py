@@ -113,6 +113,7 @@ class PipelinedGather:
         self.offset = 0          # bytes of the joined stream placed so far (all rounds before this one)
         self.pending = []
         self.peer_dst = None
+        self.symm = symm_handle
         if symm_handle is not None:
             n = recv_buf.numel()
             self.peer_dst = symm_handle.get_buffer(dst, (n,), torch.uint8)   # the destination's buffer, peer-mapped
@@ -150,8 +151,209 @@ class PipelinedGather:
             w.wait()
         self.pending = []
         if self.peer_dst is not None:
-            # one-sided writes: the destination may only read once every writer's copies have landed
-            torch.cuda.current_stream().synchronize()
-            dist.barrier()
+            # one-sided writes: the destination may only read once every writer's copies have landed.  A
+            # symmetric-memory barrier is a few flag writes over NVLink, ordered on the current stream behind the
+            # copies -- no host synchronisation, no NCCL kernel (B200_GATHER_HOST_BARRIER=1: the round-1 way)
+            import os
+            if self.symm is not None and hasattr(self.symm, "barrier") and os.environ.get("B200_GATHER_HOST_BARRIER", "0") != "1":
+                self.symm.barrier()
+            else:
+                torch.cuda.current_stream().synchronize()
+                dist.barrier()
         total, self.offset = self.offset, 0
         return total
+
+
+# ---- the product-level multi-GPU calls --------------------------------------------------------------
+# BASELINE config 5: one large input partitioned across the GPUs of a box, every GPU's compressed bytes
+# gathered to rank 0 for concatenation; and the way back: the joined stream on rank 0 is cut into byte
+# ranges, every rank pulls its range and inflates the chunks that start inside it.
+
+CHUNK = 65536
+WINDOW_SLACK = CHUNK + 4096          # a chunk that starts just below a range's end reaches at most this far past it
+                                     # (stored chunk: 64 KiB + 2 block headers + separator; the segment index only
+                                     # goes in front of chunks that save at least 1280 bytes)
+
+
+def round_plan(chunks_per_rank: int, min_round: int = 1024) -> List[int]:
+    """Chunks per round for one rank.  What a step cannot hide is the copy of the LAST round, so the rounds
+    shrink: 4/16, 4/16, 4/16, 2/16, 1/16, 1/16 of the shard -- as long as the smallest round keeps `min_round`
+    chunks (below 64 MiB the persistent matcher starves); smaller shards get four
+    equal rounds, or one."""
+    c = int(chunks_per_rank)
+    if c <= 0:
+        return []
+    if c // 16 >= min_round:
+        u = c // 16
+        plan = [4 * u, 4 * u, 4 * u, 2 * u, u, u]
+        plan[0] += c - 16 * u
+        return plan
+    if c // 4 >= min_round:
+        u = c // 4
+        return [u + (c - 4 * u), u, u, u]
+    return [c]
+
+
+def round_layout(plan: List[int], rank: int, world: int) -> List[Tuple[int, int, int]]:
+    """For every round k: (global index of the first chunk this rank compresses, chunks, first chunk inside the
+    rank's local buffer).  Round k covers global chunks [world * P_k, world * (P_k + S_k)), P_k = sum of the rounds
+    before it; rank r takes [world * P_k + r * S_k, + S_k).  Concatenating rounds in order, ranks in order inside a
+    round, gives the corpus in order."""
+    out, before = [], 0
+    for s in plan:
+        out.append((world * before + rank * s, s, before))
+        before += s
+    return out
+
+
+class ShardedDeflate:
+    """deflate::compress / inflate::decompress of ONE stream over the GPUs of one box (one process per GPU,
+    torch.distributed; BASELINE config 5).
+
+    compress(): every rank compresses its block-cyclic share round by round (F_NOT_LAST everywhere but on the very
+    last slice), the 8-byte sizes of a round travel through an all_gather that is enqueued between two rounds on the
+    compute stream, and every rank writes its compressed slice at its final offset of the joined stream in rank
+    `dst`'s memory -- NVLink peer copies on the copy engines (symmetric memory) while the next round is being
+    compressed, NCCL send/recv where symmetric memory is not available.  The result on `dst` is one valid raw
+    DEFLATE stream, byte-identical to what one GPU produces for the whole input when the slices are whole chunks.
+
+    inflate(): the joined stream on `dst` is cut into `world` byte ranges; every rank pulls its range (plus slack for
+    the chunk that straddles the range's end) over NVLink and decodes the chunks that START inside the range
+    (b200_inflate_shard_dev).  Outputs stay sharded: rank r holds the stream's bytes [out_first, out_first + out_n).
+
+    `codec` needs compress_dev / inflate_shard_dev / deflate_bound with the signatures of api.Context (tests inject a
+    CPU stand-in; the product passes the Context of the rank's GPU).
+    """
+
+    def __init__(self, codec, device, chunks_per_rank: int, dst: int = 0, plan: List[int] = None,
+                 not_last_flag: int = 1, bound=None, transport: str = "auto"):
+        self.codec, self.device, self.dst = codec, device, dst
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        self.plan = list(plan) if plan else round_plan(chunks_per_rank)
+        assert sum(self.plan) == chunks_per_rank
+        self.layout = round_layout(self.plan, self.rank, self.world)
+        self.not_last = not_last_flag
+        self.bound = bound
+        self.cuda = torch.device(device).type == "cuda"
+        rounds = len(self.plan)
+        self.dst_cap = [bound(s * CHUNK) for s in self.plan]
+        self.dst_off = [sum(self.dst_cap[:k]) for k in range(rounds)]
+        self.local = torch.empty(sum(self.dst_cap) + 4096, dtype=torch.uint8, device=device)
+        total_cap = bound(chunks_per_rank * CHUNK) * self.world
+        self.symm = None
+        self.joined_buf = None
+        if self.cuda and transport in ("auto", "p2p_copy"):
+            self.joined_buf, self.symm = symmetric_buffer(total_cap, device)
+        if self.symm is None:
+            self.joined_buf = torch.empty(total_cap, dtype=torch.uint8, device=device) if self.rank == dst else None
+        self.transport = ("nvlink peer copy (symmetric memory, copy engines)" if self.symm is not None
+                          else "send/recv (%s)" % dist.get_backend())
+        self.gather = PipelinedGather(self.joined_buf, dst=dst, symm_handle=self.symm)
+        self.sizes_dev = torch.zeros(rounds, dtype=torch.int64, device=device)
+        self.allsz_dev = torch.zeros(rounds, self.world, dtype=torch.int64, device=device)
+        self.allsz_host = torch.zeros(rounds, self.world, dtype=torch.int64)
+        if self.cuda:
+            self.allsz_host = self.allsz_host.pin_memory()
+            self.side = torch.cuda.Stream(device=device)
+            self.round_done = [torch.cuda.Event() for _ in range(rounds)]
+        self.joined_n = 0
+
+    # -- compress ------------------------------------------------------------------------------------
+    def compress(self, src: torch.Tensor, level: int) -> int:
+        """src: this rank's slices back to back in round order (round k at chunk offset layout[k][2]).  Returns the size of the
+        joined stream (every rank gets it); the bytes are in self.joined_buf on rank `dst`."""
+        rounds = len(self.plan)
+        last_rank = self.rank == self.world - 1
+        if self.cuda:
+            main = torch.cuda.current_stream()
+            st = main.cuda_stream
+        for k, (_, nchunks, first) in enumerate(self.layout):
+            flags = 0 if (k == rounds - 1 and last_rank) else self.not_last      # only the stream's very last chunk is final
+            out = self.local[self.dst_off[k]:self.dst_off[k] + self.dst_cap[k]]
+            if self.cuda:
+                self.codec.compress_dev(src.data_ptr() + first * CHUNK, nchunks * CHUNK, level, out.data_ptr(), self.dst_cap[k],
+                                        flags=flags, stream=st, d_out_n=self.sizes_dev[k:k + 1].data_ptr(), sync=False)
+            else:
+                self.sizes_dev[k] = self.codec.compress_dev(src[first * CHUNK:(first + nchunks) * CHUNK], level, out, flags)
+            # the sizes of this round: on the compute stream, BETWEEN two rounds (a collective posted on a side stream
+            # waits for an SM until the persistent matcher of the next round ends)
+            dist.all_gather_into_tensor(self.allsz_dev[k], self.sizes_dev[k:k + 1])
+            self.allsz_host[k].copy_(self.allsz_dev[k], non_blocking=True)
+            if self.cuda:
+                self.round_done[k].record(main)
+        # trail the rounds on a side stream: each slice goes to its final offset as soon as its round's sizes are known
+        if self.cuda:
+            with torch.cuda.stream(self.side):
+                for k in range(rounds):
+                    self.round_done[k].synchronize()           # host: this round's sizes are in pinned memory
+                    self.side.wait_event(self.round_done[k])
+                    self.gather.post_round(self.local[self.dst_off[k]:self.dst_off[k] + self.dst_cap[k]], None,
+                                           sizes=[int(x) for x in self.allsz_host[k].tolist()])
+                self.joined_n = self.gather.finish()
+            main.wait_stream(self.side)
+        else:
+            for k in range(rounds):
+                self.gather.post_round(self.local[self.dst_off[k]:self.dst_off[k] + self.dst_cap[k]], None,
+                                       sizes=[int(x) for x in self.allsz_host[k].tolist()])
+            self.joined_n = self.gather.finish()
+        return self.joined_n
+
+    def local_compressed_bytes(self) -> int:
+        return int(self.allsz_host[:, self.rank].sum())
+
+    # -- inflate -------------------------------------------------------------------------------------
+    def byte_range(self, n: int, rank: int = None) -> Tuple[int, int]:
+        r = self.rank if rank is None else rank
+        return (n * r) // self.world, (n * (r + 1)) // self.world
+
+    def inflate(self, joined_n: int, out: torch.Tensor, window: torch.Tensor = None):
+        """Decode this rank's share of the joined stream (joined_n bytes in rank dst's joined_buf) into `out`.
+        Returns (out_n, n_chunks, out_first): this rank produced the stream's bytes [out_first, out_first + out_n)."""
+        lo, hi = self.byte_range(joined_n)
+        ws = 0 if self.rank == 0 else max(0, (lo - 16) & ~15)
+        we = min(joined_n, hi + WINDOW_SLACK)
+        if window is None or window.numel() < we - ws:
+            window = torch.empty(max(we - ws, 16), dtype=torch.uint8, device=self.device)
+        self.pull(window, ws, we, joined_n)
+        ends = we == joined_n
+        if self.cuda:
+            st = torch.cuda.current_stream().cuda_stream
+            out_n, nch, _ = self.codec.inflate_shard_dev(window.data_ptr(), we - ws, lo - ws, hi - ws, self.rank == 0, ends,
+                                                         out.data_ptr(), out.numel(), stream=st)
+        else:
+            out_n, nch, _ = self.codec.inflate_shard_dev(window[:we - ws], lo - ws, hi - ws, self.rank == 0, ends, out)
+        mine = torch.tensor([out_n, nch], dtype=torch.int64, device=self.device)
+        allv = torch.zeros(self.world * 2, dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(allv, mine)
+        self.inflate_sizes = [int(x) for x in allv[0::2].tolist()]
+        out_first = sum(self.inflate_sizes[:self.rank])
+        return out_n, nch, out_first
+
+    def pull(self, window: torch.Tensor, ws: int, we: int, joined_n: int):
+        """window[0 : we - ws) <- joined stream bytes [ws, we) from rank dst."""
+        n = we - ws
+        if n <= 0:
+            return
+        if self.symm is not None:
+            peer = self.symm.get_buffer(self.dst, (self.joined_buf.numel(),), torch.uint8)
+            self.symm.barrier()                          # dst's buffer is complete (and nobody is still writing it)
+            window[:n].copy_(peer[ws:we], non_blocking=True)
+            return
+        # no peer mapping: dst sends every rank its window
+        if self.rank == self.dst:
+            ops = []
+            for r in range(self.world):
+                if r == self.dst:
+                    continue
+                rlo, rhi = self.byte_range(joined_n, r)
+                rws = 0 if r == 0 else max(0, (rlo - 16) & ~15)
+                rwe = min(joined_n, rhi + WINDOW_SLACK)
+                if rwe > rws:
+                    ops.append(dist.P2POp(dist.isend, self.joined_buf[rws:rwe], r))
+            window[:n].copy_(self.joined_buf[ws:we])
+            if ops:
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()
+        else:
+            for w in dist.batch_isend_irecv([dist.P2POp(dist.irecv, window[:n], self.dst)]):
+                w.wait()

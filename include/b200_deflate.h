@@ -161,6 +161,18 @@ int b200_inflate_dev(b200_ctx* ctx, const void* d_in, size_t n, void* d_out, siz
                      uint64_t* d_out_n, size_t* h_out_n, size_t* h_full_n, int32_t* d_status,
                      unsigned flags, void* stream);
 
+/* Multi-GPU inflate of one stream of this library's format: every GPU takes a WINDOW d_in[0..n) of the joined
+ * stream -- its byte range plus slack for the chunk that straddles the range's end -- and decodes the chunks that
+ * START at window offsets in [lo, hi) (hi >= n: up to the end).  first_is_start: a chunk begins at byte 0 of the
+ * window (true for the window at offset 0 of the stream; lo is then ignored); otherwise chunk starts are the bytes
+ * behind the chunk separators found in the window (the window must begin at least 9 bytes below lo).  ends_stream: the window contains the end of the stream (its last chunk carries BFINAL).
+ * Chunk k of the window goes to d_out + k * 64 KiB.  *h_out_n = decoded bytes, *h_nchunks = chunks decoded,
+ * *h_next_start = window offset of the first chunk NOT decoded (n if none).  B200_E_DATA if the window is not a run
+ * of this library's chunks.  Synchronizes `stream`. */
+int b200_inflate_shard_dev(b200_ctx* ctx, const void* d_in, size_t n, size_t lo, size_t hi, int first_is_start,
+                           int ends_stream, void* d_out, size_t cap, size_t* h_out_n, size_t* h_nchunks,
+                           size_t* h_next_start, unsigned flags, void* stream);
+
 /* Batch inflate: n_streams independent raw streams, one warp each (BASELINE config 4).
  * Stream i is d_in + d_in_off[i], d_in_len[i] bytes; output goes to d_out + d_out_off[i], at most
  * d_out_cap[i] bytes (truncating); d_out_len[i] = full decoded size; d_status[i] = B200_* code. */

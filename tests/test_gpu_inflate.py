@@ -346,3 +346,83 @@ print("ok", b200.launch_count())
     env = dict(os.environ, B200_HOST_INFLATE_SLICE=str(1 << 20))
     r = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_zlib_strict_with_truncating_buffer(b200):
+    """with a caller buffer smaller than the decoded size, strict mode must still verify the trailer
+    (the whole stream is decoded on the device; only the copy back is truncated)."""
+    data = datagen.text_like(300000, seed=35)
+    z = zlib.compress(data, 6)
+    assert b200.decompress_zlib(z, out_size=1000, flags=b200.F_STRICT) == data[:1000]
+    bad = z[:-1] + bytes([z[-1] ^ 1])
+    assert b200.decompress_zlib(bad, out_size=1000) == data[:1000]            # reference behaviour: trailer ignored
+    with pytest.raises(b200.B200Error) as e:
+        b200.decompress_zlib(bad, out_size=1000, flags=b200.F_STRICT)
+    assert e.value.code == 2
+
+
+def test_one_warp_decoder_beyond_4gib(b200, monkeypatch):
+    """the sequential one-warp decoder keeps 64-bit output positions (rebased every 2 GiB).  The stream is
+    built on the device: 4.25 GiB in stored blocks of 65535 bytes, then a zlib-6 coded tail (literals and matches
+    decoded with positions beyond 4 GiB).  Decoded by ONE warp (B200_INFLATE_SEQUENTIAL=1): exact size, right bytes
+    on both sides of the 2 GiB and 4 GiB marks and in the tail; a smaller capacity truncates and still reports the
+    full size."""
+    import torch
+    nblocks = (17 << 28) // 65535 + 1
+    nstored = nblocks * 65535
+    tail = datagen.text_like(300000, seed=77)
+    ztail = zlib.compressobj(6, zlib.DEFLATED, -15)
+    ztail = ztail.compress(tail) + ztail.flush()
+    dev = "cuda"
+    payload = (torch.arange(nstored, device=dev, dtype=torch.int64) * 2654435761 >> 7).to(torch.uint8)
+    stream = torch.empty(nblocks * 65540 + len(ztail), dtype=torch.uint8, device=dev)
+    blocks = stream[:nblocks * 65540].view(nblocks, 65540)
+    blocks[:, 0] = 0
+    blocks[:, 1:3] = 0xFF
+    blocks[:, 3:5] = 0
+    blocks[:, 5:] = payload.view(nblocks, 65535)
+    stream[nblocks * 65540:] = torch.frombuffer(bytearray(ztail), dtype=torch.uint8).to(dev)
+    n = nstored + len(tail)
+    assert n > (1 << 32) + (1 << 28)
+    monkeypatch.setenv("B200_INFLATE_SEQUENTIAL", "1")
+    ctx = b200.Context(0)
+    out = torch.zeros(n + 64, dtype=torch.uint8, device=dev)
+    w, full = ctx.inflate_dev(stream.data_ptr(), stream.numel(), out.data_ptr(), n + 64)
+    assert w == full == n
+    for lo in range(0, nstored, 1 << 30):
+        assert torch.equal(out[lo:min(nstored, lo + (1 << 30))], payload[lo:min(nstored, lo + (1 << 30))]), lo
+    assert bytes(out[nstored:n].cpu().numpy()) == tail
+    assert int(out[n:].sum().item()) == 0
+    out.zero_()
+    cap = (1 << 32) + 5
+    w, full = ctx.inflate_dev(stream.data_ptr(), stream.numel(), out.data_ptr(), cap)
+    assert w == cap and full == n
+    assert torch.equal(out[cap - 4096:cap], payload[cap - 4096:cap]) and int(out[cap:cap + 4096].sum().item()) == 0
+
+
+def test_inflate_shard_windows(b200):
+    """b200_inflate_shard_dev: a stream of this library cut into byte ranges; every range (plus slack) decodes exactly the
+    chunks that START inside it, the pieces tile the output (what ShardedDeflate.inflate does on N GPUs)."""
+    import torch
+    nchunks = 40
+    n = nchunks * b200.CHUNK - 777                            # the last chunk is partial
+    ctx = b200.Context(0)
+    src = torch.empty(nchunks * b200.CHUNK, dtype=torch.uint8, device="cuda")
+    ctx.corpus_generate_dev(src.data_ptr(), 20261018, 5, nchunks)
+    cap = b200.deflate_bound(n)
+    dst = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    cn = ctx.compress_dev(src.data_ptr(), n, 2, dst.data_ptr(), cap)
+    slack = b200.CHUNK + 4096
+    for world in (1, 2, 3, 7, 64):
+        pos = 0
+        for r in range(world):
+            lo, hi = cn * r // world, cn * (r + 1) // world
+            ws = 0 if r == 0 else max(0, (lo - 16) & ~15)
+            we = min(cn, hi + slack)
+            win = dst[ws:we].clone()
+            out = torch.zeros(n + 64, dtype=torch.uint8, device="cuda")
+            out_n, nch, nxt = ctx.inflate_shard_dev(win.data_ptr(), we - ws, lo - ws, hi - ws, r == 0, we == cn, out.data_ptr(), n + 64)
+            assert torch.equal(out[:out_n], src[pos:pos + out_n]), (world, r)
+            assert out_n == nch * b200.CHUNK or pos + out_n == n
+            pos += out_n
+        assert pos == n, world

@@ -129,3 +129,122 @@ def test_pipelined_gather_gloo(pre_exchanged):
         assert p.exitcode == 0
     expect = b"".join(bytes([97 + r + 3 * k]) * (50 * (r + 1) + 7 * k) for k in range(3) for r in range(world))
     assert joined == expect
+
+
+# ---- ShardedDeflate (the product-level multi-GPU call) with a CPU stand-in codec ---------------------
+SEP_TAIL = b"\x00\x00\xff\xff\x00\x00\x00\xff\xff"
+
+
+class _ZlibChunkCodec:
+    """Same stream STRUCTURE as the GPU compressor (independent 64 KiB chunks, each followed by the doubled empty
+    stored block, BFINAL on the last), produced with zlib so that the host logic can be tested without a GPU."""
+    CH = 65536
+
+    def deflate_bound(self, n):
+        return n + 64 * ((n + self.CH - 1) // self.CH) + 64
+
+    def compress_dev(self, src, level, out, flags):
+        data = bytes(src.numpy())
+        parts = []
+        nch = (len(data) + self.CH - 1) // self.CH
+        for i in range(nch):
+            co = zlib.compressobj(6, zlib.DEFLATED, -15)
+            last = i == nch - 1 and not (flags & 1)
+            body = co.compress(data[i * self.CH:(i + 1) * self.CH])
+            parts.append(body + (co.flush() if last else co.flush(zlib.Z_FULL_FLUSH) + b"\x00\x00\x00\xff\xff"))
+        blob = b"".join(parts)
+        out[:len(blob)] = torch.frombuffer(bytearray(blob), dtype=torch.uint8)
+        return len(blob)
+
+    def inflate_shard_dev(self, window, lo, hi, first_is_start, ends_stream, out):
+        w = bytes(window.numpy())
+        starts = [0] if first_is_start else []
+        p = w.find(SEP_TAIL)
+        while p >= 0:
+            s = p + len(SEP_TAIL)
+            if s < len(w) and (s >= lo or first_is_start) and s > 0:
+                starts.append(s)
+            p = w.find(SEP_TAIL, p + 1)
+        starts = sorted(set(starts))
+        mine = [s for s in starts if s < hi]
+        bounds = starts + [len(w)]
+        pos = 0
+        for s in mine:
+            e = bounds[bounds.index(s) + 1]
+            piece = zlib.decompressobj(-15).decompress(w[s:e])
+            out[pos:pos + len(piece)] = torch.frombuffer(bytearray(piece), dtype=torch.uint8)
+            pos += len(piece)
+        nxt = bounds[len(mine)] if len(mine) < len(bounds) else len(w)
+        return pos, len(mine), nxt
+
+
+def _corpus_chunk(i):
+    import numpy as np
+    rng = np.random.default_rng(1000 + i)
+    if i % 3 == 2:
+        return rng.integers(0, 256, 65536, dtype=np.uint8).tobytes()
+    return (bytes([97 + i % 26]) * 61 + bytes(rng.integers(0, 256, 3, dtype=np.uint8))) * 1024
+
+
+def _sharded_worker(rank, world, port, q, chunks_per_rank, plan):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sh = _shard_mod()
+        codec = _ZlibChunkCodec()
+        sd = sh.ShardedDeflate(codec, "cpu", chunks_per_rank, plan=plan, bound=codec.deflate_bound)
+        src = bytearray()
+        for first, nch, local_first in sd.layout:
+            assert local_first * 65536 == len(src)
+            for cidx in range(first, first + nch):
+                src += _corpus_chunk(cidx)
+        n = sd.compress(torch.frombuffer(src, dtype=torch.uint8), 2)
+        out = torch.zeros(chunks_per_rank * world * 65536, dtype=torch.uint8)
+        out_n, nch, out_first = sd.inflate(n, out)
+        q.put((rank, bytes(sd.joined_buf[:n].numpy()) if rank == 0 else None, out_n, nch, out_first, bytes(out[:out_n].numpy())))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,chunks_per_rank,plan", [(2, 4, [2, 1, 1]), (3, 3, [1, 1, 1]), (2, 5, None)])
+def test_sharded_deflate_gloo(world, chunks_per_rank, plan):
+    """compress: block-cyclic rounds land in order on rank 0 as ONE valid stream; inflate: byte-range windows, each
+    rank decodes exactly the chunks that start in its range, together they cover the stream once, in order."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + os.getpid() % 2000 + world * 7 + chunks_per_rank
+    procs = [ctx.Process(target=_sharded_worker, args=(r, world, port, q, chunks_per_rank, plan)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    total = b"".join(_corpus_chunk(i) for i in range(world * chunks_per_rank))
+    joined = got[0][1]
+    o = zlib.decompressobj(-15)
+    assert o.decompress(joined) == total and o.eof
+    pos = 0
+    for rank, _, out_n, nch, out_first, data in got:
+        assert out_first == pos and out_n == nch * 65536
+        assert data == total[pos:pos + out_n]
+        pos += out_n
+    assert pos == len(total)
+
+
+def test_round_plan():
+    sh = _shard_mod()
+    for c in (1, 5, 1024, 4096, 4097, 16384, 32768, 32771, 131072):
+        plan = sh.round_plan(c)
+        assert sum(plan) == c and all(x > 0 for x in plan)
+        if c >= 16384:
+            assert plan[-1] * 16 <= c and plan[-1] >= 1024
+        for world in (1, 2, 8):
+            seen = []
+            for r in range(world):
+                seen += [(f, f + s) for f, s, _ in sh.round_layout(plan, r, world)]
+            seen.sort()
+            assert seen[0][0] == 0 and seen[-1][1] == world * c
+            assert all(a[1] == b[0] for a, b in zip(seen, seen[1:]))

@@ -1,0 +1,30 @@
+#!/bin/bash
+# One gpurun call = several measurements; everything lands in gpurun_out/ (merged back by gpurun).
+# usage: tools/gpu_session.sh <tag> [steps...]   steps: pytest bench ncu_list ncu_full sanitizer probe
+tag=$1; shift
+out=gpurun_out
+mkdir -p $out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > $out/${tag}_smi.txt 2>&1
+for step in "$@"; do
+  case $step in
+    pytest)
+      timeout 1500 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest.log 2>&1; echo "pytest exit $?" >> $out/${tag}_pytest.log ;;
+    bench)
+      timeout 900 python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err; echo "bench exit $?" >> $out/${tag}_bench.err ;;
+    bench_quick)
+      timeout 600 python bench.py --steps 3 --warmup 3 --skip config5,dropin > $out/${tag}_benchq.json 2> $out/${tag}_benchq.err; echo "bench exit $?" >> $out/${tag}_benchq.err ;;
+    ncu_list)
+      timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file $out/${tag}_launches.csv \
+        python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --skip config5,dropin,batch > $out/${tag}_ncu_list.log 2>&1 ;;
+    ncu_full)
+      timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"${NCU_KERNELS:-lz77_fast_kernel|encode_kernel|huffman_kernel}" -c ${NCU_COUNT:-4} \
+        -o $out/${tag}_full -f python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --only none > $out/${tag}_ncu_full.log 2>&1 ;;
+    sanitizer)
+      timeout 1500 compute-sanitizer --tool memcheck --log-file $out/${tag}_memcheck.log python -m pytest tests -m gpu -x -q -k "${SAN_K:-edge or fixture or quirk or fuzz}" > $out/${tag}_memcheck_pytest.log 2>&1
+      timeout 1500 compute-sanitizer --tool racecheck --log-file $out/${tag}_racecheck.log python -m pytest tests -m gpu -x -q -k "${SAN_K:-edge or fixture or quirk or fuzz}" > $out/${tag}_racecheck_pytest.log 2>&1 ;;
+    probe)
+      timeout 900 python tools/dev_probe.py ${PROBE_ARGS} > $out/${tag}_probe.log 2>&1 ;;
+    *) echo "unknown step $step" ;;
+  esac
+done
+echo done > $out/${tag}_done.txt
