@@ -21,6 +21,11 @@ from .api import (  # noqa: F401
     F_NOT_LAST,
     F_NO_INDEX,
     F_STRICT,
+    F_ZLIB,
+    F_GZIP,
+    decompress_gzip,
+    compress_file,
+    decompress_file,
     compress,
     decompress,
     decompress_zlib,

@@ -22,8 +22,10 @@ CHUNK = 65536
 LEVEL_STORED, LEVEL_HUFFMAN, LEVEL_FAST, LEVEL_BETTER = 0, 1, 2, 3
 F_NOT_LAST = 1
 F_NO_INDEX = 2
+F_ZLIB = 4
+F_GZIP = 8
 F_STRICT = 1
-E_OVERRUN, E_DATA, E_OUTPUT, E_CUDA, E_ARG, E_NOMEM = 1, 2, 3, 4, 5, 6
+E_OVERRUN, E_DATA, E_OUTPUT, E_CUDA, E_ARG, E_NOMEM, E_IO = 1, 2, 3, 4, 5, 6, 7
 
 
 class B200Error(RuntimeError):
@@ -74,6 +76,17 @@ def lib():
     L.b200_inflate_alloc.argtypes = [c_void_p, c_size_t, P(c_void_p), P(c_size_t), c_uint]
     L.b200_inflate_zlib.argtypes = [c_void_p, c_size_t, c_void_p, c_size_t, P(c_size_t), P(c_size_t), c_uint]
     L.b200_inflate_zlib_alloc.argtypes = [c_void_p, c_size_t, P(c_void_p), P(c_size_t), c_uint]
+    L.b200_deflate_compress_ex.argtypes = [c_void_p, c_size_t, c_int, c_uint, P(c_void_p), P(c_size_t)]
+    L.b200_deflate_compress_into_ex.argtypes = [c_void_p, c_size_t, c_int, c_uint, c_void_p, c_size_t, P(c_size_t)]
+    L.b200_inflate_gzip.argtypes = [c_void_p, c_size_t, c_void_p, c_size_t, P(c_size_t), P(c_size_t), c_uint]
+    L.b200_inflate_gzip_alloc.argtypes = [c_void_p, c_size_t, P(c_void_p), P(c_size_t), c_uint]
+    L.b200_crc32_dev.argtypes = [c_void_p, c_void_p, c_size_t, P(ctypes.c_uint32), c_void_p, c_void_p]
+    for f in ("b200_deflate_compress_ex", "b200_deflate_compress_into_ex", "b200_inflate_gzip", "b200_inflate_gzip_alloc", "b200_crc32_dev"):
+        getattr(L, f).restype = c_int
+    L.b200_deflate_compress_file.argtypes = [ctypes.c_char_p, ctypes.c_char_p, c_int, c_uint, P(c_size_t), P(c_size_t)]
+    L.b200_deflate_compress_file.restype = c_int
+    L.b200_inflate_file.argtypes = [ctypes.c_char_p, ctypes.c_char_p, c_uint, P(c_size_t), P(c_size_t)]
+    L.b200_inflate_file.restype = c_int
     L.b200_free.argtypes = [c_void_p]
     L.b200_deflate_compress_dev.argtypes = [c_void_p, c_void_p, c_size_t, c_int, c_uint, c_void_p, c_size_t,
                                             c_void_p, P(c_size_t), c_void_p, c_void_p]
@@ -131,13 +144,14 @@ def launch_count():
     return lib().b200_launch_count()
 
 
-def compress(data, level=LEVEL_FAST):
-    """deflate::compress(char* data, size_t data_size, int compression_level) -> vector<uint8_t>."""
+def compress(data, level=LEVEL_FAST, flags=0):
+    """deflate::compress(char* data, size_t data_size, int compression_level) -> vector<uint8_t>.
+    flags: F_NO_INDEX, F_ZLIB (zlib framing, what zlib.decompress reads), F_GZIP (one gzip member)."""
     L = lib()
     addr, n, keep = _as_buffer(data)
     out = ctypes.c_void_p()
     out_n = ctypes.c_size_t()
-    rc = L.b200_deflate_compress(addr, n, _level(level), ctypes.byref(out), ctypes.byref(out_n))
+    rc = L.b200_deflate_compress_ex(addr, n, _level(level), flags, ctypes.byref(out), ctypes.byref(out_n))
     del keep
     if rc:
         raise B200Error(rc, "deflate::compress")
@@ -183,6 +197,30 @@ def decompress_zlib(data, out_size=None, flags=0):
     """inflate::decompressZlib (inflate.hpp:326,352)."""
     L = lib()
     return _inflate(L.b200_inflate_zlib_alloc, L.b200_inflate_zlib, data, out_size, flags, "inflate::decompressZlib")
+
+
+def compress_file(src, dst, level=LEVEL_FAST, flags=0):
+    """deflate::compress(std::string file_path, std::string new_file, int level): streamed in slices.  -> (bytes in, bytes out)"""
+    a, b = ctypes.c_size_t(), ctypes.c_size_t()
+    rc = lib().b200_deflate_compress_file(os.fsencode(src), os.fsencode(dst), _level(level), flags, ctypes.byref(a), ctypes.byref(b))
+    if rc:
+        raise B200Error(rc, "deflate::compress(file)")
+    return a.value, b.value
+
+
+def decompress_file(src, dst, flags=0):
+    """inflate::decompress(std::string file_path, std::string new_file).  -> (bytes in, bytes out)"""
+    a, b = ctypes.c_size_t(), ctypes.c_size_t()
+    rc = lib().b200_inflate_file(os.fsencode(src), os.fsencode(dst), flags, ctypes.byref(a), ctypes.byref(b))
+    if rc:
+        raise B200Error(rc, "inflate::decompress(file)")
+    return a.value, b.value
+
+
+def decompress_gzip(data, out_size=None, flags=0):
+    """first member of a gzip buffer (RFC 1952); F_STRICT verifies CRC-32 and ISIZE on the GPU."""
+    L = lib()
+    return _inflate(L.b200_inflate_gzip_alloc, L.b200_inflate_gzip, data, out_size, flags, "inflate (gzip)")
 
 
 class Context:
@@ -289,6 +327,14 @@ class Context:
         rc = lib().b200_adler32_dev(self._h, d_data or None, n, ctypes.byref(out), None, stream or None)
         if rc:
             raise B200Error(rc, "b200_adler32_dev")
+        return out.value
+
+    def crc32_dev(self, d_data, n, stream=0):
+        """CRC-32 of n device bytes, computed on the GPU."""
+        out = ctypes.c_uint32()
+        rc = lib().b200_crc32_dev(self._h, d_data or None, n, ctypes.byref(out), None, stream or None)
+        if rc:
+            raise B200Error(rc, "b200_crc32_dev")
         return out.value
 
     @staticmethod

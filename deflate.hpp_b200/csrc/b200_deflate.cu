@@ -14,11 +14,17 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <fcntl.h>
+#include <future>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <thread>
 #include <type_traits>
 #include <vector>
 
@@ -29,6 +35,7 @@
 #include "huffman.cuh"
 #include "inflate.cuh"
 #include "inflate_tp.cuh"
+#include "inflate_foreign.cuh"
 #include "lz77.cuh"
 
 using namespace b200;
@@ -58,11 +65,14 @@ std::atomic<uint64_t> g_launches{0};
 #define PROF_END(c, st) (c)->prof.end((st))
 
 enum KernelId { K_LZ77 = 0, K_HUFFMAN, K_SCAN, K_ENCODE, K_FIND_SYNC, K_INFLATE_CHUNKS, K_VALIDATE, K_INFLATE_BATCH, K_CORPUS,
-                K_INFLATE_SYMBOLS, K_INFLATE_FALLBACK, K_INFLATE_COPY, K_INFLATE_CLASSIFY, K_COUNT };
+                K_INFLATE_SYMBOLS, K_INFLATE_FALLBACK, K_INFLATE_COPY, K_INFLATE_CLASSIFY,
+                K_F_FIND, K_F_COUNT, K_F_EMIT, K_F_COPY, K_F_WINDOW, K_F_RESOLVE, K_COUNT };
 const char* const kKernelNames[K_COUNT] = {"lz77_kernel", "huffman_kernel", "scan_sizes_kernel", "encode_kernel",
                                            "find_sync_kernel", "inflate_chunks_kernel", "validate_chunks_kernel",
                                            "inflate_batch_kernel", "corpus_kernels", "inflate_segments_kernel",
-                                           "inflate_fallback_kernel", "inflate_copy_kernel", "inflate_classify_kernel"};
+                                           "inflate_fallback_kernel", "inflate_copy_kernel", "inflate_classify_kernel",
+                                           "foreign_find_blocks_kernel", "foreign_decode_kernel<count>", "foreign_decode_kernel<emit>",
+                                           "foreign_copy_kernel", "foreign_window_kernels", "foreign_resolve_kernel"};
 
 // Optional per-kernel timing: CUDA events recorded on the launching stream around every launch.
 struct Prof {
@@ -141,6 +151,10 @@ struct b200_ctx {
     Buf tok, ntok, hist, codes, hdr, desc, sizes, offsets, total;
     // inflate scratch
     Buf counts, woffs, cand, res, result, one_off, counter, cand16, ops, tpres, segnops, chunk_list, group_cnt, sync_cache, adler_parts, batch_nch, batch_first, batch_srcs;
+    Buf f_cand, f_starts, f_stops, f_res, f_base, f_opsbase, f_sym, f_ops, f_gmap, f_gwin, f_slabs, f_misc;   // foreign streams
+    bool size_probe = false;                  // set by inflate_host while it does not know the decoded size yet
+    size_t foreign_min = (size_t)256 << 10;   // streams shorter than this stay with the one-warp decoder (B200_FOREIGN_MIN)
+    uint32_t foreign_group = 0;               // units per window-propagation group (0 = auto); B200_FOREIGN_GROUP
     std::vector<cudaEvent_t> group_events;
     cudaStream_t s_side = nullptr;   // inflate: copy pass of group g while group g + 1 is in pass A
     uint64_t inflate_group_chunks = 0;   // 0 = auto (32768 chunks); B200_INFLATE_GROUP
@@ -156,6 +170,7 @@ struct b200_ctx {
                                      // workloads with very many tiny streams)
     bool inflate_warp_path = false;  // B200_INFLATE_WARP=1: the one-warp-per-unit decoder only (A/B comparisons)
     uint32_t lzf_grid = 148 * 2;     // persistent two-phase matcher: SMs x resident CTAs
+    uint32_t lzf_adaptive = 1;       // skip the match search where sample tiles find nothing (lz77.cuh); B200_LZF_ADAPTIVE=0: off
     uint32_t inf_grid = 148 * 7;     // persistent inflate grid: SMs x resident CTAs
     // host-API staging
     Buf d_in, d_out;
@@ -167,6 +182,25 @@ struct b200_ctx {
     size_t host_inflate_slice = (size_t)256 << 20;  // host-buffer inflate: bytes of input per pipeline slice (0 = off; measured best of
                                                     // 64..384 MiB: smaller groups of chunks run as partial waves); B200_HOST_INFLATE_SLICE
     uint32_t host_slice_chunks = 1024;   // 64 MiB: measured best (smaller slices starve the persistent matcher)
+    // pageable caller memory: a ring of pinned staging buffers, filled / drained by a few host threads (host-buffer API)
+    static constexpr int STG_N = 4;
+    static constexpr size_t STG_BYTES = (size_t)8 << 20;
+    void* stg_in[STG_N] = {};
+    void* stg_out[STG_N] = {};
+    cudaEvent_t stg_in_ev[STG_N] = {}, stg_out_ev[STG_N] = {};
+    bool stg_in_busy[STG_N] = {};
+    int stg_threads = 0;                            // 0 = auto (B200_STAGE_THREADS); 1 disables the thread fan-out
+    bool stage_pageable = true;                     // B200_STAGE=0: hand pageable memory to cudaMemcpyAsync as round 1 did
+    void* arena = nullptr;                          // pinned output arena of the *_view calls
+    size_t arena_cap = 0;
+    bool view_locked = false;
+    // file API: pinned host staging (two slices in, two out), device ring
+    void* pin_in[2] = {nullptr, nullptr};
+    void* pin_out[2] = {nullptr, nullptr};
+    size_t pin_in_cap[2] = {0, 0}, pin_out_cap[2] = {0, 0};
+    Buf file_in[2], file_out[2];
+    size_t file_slice = (size_t)64 << 20;           // bytes of input per slice (B200_FILE_SLICE; whole chunks)
+    cudaEvent_t file_ev[2] = {nullptr, nullptr};
     std::mutex mu;
     Prof prof;
 };
@@ -181,6 +215,12 @@ int set_attrs(b200_ctx* c) {
     CK(cudaFuncSetAttribute(inflate_segments_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM_BYTES + 65536));
     CK(cudaFuncSetAttribute(inflate_segments_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM_BYTES));
     CK(cudaFuncSetAttribute(inflate_symbols_kernel<BatchUnits>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(foreign_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(foreign_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(foreign_find_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FB_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(foreign_window_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FW_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(foreign_window_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FW_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(foreign_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FW_SMEM_BYTES));
     c->attrs_set = true;
     return B200_OK;
 }
@@ -202,7 +242,7 @@ __global__ void batch_count_kernel(const uint64_t* __restrict__ in_len, uint64_t
     const uint64_t len = in_len[f];
     const uint64_t k = len ? (len + CHUNK - 1) / CHUNK : 1;
     nch[f] = (uint32_t)k;
-    atomicAdd(need, (unsigned long long)(len + 20 * ((len + CHUNK - 1) / CHUNK) + 16));      // = b200_deflate_bound(len)
+    atomicAdd(need, (unsigned long long)(len + 20 * ((len + CHUNK - 1) / CHUNK) + 34));      // = b200_deflate_bound(len)
 }
 __global__ void batch_srcs_kernel(const uint64_t* __restrict__ in_off, const uint64_t* __restrict__ in_len,
                                   const uint64_t* __restrict__ first, uint64_t n, ChunkSrc* __restrict__ srcs) {
@@ -350,6 +390,7 @@ const char* b200_strerror(int code) {
         case B200_E_CUDA: return "CUDA error or no sm_100 device (this library has no CPU path)";
         case B200_E_ARG: return "bad argument";
         case B200_E_NOMEM: return "out of memory";
+        case B200_E_IO: return "file I/O error";
         default: return "unknown error";
     }
 }
@@ -378,6 +419,7 @@ int b200_ctx_create(int device, b200_ctx** ctx) {
     }
     if (const char* e = getenv("B200_BETTER_DEPTH")) { int v = atoi(e); if (v > 0) c->better_depth = (uint32_t)v; }
     if (const char* e = getenv("B200_BETTER_NICE")) { int v = atoi(e); if (v >= 3) c->better_nice = (uint32_t)v; }
+    if (const char* e = getenv("B200_LZF_ADAPTIVE")) c->lzf_adaptive = atoi(e) != 0;
     if (const char* e = getenv("B200_NO_INDEX")) c->with_index = atoi(e) == 0;
     if (const char* e = getenv("B200_INFLATE_GROUP")) { long v = atol(e); if (v > 0) c->inflate_group_chunks = (uint64_t)v; }
     if (const char* e = getenv("B200_INFLATE_OVERLAP")) c->inflate_overlap = atoi(e) != 0;
@@ -387,6 +429,11 @@ int b200_ctx_create(int device, b200_ctx** ctx) {
     if (const char* e = getenv("B200_COPY_TUNE")) c->copy_tune = (unsigned)atoi(e);
     if (const char* e = getenv("B200_BATCH_TP")) c->batch_two_pass = atoi(e) != 0;
     if (const char* e = getenv("B200_INFLATE_WARP")) c->inflate_warp_path = atoi(e) != 0;
+    if (const char* e = getenv("B200_FOREIGN_MIN")) { long long v = atoll(e); if (v >= 0) c->foreign_min = (size_t)v; }
+    if (const char* e = getenv("B200_FOREIGN_GROUP")) { int v = atoi(e); if (v > 0) c->foreign_group = (uint32_t)v; }
+    if (const char* e = getenv("B200_STAGE")) c->stage_pageable = atoi(e) != 0;
+    if (const char* e = getenv("B200_STAGE_THREADS")) c->stg_threads = atoi(e);
+    if (const char* e = getenv("B200_FILE_SLICE")) { long long v = atoll(e); if (v >= (long long)CHUNK) c->file_slice = (size_t)v / CHUNK * CHUNK; }
     if (const char* e = getenv("B200_BATCH_CHUNKS")) { int v = atoi(e); if (v > 0) c->batch_chunks = (uint32_t)v; }
     if (const char* e = getenv("B200_HOST_INFLATE_SLICE")) { long long v = atoll(e); if (v >= 0) c->host_inflate_slice = (size_t)v; }
     if (const char* e = getenv("B200_HOST_SLICE_CHUNKS")) { int v = atoi(e); if (v > 0) c->host_slice_chunks = (uint32_t)v; }
@@ -405,13 +452,27 @@ void b200_ctx_destroy(b200_ctx* c) {
     DeviceGuard dev_guard__(c->device);
     Buf* all[] = {&c->tok, &c->ntok, &c->hist, &c->codes, &c->hdr, &c->desc, &c->sizes, &c->offsets, &c->total,
                   &c->counts, &c->woffs, &c->cand, &c->res, &c->result, &c->one_off, &c->counter, &c->cand16, &c->ops, &c->tpres, &c->segnops, &c->chunk_list, &c->group_cnt, &c->sync_cache, &c->adler_parts, &c->batch_nch, &c->batch_first, &c->batch_srcs,
-                  &c->d_in, &c->d_out};
+                  &c->d_in, &c->d_out, &c->f_cand, &c->f_starts, &c->f_stops, &c->f_res, &c->f_base, &c->f_opsbase, &c->f_sym, &c->f_ops,
+                  &c->f_gmap, &c->f_gwin, &c->f_slabs, &c->f_misc};
     for (Buf* b : all) b->release();
     c->prof.destroy();
     for (auto e : c->events) cudaEventDestroy(e);
     for (auto e : c->group_events) cudaEventDestroy(e);
     if (c->s_side) cudaStreamDestroy(c->s_side);
     if (c->mailbox) cudaFreeHost(c->mailbox);
+    if (c->arena) cudaFreeHost(c->arena);
+    for (int k = 0; k < b200_ctx::STG_N; k++) {
+        if (c->stg_in[k]) cudaFreeHost(c->stg_in[k]);
+        if (c->stg_out[k]) cudaFreeHost(c->stg_out[k]);
+        if (c->stg_in_ev[k]) cudaEventDestroy(c->stg_in_ev[k]);
+        if (c->stg_out_ev[k]) cudaEventDestroy(c->stg_out_ev[k]);
+    }
+    for (int k = 0; k < 2; k++) {
+        if (c->pin_in[k]) cudaFreeHost(c->pin_in[k]);
+        if (c->pin_out[k]) cudaFreeHost(c->pin_out[k]);
+        if (c->file_ev[k]) cudaEventDestroy(c->file_ev[k]);
+        c->file_in[k].release(); c->file_out[k].release();
+    }
     if (c->s_in) cudaStreamDestroy(c->s_in);
     if (c->s_out) cudaStreamDestroy(c->s_out);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -448,7 +509,7 @@ const char* b200_kernel_name(int kernel_id) {
 
 size_t b200_deflate_bound(size_t n) {
     const size_t nchunks = (n + CHUNK - 1) / CHUNK;
-    return n + 20 * nchunks + 16;   // per chunk: two stored blocks (2 x 5) + separator (10)
+    return n + 20 * nchunks + 34;   // per chunk: two stored blocks (2 x 5) + separator (10); + 16 slack + 18 for gzip framing
 }
 
 void b200_free(void* p) { free(p); }
@@ -458,7 +519,10 @@ void b200_free(void* p) { free(p); }
 // stages: bit 0 = K1..K3 (tokenise, code, size, scan), bit 1 = K4 (encode + write)
 static int compress_batch(b200_ctx* c, const uint8_t* bin, uint64_t bn, uint32_t nb, uint64_t b0, bool final_batch,
                           int level, uint64_t* offs, uint64_t* d_total, void* d_out, cudaStream_t st,
-                          int stages = 3, const uint64_t* d_extra_base = nullptr, const ChunkSrc* srcs = nullptr) {
+                          int stages = 3, const uint64_t* d_extra_base = nullptr, const ChunkSrc* srcs = nullptr,
+                          const uint64_t* d_first_base = nullptr) {
+    // d_first_base: where the FIRST batch's first chunk goes (zlib / gzip framing puts a header in front); later batches
+    // continue at the previous batch's end
     // srcs: batch compression -- chunk k of this batch is described by srcs[k] (absolute offsets into bin)
     if (stages & 1) {
     if (level == 2) {
@@ -471,26 +535,26 @@ static int compress_batch(b200_ctx* c, const uint8_t* bin, uint64_t bn, uint32_t
         PROF_BEGIN(c, K_LZ77, st);
         if (level == 3)
             lz77_better_kernel<<<nb, LZB_THREADS, LZB_SMEM_BYTES, st>>>(bin, bn, (uint32_t*)c->tok.p, (uint32_t*)c->ntok.p,
-                                                                     (uint32_t*)c->hist.p, c->better_depth, c->better_nice, srcs);
+                                                                     (uint16_t*)c->hist.p, c->better_depth, c->better_nice, srcs);
         else if (level == 2) {
             const uint32_t grid = nb < c->lzf_grid ? nb : c->lzf_grid;
             lz77_fast_kernel<<<grid, LZF_THREADS, LZF_SMEM_BYTES, st>>>(bin, bn, nb, (uint32_t*)c->tok.p, (uint32_t*)c->ntok.p,
-                                                                     (uint32_t*)c->hist.p, (uint16_t*)c->cand16.p,
-                                                                     (unsigned int*)c->counter.p, srcs);
+                                                                     (uint16_t*)c->hist.p, (uint16_t*)c->cand16.p,
+                                                                     (unsigned int*)c->counter.p, srcs, c->lzf_adaptive);
         }
         else
-            lz77_literal_kernel<<<nb, LZL_THREADS, 0, st>>>(bin, bn, (uint32_t*)c->tok.p, (uint32_t*)c->ntok.p, (uint32_t*)c->hist.p, srcs);
+            lz77_literal_kernel<<<nb, LZL_THREADS, 0, st>>>(bin, bn, (uint32_t*)c->tok.p, (uint32_t*)c->ntok.p, (uint16_t*)c->hist.p, srcs);
         LAUNCHED();
         PROF_END(c, st);
     }
     PROF_BEGIN(c, K_HUFFMAN, st);
     huffman_kernel<<<(nb + HUF_WARPS - 1) / HUF_WARPS, HUF_THREADS, 0, st>>>(
-        (const uint32_t*)c->hist.p, bn, nb, level, final_batch ? 1 : 0, c->with_index ? 1 : 0, srcs, (uint32_t*)c->codes.p,
+        (const uint16_t*)c->hist.p, bn, nb, level, final_batch ? 1 : 0, c->with_index ? 1 : 0, srcs, (uint32_t*)c->codes.p,
         (uint32_t*)c->hdr.p, (BlockDesc*)c->desc.p, (uint32_t*)c->sizes.p);
     LAUNCHED();
     PROF_END(c, st);
     PROF_BEGIN(c, K_SCAN, st);
-    scan_sizes_kernel<<<1, SCAN_THREADS, 0, st>>>((const uint32_t*)c->sizes.p, nb, b0 ? offs + b0 : nullptr,
+    scan_sizes_kernel<<<1, SCAN_THREADS, 0, st>>>((const uint32_t*)c->sizes.p, nb, b0 ? offs + b0 : d_first_base,
                                                  offs + b0, d_total);
     LAUNCHED();
     PROF_END(c, st);
@@ -506,6 +570,40 @@ static int compress_batch(b200_ctx* c, const uint8_t* bin, uint64_t bn, uint32_t
     return B200_OK;
 }
 
+// ---- zlib (RFC 1950) / gzip (RFC 1952) framing around the raw stream ------------------------------------------
+static const uint8_t kZlibHeader[2] = {0x78, 0x9C};                                        // CM 8, 32 KiB window, default level, no dictionary
+static const uint8_t kGzipHeader[10] = {0x1F, 0x8B, 8, 0, 0, 0, 0, 0, 0, 0xFF};            // no name, no mtime, OS unknown
+static const uint64_t kFrameLen[3] = {0, 2, 10};
+static int frame_mode(unsigned flags) { return (flags & B200_F_GZIP) ? 2 : (flags & B200_F_ZLIB) ? 1 : 0; }
+
+// checksum of d_data[0..n) into *d_sum (device): Adler-32 (mode 1) or CRC-32 (mode 2)
+// d_seed (may be NULL, may be d_sum): checksum of the bytes before this buffer, for streaming over slices
+static int checksum_dev(b200_ctx* c, const uint8_t* d_data, uint64_t n, int mode, uint32_t* d_sum, cudaStream_t st,
+                        const uint32_t* d_seed = nullptr) {
+    int rc;
+    const uint64_t nblocks = (n + CHUNK - 1) / CHUNK;
+    if (mode == 1) {
+        if ((rc = c->adler_parts.ensure((nblocks + 1) * sizeof(AdlerPart) + 16))) return rc;
+        AdlerPart* parts = (AdlerPart*)c->adler_parts.p;
+        if (nblocks) {
+            adler_partial_kernel<<<(uint32_t)nblocks, ADLER_THREADS, 0, st>>>(d_data, n, parts);
+            LAUNCHED();
+        }
+        adler_fold_kernel<<<1, 32, 0, st>>>(parts, nblocks, n, d_sum, d_seed);
+        LAUNCHED();
+    } else {
+        if ((rc = c->adler_parts.ensure((nblocks + 1) * sizeof(CrcPart) + 16))) return rc;
+        CrcPart* parts = (CrcPart*)c->adler_parts.p;
+        if (nblocks) {
+            crc32_partial_kernel<<<(uint32_t)nblocks, CRC_THREADS, 0, st>>>(d_data, n, parts);
+            LAUNCHED();
+        }
+        crc32_fold_kernel<<<1, CRC_FOLD_THREADS, 0, st>>>(parts, nblocks, d_seed, d_sum);
+        LAUNCHED();
+    }
+    return B200_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 int b200_deflate_compress_dev(b200_ctx* c, const void* d_in, size_t n, int level, unsigned flags, void* d_out,
                               size_t cap, uint64_t* d_out_n, size_t* h_out_n, uint64_t* d_chunk_off,
@@ -515,28 +613,46 @@ int b200_deflate_compress_dev(b200_ctx* c, const void* d_in, size_t n, int level
     cudaStream_t st = (cudaStream_t)stream_;
     ON_DEVICE(c);
     const bool final_here = !(flags & B200_F_NOT_LAST);
+    const int frame = frame_mode(flags);
+    if (frame && !final_here) return B200_E_ARG;          // a frame wraps a whole stream, not a shard of one
     const uint64_t nchunks = (n + CHUNK - 1) / CHUNK;
     IndexGuard guard(c, flags);
     int rc;
-    if ((rc = c->total.ensure(16))) return rc;
-    uint64_t* d_total = (uint64_t*)c->total.p;
+    if ((rc = c->total.ensure(64))) return rc;
+    uint64_t* d_total = (uint64_t*)c->total.p;            // [0] running total, [2] frame header length, [4] checksum
+    const uint64_t* d_first_base = nullptr;
+    if (frame) {
+        CK(cudaMemcpyAsync(d_out, frame == 1 ? kZlibHeader : kGzipHeader, kFrameLen[frame], cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_total + 2, &kFrameLen[frame], 8, cudaMemcpyHostToDevice, st));
+        d_first_base = d_total + 2;
+    }
+    auto finish_frame = [&]() -> int {
+        if (!frame) return B200_OK;
+        int rc2 = checksum_dev(c, (const uint8_t*)d_in, n, frame, (uint32_t*)(d_total + 4), st);
+        if (rc2) return rc2;
+        write_trailer_kernel<<<1, 1, 0, st>>>((uint8_t*)d_out, d_total, (const uint32_t*)(d_total + 4), (uint64_t)n, frame);
+        LAUNCHED();
+        return B200_OK;
+    };
 
     if (nchunks == 0) {
         // empty input: a final empty fixed block (BFINAL=1, BTYPE=01, EOB) = 03 00
         static const uint8_t empty_final[2] = {0x03, 0x00};
-        const uint64_t tot = final_here ? 2 : 0;
-        if (final_here) CK(cudaMemcpyAsync(d_out, empty_final, 2, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(d_total, &tot, 8, cudaMemcpyHostToDevice, st));
+        static uint64_t tots[3][2] = {{0, 2}, {2, 4}, {10, 12}};
+        const uint64_t tot = tots[frame][final_here ? 1 : 0];
+        if (final_here) CK(cudaMemcpyAsync((uint8_t*)d_out + kFrameLen[frame], empty_final, 2, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_total, &tots[frame][final_here ? 1 : 0], 8, cudaMemcpyHostToDevice, st));
         if (d_chunk_off) CK(cudaMemcpyAsync(d_chunk_off, d_total, 8, cudaMemcpyDeviceToDevice, st));
+        if ((rc = finish_frame())) return rc;
         if (d_out_n) CK(cudaMemcpyAsync(d_out_n, d_total, 8, cudaMemcpyDeviceToDevice, st));
-        if (h_out_n) { CK(cudaStreamSynchronize(st)); *h_out_n = (size_t)tot; }
+        if (h_out_n) { CK(cudaStreamSynchronize(st)); *h_out_n = (size_t)(tot + (frame == 1 ? 4 : frame == 2 ? 8 : 0)); }
         return B200_OK;
     }
 
     const uint64_t B = nchunks < c->batch_chunks ? nchunks : c->batch_chunks;
     if ((rc = c->tok.ensure(B * CHUNK * 4))) return rc;
     if ((rc = c->ntok.ensure(B * NSEG * 4))) return rc;
-    if ((rc = c->hist.ensure(B * NSEG * NSYM * 4))) return rc;
+    if ((rc = c->hist.ensure(B * NSEG * NSYM * 2))) return rc;
     if ((rc = c->codes.ensure(B * NSYM * 4))) return rc;
     if ((rc = c->hdr.ensure(B * HDR_WORDS * 4))) return rc;
     if ((rc = c->desc.ensure(B * sizeof(BlockDesc)))) return rc;
@@ -553,8 +669,11 @@ int b200_deflate_compress_dev(b200_ctx* c, const void* d_in, size_t n, int level
         const uint8_t* bin = in + b0 * CHUNK;
         const uint64_t bn = n - b0 * CHUNK;
         const bool last_batch = b0 + nb == nchunks;
-        if ((rc = compress_batch(c, bin, bn, nb, b0, last_batch && final_here, level, offs, d_total, d_out, st))) return rc;
+        if ((rc = compress_batch(c, bin, bn, nb, b0, last_batch && final_here, level, offs, d_total, d_out, st, 3, nullptr, nullptr,
+                                 d_first_base)))
+            return rc;
     }
+    if ((rc = finish_frame())) return rc;
     if (d_out_n) CK(cudaMemcpyAsync(d_out_n, d_total, 8, cudaMemcpyDeviceToDevice, st));
     if (h_out_n) {
         uint64_t tot = 0;
@@ -603,7 +722,7 @@ int b200_deflate_compress_batch_dev(b200_ctx* c, const void* d_in, const uint64_
     const uint64_t B = nchunks < c->batch_chunks ? nchunks : c->batch_chunks;
     if ((rc = c->tok.ensure(B * CHUNK * 4))) return rc;
     if ((rc = c->ntok.ensure(B * NSEG * 4))) return rc;
-    if ((rc = c->hist.ensure(B * NSEG * NSYM * 4))) return rc;
+    if ((rc = c->hist.ensure(B * NSEG * NSYM * 2))) return rc;
     if ((rc = c->codes.ensure(B * NSYM * 4))) return rc;
     if ((rc = c->hdr.ensure(B * HDR_WORDS * 4))) return rc;
     if ((rc = c->desc.ensure(B * sizeof(BlockDesc)))) return rc;
@@ -644,7 +763,7 @@ int b200_deflate_compress_stage1_dev(b200_ctx* c, const void* d_in, size_t n, in
     if ((rc = c->total.ensure(16))) return rc;
     if ((rc = c->tok.ensure(B * CHUNK * 4))) return rc;
     if ((rc = c->ntok.ensure(B * NSEG * 4))) return rc;
-    if ((rc = c->hist.ensure(B * NSEG * NSYM * 4))) return rc;
+    if ((rc = c->hist.ensure(B * NSEG * NSYM * 2))) return rc;
     if ((rc = c->codes.ensure(B * NSYM * 4))) return rc;
     if ((rc = c->hdr.ensure(B * HDR_WORDS * 4))) return rc;
     if ((rc = c->desc.ensure(B * sizeof(BlockDesc)))) return rc;
@@ -731,7 +850,8 @@ __global__ void count_below_kernel(const uint64_t* __restrict__ cand, uint64_t n
 // chunks decoded; *next_start = offset of the first chunk that was NOT decoded (n if none).  Synchronizes `st`.
 static int inflate_chunked(b200_ctx* c, const uint8_t* in, uint64_t n, uint64_t lo, uint64_t hi, bool first_is_start, bool expect_final,
                            uint8_t* out, uint64_t cap, unsigned flags, cudaStream_t st, bool* valid, uint64_t* total,
-                           uint64_t* nunits, uint64_t* next_start) {
+                           uint64_t* nunits, uint64_t* next_start, Buf* grow_out = nullptr) {
+    // grow_out: decode into this buffer instead of out / cap, grown to 64 KiB per chunk once the chunk count is known
     int rc;
     *valid = false; *total = 0;
     if (nunits) *nunits = 0;
@@ -780,6 +900,11 @@ static int inflate_chunked(b200_ctx* c, const uint8_t* in, uint64_t n, uint64_t 
         CK(cudaStreamSynchronize(st));
     }
     if (units == 0) { *valid = true; return B200_OK; }
+    if (grow_out) {
+        if ((rc = grow_out->ensure(units * CHUNK + 64))) return rc;
+        out = (uint8_t*)grow_out->p;
+        cap = units * CHUNK;
+    }
     const bool ends_stream = expect_final && units == ncand;
     const unsigned long long init[2] = {1ull, 0ull};
     CK(cudaMemcpyAsync(d_result, init, 16, cudaMemcpyHostToDevice, st));
@@ -893,9 +1018,191 @@ int b200_inflate_shard_dev(b200_ctx* c, const void* d_in, size_t n, size_t lo, s
     return B200_OK;
 }
 
-// (stub until inflate_foreign.cuh lands)
-static int inflate_foreign(b200_ctx*, const uint8_t*, uint64_t, uint8_t*, uint64_t, unsigned, cudaStream_t, bool* done, uint64_t*) {
+// Block-parallel inflate of a stream that is not made of this library's chunks (inflate_foreign.cuh).  *done = false:
+// nothing was decided (too small, too few blocks found, an error, no memory): the caller decodes sequentially, which
+// also produces the right error code.  Synchronizes `st` several times (candidate list, chain walk, verdict).
+static int inflate_foreign(b200_ctx* c, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t cap, unsigned flags, cudaStream_t st,
+                           bool* done, uint64_t* full) {
     *done = false;
+    if (n < c->foreign_min || n >= (1ull << 33)) return B200_OK;
+    int rc = 0;
+    (void)rc;
+    // ---- F1: candidate block starts ----
+    const uint64_t npieces = (n + FB_PIECE - 1) / FB_PIECE;
+    if ((rc = c->f_cand.ensure(npieces * 8))) return B200_OK;
+    PROF_BEGIN(c, K_F_FIND, st);
+    foreign_find_blocks_kernel<<<(uint32_t)((npieces + FB_WARPS - 1) / FB_WARPS), FB_THREADS, FB_SMEM_BYTES, st>>>(
+        in, n, npieces, (unsigned long long*)c->f_cand.p);
+    LAUNCHED();
+    PROF_END(c, st);
+    std::vector<uint64_t> piece(npieces);
+    CK(cudaMemcpyAsync(piece.data(), c->f_cand.p, npieces * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    std::vector<uint64_t> starts;
+    starts.reserve(npieces + 2);
+    starts.push_back(0);                                    // the stream itself starts a block
+    for (uint64_t p = 0; p < npieces; p++)
+        if (piece[p] != ~0ull && piece[p] != 0) starts.push_back(piece[p]);
+    if (starts.size() < 4) return B200_OK;                  // nothing to parallelise over
+
+    // ---- F2: sizes of every candidate unit; chain walk; missing starts are added and counted in further rounds ----
+    struct Unit { uint64_t start, stop; FUnitRes r; bool have; };
+    std::vector<Unit> units(starts.size());
+    for (size_t i = 0; i < starts.size(); i++) units[i] = Unit{starts[i], i + 1 < starts.size() ? starts[i + 1] : ~0ull, FUnitRes{}, false};
+    std::vector<size_t> chain;
+    for (int round = 0;; round++) {
+        // count the units that have no result yet
+        std::vector<uint64_t> hs, hp;
+        std::vector<size_t> idx;
+        for (size_t i = 0; i < units.size(); i++)
+            if (!units[i].have) { hs.push_back(units[i].start); hp.push_back(units[i].stop); idx.push_back(i); }
+        const uint64_t m = hs.size();
+        if (m) {
+            if ((rc = c->f_starts.ensure(m * 8)) || (rc = c->f_stops.ensure(m * 8)) || (rc = c->f_res.ensure(m * sizeof(FUnitRes)))) return B200_OK;
+            CK(cudaMemcpyAsync(c->f_starts.p, hs.data(), m * 8, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(c->f_stops.p, hp.data(), m * 8, cudaMemcpyHostToDevice, st));
+            PROF_BEGIN(c, K_F_COUNT, st);
+            foreign_decode_kernel<false><<<(uint32_t)((m + FD_THREADS - 1) / FD_THREADS), FD_THREADS, TP_SMEM_BYTES, st>>>(
+                in, n, (const uint64_t*)c->f_starts.p, (const uint64_t*)c->f_stops.p, m, (FUnitRes*)c->f_res.p, nullptr, nullptr, nullptr, nullptr, flags);
+            LAUNCHED();
+            PROF_END(c, st);
+            std::vector<FUnitRes> hr(m);
+            CK(cudaMemcpyAsync(hr.data(), c->f_res.p, m * sizeof(FUnitRes), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            for (uint64_t k = 0; k < m; k++) { units[idx[k]].r = hr[k]; units[idx[k]].have = true; }
+        }
+        // walk the chain from bit 0
+        chain.clear();
+        std::vector<uint64_t> missing;
+        size_t u = 0;
+        bool closed = false;
+        for (;;) {
+            const FUnitRes& r = units[u].r;
+            if (r.status != ST_OK) return B200_OK;          // an error on the true path: the sequential decoder reports it
+            chain.push_back(u);
+            if (r.flags & FU_FINAL) { closed = true; break; }
+            if (!(r.flags & FU_REACHED)) return B200_OK;
+            // the next unit must start exactly where this one ended
+            auto it = std::lower_bound(units.begin(), units.end(), r.end_bit, [](const Unit& a, uint64_t v) { return a.start < v; });
+            if (it != units.end() && it->start == r.end_bit) { u = (size_t)(it - units.begin()); continue; }
+            missing.push_back(r.end_bit);
+            break;
+        }
+        if (closed) break;
+        if (round >= 6) return B200_OK;
+        // every unit (on the chain or not) whose end is nobody's start asks for a new unit: one round fixes them all
+        for (size_t i = 0; i < units.size(); i++) {
+            const FUnitRes& r = units[i].r;
+            if (!units[i].have || r.status != ST_OK || (r.flags & FU_FINAL) || !(r.flags & FU_REACHED)) continue;
+            auto it = std::lower_bound(units.begin(), units.end(), r.end_bit, [](const Unit& a, uint64_t v) { return a.start < v; });
+            if (it == units.end() || it->start != r.end_bit) missing.push_back(r.end_bit);
+        }
+        std::sort(missing.begin(), missing.end());
+        missing.erase(std::unique(missing.begin(), missing.end()), missing.end());
+        std::vector<Unit> merged;
+        merged.reserve(units.size() + missing.size());
+        size_t a = 0, b = 0;
+        while (a < units.size() || b < missing.size()) {
+            if (b >= missing.size() || (a < units.size() && units[a].start < missing[b])) merged.push_back(units[a++]);
+            else merged.push_back(Unit{missing[b++], 0, FUnitRes{}, false});
+        }
+        for (size_t i = 0; i < merged.size(); i++)
+            if (!merged[i].have) merged[i].stop = i + 1 < merged.size() ? merged[i + 1].start : ~0ull;
+        units.swap(merged);
+    }
+
+    // ---- layout ----
+    const uint64_t nu = chain.size();
+    std::vector<uint64_t> hs(nu), hp(nu), hbase(nu + 1), hops(nu + 1);
+    uint64_t total = 0, total_ops = 0;
+    for (uint64_t k = 0; k < nu; k++) {
+        const Unit& U = units[chain[k]];
+        hs[k] = U.start; hp[k] = U.r.end_bit;               // decode exactly what was counted
+        hbase[k] = total; hops[k] = total_ops;
+        total += U.r.out_len; total_ops += U.r.nops;
+    }
+    hbase[nu] = total; hops[nu] = total_ops;
+    *full = total;
+    if (total > cap) {
+        // truncating caller: the sequential decoder handles it -- unless the caller only wants to learn the size
+        // (the vector-returning host overloads probe with a guessed capacity and come back with the exact one)
+        if (c->size_probe) *done = true;
+        return B200_OK;
+    }
+    if (total == 0) { *done = true; return B200_OK; }
+    if (c->f_sym.ensure(total * 2 + 64) || c->f_ops.ensure((total_ops + 64) * 8)) return B200_OK;     // no memory: sequential
+    if ((rc = c->f_starts.ensure(nu * 8)) || (rc = c->f_stops.ensure(nu * 8)) || (rc = c->f_res.ensure(nu * sizeof(FUnitRes))) ||
+        (rc = c->f_base.ensure((nu + 1) * 8)) || (rc = c->f_opsbase.ensure((nu + 1) * 8)) || (rc = c->f_misc.ensure(64)))
+        return B200_OK;
+    CK(cudaMemcpyAsync(c->f_starts.p, hs.data(), nu * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->f_stops.p, hp.data(), nu * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->f_base.p, hbase.data(), (nu + 1) * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->f_opsbase.p, hops.data(), (nu + 1) * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(c->f_misc.p, 0, 64, st));
+    unsigned long long* d_counter = (unsigned long long*)c->f_misc.p;
+    unsigned int* d_err = (unsigned int*)((unsigned long long*)c->f_misc.p + 1);
+    uint16_t* S = (uint16_t*)c->f_sym.p;
+    const uint64_t* d_base = (const uint64_t*)c->f_base.p;
+
+    // ---- F3: decode with known offsets ----
+    PROF_BEGIN(c, K_F_EMIT, st);
+    foreign_decode_kernel<true><<<(uint32_t)((nu + FD_THREADS - 1) / FD_THREADS), FD_THREADS, TP_SMEM_BYTES, st>>>(
+        in, n, (const uint64_t*)c->f_starts.p, (const uint64_t*)c->f_stops.p, nu, (FUnitRes*)c->f_res.p, d_base,
+        (const uint64_t*)c->f_opsbase.p, S, (uint64_t*)c->f_ops.p, flags);
+    LAUNCHED();
+    PROF_END(c, st);
+    // ---- F4: ops inside the symbol image ----
+    {
+        const uint64_t want = (nu + INF_WARPS - 1) / INF_WARPS;
+        const uint64_t gmax = (uint64_t)(c->inf_grid / INF_MAX_CTAS_PER_SM) * 12;
+        PROF_BEGIN(c, K_F_COPY, st);
+        foreign_copy_kernel<<<(uint32_t)(want < gmax ? want : gmax), INF_THREADS, 0, st>>>(
+            in, (const FUnitRes*)c->f_res.p, d_base, (const uint64_t*)c->f_opsbase.p, nu, S, (const uint64_t*)c->f_ops.p, d_counter, d_err);
+        LAUNCHED();
+        PROF_END(c, st);
+    }
+    // ---- F5: window propagation, two levels ----
+    uint32_t G = c->foreign_group;
+    if (!G) { G = 1; while ((uint64_t)G * G < nu) G++; if (G < 8) G = 8; }       // ~sqrt(units): group chains and the chain of groups are equally long
+    const uint64_t ngroups = (nu + G - 1) / G;
+    if ((rc = c->f_gmap.ensure(ngroups * F_WINDOW * 2)) || (rc = c->f_gwin.ensure((ngroups + 1) * F_WINDOW))) return B200_OK;
+    PROF_BEGIN(c, K_F_WINDOW, st);
+    if (ngroups > 1) {
+        foreign_window_kernel<0><<<(uint32_t)ngroups, FW_THREADS, FW_SMEM_BYTES, st>>>(S, d_base, nu, total, G, (uint16_t*)c->f_gmap.p, nullptr, nullptr, d_err);
+        LAUNCHED();
+        foreign_chain_kernel<<<1, FW_THREADS, FW_SMEM_BYTES, st>>>((const uint16_t*)c->f_gmap.p, (uint8_t*)c->f_gwin.p, ngroups, d_err);
+        LAUNCHED();
+    }
+    foreign_window_kernel<1><<<(uint32_t)ngroups, FW_THREADS, FW_SMEM_BYTES, st>>>(S, d_base, nu, total, G, nullptr, (const uint8_t*)c->f_gwin.p, out, d_err);
+    LAUNCHED();
+    PROF_END(c, st);
+    // ---- F6: the rest ----
+    std::vector<FSlab> slabs;
+    for (uint64_t k = 0; k < nu; k++) {
+        const uint64_t len = hbase[k + 1] - hbase[k];
+        if (len <= F_WINDOW) continue;
+        for (uint64_t lo = hbase[k]; lo < hbase[k + 1] - F_WINDOW; lo += FR_SLAB) slabs.push_back(FSlab{k, lo});
+    }
+    if (!slabs.empty()) {
+        if ((rc = c->f_slabs.ensure(slabs.size() * sizeof(FSlab)))) return B200_OK;
+        CK(cudaMemcpyAsync(c->f_slabs.p, slabs.data(), slabs.size() * sizeof(FSlab), cudaMemcpyHostToDevice, st));
+        PROF_BEGIN(c, K_F_RESOLVE, st);
+        foreign_resolve_kernel<<<(uint32_t)slabs.size(), FR_THREADS, 0, st>>>(S, d_base, nu, total, (const FSlab*)c->f_slabs.p, out, d_err);
+        LAUNCHED();
+        PROF_END(c, st);
+    }
+    unsigned int herr = 1;
+    std::vector<FUnitRes> emitted(nu);
+    CK(cudaMemcpyAsync(emitted.data(), c->f_res.p, nu * sizeof(FUnitRes), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&herr, d_err, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));            // also keeps hs / hp / hbase / hops / slabs alive until the copies are done
+    if (herr) return B200_OK;                 // sequential decoder redoes the stream
+    for (uint64_t k = 0; k < nu; k++) {       // the second decode must have produced exactly what the first one counted
+        const FUnitRes& a = emitted[k];
+        const FUnitRes& b = units[chain[k]].r;
+        if (a.status != ST_OK || a.out_len != b.out_len || a.nops != b.nops || a.end_bit != b.end_bit) return B200_OK;
+    }
+    *done = true;
     return B200_OK;
 }
 
@@ -921,6 +1228,21 @@ int b200_adler32_dev(b200_ctx* c, const void* d_data, size_t n, uint32_t* h_out,
     return B200_OK;
 }
 
+int b200_crc32_dev(b200_ctx* c, const void* d_data, size_t n, uint32_t* h_out, uint32_t* d_out, void* stream_) {
+    if (!c || (!d_data && n) || (!h_out && !d_out)) return B200_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream_;
+    ON_DEVICE(c);
+    int rc;
+    if ((rc = c->total.ensure(64))) return rc;
+    uint32_t* d_res = d_out ? d_out : (uint32_t*)((uint64_t*)c->total.p + 6);
+    if ((rc = checksum_dev(c, (const uint8_t*)d_data, n, 2, d_res, st))) return rc;
+    if (h_out) {
+        CK(cudaMemcpyAsync(h_out, d_res, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    return B200_OK;
+}
+
 int b200_corpus_generate_dev(void* d_out, uint64_t seed, uint64_t first_chunk, uint64_t n_chunks, void* stream_) {
     if (!d_out && n_chunks) return B200_E_ARG;
     if (!n_chunks) return B200_OK;
@@ -934,6 +1256,109 @@ int b200_corpus_generate_dev(void* d_out, uint64_t seed, uint64_t first_chunk, u
 }
 
 // ------------------------------------------------------------------------------------------------
+// Pageable caller memory.  cudaMemcpyAsync on pageable memory is a synchronous, single-threaded bounce through the
+// driver's own staging buffer (6-12 GB/s) -- what a user of deflate::compress(char*, n, level) hands us is exactly
+// that.  Large pageable buffers therefore travel through a ring of pinned 8 MiB buffers of our own: a few host threads
+// copy user memory <-> ring in parallel, the DMA engines move ring <-> HBM asynchronously behind them.
+static bool is_pageable(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+static int stage_threads(const b200_ctx* c) {
+    if (c->stg_threads > 0) return c->stg_threads;
+    const unsigned hw = std::thread::hardware_concurrency();
+    return hw >= 16 ? 8 : hw >= 8 ? 4 : hw >= 4 ? 2 : 1;
+}
+static void par_memcpy(void* dst, const void* src, size_t len, int threads) {
+    if (threads <= 1 || len < ((size_t)1 << 20)) { memcpy(dst, src, len); return; }
+    std::vector<std::thread> pool;
+    const size_t per = ((len + threads - 1) / threads + 4095) & ~(size_t)4095;
+    for (int t = 1; t < threads; t++) {
+        const size_t lo = (size_t)t * per;
+        if (lo >= len) break;
+        const size_t l = len - lo < per ? len - lo : per;
+        pool.emplace_back([=]() { memcpy((uint8_t*)dst + lo, (const uint8_t*)src + lo, l); });
+    }
+    memcpy(dst, src, len < per ? len : per);
+    for (auto& th : pool) th.join();
+}
+static int stage_init(b200_ctx* c) {
+    for (int k = 0; k < b200_ctx::STG_N; k++) {
+        if (!c->stg_in[k] && cudaHostAlloc(&c->stg_in[k], b200_ctx::STG_BYTES, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return B200_E_NOMEM; }
+        if (!c->stg_out[k] && cudaHostAlloc(&c->stg_out[k], b200_ctx::STG_BYTES, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return B200_E_NOMEM; }
+        if (!c->stg_in_ev[k]) CK(cudaEventCreateWithFlags(&c->stg_in_ev[k], cudaEventDisableTiming));
+        if (!c->stg_out_ev[k]) CK(cudaEventCreateWithFlags(&c->stg_out_ev[k], cudaEventDisableTiming));
+    }
+    return B200_OK;
+}
+// host -> device.  Pinned source: one asynchronous copy.  Pageable source: staged; returns when the last piece has
+// been HANDED to the DMA engine (the copies themselves complete in stream order, like any cudaMemcpyAsync).
+static int copy_h2d(b200_ctx* c, void* d_dst, const void* h_src, size_t len, cudaStream_t st) {
+    if (!len) return B200_OK;
+    if (!c->stage_pageable || len < ((size_t)4 << 20) || !is_pageable(h_src)) {
+        CK(cudaMemcpyAsync(d_dst, h_src, len, cudaMemcpyHostToDevice, st));
+        return B200_OK;
+    }
+    int rc = stage_init(c);
+    if (rc) return rc;
+    const int T = stage_threads(c);
+    size_t off = 0;
+    for (int i = 0; off < len; i++) {
+        const int slot = i % b200_ctx::STG_N;
+        const size_t l = len - off < b200_ctx::STG_BYTES ? len - off : b200_ctx::STG_BYTES;
+        if (c->stg_in_busy[slot]) CK(cudaEventSynchronize(c->stg_in_ev[slot]));       // the DMA that last read this slot is done
+        par_memcpy(c->stg_in[slot], (const uint8_t*)h_src + off, l, T);
+        CK(cudaMemcpyAsync((uint8_t*)d_dst + off, c->stg_in[slot], l, cudaMemcpyHostToDevice, st));
+        CK(cudaEventRecord(c->stg_in_ev[slot], st));
+        c->stg_in_busy[slot] = true;
+        off += l;
+    }
+    return B200_OK;
+}
+// device -> host.  Pinned destination: one asynchronous copy (*sync = false: the caller synchronises the stream).
+// Pageable destination: staged and COMPLETE on return.
+static int copy_d2h(b200_ctx* c, void* h_dst, const void* d_src, size_t len, cudaStream_t st) {
+    if (!len) return B200_OK;
+    if (!c->stage_pageable || len < ((size_t)4 << 20) || !is_pageable(h_dst)) {
+        CK(cudaMemcpyAsync(h_dst, d_src, len, cudaMemcpyDeviceToHost, st));
+        return B200_OK;
+    }
+    int rc = stage_init(c);
+    if (rc) return rc;
+    const int T = stage_threads(c);
+    const size_t P = b200_ctx::STG_BYTES;
+    const size_t npieces = (len + P - 1) / P;
+    const int N = b200_ctx::STG_N;
+    for (size_t i = 0; i < npieces + (size_t)(N - 1); i++) {
+        if (i < npieces) {                                   // keep N - 1 device -> ring copies in flight
+            const size_t off = i * P, l = len - off < P ? len - off : P;
+            CK(cudaMemcpyAsync(c->stg_out[i % N], (const uint8_t*)d_src + off, l, cudaMemcpyDeviceToHost, st));
+            CK(cudaEventRecord(c->stg_out_ev[i % N], st));
+        }
+        if (i >= (size_t)(N - 1)) {
+            const size_t j = i - (N - 1), off = j * P, l = len - off < P ? len - off : P;
+            CK(cudaEventSynchronize(c->stg_out_ev[j % N]));
+            par_memcpy((uint8_t*)h_dst + off, c->stg_out[j % N], l, T);
+        }
+    }
+    return B200_OK;
+}
+
+static int arena_ensure(b200_ctx* c, size_t need) {
+    if (need <= c->arena_cap) return B200_OK;
+    if (c->arena) cudaFreeHost(c->arena);
+    c->arena = nullptr; c->arena_cap = 0;
+    const size_t want = need + need / 8 + 4096;
+    if (cudaHostAlloc(&c->arena, want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return B200_E_NOMEM; }
+    c->arena_cap = want;
+    return B200_OK;
+}
+
+static int inflate_host(const uint8_t* in, size_t n, void* out, size_t cap, void** out_alloc, size_t* out_n,
+                        size_t* full_n, unsigned flags, const uint8_t* adler_expect = nullptr, int tkind = 1, bool to_arena = false);
+
+// ------------------------------------------------------------------------------------------------
 // Host-buffer API
 //
 // Compress host memory into host memory.  The input is cut into slices (host_slice_chunks, 64 MiB by
@@ -941,16 +1366,18 @@ int b200_corpus_generate_dev(void* d_out, uint64_t seed, uint64_t first_chunk, u
 // three streams, chained by events, so with pinned host buffers the call is bound by the slower PCIe
 // direction instead of the sum of copy + compute + copy.  Output offsets chain on the device (K3's
 // carry), the host only learns each slice's end offset through a pinned mailbox.
-static int compress_host(b200_ctx* c, const uint8_t* in, size_t n, int level, uint8_t* out, size_t cap, size_t* out_n) {
+static int compress_host(b200_ctx* c, const uint8_t* in, size_t n, int level, unsigned flags, uint8_t* out, size_t cap, size_t* out_n) {
     ON_DEVICE(c);
     int rc;
+    const int frame = frame_mode(flags);
+    IndexGuard guard(c, flags);
     const size_t bound = b200_deflate_bound(n);
     if ((rc = c->d_in.ensure(n + 64))) return rc;
     if ((rc = c->d_out.ensure(bound + 64))) return rc;
     const uint64_t nchunks = (n + CHUNK - 1) / CHUNK;
     if (nchunks == 0) {
         size_t cn = 0;
-        rc = b200_deflate_compress_dev(c, c->d_in.p, 0, level, 0, c->d_out.p, c->d_out.cap, nullptr, &cn, nullptr, c->stream);
+        rc = b200_deflate_compress_dev(c, c->d_in.p, 0, level, flags & (B200_F_ZLIB | B200_F_GZIP), c->d_out.p, c->d_out.cap, nullptr, &cn, nullptr, c->stream);
         if (rc) return rc;
         *out_n = cn;
         if (cn > cap) return B200_E_OUTPUT;
@@ -962,16 +1389,24 @@ static int compress_host(b200_ctx* c, const uint8_t* in, size_t n, int level, ui
     const uint64_t nslices = (nchunks + B - 1) / B;
     if ((rc = c->tok.ensure(B * CHUNK * 4))) return rc;
     if ((rc = c->ntok.ensure(B * NSEG * 4))) return rc;
-    if ((rc = c->hist.ensure(B * NSEG * NSYM * 4))) return rc;
+    if ((rc = c->hist.ensure(B * NSEG * NSYM * 2))) return rc;
     if ((rc = c->codes.ensure(B * NSYM * 4))) return rc;
     if ((rc = c->hdr.ensure(B * HDR_WORDS * 4))) return rc;
     if ((rc = c->desc.ensure(B * sizeof(BlockDesc)))) return rc;
     if ((rc = c->sizes.ensure(B * 4))) return rc;
     if ((rc = c->offsets.ensure((nchunks + 1) * 8))) return rc;
-    if ((rc = c->total.ensure(16))) return rc;
+    if ((rc = c->total.ensure(64))) return rc;
     uint64_t* offs = (uint64_t*)c->offsets.p;
     uint64_t* d_total = (uint64_t*)c->total.p;
-    if (c->mailbox_cap < nslices) {
+    const uint64_t* d_first_base = nullptr;
+    if (frame) {
+        // the header goes straight into the caller's buffer; on the device the stream starts behind a gap of the same size
+        if (cap < kFrameLen[frame]) return B200_E_OUTPUT;
+        memcpy(out, frame == 1 ? kZlibHeader : kGzipHeader, kFrameLen[frame]);
+        CK(cudaMemcpyAsync(d_total + 2, &kFrameLen[frame], 8, cudaMemcpyHostToDevice, c->stream));
+        d_first_base = d_total + 2;
+    }
+    if (c->mailbox_cap < nslices + 1) {
         if (c->mailbox) cudaFreeHost(c->mailbox);
         c->mailbox = nullptr; c->mailbox_cap = 0;
         CK(cudaHostAlloc((void**)&c->mailbox, (nslices + 16) * 8, cudaHostAllocDefault));
@@ -984,47 +1419,133 @@ static int compress_host(b200_ctx* c, const uint8_t* in, size_t n, int level, ui
     }
     uint8_t* d_in = (uint8_t*)c->d_in.p;
     uint8_t* d_out = (uint8_t*)c->d_out.p;
+    uint64_t begin = kFrameLen[frame], drained = 0;
+    int result = B200_OK;
     // enqueue every slice: H2D on s_in, kernels on stream (after the slice's H2D), mailbox write
     for (uint64_t k = 0; k < nslices; k++) {
         const uint64_t b0 = k * B;
         const uint32_t nb = (uint32_t)((nchunks - b0 < B) ? nchunks - b0 : B);
         const size_t off = (size_t)b0 * CHUNK;
         const size_t len = (size_t)((b0 + nb == nchunks) ? n - off : (size_t)nb * CHUNK);
-        CK(cudaMemcpyAsync(d_in + off, in + off, len, cudaMemcpyHostToDevice, c->s_in));
-        CK(cudaEventRecord(c->events[2 * k], c->s_in));
+        if ((rc = copy_h2d(c, d_in + off, in + off, len, c->s_in))) return rc;          // pageable input: the host stages slice k
+        CK(cudaEventRecord(c->events[2 * k], c->s_in));                                  // while the GPU works on slice k - 1
         CK(cudaStreamWaitEvent(c->stream, c->events[2 * k], 0));
-        if ((rc = compress_batch(c, d_in + off, n - off, nb, b0, b0 + nb == nchunks, level, offs, d_total, d_out, c->stream))) return rc;
+        if ((rc = compress_batch(c, d_in + off, n - off, nb, b0, b0 + nb == nchunks, level, offs, d_total, d_out, c->stream, 3, nullptr,
+                                 nullptr, d_first_base)))
+            return rc;
         CK(cudaMemcpyAsync(&c->mailbox[k], offs + b0 + nb, 8, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaEventRecord(c->events[2 * k + 1], c->stream));
+        // slices that are finished already start their way back now instead of after the last slice was enqueued
+        while (drained + 1 < k && cudaEventQuery(c->events[2 * drained + 1]) == cudaSuccess) {
+            const uint64_t endo = c->mailbox[drained];
+            if (endo > cap) result = B200_E_OUTPUT;
+            if (result == B200_OK && endo > begin && (rc = copy_d2h(c, out + begin, d_out + begin, endo - begin, c->s_out))) return rc;
+            begin = endo;
+            drained++;
+        }
+    }
+    if (frame) {
+        // trailer: checksum of the INPUT, which is complete on the device once the last slice's kernels have run
+        if ((rc = checksum_dev(c, d_in, n, frame, (uint32_t*)(d_total + 4), c->stream))) return rc;
+        write_trailer_kernel<<<1, 1, 0, c->stream>>>(d_out, d_total, (const uint32_t*)(d_total + 4), (uint64_t)n, frame);
+        LAUNCHED();
+        CK(cudaMemcpyAsync(&c->mailbox[nslices], d_total, 8, cudaMemcpyDeviceToHost, c->stream));
     }
     // drain: as each slice finishes, copy its compressed bytes out on s_out
-    uint64_t begin = 0;
-    int result = B200_OK;
-    for (uint64_t k = 0; k < nslices; k++) {
+    for (uint64_t k = drained; k < nslices; k++) {
         CK(cudaEventSynchronize(c->events[2 * k + 1]));
         const uint64_t endo = c->mailbox[k];
         if (endo > cap) result = B200_E_OUTPUT;
-        if (result == B200_OK && endo > begin)
-            CK(cudaMemcpyAsync(out + begin, d_out + begin, endo - begin, cudaMemcpyDeviceToHost, c->s_out));
+        if (result == B200_OK && endo > begin && (rc = copy_d2h(c, out + begin, d_out + begin, endo - begin, c->s_out))) return rc;
+        begin = endo;
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    if (frame) {
+        const uint64_t endo = c->mailbox[nslices];
+        if (endo > cap) result = B200_E_OUTPUT;
+        if (result == B200_OK && endo > begin) CK(cudaMemcpyAsync(out + begin, d_out + begin, endo - begin, cudaMemcpyDeviceToHost, c->s_out));
         begin = endo;
     }
     CK(cudaStreamSynchronize(c->s_out));
-    CK(cudaStreamSynchronize(c->stream));
     *out_n = (size_t)begin;
     return result;
 }
 
-int b200_deflate_compress_into(const void* in, size_t n, int level, void* out, size_t cap, size_t* out_n) {
-    if ((!in && n) || !out_n || level < 0 || level > 3 || (!out && cap)) return B200_E_ARG;
+int b200_deflate_compress_into_ex(const void* in, size_t n, int level, unsigned flags, void* out, size_t cap, size_t* out_n) {
+    if ((!in && n) || !out_n || level < 0 || level > 3 || (!out && cap) || (flags & B200_F_NOT_LAST)) return B200_E_ARG;
     b200_ctx* c;
     int rc = default_ctx(&c);
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(c->mu);
-    return compress_host(c, (const uint8_t*)in, n, level, (uint8_t*)out, cap, out_n);
+    return compress_host(c, (const uint8_t*)in, n, level, flags, (uint8_t*)out, cap, out_n);
+}
+
+int b200_deflate_compress_into(const void* in, size_t n, int level, void* out, size_t cap, size_t* out_n) {
+    return b200_deflate_compress_into_ex(in, n, level, 0, out, cap, out_n);
+}
+
+// Views: the result stays in the library's pinned arena (the DMA engine writes it there at full PCIe speed, no page
+// faults) and the caller copies it once into wherever it must live -- the drop-in header builds its std::vector with
+// one assign().  The default context is locked from a successful *_view call until b200_view_release().
+int b200_deflate_compress_view(const void* in, size_t n, int level, unsigned flags, const void** view, size_t* out_n) {
+    if (!view || !out_n || (!in && n) || level < 0 || level > 3 || (flags & B200_F_NOT_LAST)) return B200_E_ARG;
+    *view = nullptr; *out_n = 0;
+    b200_ctx* c;
+    int rc = default_ctx(&c);
+    if (rc) return rc;
+    std::unique_lock<std::mutex> lk(c->mu);
+    {
+        ON_DEVICE(c);
+        if ((rc = arena_ensure(c, b200_deflate_bound(n) + 64))) return rc;
+    }
+    size_t cn = 0;
+    rc = compress_host(c, (const uint8_t*)in, n, level, flags, (uint8_t*)c->arena, c->arena_cap, &cn);
+    if (rc) return rc;
+    *view = c->arena; *out_n = cn;
+    c->view_locked = true;
+    lk.release();
+    return B200_OK;
+}
+
+int b200_inflate_view(const void* in, size_t n, unsigned flags, int framing, const void** view, size_t* out_n) {
+    if (!view || !out_n || (!in && n) || framing < 0 || framing > 2) return B200_E_ARG;
+    *view = nullptr; *out_n = 0;
+    const uint8_t* p = (const uint8_t*)in;
+    void* v = nullptr;
+    int rc;
+    if (framing == 1) {
+        if (n < 2) return B200_E_OVERRUN;
+        const size_t s = p[1] & 0x20 ? 6 : 2;
+        if (s > n) return B200_E_OVERRUN;
+        if (flags & B200_F_STRICT) {
+            if (n < s + 4) return B200_E_OVERRUN;
+            if ((p[0] & 15) != 8 || (((uint32_t)p[0] << 8) | p[1]) % 31 != 0) return B200_E_DATA;
+            rc = inflate_host(p + s, n - s - 4, nullptr, 0, &v, out_n, nullptr, flags, p + n - 4, 1, true);
+        } else {
+            rc = inflate_host(p + s, n - s, nullptr, 0, &v, out_n, nullptr, flags, nullptr, 1, true);
+        }
+    } else {
+        rc = inflate_host(p, n, nullptr, 0, &v, out_n, nullptr, flags, nullptr, 1, true);
+    }
+    if (rc) { *out_n = 0; return rc; }
+    *view = v;
+    return B200_OK;
+}
+
+void b200_view_release(void) {
+    std::lock_guard<std::mutex> g(g_default_mu);
+    if (g_default && g_default->view_locked) {
+        g_default->view_locked = false;
+        g_default->mu.unlock();
+    }
 }
 
 int b200_deflate_compress(const void* in, size_t n, int level, void** out, size_t* out_n) {
-    if (!out || !out_n || (!in && n) || level < 0 || level > 3) return B200_E_ARG;
+    return b200_deflate_compress_ex(in, n, level, 0, out, out_n);
+}
+
+int b200_deflate_compress_ex(const void* in, size_t n, int level, unsigned flags, void** out, size_t* out_n) {
+    if (!out || !out_n || (!in && n) || level < 0 || level > 3 || (flags & B200_F_NOT_LAST)) return B200_E_ARG;
     *out = nullptr; *out_n = 0;
     b200_ctx* c;
     int rc = default_ctx(&c);
@@ -1035,7 +1556,7 @@ int b200_deflate_compress(const void* in, size_t n, int level, void** out, size_
     size_t cn = 0;
     {
         std::lock_guard<std::mutex> lk(c->mu);
-        rc = compress_host(c, (const uint8_t*)in, n, level, buf, bound, &cn);
+        rc = compress_host(c, (const uint8_t*)in, n, level, flags, buf, bound, &cn);
     }
     if (rc) { free(buf); return rc; }
     void* shrunk = realloc(buf, cn ? cn : 1);
@@ -1051,8 +1572,9 @@ int b200_deflate_compress(const void* in, size_t n, int level, void** out, size_
 // *handled = false: the stream did not validate (foreign, damaged, ...): nothing is reported, the caller takes the
 // plain path, which also produces the proper error code.  The decoded bytes stay in c->d_out.
 static int inflate_host_pipelined(b200_ctx* c, const uint8_t* in, size_t n, uint8_t* out, size_t cap, size_t* out_n,
-                                  size_t* full_n, unsigned flags, bool* handled) {
+                                  size_t* full_n, unsigned flags, bool* handled, bool* in_resident) {
     *handled = false;
+    *in_resident = false;
     const size_t S = c->host_inflate_slice & ~(size_t)15;
     if (!S || n < 2 * S || !cap || c->inflate_warp_path) return B200_OK;
     int rc;
@@ -1069,14 +1591,26 @@ static int inflate_host_pipelined(b200_ctx* c, const uint8_t* in, size_t n, uint
     uint8_t* d_out = (uint8_t*)c->d_out.p;
     unsigned long long* d_result = (unsigned long long*)c->result.p;
     cudaStream_t st = c->stream;
-    for (size_t k = 0; k < nsl; k++) {
-        const size_t off = k * S, len = off + S < n ? S : n - off;
-        CK(cudaMemcpyAsync(d_in + off, in + off, len, cudaMemcpyHostToDevice, c->s_in));
-        CK(cudaEventRecord(c->events[k], c->s_in));
-    }
+    // the input travels on its own host thread: with pageable caller memory every slice is staged through the pinned
+    // ring by host threads (copy_h2d), which must not hold up the decode loop below
+    std::atomic<size_t> arrived{0};
+    std::atomic<int> feed_rc{B200_OK};
+    std::thread feeder([&]() {
+        cudaSetDevice(c->device);
+        for (size_t k = 0; k < nsl; k++) {
+            const size_t off = k * S, len = off + S < n ? S : n - off;
+            int r = copy_h2d(c, d_in + off, in + off, len, c->s_in);
+            if (r == B200_OK && cudaEventRecord(c->events[k], c->s_in) != cudaSuccess) r = B200_E_CUDA;
+            if (r) { feed_rc.store(r); arrived.store(nsl, std::memory_order_release); return; }
+            arrived.store(k + 1, std::memory_order_release);
+        }
+    });
+    struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{feeder};
     uint64_t start = 0, chunk0 = 0, total = 0;
     bool ok = true;
     for (size_t k = 0; k < nsl && ok; k++) {
+        while (arrived.load(std::memory_order_acquire) <= k) std::this_thread::yield();     // events[k] has been recorded
+        if (feed_rc.load()) return feed_rc.load();
         CK(cudaStreamWaitEvent(st, c->events[k], 0));
         const bool last = k + 1 == nsl;
         const uint64_t avail = last ? n : (k + 1) * S;
@@ -1129,13 +1663,16 @@ static int inflate_host_pipelined(b200_ctx* c, const uint8_t* in, size_t n, uint
         CK(cudaStreamSynchronize(st));
         if (verdict[0] != 1) { ok = false; break; }
         const uint64_t lo = o0 < cap ? o0 : cap, hi = o0 + verdict[1] < cap ? o0 + verdict[1] : cap;
-        if (hi > lo) CK(cudaMemcpyAsync(out + lo, d_out + lo, hi - lo, cudaMemcpyDeviceToHost, c->s_out));
+        if (hi > lo && (rc = copy_d2h(c, out + lo, d_out + lo, hi - lo, c->s_out))) return rc;
         total = o0 + verdict[1];
         chunk0 += units;
         start = base + next_rel;
     }
+    feeder.join();
     CK(cudaStreamSynchronize(c->s_in));
     CK(cudaStreamSynchronize(c->s_out));
+    if (feed_rc.load()) return feed_rc.load();
+    *in_resident = true;                       // whatever happens next, the whole input sits in c->d_in
     if (!ok) return B200_OK;
     *handled = true;
     if (out_n) *out_n = (size_t)(total < cap ? total : cap);
@@ -1143,30 +1680,35 @@ static int inflate_host_pipelined(b200_ctx* c, const uint8_t* in, size_t n, uint
     return B200_OK;
 }
 
-// adler_expect: if non-NULL, the 4-byte big-endian Adler-32 trailer the decoded bytes must match (strict zlib)
+// adler_expect: if non-NULL, the trailer the decoded bytes must match (strict mode): tkind 1 = 4-byte big-endian
+// Adler-32 (zlib), tkind 2 = CRC-32 + ISIZE, little endian (gzip)
+// to_arena: *out_alloc receives a pointer into the context's pinned arena instead of a malloc'ed buffer, and the
+// context stays locked until b200_view_release()
 static int inflate_host(const uint8_t* in, size_t n, void* out, size_t cap, void** out_alloc, size_t* out_n,
-                        size_t* full_n, unsigned flags, const uint8_t* adler_expect = nullptr) {
+                        size_t* full_n, unsigned flags, const uint8_t* adler_expect, int tkind, bool to_arena) {
     b200_ctx* c;
     int rc = default_ctx(&c);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(c->mu);
+    std::unique_lock<std::mutex> lk(c->mu);
     ON_DEVICE(c);
     size_t written = 0, full = 0;
     size_t dcap = cap;
-    bool piped = false;
+    bool piped = false, in_resident = false;
     if (!out_alloc) {
-        if ((rc = inflate_host_pipelined(c, in, n, (uint8_t*)out, cap, &written, &full, flags, &piped))) return rc;
+        if ((rc = inflate_host_pipelined(c, in, n, (uint8_t*)out, cap, &written, &full, flags, &piped, &in_resident))) return rc;
         // strict zlib: the trailer covers the WHOLE decoded stream; a truncating caller buffer does not excuse it
         if (piped && adler_expect && full > cap) piped = false;
     }
     if (!piped) {
     if ((rc = c->d_in.ensure(n + 64))) return rc;
-    if (n) CK(cudaMemcpyAsync(c->d_in.p, in, n, cudaMemcpyHostToDevice, c->stream));
+    if (n && !in_resident && (rc = copy_h2d(c, c->d_in.p, in, n, c->stream))) return rc;
     const bool need_full = out_alloc || adler_expect;      // the device buffer must hold every decoded byte
     if (out_alloc) dcap = n * 4 + 65536 > (size_t)1 << 20 ? n * 4 + 65536 : (size_t)1 << 20;   // first guess
     for (int attempt = 0; attempt < 3; attempt++) {
         if ((rc = c->d_out.ensure(dcap + 64))) return rc;
+        c->size_probe = need_full && attempt == 0;
         rc = b200_inflate_dev(c, c->d_in.p, n, c->d_out.p, dcap, nullptr, &written, &full, nullptr, flags, c->stream);
+        c->size_probe = false;
         if (!need_full || full <= dcap) break;
         dcap = full;                       // decoded size is now known exactly: one more pass
     }
@@ -1175,20 +1717,39 @@ static int inflate_host(const uint8_t* in, size_t n, void* out, size_t cap, void
     if (rc == B200_OK && adler_expect && full <= dcap) {
         // the whole decoded stream sits in d_out: check it there
         uint32_t got = 0;
-        const int rc2 = b200_adler32_dev(c, c->d_out.p, full, &got, nullptr, c->stream);
-        if (rc2) return rc2;
-        const uint32_t want = ((uint32_t)adler_expect[0] << 24) | ((uint32_t)adler_expect[1] << 16) |
-                              ((uint32_t)adler_expect[2] << 8) | adler_expect[3];
-        if (got != want) rc = B200_E_DATA;
+        if (tkind == 1) {
+            const int rc2 = b200_adler32_dev(c, c->d_out.p, full, &got, nullptr, c->stream);
+            if (rc2) return rc2;
+            const uint32_t want = ((uint32_t)adler_expect[0] << 24) | ((uint32_t)adler_expect[1] << 16) |
+                                  ((uint32_t)adler_expect[2] << 8) | adler_expect[3];
+            if (got != want) rc = B200_E_DATA;
+        } else {
+            const int rc2 = b200_crc32_dev(c, c->d_out.p, full, &got, nullptr, c->stream);
+            if (rc2) return rc2;
+            const uint32_t want = (uint32_t)adler_expect[0] | ((uint32_t)adler_expect[1] << 8) | ((uint32_t)adler_expect[2] << 16) |
+                                  ((uint32_t)adler_expect[3] << 24);
+            const uint32_t isize = (uint32_t)adler_expect[4] | ((uint32_t)adler_expect[5] << 8) | ((uint32_t)adler_expect[6] << 16) |
+                                   ((uint32_t)adler_expect[7] << 24);
+            if (got != want || isize != (uint32_t)full) rc = B200_E_DATA;
+        }
     }
-    if (out_alloc) {
+    if (out_alloc && to_arena) {
+        if (rc == B200_OK || written) {
+            int rc2 = arena_ensure(c, written + 64);
+            if (rc2) return rc2;
+            if (written) CK(cudaMemcpyAsync(c->arena, c->d_out.p, written, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+        }
+        *out_alloc = c->arena;
+        if (rc == B200_OK) { c->view_locked = true; lk.release(); }      // b200_view_release() unlocks
+    } else if (out_alloc) {
         void* buf = malloc(written ? written : 1);
         if (!buf) return B200_E_NOMEM;
         if (written && cudaMemcpyAsync(buf, c->d_out.p, written, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) { free(buf); return B200_E_CUDA; }
         if (cudaStreamSynchronize(c->stream) != cudaSuccess) { free(buf); return B200_E_CUDA; }
         *out_alloc = buf;
     } else if (written && !piped) {
-        CK(cudaMemcpyAsync(out, c->d_out.p, written, cudaMemcpyDeviceToHost, c->stream));
+        if ((rc = copy_d2h(c, out, c->d_out.p, written, c->stream))) return rc;
         CK(cudaStreamSynchronize(c->stream));
     }
     if (out_n) *out_n = written;
@@ -1236,6 +1797,43 @@ int b200_inflate_zlib(const void* in, size_t n, void* out, size_t cap, size_t* o
     return b200_inflate(p + s, n - s, out, cap, out_n, full_n, flags);
 }
 
+// RFC 1952 member header: fixed 10 bytes, then FEXTRA / FNAME / FCOMMENT / FHCRC as flagged.  Returns the offset of the
+// raw stream, or 0 if this is not a gzip member / the header runs past the input.
+static size_t gzip_header_skip(const uint8_t* in, size_t n) {
+    if (n < 18 || in[0] != 0x1F || in[1] != 0x8B || in[2] != 8 || (in[3] & 0xE0)) return 0;
+    const uint8_t flg = in[3];
+    size_t p = 10;
+    if (flg & 4) { if (p + 2 > n) return 0; p += 2 + ((size_t)in[p] | ((size_t)in[p + 1] << 8)); }
+    if (flg & 8) { while (p < n && in[p]) p++; p++; }
+    if (flg & 16) { while (p < n && in[p]) p++; p++; }
+    if (flg & 2) p += 2;
+    return p + 8 <= n ? p : 0;
+}
+
+// gzip (RFC 1952) around the raw stream: an addition next to decompressZlib (the reference has no gzip entry point).
+// The first member is decoded; the CRC-32 / ISIZE trailer is ignored unless B200_F_STRICT is set, then the CRC-32 is
+// computed on the GPU over the decoded bytes.
+int b200_inflate_gzip(const void* in, size_t n, void* out, size_t cap, size_t* out_n, size_t* full_n, unsigned flags) {
+    if (!in) return B200_E_ARG;
+    if ((!out && cap)) return B200_E_ARG;
+    const uint8_t* p = (const uint8_t*)in;
+    const size_t s = gzip_header_skip(p, n);
+    if (!s) return n < 18 ? B200_E_OVERRUN : B200_E_DATA;
+    if (flags & B200_F_STRICT) return inflate_host(p + s, n - s - 8, out, cap, nullptr, out_n, full_n, flags, p + n - 8, 2);
+    return b200_inflate(p + s, n - s, out, cap, out_n, full_n, flags);
+}
+
+int b200_inflate_gzip_alloc(const void* in, size_t n, void** out, size_t* out_n, unsigned flags) {
+    if (!out || !out_n) return B200_E_ARG;
+    *out = nullptr; *out_n = 0;
+    if (!in) return B200_E_ARG;
+    const uint8_t* p = (const uint8_t*)in;
+    const size_t s = gzip_header_skip(p, n);
+    if (!s) return n < 18 ? B200_E_OVERRUN : B200_E_DATA;
+    if (flags & B200_F_STRICT) return inflate_host(p + s, n - s - 8, nullptr, 0, out, out_n, nullptr, flags, p + n - 8, 2);
+    return b200_inflate_alloc(p + s, n - s, out, out_n, flags);
+}
+
 int b200_inflate_zlib_alloc(const void* in, size_t n, void** out, size_t* out_n, unsigned flags) {
     if (!in || n < 2) { if (out) *out = nullptr; if (out_n) *out_n = 0; return B200_E_OVERRUN; }
     if (!out || !out_n) return B200_E_ARG;
@@ -1248,6 +1846,212 @@ int b200_inflate_zlib_alloc(const void* in, size_t n, void** out, size_t* out_n,
         return inflate_host(p + s, n - s - 4, nullptr, 0, out, out_n, nullptr, flags, p + n - 4);
     }
     return b200_inflate_alloc(p + s, n - s, out, out_n, flags);
+}
+
+// ------------------------------------------------------------------------------------------------
+// File-path API: what deflate::compress(string, string, int) (reference include/deflate.hpp:755-777) and
+// inflate::decompress(string, string) (include/inflate.hpp:390-408) do -- stream a file through the codec in slices with
+// bounded memory -- as pinned, double-buffered host <-> device pipelines.  (The reference reads 32 KB at a time and its
+// inflate side fails on multi-block files; these handle any size, any of the stream kinds the
+// memory API handles.)
+static int pin_ensure(void** p, size_t* cap, size_t need) {
+    if (need <= *cap) return B200_OK;
+    if (*p) cudaFreeHost(*p);
+    *p = nullptr; *cap = 0;
+    if (cudaHostAlloc(p, need, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return B200_E_NOMEM; }
+    *cap = need;
+    return B200_OK;
+}
+static bool read_fully(int fd, void* buf, size_t len, off_t off) {
+    uint8_t* p = (uint8_t*)buf;
+    while (len) {
+        const ssize_t r = pread(fd, p, len, off);
+        if (r <= 0) return false;
+        p += r; len -= (size_t)r; off += r;
+    }
+    return true;
+}
+static bool write_fully(int fd, const void* buf, size_t len) {
+    const uint8_t* p = (const uint8_t*)buf;
+    while (len) {
+        const ssize_t r = write(fd, p, len);
+        if (r <= 0) return false;
+        p += r; len -= (size_t)r;
+    }
+    return true;
+}
+struct FdCloser { int fd; ~FdCloser() { if (fd >= 0) close(fd); } };
+
+int b200_deflate_compress_file(const char* in_path, const char* out_path, int level, unsigned flags, size_t* in_n, size_t* out_n) {
+    if (!in_path || !out_path || level < 0 || level > 3 || (flags & B200_F_NOT_LAST)) return B200_E_ARG;
+    b200_ctx* c;
+    int rc = default_ctx(&c);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    ON_DEVICE(c);
+    FdCloser fi{open(in_path, O_RDONLY)};
+    if (fi.fd < 0) return B200_E_IO;
+    struct stat sb;
+    if (fstat(fi.fd, &sb) != 0 || !S_ISREG(sb.st_mode)) return B200_E_IO;
+    FdCloser fo{open(out_path, O_WRONLY | O_CREAT | O_TRUNC, 0644)};
+    if (fo.fd < 0) return B200_E_IO;
+    const uint64_t n = (uint64_t)sb.st_size;
+    const size_t S = c->file_slice;
+    const uint64_t nslices = n ? (n + S - 1) / S : 1;
+    const size_t ocap = b200_deflate_bound(S);
+    const int frame = frame_mode(flags);
+    const unsigned cflags = flags & B200_F_NO_INDEX;
+    uint64_t written = 0;
+    if (frame) {
+        if (!write_fully(fo.fd, frame == 1 ? kZlibHeader : kGzipHeader, kFrameLen[frame])) return B200_E_IO;
+        written += kFrameLen[frame];
+    }
+    if ((rc = c->total.ensure(64))) return rc;
+    uint32_t* d_sum = (uint32_t*)((uint64_t*)c->total.p + 5);       // running checksum of the input (framing)
+    for (int k = 0; k < 2; k++) {
+        if ((rc = pin_ensure(&c->pin_in[k], &c->pin_in_cap[k], S))) return rc;
+        if ((rc = pin_ensure(&c->pin_out[k], &c->pin_out_cap[k], ocap))) return rc;
+        if ((rc = c->file_in[k].ensure(S + 64)) || (rc = c->file_out[k].ensure(ocap + 64))) return rc;
+        if (!c->file_ev[k]) CK(cudaEventCreateWithFlags(&c->file_ev[k], cudaEventDisableTiming));
+    }
+    if (c->mailbox_cap < 4) {
+        if (c->mailbox) cudaFreeHost(c->mailbox);
+        c->mailbox = nullptr; c->mailbox_cap = 0;
+        CK(cudaHostAlloc((void**)&c->mailbox, 32 * 8, cudaHostAllocDefault));
+        c->mailbox_cap = 32;
+    }
+    auto retire = [&](uint64_t j) -> int {           // slice j: wait for its kernels, fetch its bytes, append them to the file
+        const int idx = (int)(j & 1);
+        CK(cudaEventSynchronize(c->file_ev[idx]));
+        const uint64_t sz = c->mailbox[idx];
+        if (sz > ocap) return B200_E_OUTPUT;
+        CK(cudaMemcpyAsync(c->pin_out[idx], c->file_out[idx].p, sz, cudaMemcpyDeviceToHost, c->s_out));
+        CK(cudaStreamSynchronize(c->s_out));
+        if (!write_fully(fo.fd, c->pin_out[idx], sz)) return B200_E_IO;
+        written += sz;
+        return B200_OK;
+    };
+    for (uint64_t k = 0; k < nslices; k++) {
+        const int idx = (int)(k & 1);
+        if (k >= 2 && (rc = retire(k - 2))) return rc;                 // frees pin_in / file_in / file_out / pin_out [idx]
+        const uint64_t off = k * S;
+        const size_t len = (size_t)(n - off < S ? n - off : S);
+        if (len && !read_fully(fi.fd, c->pin_in[idx], len, (off_t)off)) return B200_E_IO;      // the GPU works on slice k - 1 meanwhile
+        if (len) CK(cudaMemcpyAsync(c->file_in[idx].p, c->pin_in[idx], len, cudaMemcpyHostToDevice, c->stream));
+        const bool last = k + 1 == nslices;
+        if ((rc = b200_deflate_compress_dev(c, c->file_in[idx].p, len, level, cflags | (last ? 0u : B200_F_NOT_LAST), c->file_out[idx].p,
+                                            c->file_out[idx].cap, nullptr, nullptr, nullptr, c->stream)))
+            return rc;
+        if (frame && (rc = checksum_dev(c, (const uint8_t*)c->file_in[idx].p, len, frame, d_sum, c->stream, k ? d_sum : nullptr))) return rc;
+        CK(cudaMemcpyAsync(&c->mailbox[idx], c->total.p, 8, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaEventRecord(c->file_ev[idx], c->stream));
+    }
+    if (nslices >= 2 && (rc = retire(nslices - 2))) return rc;
+    if ((rc = retire(nslices - 1))) return rc;
+    if (frame) {
+        uint32_t sum = 0;
+        CK(cudaMemcpyAsync(&sum, d_sum, 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        uint8_t t[8];
+        if (frame == 1) { t[0] = (uint8_t)(sum >> 24); t[1] = (uint8_t)(sum >> 16); t[2] = (uint8_t)(sum >> 8); t[3] = (uint8_t)sum; }
+        else for (int k = 0; k < 4; k++) { t[k] = (uint8_t)(sum >> (8 * k)); t[4 + k] = (uint8_t)((uint32_t)n >> (8 * k)); }
+        if (!write_fully(fo.fd, t, frame == 1 ? 4 : 8)) return B200_E_IO;
+        written += frame == 1 ? 4 : 8;
+    }
+    if (in_n) *in_n = (size_t)n;
+    if (out_n) *out_n = (size_t)written;
+    return B200_OK;
+}
+
+int b200_inflate_file(const char* in_path, const char* out_path, unsigned flags, size_t* in_n, size_t* out_n) {
+    if (!in_path || !out_path) return B200_E_ARG;
+    b200_ctx* c;
+    int rc = default_ctx(&c);
+    if (rc) return rc;
+    FdCloser fi{open(in_path, O_RDONLY)};
+    if (fi.fd < 0) return B200_E_IO;
+    struct stat sb;
+    if (fstat(fi.fd, &sb) != 0 || !S_ISREG(sb.st_mode)) return B200_E_IO;
+    const uint64_t n = (uint64_t)sb.st_size;
+    if (in_n) *in_n = (size_t)n;
+    const size_t S = c->file_slice;
+    const size_t slack = CHUNK + 4096, lead = 16;
+    uint64_t total = 0;
+    bool windowed = n > 2 * S;
+    FdCloser fo{-1};
+    if (windowed) {
+        std::lock_guard<std::mutex> lk(c->mu);
+        ON_DEVICE(c);
+        const uint64_t nw = (n + S - 1) / S;
+        const size_t wcap = S + slack + lead + 64;
+        for (int k = 0; k < 2; k++)
+            if ((rc = pin_ensure(&c->pin_in[k], &c->pin_in_cap[k], wcap))) return rc;
+        if ((rc = c->file_in[0].ensure(wcap))) return rc;
+        auto window = [&](uint64_t k, uint64_t* ws, uint64_t* we) {
+            const uint64_t lo = k * S, hi = lo + S < n ? lo + S : n;
+            *ws = k == 0 ? 0 : (lo - lead) & ~15ull;
+            *we = hi + slack < n ? hi + slack : n;
+        };
+        auto read_window = [&](uint64_t k) -> bool {
+            uint64_t ws, we;
+            window(k, &ws, &we);
+            return read_fully(fi.fd, c->pin_in[k & 1], (size_t)(we - ws), (off_t)ws);
+        };
+        std::future<bool> reader = std::async(std::launch::async, read_window, (uint64_t)0);
+        std::future<bool> writer;
+        for (uint64_t k = 0; k < nw && windowed; k++) {
+            const bool got = reader.get();
+            if (k + 1 < nw) reader = std::async(std::launch::async, read_window, k + 1);       // the next window arrives while this one is decoded
+            if (!got) { if (writer.valid()) writer.get(); if (reader.valid()) reader.get(); return B200_E_IO; }
+            uint64_t ws, we;
+            window(k, &ws, &we);
+            const uint64_t lo = k * S, hi = lo + S < n ? lo + S : n;
+            CK(cudaMemcpyAsync(c->file_in[0].p, c->pin_in[k & 1], we - ws, cudaMemcpyHostToDevice, c->stream));
+            bool valid = false;
+            uint64_t wtotal = 0, units = 0, nxt = 0;
+            rc = inflate_chunked(c, (const uint8_t*)c->file_in[0].p, we - ws, k == 0 ? 0 : lo - ws, hi - ws, k == 0, we == n, nullptr, 0, flags,
+                                 c->stream, &valid, &wtotal, &units, &nxt, &c->file_out[0]);
+            if (rc == B200_OK && !valid) {
+                // not (only) this library's chunks -- a foreign stream, or stored user data that contains the separator
+                // pattern: start over with the whole file through the memory API
+                windowed = false;
+                break;
+            }
+            if (rc) { if (writer.valid()) writer.get(); if (reader.valid()) reader.get(); return rc; }
+            if (writer.valid() && !writer.get()) { if (reader.valid()) reader.get(); return B200_E_IO; }      // pin_out[k & 1] was used by window k - 2 ... and the file stays in order
+            if (wtotal) {
+                if ((rc = pin_ensure(&c->pin_out[k & 1], &c->pin_out_cap[k & 1], wtotal))) { if (reader.valid()) reader.get(); return rc; }
+                CK(cudaMemcpyAsync(c->pin_out[k & 1], c->file_out[0].p, wtotal, cudaMemcpyDeviceToHost, c->stream));
+                CK(cudaStreamSynchronize(c->stream));
+                if (fo.fd < 0) { fo.fd = open(out_path, O_WRONLY | O_CREAT | O_TRUNC, 0644); if (fo.fd < 0) { if (reader.valid()) reader.get(); return B200_E_IO; } }
+                const void* src = c->pin_out[k & 1];
+                const int fd = fo.fd;
+                writer = std::async(std::launch::async, [fd, src, wtotal]() { return write_fully(fd, src, (size_t)wtotal); });
+            }
+            total += wtotal;
+        }
+        if (reader.valid()) reader.get();
+        if (writer.valid() && !writer.get()) return B200_E_IO;
+        if (windowed) {
+            if (fo.fd < 0) { fo.fd = open(out_path, O_WRONLY | O_CREAT | O_TRUNC, 0644); if (fo.fd < 0) return B200_E_IO; }
+            if (out_n) *out_n = (size_t)total;
+            return B200_OK;
+        }
+    }
+    // small files and streams this library did not write: the whole stream through the memory API
+    std::vector<uint8_t> in(n);
+    if (n && !read_fully(fi.fd, in.data(), n, 0)) return B200_E_IO;
+    void* out = nullptr;
+    size_t on = 0;
+    rc = inflate_host(in.data(), n, nullptr, 0, &out, &on, nullptr, flags);
+    if (rc) { if (out) free(out); return rc; }
+    if (fo.fd >= 0) close(fo.fd);
+    fo.fd = open(out_path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    const bool ok = fo.fd >= 0 && write_fully(fo.fd, out, on);
+    free(out);
+    if (!ok) return B200_E_IO;
+    if (out_n) *out_n = on;
+    return B200_OK;
 }
 
 }  // extern "C"

@@ -1,4 +1,4 @@
-// checksum.cuh -- Adler-32 (RFC 1950) on the device.
+// checksum.cuh -- Adler-32 (RFC 1950) and CRC-32 (RFC 1952) on the device.
 //
 // The reference's inflate::decompressZlib (include/inflate.hpp:326-361) skips the two header bytes and never
 // looks at the Adler-32 trailer; with B200_F_STRICT this library verifies it (and the header check bits) on the
@@ -64,7 +64,9 @@ adler_partial_kernel(const uint8_t* __restrict__ data, uint64_t n, AdlerPart* __
 // Folds the block contributions in order.  Every full block has L = CHUNK; only the last may be shorter.
 // state (A, B) -> after a block: B += L * A + b, A += a.  Lanes fold contiguous runs of blocks starting from
 // (A, B) = (0, 0); a run of blocks is itself "a block" of the summed length, so lane results combine the same way.
-__global__ void adler_fold_kernel(const AdlerPart* __restrict__ parts, uint64_t nblocks, uint64_t n, uint32_t* __restrict__ out) {
+// seed (may be NULL): the Adler-32 of everything before this buffer (streaming over slices); out may alias seed.
+__global__ void adler_fold_kernel(const AdlerPart* __restrict__ parts, uint64_t nblocks, uint64_t n, uint32_t* __restrict__ out,
+                                  const uint32_t* __restrict__ seed = nullptr) {
     const uint32_t lane = threadIdx.x;
     const uint64_t per = (nblocks + 31) / 32;
     const uint64_t lo = min(nblocks, lane * per), hi = min(nblocks, lo + per);
@@ -81,11 +83,164 @@ __global__ void adler_fold_kernel(const AdlerPart* __restrict__ parts, uint64_t 
     __syncwarp();
     if (lane == 0) {
         unsigned long long a = 1, b = 0;                    // Adler-32 start state
+        if (seed) { a = *seed & 0xFFFFu; b = *seed >> 16; }
         for (uint32_t k = 0; k < 32; k++) {
             b = (b + (sL[k] % ADLER_MOD) * a + sB[k]) % ADLER_MOD;
             a = (a + sA[k]) % ADLER_MOD;
         }
         *out = (uint32_t)((b << 16) | a);
+    }
+}
+
+// ---- CRC-32 (gzip, RFC 1952; the reflected polynomial 0xEDB88320) -----------------------------------------------
+// gzip framing is the wire format next to the path; the reference has no gzip entry point,
+// so this is an addition, not a replacement.  One CTA per 64 KiB block: every thread runs the byte-wise table CRC
+// over its 256-byte slice (table in shared memory, replicated x4 against bank conflicts is not needed: the index is
+// data dependent), slices and then blocks are COMBINED with the zlib identity
+//   crc(A || B) = crc(A) * x^(8 |B|)  xor  crc(B)      (multiplication of polynomials over GF(2) modulo P)
+// so the order of evaluation does not matter and the fold over blocks is a tree.
+constexpr uint32_t CRC_POLY = 0xEDB88320u;
+constexpr uint32_t CRC_THREADS = 256;
+constexpr uint32_t CRC_SLICE = CHUNK / CRC_THREADS;      // 256 bytes per thread
+
+// a(x) * b(x) mod P, reflected bit order (bit 31 = x^0), as in zlib's multmodp()
+__host__ __device__ __forceinline__ uint32_t crc_multmodp(uint32_t a, uint32_t b) {
+    uint32_t m = 1u << 31, p = 0;
+    for (;;) {
+        if (a & m) {
+            p ^= b;
+            if ((a & (m - 1)) == 0) break;
+        }
+        m >>= 1;
+        b = (b & 1u) ? (b >> 1) ^ CRC_POLY : b >> 1;
+    }
+    return p;
+}
+// x^(8 * nbytes) mod P from the table x2n[k] = x^(2^k) mod P
+__host__ __device__ __forceinline__ uint32_t crc_x8n(const uint32_t* x2n, uint64_t nbytes) {
+    uint32_t p = 1u << 31;                                // x^0
+    uint32_t k = 3;                                       // bytes -> bits
+    while (nbytes) {
+        if (nbytes & 1) p = crc_multmodp(x2n[k & 31], p);
+        nbytes >>= 1;
+        k++;
+    }
+    return p;
+}
+__host__ __device__ __forceinline__ void crc_x2n_table(uint32_t* x2n) {
+    uint32_t p = 1u << 30;                                // x^1
+    x2n[0] = p;
+    for (uint32_t n = 1; n < 32; n++) x2n[n] = p = crc_multmodp(p, p);
+}
+
+struct CrcPart { uint32_t crc; uint32_t len; };           // finalised CRC-32 of one block and its length
+
+__global__ void __launch_bounds__(CRC_THREADS)
+crc32_partial_kernel(const uint8_t* __restrict__ data, uint64_t n, CrcPart* __restrict__ parts) {
+    __shared__ uint32_t s_tab[256];
+    __shared__ uint32_t s_x2n[32];
+    __shared__ uint32_t s_crc[CRC_THREADS];
+    __shared__ uint32_t s_len[CRC_THREADS];
+    const uint32_t tid = threadIdx.x;
+    {
+        uint32_t c = tid;
+        #pragma unroll
+        for (int k = 0; k < 8; k++) c = (c & 1u) ? (c >> 1) ^ CRC_POLY : c >> 1;
+        s_tab[tid] = c;
+    }
+    if (tid == 0) crc_x2n_table(s_x2n);
+    __syncthreads();
+    const uint64_t base = (uint64_t)blockIdx.x * CHUNK;
+    const uint32_t L = (uint32_t)min((uint64_t)CHUNK, n - base);
+    const uint32_t lo = min(L, tid * CRC_SLICE), hi = min(L, lo + CRC_SLICE);
+    const uint8_t* p = data + base;
+    uint32_t c = 0xFFFFFFFFu;
+    uint32_t i = lo;
+    if ((reinterpret_cast<uintptr_t>(p + lo) & 15) == 0) {
+        for (; i + 16 <= hi; i += 16) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(p + i));
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+            #pragma unroll
+            for (uint32_t k = 0; k < 4; k++) {
+                #pragma unroll
+                for (uint32_t j = 0; j < 4; j++) c = s_tab[(c ^ (w[k] >> (8 * j))) & 0xFFu] ^ (c >> 8);
+            }
+        }
+    }
+    for (; i < hi; i++) c = s_tab[(c ^ p[i]) & 0xFFu] ^ (c >> 8);
+    s_crc[tid] = ~c;                                      // finalised CRC of the slice (of nothing: 0)
+    s_len[tid] = hi - lo;
+    __syncthreads();
+    // tree combine: [t] <- [t] || [t + stride]
+    for (uint32_t stride = 1; stride < CRC_THREADS; stride <<= 1) {
+        if ((tid & (2 * stride - 1)) == 0) {
+            const uint32_t lb = s_len[tid + stride];
+            if (lb) {
+                s_crc[tid] = crc_multmodp(crc_x8n(s_x2n, lb), s_crc[tid]) ^ s_crc[tid + stride];
+                s_len[tid] += lb;
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) { CrcPart r; r.crc = s_crc[0]; r.len = s_len[0]; parts[blockIdx.x] = r; }
+}
+
+// Folds the block CRCs (in order) into *out, continuing from *seed_ptr (the CRC of everything before; NULL to start).
+constexpr uint32_t CRC_FOLD_THREADS = 1024;
+__global__ void __launch_bounds__(CRC_FOLD_THREADS)
+crc32_fold_kernel(const CrcPart* __restrict__ parts, uint64_t nblocks, const uint32_t* __restrict__ seed_ptr, uint32_t* __restrict__ out) {
+    const uint32_t seed = seed_ptr ? *seed_ptr : 0u;       // read by every thread before thread 0 may overwrite it (out may alias)
+    __syncthreads();
+    __shared__ uint32_t s_x2n[32];
+    __shared__ uint32_t s_crc[CRC_FOLD_THREADS];
+    __shared__ unsigned long long s_len[CRC_FOLD_THREADS];
+    const uint32_t tid = threadIdx.x;
+    if (tid == 0) crc_x2n_table(s_x2n);
+    __syncthreads();
+    const uint64_t per = (nblocks + CRC_FOLD_THREADS - 1) / CRC_FOLD_THREADS;
+    const uint64_t lo = min(nblocks, tid * per), hi = min(nblocks, lo + per);
+    uint32_t c = 0;
+    unsigned long long len = 0;
+    for (uint64_t k = lo; k < hi; k++) {
+        const CrcPart q = parts[k];
+        if (!q.len) continue;
+        c = len ? (crc_multmodp(crc_x8n(s_x2n, q.len), c) ^ q.crc) : q.crc;
+        len += q.len;
+    }
+    s_crc[tid] = c; s_len[tid] = len;
+    __syncthreads();
+    for (uint32_t stride = 1; stride < CRC_FOLD_THREADS; stride <<= 1) {
+        if ((tid & (2 * stride - 1)) == 0) {
+            const unsigned long long lb = s_len[tid + stride];
+            if (lb) {
+                s_crc[tid] = s_len[tid] ? (crc_multmodp(crc_x8n(s_x2n, lb), s_crc[tid]) ^ s_crc[tid + stride]) : s_crc[tid + stride];
+                s_len[tid] += lb;
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        uint32_t r = s_crc[0];
+        if (seed && s_len[0]) r = crc_multmodp(crc_x8n(s_x2n, s_len[0]), seed) ^ s_crc[0];
+        else if (seed) r = seed;
+        *out = r;
+    }
+}
+
+// zlib / gzip trailer behind the raw stream: out[*total ...] <- Adler-32 big endian (mode 1) or CRC-32 + ISIZE little
+// endian (mode 2); *total grows by 4 / 8.
+__global__ void write_trailer_kernel(uint8_t* __restrict__ out, uint64_t* __restrict__ total, const uint32_t* __restrict__ sum,
+                                     uint64_t n, int mode) {
+    if (threadIdx.x || blockIdx.x) return;
+    uint8_t* p = out + *total;
+    const uint32_t v = *sum;
+    if (mode == 1) {
+        p[0] = (uint8_t)(v >> 24); p[1] = (uint8_t)(v >> 16); p[2] = (uint8_t)(v >> 8); p[3] = (uint8_t)v;
+        *total += 4;
+    } else {
+        const uint32_t isize = (uint32_t)n;
+        for (int k = 0; k < 4; k++) { p[k] = (uint8_t)(v >> (8 * k)); p[4 + k] = (uint8_t)(isize >> (8 * k)); }
+        *total += 8;
     }
 }
 

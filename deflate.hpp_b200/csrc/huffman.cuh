@@ -212,13 +212,13 @@ __device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
 }
 
 // grid = ceil(nchunks / HUF_WARPS), block = 128.
-//   hist   : [nchunks][NSEG][NSYM] from K1
+//   hist   : [nchunks][NSEG][NSYM] u16 from K1 (a segment has at most 4096 tokens)
 //   codes  : [nchunks][NSYM]   len | reversed code << 8   (what the encoder indexes by symbol)
 //   hdr    : [nchunks][HDR_WORDS] block header bits (BFINAL/BTYPE + dynamic tables)
 //   desc   : [nchunks] BlockDesc;  sizes: [nchunks] bytes per chunk (input of the offset scan)
 // level 0 forces stored blocks.  last_is_final: the final chunk of this buffer carries BFINAL.
 __global__ void __launch_bounds__(HUF_THREADS)
-huffman_kernel(const uint32_t* __restrict__ hist, uint64_t n, uint32_t nchunks, int level, int last_is_final,
+huffman_kernel(const uint16_t* __restrict__ hist, uint64_t n, uint32_t nchunks, int level, int last_is_final,
                int with_index, const ChunkSrc* __restrict__ srcs, uint32_t* __restrict__ codes, uint32_t* __restrict__ hdr, BlockDesc* __restrict__ desc,
                uint32_t* __restrict__ sizes) {
     __shared__ HufScratch scratch[HUF_WARPS];
@@ -228,7 +228,7 @@ huffman_kernel(const uint32_t* __restrict__ hist, uint64_t n, uint32_t nchunks, 
     HufScratch* s = &scratch[warp];
     const uint32_t clen = srcs ? srcs[chunk].clen : (uint32_t)min((uint64_t)CHUNK, n - (uint64_t)chunk * CHUNK);
     const bool last = srcs ? srcs[chunk].last != 0 : (last_is_final && chunk == nchunks - 1);
-    const uint32_t* h = hist + (size_t)chunk * NSEG * NSYM;
+    const uint16_t* h = hist + (size_t)chunk * NSEG * NSYM;
     uint32_t* mycodes = codes + (size_t)chunk * NSYM;
     uint32_t* myhdr = hdr + (size_t)chunk * HDR_WORDS;
     BlockDesc* d = desc + chunk;

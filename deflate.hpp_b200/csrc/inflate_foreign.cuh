@@ -1,0 +1,660 @@
+// inflate_foreign.cuh -- block-parallel INFLATE of ONE stream this library did not write (zlib, the reference's
+// own compressor, ...): SURVEY.md 8(f) rank 1.
+//
+// Replaces, for long foreign streams, the serial block loop of the reference's realDecompress
+// (include/inflate.hpp:277-322): one growing output that every block may reference up to 32 KiB back
+// (decompressHuffmanBlock, :262-272) and blocks that start at arbitrary BIT offsets.  Nothing in such a stream says
+// where a block starts or what the 32 KiB before it will hold, so the work is cut in two the way pugz / rapidgzip do
+// on CPUs, with the pieces laid out for a GPU:
+//
+//   F1 foreign_find_blocks_kernel   one warp per 16 KiB piece of the input tests EVERY bit offset of its piece as the
+//        start of a dynamic-Huffman block: 17 header bits (BFINAL 0, BTYPE 10, HLIT <= 29, HDIST <= 29) pass 1 offset
+//        in 9; survivors are queued in shared memory and checked 32 at a time for a COMPLETE precode (1-3 % pass) and
+//        then by decoding the code-length lists (exact count, complete literal/length code with an end-of-block
+//        symbol, complete / single / empty distance code).  What passes all three by chance is ~1e-9 per offset; the
+//        chain check below catches it.  The piece's first hit is a candidate unit start.
+//   F2 foreign_decode_kernel<COUNT>  one THREAD per candidate decodes from its bit offset, block after block, until a
+//        block ends at or behind the next candidate: end bit, output bytes, number of back-references.  The host
+//        walks the chain from bit 0 (unit k + 1 must start exactly where unit k ended; candidates the chain jumps
+//        over were false, a missing one is added and counted in a second round) and prefix-sums the sizes.
+//   F3 foreign_decode_kernel<EMIT>   the same decode with known offsets: literals go to a u16 SYMBOL image S of the
+//        output (one u16 per output byte), back-references and stored blocks to the unit's op list.
+//   F4 foreign_copy_kernel           one warp per unit applies the ops in order INSIDE S: a source below the unit's
+//        first byte is not known yet and becomes a marker 0x8000 | index into the 32 KiB window before the unit;
+//        markers are copied like bytes, so afterwards every symbol of a unit is a literal or a window marker.
+//   F5 foreign_window_kernel         window propagation.  The last 32 KiB of every unit are resolved against the
+//        window before it, unit after unit, in a ring in shared memory.  Sequential over units but two-level: groups
+//        of units compose their windows symbolically in parallel (the ring starts as identity markers), one CTA
+//        chains the ~150 group maps, then the groups run again with their real start window and write the tails.
+//   F6 foreign_resolve_kernel        everything that is not a tail: out[p] = literal or out[unit_start - 32768 + idx].
+//
+// Results are bit-identical to the one-warp decoder in inflate.cuh (same decisions, reference quirks included: the
+// only position-dependent one -- a distance that reaches before the start of the output copies nothing,
+// inflate.hpp:268-270 -- can only happen in the first 32 KiB and is decided by unit 0, which knows its position).
+// Any error, a chain that does not close in a few rounds, or an output buffer smaller than the stream hands the
+// stream back to the sequential decoder, which also produces the reference's error codes.
+#pragma once
+#include "inflate_tp.cuh"
+
+namespace b200 {
+
+constexpr uint32_t FB_PIECE = 16384;                 // input bytes whose bit offsets one warp tests
+constexpr uint32_t FB_SLACK = 1024;                  // staged behind the piece: a dynamic header is < 2400 bits long
+constexpr uint32_t FB_WARPS = 4;
+constexpr uint32_t FB_THREADS = FB_WARPS * 32;
+constexpr uint32_t FB_QUEUE = 96;                    // survivors per stage queue (flushed when >= 32 are waiting)
+constexpr uint32_t FB_STAGE_WORDS = (FB_PIECE + FB_SLACK) / 4 + 4;
+struct __align__(16) FbWarp {
+    uint32_t data[FB_STAGE_WORDS];
+    uint32_t q1[FB_QUEUE], q2[FB_QUEUE];             // bit offsets relative to the piece
+    uint8_t pre[128 * 32];                           // per-lane 7-bit precode table: entry e of lane l at [e * 32 + l]
+};
+constexpr size_t FB_SMEM_BYTES = FB_WARPS * sizeof(FbWarp);
+
+// 64 bits of the staged piece starting at bit q (q + 64 <= staged bits)
+__device__ __forceinline__ uint64_t fb_bits64(const uint32_t* w, uint32_t q) {
+    const uint32_t i = q >> 5, sh = q & 31;
+    const uint32_t a = w[i], b = w[i + 1], c = w[i + 2];
+    return (uint64_t)__funnelshift_r(a, b, sh) | ((uint64_t)__funnelshift_r(b, c, sh) << 32);
+}
+__device__ __forceinline__ uint32_t fb_bits32(const uint32_t* w, uint32_t q) {
+    const uint32_t i = q >> 5;
+    return __funnelshift_r(w[i], w[i + 1], q & 31);
+}
+
+// stage 2: the precode (HCLEN x 3 bits from bit 17) must be a complete prefix code
+__device__ __forceinline__ bool fb_precode_complete(const uint32_t* w, uint32_t q) {
+    const uint64_t h = fb_bits64(w, q);
+    const uint32_t hclen = ((uint32_t)(h >> 13) & 15u) + 4;
+    const uint64_t lo = h >> 17;                                   // 47 bits = 15 lengths
+    const uint32_t hi = fb_bits32(w, q + 62);                      // lengths 15..18
+    uint32_t kraft = 0;
+    #pragma unroll
+    for (uint32_t i = 0; i < 19; i++) {
+        const uint32_t l = i < 15 ? (uint32_t)(lo >> (3 * i)) & 7u : (hi >> (3 * (i - 15))) & 7u;
+        if (i < hclen && l) kraft += 128u >> l;
+    }
+    return kraft == 128u;
+}
+
+// stage 3: decode HLIT + HDIST code lengths through the precode and check what a valid block guarantees
+__device__ bool fb_header_valid(const uint32_t* w, uint32_t q, uint8_t* pre /* this lane's column */) {
+    const uint64_t h = fb_bits64(w, q);
+    const uint32_t hlit = ((uint32_t)(h >> 3) & 31u) + 257, hdist = ((uint32_t)(h >> 8) & 31u) + 1;
+    const uint32_t hclen = ((uint32_t)(h >> 13) & 15u) + 4;
+    uint32_t pl[19];
+    #pragma unroll
+    for (uint32_t i = 0; i < 19; i++) pl[i] = 0;
+    #pragma unroll
+    for (uint32_t i = 0; i < 19; i++) {
+        const uint32_t v = i < hclen ? (fb_bits32(w, q + 17 + 3 * i) & 7u) : 0u;
+        // C_PRECODE_ORDER[i] with a compile-time index after unrolling
+        constexpr uint8_t ORD[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+        pl[ORD[i]] = v;
+    }
+    // canonical precode -> 128-entry table (sym | len << 5); the code is complete (stage 2), so every entry is set
+    uint32_t cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    #pragma unroll
+    for (uint32_t s = 0; s < 19; s++) cnt[pl[s]]++;
+    uint32_t next[8];
+    {
+        uint32_t code = 0;
+        cnt[0] = 0;
+        #pragma unroll
+        for (uint32_t l = 1; l <= 7; l++) { code = (code + cnt[l - 1]) << 1; next[l] = code; }
+    }
+    #pragma unroll
+    for (uint32_t s = 0; s < 19; s++) {
+        const uint32_t l = pl[s];
+        if (!l) continue;
+        const uint32_t rev = __brev(next[l]++) >> (32 - l);
+        for (uint32_t k = rev; k < 128; k += 1u << l) pre[k * 32] = (uint8_t)(s | (l << 5));
+    }
+    uint32_t pos = q + 17 + 3 * hclen;
+    const uint32_t total = hlit + hdist;
+    uint32_t i = 0, prev = 0, klit = 0, kdist = 0, ndist = 0, eob = 0;
+    while (i < total) {
+        const uint32_t b = fb_bits32(w, pos);
+        const uint32_t e = pre[(b & 127u) * 32];
+        const uint32_t l = e >> 5, sym = e & 31u;
+        pos += l;
+        uint32_t rep = 1, val = sym;
+        if (sym >= 16) {
+            const uint32_t x = b >> l;
+            if (sym == 16) { if (i == 0) return false; rep = 3 + (x & 3u); val = prev; pos += 2; }
+            else if (sym == 17) { rep = 3 + (x & 7u); val = 0; pos += 3; }
+            else { rep = 11 + (x & 127u); val = 0; pos += 7; }
+        }
+        if (i + rep > total) return false;
+        if (val) {
+            // a run may straddle the literal/length -> distance boundary (RFC 1951 3.2.7)
+            const uint32_t in_lit = i < hlit ? min(rep, hlit - i) : 0;
+            klit += in_lit * (32768u >> val);
+            kdist += (rep - in_lit) * (32768u >> val);
+            ndist += rep - in_lit;
+            if (i <= 256 && 256 < i + rep) eob = 1;
+        }
+        i += rep;
+        prev = val;
+        if (pos > (FB_PIECE + FB_SLACK) * 8 - 64) return false;    // cannot happen for a real header (< 2400 bits)
+    }
+    if (!eob || klit != 32768u) return false;
+    // distance code: complete, or a single code of length 1 (zlib accepts exactly that), or none at all
+    return kdist == 32768u || (ndist == 1 && kdist == 16384u) || ndist == 0;
+}
+
+// cand[p] = absolute bit offset of the first valid-looking dynamic block header that STARTS in piece p, or ~0
+__global__ void __launch_bounds__(FB_THREADS)
+foreign_find_blocks_kernel(const uint8_t* __restrict__ in, uint64_t n, uint64_t npieces, unsigned long long* __restrict__ cand) {
+    extern __shared__ __align__(16) uint8_t fb_smem[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t p = (uint64_t)blockIdx.x * FB_WARPS + warp;
+    if (p >= npieces) return;
+    FbWarp* W = reinterpret_cast<FbWarp*>(fb_smem) + warp;
+    const uint32_t FULL = 0xFFFFFFFFu;
+    const uint64_t byte0 = p * FB_PIECE;
+    // stage the piece (+ slack), zero-filled past the end of the stream; `in` is only byte-aligned in general
+    const uint64_t avail = n - byte0;
+    if ((reinterpret_cast<uintptr_t>(in + byte0) & 3) == 0) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(in + byte0);
+        const uint32_t full_words = (uint32_t)min((uint64_t)FB_STAGE_WORDS, avail >> 2);
+        for (uint32_t i = lane; i < full_words; i += 32) W->data[i] = __ldg(src + i);
+        for (uint32_t i = full_words + lane; i < FB_STAGE_WORDS; i += 32) {
+            uint32_t v = 0;
+            for (uint32_t k = 0; k < 4; k++) { const uint64_t b = (uint64_t)i * 4 + k; if (b < avail) v |= (uint32_t)in[byte0 + b] << (8 * k); }
+            W->data[i] = v;
+        }
+    } else {
+        for (uint32_t i = lane; i < FB_STAGE_WORDS; i += 32) {
+            uint32_t v = 0;
+            for (uint32_t k = 0; k < 4; k++) { const uint64_t b = (uint64_t)i * 4 + k; if (b < avail) v |= (uint32_t)in[byte0 + b] << (8 * k); }
+            W->data[i] = v;
+        }
+    }
+    __syncwarp();
+    const uint32_t nbits = (uint32_t)min((uint64_t)FB_PIECE, avail) * 8;     // offsets tested: [0, nbits)
+    // a header needs at least 17 + 12 bits and an end-of-block: offsets in the stream's last bytes cannot start a block
+    uint32_t best = 0xFFFFFFFFu;
+    uint32_t n1 = 0, n2 = 0;
+    const uint32_t* w = W->data;
+    auto drain2 = [&](uint32_t count) {          // stage 3 on the first `count` entries of q2
+        const bool have = lane < count;
+        const uint32_t q = have ? W->q2[lane] : 0;
+        bool ok = false;
+        if (have && q < best) ok = fb_header_valid(w, q, W->pre + lane);
+        uint32_t m = __ballot_sync(FULL, ok);
+        while (m) {
+            const uint32_t j = __ffs(m) - 1;
+            m &= m - 1;
+            best = min(best, __shfl_sync(FULL, q, j));
+        }
+        __syncwarp();
+        // compact the queue
+        const uint32_t rest = n2 - count;
+        uint32_t v = 0;
+        if (lane < rest) v = W->q2[count + lane];
+        uint32_t v2 = 0;
+        if (lane + 32 < rest) v2 = W->q2[count + lane + 32];
+        __syncwarp();
+        if (lane < rest) W->q2[lane] = v;
+        if (lane + 32 < rest) W->q2[lane + 32] = v2;
+        n2 = rest;
+        __syncwarp();
+    };
+    auto drain1 = [&](uint32_t count) {          // stage 2 on the first `count` entries of q1
+        const bool have = lane < count;
+        const uint32_t q = have ? W->q1[lane] : 0;
+        const bool ok = have && q < best && fb_precode_complete(w, q);
+        const uint32_t m = __ballot_sync(FULL, ok);
+        if (ok) W->q2[n2 + __popc(m & ((1u << lane) - 1u))] = q;
+        n2 += __popc(m);
+        __syncwarp();
+        const uint32_t rest = n1 - count;
+        uint32_t v = 0, v2 = 0;
+        if (lane < rest) v = W->q1[count + lane];
+        if (lane + 32 < rest) v2 = W->q1[count + lane + 32];
+        __syncwarp();
+        if (lane < rest) W->q1[lane] = v;
+        if (lane + 32 < rest) W->q1[lane + 32] = v2;
+        n1 = rest;
+        __syncwarp();
+        if (n2 >= 32) drain2(32);
+    };
+    for (uint32_t b0 = 0; b0 < nbits; b0 += 32) {
+        if (b0 > best) break;                    // only the FIRST hit of the piece matters
+        const uint32_t q = b0 + lane;
+        const uint32_t h = fb_bits32(w, q);
+        // stage 1: BFINAL = 0, BTYPE = 10 (bits 1, 2 = 0, 1), HLIT <= 29, HDIST <= 29
+        const bool ok = q < nbits && (h & 7u) == 4u && ((h >> 3) & 31u) <= 29u && ((h >> 8) & 31u) <= 29u;
+        const uint32_t m = __ballot_sync(FULL, ok);
+        if (ok) W->q1[n1 + __popc(m & ((1u << lane) - 1u))] = q;
+        n1 += __popc(m);
+        __syncwarp();
+        if (n1 >= 32) drain1(32);
+    }
+    while (n1) drain1(min(n1, 32u));
+    while (n2) drain2(min(n2, 32u));
+    if (lane == 0) cand[p] = best == 0xFFFFFFFFu ? ~0ull : (unsigned long long)(byte0 * 8 + best);
+}
+
+// ---- F2 / F3: one thread per unit ---------------------------------------------------------------------------
+constexpr uint32_t FD_THREADS = TP_THREADS;                       // 128 threads, private interleaved tables (TP_SMEM_BYTES)
+constexpr uint32_t FU_FINAL = 1;                                  // the unit ended with a BFINAL block
+constexpr uint32_t FU_REACHED = 2;                                // ... at a block end at or behind its stop offset
+struct FUnitRes { uint64_t end_bit; uint64_t out_len; uint32_t nops; int32_t status; uint32_t flags; uint32_t pad; };
+constexpr uint32_t F_MARK = 0x8000u;                              // symbol image: 0x8000 | index into the 32 KiB window before the unit
+constexpr uint32_t F_WINDOW = 32768;
+constexpr uint32_t FD_MAX_OUT = 0xF0000000u;                      // positions inside a unit are 32-bit
+
+struct FdState {
+    TBits br;
+    uint32_t pos;            // bytes produced by this unit
+    uint32_t nops;
+    uint32_t state, bfinal, flags;
+    int st;
+};
+
+// One block header (single thread): stored blocks become ops, Huffman blocks get their tables built.
+template <bool EMIT>
+__device__ __noinline__ void fd_block(FdState& s, uint16_t* lit, uint16_t* dst, uint32_t NT, TpTables& T, uint64_t in_len, uint64_t in_bits,
+                                      bool strict, uint64_t stop_bit, uint16_t* S, uint64_t* ops, const uint8_t* in) {
+    TBits& br = s.br;
+    if (tb_bitpos(br) + 3 > in_bits) { s.st = ST_OVERRUN; s.state = TS_DONE; return; }
+    tb_refill(br);
+    const uint32_t hdr = tb_get(br, 3);
+    s.bfinal = hdr & 1;
+    const uint32_t btype = hdr >> 1;
+    if (btype == 0) {
+        tb_drop(br, br.bc & 7);
+        tb_refill(br);
+        const uint32_t len = tb_get(br, 16);
+        const uint32_t nlen = tb_get(br, 16);
+        if (strict && (len ^ nlen) != 0xFFFFu) { s.st = ST_DATA; s.state = TS_DONE; return; }
+        const uint64_t bpos = tb_bitpos(br) >> 3;
+        if (bpos + len > in_len) { s.st = ST_OVERRUN; s.state = TS_DONE; return; }
+        if (len) {
+            if (EMIT) { ops[s.nops] = tp_op(s.pos, len, 0); ops[s.nops + 1] = bpos; }
+            s.nops += 2;
+            s.pos += len;
+        }
+        tb_seek(br, bpos + len);
+    } else if (btype == 3) {
+        if (strict) { s.st = ST_DATA; s.state = TS_DONE; return; }           // the reference's switch has no case 3: skipped
+    } else {
+        uint32_t hlit = NLIT, hdist = NDIST;
+        if (btype == 1) {
+            for (uint32_t i = 0; i < NLIT; i++) T.lens[i] = (uint8_t)fixed_lit_len(i);
+            for (uint32_t i = 0; i < NDIST; i++) T.lens[NLIT + i] = 5;
+        } else {
+            hlit = tb_get(br, 5) + 257;
+            hdist = tb_get(br, 5) + 1;
+            const uint32_t hclen = tb_get(br, 4) + 4;
+            uint8_t pl[19];
+            #pragma unroll 1
+            for (uint32_t i = 0; i < 19; i++) pl[i] = 0;
+            #pragma unroll 1
+            for (uint32_t i = 0; i < hclen; i++) {
+                tb_refill(br);
+                pl[C_PRECODE_ORDER[i]] = (uint8_t)tb_get(br, 3);
+            }
+            if (!tp_build(dst, NT, T, pl, 19, 1, 7, false)) { s.st = ST_DATA; s.state = TS_DONE; return; }
+            const uint32_t total = hlit + hdist;
+            uint32_t i = 0, prev = 0;
+            #pragma unroll 1
+            while (i < total) {
+                tb_refill(br);
+                const uint32_t e = dst[tb_peek(br, 7) * NT];
+                const uint32_t l = e & 15u, sym = e >> 4;
+                if (l == 0) { s.st = ST_OVERRUN; s.state = TS_DONE; return; }
+                tb_drop(br, l);
+                uint32_t rep = 1, val = sym;
+                if (sym == 16) { rep = 3 + tb_get(br, 2); val = prev; }
+                else if (sym == 17) { rep = 3 + tb_get(br, 3); val = 0; }
+                else if (sym == 18) { rep = 11 + tb_get(br, 7); val = 0; }
+                if (i + rep > total) { s.st = ST_DATA; s.state = TS_DONE; return; }
+                #pragma unroll 1
+                for (uint32_t j = 0; j < rep; j++) {
+                    const uint32_t p = i + j;
+                    T.lens[p < hlit ? p : NLIT + (p - hlit)] = (uint8_t)val;
+                }
+                i += rep;
+                prev = val;
+            }
+            if (T.lens[256] == 0) { s.st = ST_DATA; s.state = TS_DONE; return; }
+        }
+        if (!tp_build(lit, NT, T, T.lens, hlit, 0, TP_LIT_BITS, true)) { s.st = ST_DATA; s.state = TS_DONE; return; }
+        if (!tp_build(dst, NT, T, T.lens + NLIT, hdist, 1, TP_DST_BITS, false)) { s.st = ST_DATA; s.state = TS_DONE; return; }
+        s.state = TS_SYM;
+        return;
+    }
+    // stored or skipped block: what follows every block
+    if (s.pos > FD_MAX_OUT) { s.st = ST_FALLBACK; s.state = TS_DONE; }
+    else if (s.bfinal) { s.flags |= FU_FINAL; s.state = TS_DONE; }
+    else if (tb_bitpos(br) >= stop_bit) { s.flags |= FU_REACHED; s.state = TS_DONE; }
+}
+
+template <bool EMIT>
+__global__ void __launch_bounds__(FD_THREADS)
+foreign_decode_kernel(const uint8_t* __restrict__ in, uint64_t n, const uint64_t* __restrict__ starts, const uint64_t* __restrict__ stops,
+                      uint64_t nunits, FUnitRes* __restrict__ res, const uint64_t* __restrict__ out_base, const uint64_t* __restrict__ ops_base,
+                      uint16_t* __restrict__ S, uint64_t* __restrict__ ops_all, unsigned flags) {
+    extern __shared__ __align__(16) uint8_t tp_smem[];
+    __shared__ uint32_t s_ring[TB_RING * FD_THREADS];
+    uint32_t* s_lut = reinterpret_cast<uint32_t*>(tp_smem);
+    uint16_t* tabs = reinterpret_cast<uint16_t*>(tp_smem + TP_LUT_WORDS * 4);
+    tp_lut_init(s_lut, threadIdx.x);
+    __syncthreads();
+    const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = u < nunits;
+    const uint32_t NT = blockDim.x;
+    uint16_t* lit = tabs + threadIdx.x;
+    uint16_t* dst = tabs + threadIdx.x + (size_t)(1u << TP_LIT_BITS) * NT;
+    const uint32_t lit_sa = (uint32_t)__cvta_generic_to_shared(lit);
+    const uint32_t dst_sa = (uint32_t)__cvta_generic_to_shared(dst);
+    const uint32_t lut_sa = (uint32_t)__cvta_generic_to_shared(s_lut);
+    const uint32_t ntb = NT * 2;
+    const bool strict = flags & 1u;
+    const uint64_t in_bits = n * 8;
+    TpTables T;
+    FdState s;
+    s.br.ring_sa = (uint32_t)__cvta_generic_to_shared(s_ring + threadIdx.x);
+    s.br.ring_stride = NT * 4;
+    s.br.skip = (uint32_t)(reinterpret_cast<uintptr_t>(in) & 3);
+    s.br.wp = reinterpret_cast<const uint32_t*>(in - s.br.skip);
+    s.br.nw = live ? (uint32_t)((s.br.skip + n + 3) >> 2) : 0;
+    s.br.wi = 0; s.br.w0 = 0; s.br.bb = 0; s.br.bc = 0;
+    s.pos = 0; s.nops = 0; s.bfinal = 0; s.flags = 0; s.st = ST_OK;
+    s.state = live ? TS_BLOCK : TS_DONE;
+    uint64_t stop_bit = ~0ull, start_bit = 0;
+    uint16_t* Su = nullptr;
+    uint64_t* ops = nullptr;
+    if (live) {
+        start_bit = starts[u];
+        stop_bit = stops[u];
+        tb_seek(s.br, start_bit >> 3);
+        tb_drop(s.br, (uint32_t)(start_bit & 7));
+        if (EMIT) { Su = S + out_base[u]; ops = ops_all + ops_base[u]; }
+    }
+    const bool first_unit = live && start_bit == 0;           // knows its absolute position: the too-far quirk is decided here
+    // A unit that started on a false candidate decodes garbage; it normally dies within a few thousand symbols (an
+    // end-of-block turns up, what follows is no header), but nothing guarantees that: it may not read more than 1 MiB
+    // past its stop offset (no real producer writes blocks that long; if one did, the stream goes to the sequential decoder)
+    const uint32_t wi_end = s.br.nw + 4;
+    const uint64_t stop_word = stop_bit == ~0ull ? (uint64_t)wi_end : ((stop_bit + (uint64_t)s.br.skip * 8) >> 5) + (1u << 18);
+    const uint32_t wi_lim = (uint32_t)min((uint64_t)wi_end, stop_word);
+
+    while (__any_sync(0xFFFFFFFFu, s.state != TS_DONE)) {
+        if (s.state == TS_SYM) {
+            TBits& br = s.br;
+            if (s.pos > FD_MAX_OUT || br.wi > wi_lim) {
+                s.st = br.wi > wi_end ? ST_OVERRUN : ST_FALLBACK; s.state = TS_DONE;
+            } else {
+                if (br.bc < 33) tb_take(br);
+                uint32_t e = lds_u16(lit_sa + tb_peek(br, TP_LIT_BITS) * ntb);
+                bool ok = true;
+                if ((e & 15u) == 0) {
+                    const int r = tp_slow_symbol(T, 0, (uint32_t)br.bb, TP_LIT_BITS + 1);
+                    if (r < 0) { s.st = ST_OVERRUN; s.state = TS_DONE; ok = false; }
+                    else e = tp_lit_entry((uint32_t)r & 0xFFFFu, (uint32_t)r >> 16);
+                }
+                uint32_t l = e & 15u, p = e >> 4;
+                bool is_match = ok && p >= 0x200u && !(p & 0x100u);
+                if (ok && p < 256) {
+                    tb_drop(br, l);
+                    if (EMIT) Su[s.pos] = (uint16_t)p;
+                    s.pos++;
+                    #pragma unroll
+                    for (uint32_t k = 0; k < TP_LIT_RUN; k++) {
+                        if (k) tb_refill(br);
+                        const uint32_t e2 = lds_u16(lit_sa + tb_peek(br, TP_LIT_BITS) * ntb);
+                        const uint32_t l2 = e2 & 15u, p2 = e2 >> 4;
+                        if (l2 == 0) break;
+                        if (p2 < 256) { tb_drop(br, l2); if (EMIT) Su[s.pos] = (uint16_t)p2; s.pos++; continue; }
+                        if (p2 >= 0x200u && !(p2 & 0x100u)) { l = l2; p = p2; is_match = true; }
+                        break;
+                    }
+                }
+                if (is_match) {
+                    tb_drop(br, l);
+                    const uint32_t lt = lds_u32(lut_sa + (p & 31u) * 4);
+                    const uint32_t length = (lt & 0xFFFFu) + tb_get(br, lt >> 16);
+                    tb_refill(br);
+                    const uint32_t de = lds_u16(dst_sa + tb_peek(br, TP_DST_BITS) * ntb);
+                    uint32_t dl = de & 15u, dsym = de >> 4;
+                    if (dl == 0) {
+                        const int r = tp_slow_symbol(T, 1, (uint32_t)br.bb, TP_DST_BITS + 1);
+                        dsym = r < 0 ? 99u : ((uint32_t)r & 0xFFFFu);
+                        dl = r < 0 ? 0u : ((uint32_t)r >> 16);
+                    }
+                    if (dsym > 29) {
+                        s.st = tb_bitpos(br) + 16 > in_bits ? ST_OVERRUN : ST_DATA; s.state = TS_DONE;
+                    } else {
+                        tb_drop(br, dl);
+                        const uint32_t dt = lds_u32(lut_sa + (32 + dsym) * 4);
+                        const uint32_t dist = (dt & 0xFFFFu) + tb_get(br, dt >> 16);
+                        if (first_unit && dist > s.pos) {
+                            if (strict) { s.st = ST_DATA; s.state = TS_DONE; }
+                            // else the reference copies nothing (inflate.hpp:268-270)
+                        } else {
+                            if (EMIT) ops[s.nops] = tp_op(s.pos, length, dist);
+                            s.nops++;
+                            s.pos += length;
+                        }
+                    }
+                } else if (ok && p >= 256) {
+                    if (p == 0x100u) {                                           // end of block
+                        tb_drop(br, l);
+                        if (br.wi > wi_end || tb_bitpos(br) > in_bits) { s.st = ST_OVERRUN; s.state = TS_DONE; }
+                        else if (s.bfinal) { s.flags |= FU_FINAL; s.state = TS_DONE; }
+                        else if (tb_bitpos(br) >= stop_bit) { s.flags |= FU_REACHED; s.state = TS_DONE; }
+                        else s.state = TS_BLOCK;
+                    } else { s.st = ST_DATA; s.state = TS_DONE; }                // 286 / 287
+                }
+            }
+        } else if (s.state == TS_BLOCK) {
+            fd_block<EMIT>(s, lit, dst, NT, T, n, in_bits, strict, stop_bit, Su, ops, in);
+        }
+    }
+    if (!live) return;
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    if (s.st == ST_OK && tb_bitpos(s.br) > in_bits) s.st = ST_OVERRUN;
+    FUnitRes r;
+    r.end_bit = tb_bitpos(s.br); r.out_len = s.pos; r.nops = s.nops; r.status = s.st; r.flags = s.flags; r.pad = 0;
+    res[u] = r;
+}
+
+// ---- F4: ops inside the symbol image, one warp per unit ----------------------------------------------------------
+// err: set to 1 when something that must not happen happened (the stream then goes to the sequential decoder)
+__global__ void __launch_bounds__(INF_THREADS)
+foreign_copy_kernel(const uint8_t* __restrict__ in, const FUnitRes* __restrict__ res, const uint64_t* __restrict__ out_base,
+                    const uint64_t* __restrict__ ops_base, uint64_t nunits, uint16_t* __restrict__ S, const uint64_t* __restrict__ ops_all,
+                    unsigned long long* __restrict__ counter, unsigned int* __restrict__ err) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t FULL = 0xFFFFFFFFu;
+    for (;;) {
+        unsigned long long u = 0;
+        if (lane == 0) u = atomicAdd(counter, 1ull);
+        u = __shfl_sync(FULL, u, 0);
+        if (u >= nunits) break;
+        const uint32_t nops = res[u].nops;
+        uint16_t* Su = S + out_base[u];
+        const uint64_t* ops = ops_all + ops_base[u];
+        uint64_t o_next = lane < nops ? ops[lane] : 0ull;
+        uint32_t carry = 0;                                                      // 1: slot 0 of this batch is a stored op's source slot
+        for (uint32_t b = 0; b < nops; b += 32) {
+            const uint64_t o = o_next;
+            if (b + 32 < nops) o_next = b + 32 + lane < nops ? ops[b + 32 + lane] : 0ull;
+            const uint32_t cnt = min(32u, nops - b);
+            uint32_t j = carry;
+            carry = 0;
+            for (; j < cnt; j++) {
+                const uint64_t oj = __shfl_sync(FULL, o, j);
+                const uint32_t pos = (uint32_t)oj, len = (uint32_t)(oj >> 32) & 0xFFFFu, dist = (uint32_t)(oj >> 48);
+                if (dist == 0) {
+                    // stored block: the next slot is the source byte offset in the stream (it may sit in the next batch)
+                    const uint64_t in_batch = __shfl_sync(FULL, o, (j + 1) & 31);
+                    const uint64_t in_next = __shfl_sync(FULL, o_next, 0);
+                    const uint64_t srcoff = j + 1 < 32 ? in_batch : in_next;
+                    if (j + 1 >= 32) carry = 1;
+                    const uint8_t* sp = in + srcoff;
+                    for (uint32_t i = lane; i < len; i += 32) Su[pos + i] = sp[i];
+                    j++;                                                         // skip the source slot
+                    __syncwarp();
+                    continue;
+                }
+                // back-reference: sources below the unit's first byte are window markers
+                if (dist >= len || dist >= 32) {
+                    for (uint32_t c0 = 0; c0 < len; c0 += 32) {
+                        const uint32_t i = c0 + lane;
+                        if (i < len) {
+                            const int64_t sidx = (int64_t)pos - dist + i;
+                            Su[pos + i] = sidx < 0 ? (uint16_t)(F_MARK | (uint32_t)(sidx + F_WINDOW)) : Su[sidx];
+                        }
+                        if (dist < len) __syncwarp();                            // the next 32 may read what these wrote
+                    }
+                } else {
+                    // period < 32 and overlapping: every output byte is one of the `dist` symbols below pos
+                    uint32_t v = 0;
+                    if (lane < dist) {
+                        const int64_t sidx = (int64_t)pos - dist + lane;
+                        v = sidx < 0 ? (F_MARK | (uint32_t)(sidx + F_WINDOW)) : Su[sidx];
+                    }
+                    uint32_t r = lane % dist;
+                    const uint32_t step = 32 % dist;
+                    for (uint32_t c0 = 0; c0 < len; c0 += 32) {                  // all lanes take part in the shuffle
+                        const uint32_t x = __shfl_sync(FULL, v, r);
+                        if (c0 + lane < len) Su[pos + c0 + lane] = (uint16_t)x;
+                        r += step;
+                        if (r >= dist) r -= dist;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        if (lane == 0 && res[u].status != ST_OK) atomicExch(err, 1u);
+    }
+}
+
+// ---- F5: window propagation -----------------------------------------------------------------------------------------
+// Units [g * G, (g + 1) * G) of group g are walked in order by one CTA with the 32 KiB before the current unit in a ring
+// of u16 symbols in shared memory (ring slot of absolute output position a: a & 32767).
+//   MODE 0 (compose): the ring starts as identity markers for the 32 KiB before the GROUP; at the end the ring is the
+//                     group's map: gmap[g][i] = symbol of absolute position (group end - 32768 + i) as a literal or a
+//                     marker into the window before the group.
+//   MODE 1 (apply):   the ring starts as the real window before the group (gwin[g], bytes; group 0 has none), every
+//                     unit's resolved tail is written to out[].
+constexpr uint32_t FW_THREADS = 1024;
+constexpr uint32_t FW_PER = F_WINDOW / FW_THREADS;      // 32 symbols per thread per unit
+constexpr uint32_t FW_SMEM_BYTES = F_WINDOW * 2;
+template <int MODE>
+__global__ void __launch_bounds__(FW_THREADS)
+foreign_window_kernel(const uint16_t* __restrict__ S, const uint64_t* __restrict__ out_base, uint64_t nunits, uint64_t total,
+                      uint32_t G, uint16_t* __restrict__ gmap, const uint8_t* __restrict__ gwin, uint8_t* __restrict__ out,
+                      unsigned int* __restrict__ err) {
+    extern __shared__ __align__(16) uint8_t fw_smem[];
+    uint16_t* ring = reinterpret_cast<uint16_t*>(fw_smem);
+    const uint32_t tid = threadIdx.x;
+    const uint64_t g = blockIdx.x;
+    const uint64_t u0 = g * G, u1 = min(nunits, u0 + G);
+    if (u0 >= nunits) return;
+    const uint64_t gstart = out_base[u0];
+    for (uint32_t i = tid; i < F_WINDOW; i += FW_THREADS) {
+        // ring slot of absolute position gstart - 32768 + i
+        const uint32_t slot = (uint32_t)((gstart + i) & (F_WINDOW - 1));
+        if (MODE == 0) ring[slot] = (uint16_t)(F_MARK | i);
+        else ring[slot] = (g == 0) ? (uint16_t)(F_MARK | i) : (uint16_t)gwin[g * F_WINDOW + i];
+    }
+    __syncthreads();
+    bool bad = false;
+    for (uint64_t u = u0; u < u1; u++) {
+        const uint64_t start = out_base[u];
+        const uint64_t end = u + 1 < nunits ? out_base[u + 1] : total;
+        const uint64_t len = end - start;
+        const uint32_t T = (uint32_t)min(len, (uint64_t)F_WINDOW);
+        const uint64_t t0 = end - T;                                   // first tail position
+        uint16_t v[FW_PER];
+        #pragma unroll
+        for (uint32_t k = 0; k < FW_PER; k++) {
+            const uint32_t j = tid + k * FW_THREADS;
+            uint16_t s = 0;
+            if (j < T) {
+                s = S[t0 + j];
+                if (s & F_MARK) s = ring[(uint32_t)((start + (s & (F_MARK - 1))) & (F_WINDOW - 1))];   // position start - 32768 + idx
+            }
+            v[k] = s;
+        }
+        __syncthreads();                                               // every read of the old window is done
+        #pragma unroll
+        for (uint32_t k = 0; k < FW_PER; k++) {
+            const uint32_t j = tid + k * FW_THREADS;
+            if (j < T) {
+                ring[(uint32_t)((t0 + j) & (F_WINDOW - 1))] = v[k];
+                if (MODE == 1) {
+                    if (v[k] & F_MARK) bad = true;                     // reaches before the start of the stream
+                    out[t0 + j] = (uint8_t)v[k];
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (MODE == 0) {
+        const uint64_t gend = u1 < nunits ? out_base[u1] : total;
+        for (uint32_t i = tid; i < F_WINDOW; i += FW_THREADS) {
+            const uint16_t s = ring[(uint32_t)((gend + i) & (F_WINDOW - 1))];
+            // group 0 has nothing before it: a marker at a position that exists reaches before the start of the stream
+            if (g == 0 && (s & F_MARK) && gend + i >= F_WINDOW) bad = true;
+            gmap[g * F_WINDOW + i] = s;
+        }
+    }
+    if (bad) atomicExch(err, 1u);
+}
+
+// chain the group maps: gwin[g + 1] = gmap[g] applied to gwin[g] (one CTA, sequential over groups)
+__global__ void __launch_bounds__(FW_THREADS)
+foreign_chain_kernel(const uint16_t* __restrict__ gmap, uint8_t* __restrict__ gwin, uint64_t ngroups, unsigned int* __restrict__ err) {
+    extern __shared__ __align__(16) uint8_t fw_smem[];
+    uint8_t (*win)[F_WINDOW] = reinterpret_cast<uint8_t (*)[F_WINDOW]>(fw_smem);
+    const uint32_t tid = threadIdx.x;
+    for (uint32_t i = tid; i < F_WINDOW; i += FW_THREADS) win[0][i] = 0;
+    __syncthreads();
+    for (uint64_t g = 0; g + 1 < ngroups; g++) {
+        const uint32_t a = g & 1, b = a ^ 1;
+        for (uint32_t i = tid; i < F_WINDOW; i += FW_THREADS) {
+            const uint16_t s = gmap[g * F_WINDOW + i];
+            const uint8_t x = (s & F_MARK) ? win[a][s & (F_MARK - 1)] : (uint8_t)s;
+            win[b][i] = x;
+            gwin[(g + 1) * F_WINDOW + i] = x;
+        }
+        __syncthreads();
+    }
+    (void)err;
+}
+
+// ---- F6: everything that is not a tail -----------------------------------------------------------------------------------
+// grid = units; the CTA walks its unit's positions [start, end - 32768)
+constexpr uint32_t FR_THREADS = 256;
+constexpr uint32_t FR_SLAB = 32768;                   // positions per CTA
+struct FSlab { uint64_t unit; uint64_t lo; };         // slab list built on the host: unit index, first position
+__global__ void __launch_bounds__(FR_THREADS)
+foreign_resolve_kernel(const uint16_t* __restrict__ S, const uint64_t* __restrict__ out_base, uint64_t nunits, uint64_t total,
+                       const FSlab* __restrict__ slabs, uint8_t* __restrict__ out, unsigned int* __restrict__ err) {
+    const FSlab sl = slabs[blockIdx.x];
+    const uint64_t start = out_base[sl.unit];
+    const uint64_t end = sl.unit + 1 < nunits ? out_base[sl.unit + 1] : total;
+    const uint64_t body_end = end - start > F_WINDOW ? end - F_WINDOW : start;        // tails were written by the window pass
+    const uint64_t hi = min(body_end, sl.lo + FR_SLAB);
+    bool bad = false;
+    for (uint64_t p = sl.lo + threadIdx.x; p < hi; p += FR_THREADS) {
+        const uint16_t s = S[p];
+        uint8_t x = (uint8_t)s;
+        if (s & F_MARK) {
+            const uint64_t idx = s & (F_MARK - 1);
+            if (start + idx < F_WINDOW) bad = true;                                    // before the start of the stream
+            else x = out[start - F_WINDOW + idx];
+        }
+        out[p] = x;
+    }
+    if (bad) atomicExch(err, 1u);
+}
+
+}  // namespace b200

@@ -55,8 +55,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // SEG = 4096 tokens, so a counter cannot carry into its neighbour).
 constexpr uint32_t HIST_WORDS = NSYM / 2;
 __device__ __forceinline__ void hist_add(uint32_t* h, uint32_t sym) { atomicAdd(&h[sym >> 1], 1u << ((sym & 1) * 16)); }
-__device__ __forceinline__ void hist_store(const uint32_t* h, uint32_t* gh, uint32_t lane) {
-    for (uint32_t i = lane; i < NSYM; i += 32) gh[i] = (h[i >> 1] >> ((i & 1) * 16)) & 0xFFFFu;
+// global layout: [chunk][segment][NSYM] u16 -- exactly the shared-memory words (little endian), copied as u32
+__device__ __forceinline__ void hist_store(const uint32_t* h, uint16_t* gh, uint32_t lane) {
+    uint32_t* g32 = reinterpret_cast<uint32_t*>(gh);
+    for (uint32_t i = lane; i < HIST_WORDS; i += 32) g32[i] = h[i];
 }
 
 // =====================================================================================================
@@ -66,7 +68,7 @@ __device__ __forceinline__ void hist_store(const uint32_t* h, uint32_t* gh, uint
 constexpr uint32_t LZL_THREADS = NSEG * 32;
 __global__ void __launch_bounds__(LZL_THREADS)
 lz77_literal_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t* __restrict__ tok,
-                    uint32_t* __restrict__ ntok, uint32_t* __restrict__ hist, const ChunkSrc* __restrict__ srcs) {
+                    uint32_t* __restrict__ ntok, uint16_t* __restrict__ hist, const ChunkSrc* __restrict__ srcs) {
     __shared__ uint32_t s_hist[NSEG * HIST_WORDS];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint64_t chunk = blockIdx.x;
@@ -84,7 +86,7 @@ lz77_literal_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t* __rest
     }
     __syncwarp();
     if (lane == 0) ntok[chunk * NSEG + warp] = seg_lo < clen ? seg_hi - seg_lo : 0;
-    hist_store(hs, hist + (chunk * NSEG + warp) * NSYM, lane);
+    hist_store(hs, hist + (size_t)(chunk * NSEG + warp) * NSYM, lane);
 }
 
 // =====================================================================================================
@@ -112,7 +114,15 @@ constexpr uint32_t LZF_PER_THREAD = 2;
 constexpr uint32_t LZF_TILE = LZF_PER_THREAD * LZF_THREADS;     // 1024 positions between two table updates
 constexpr uint32_t LZF_RING_BLOCKS = 4;                 // per-warp ring of candidate blocks (32 x u16 each) in shared memory
 constexpr size_t LZF_SMEM_BYTES = CHUNK + LZ_DATA_PAD + (4u << LZF_HASH_BITS) + NSEG * HIST_WORDS * 4 + 32 +
-                                  NSEG * LZF_RING_BLOCKS * 64;
+                                  NSEG * LZF_RING_BLOCKS * 64 + (NSEG + 16) * 4;
+// Adaptive matching (LZ4-style acceleration): where the data has no repeats (random / encrypted / already compressed)
+// looking every position up is wasted work.  Tile 0 and every LZF_SAMPLE-th tile after tile 1 are always searched; if
+// such a sample tile finds fewer than LZF_SAMPLE_MIN candidates among its 1024 positions, the tiles up to the next
+// sample are not searched at all (no lookups, no inserts, candidate = none).  A segment without a single candidate is
+// parsed by a literal-only loop.  The decision is per 4 KiB, so a chunk that turns compressible is picked up again
+// after at most 3 tiles.  (B200_LZF_ADAPTIVE=0 switches it off; the corpus ratio is unchanged to 4 digits.)
+constexpr uint32_t LZF_SAMPLE = 4;
+constexpr uint32_t LZF_SAMPLE_MIN = 8;
 
 __device__ __forceinline__ uint32_t lzf_hash(uint32_t w4) { return (w4 * 0x9E3779B1u) >> (32 - LZF_HASH_BITS); }
 
@@ -125,8 +135,8 @@ __device__ __forceinline__ uint32_t lzf_score(const uint8_t* d, uint32_t q, uint
 
 __global__ void __launch_bounds__(LZF_THREADS, 2)
 lz77_fast_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t nchunks, uint32_t* __restrict__ tok,
-                 uint32_t* __restrict__ ntok, uint32_t* __restrict__ hist, uint16_t* __restrict__ cand_scratch,
-                 unsigned int* __restrict__ counter, const ChunkSrc* __restrict__ srcs) {
+                 uint32_t* __restrict__ ntok, uint16_t* __restrict__ hist, uint16_t* __restrict__ cand_scratch,
+                 unsigned int* __restrict__ counter, const ChunkSrc* __restrict__ srcs, uint32_t adaptive) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* s_data = smem;
     uint32_t* s_tab = reinterpret_cast<uint32_t*>(smem + CHUNK + LZ_DATA_PAD);
@@ -134,6 +144,8 @@ lz77_fast_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t nchunks, u
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_hist + NSEG * HIST_WORDS);
     uint32_t* s_next = reinterpret_cast<uint32_t*>(s_bar + 1);
     uint16_t* s_ring = reinterpret_cast<uint16_t*>(smem + CHUNK + LZ_DATA_PAD + (4u << LZF_HASH_BITS) + NSEG * HIST_WORDS * 4 + 32);
+    uint32_t* s_segcnt = reinterpret_cast<uint32_t*>(smem + CHUNK + LZ_DATA_PAD + (4u << LZF_HASH_BITS) + NSEG * HIST_WORDS * 4 + 32 +
+                                                     NSEG * LZF_RING_BLOCKS * 64);      // [NSEG] candidates per segment, [NSEG] = sample tile count
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t FULL = 0xFFFFFFFFu;
@@ -161,13 +173,27 @@ lz77_fast_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t nchunks, u
         for (uint32_t i = clen + tid; i < ((clen + 15u) & ~15u) + LZ_DATA_PAD && i < CHUNK + LZ_DATA_PAD; i += LZF_THREADS)
             s_data[i] = 0;
         for (uint32_t i = tid; i < (1u << LZF_HASH_BITS) + NSEG * HIST_WORDS; i += LZF_THREADS) s_tab[i] = 0;
+        if (tid < NSEG + 1) s_segcnt[tid] = 0;
         if (bulk) { mbar_wait(s_bar, parity); parity ^= 1; }
         __syncthreads();
 
         // ---- phase B: one verified candidate distance per position ----------------------------------
         // Tile = 1024 positions, 2 per thread (tid, tid+512): each warp still holds 32 consecutive
         // positions per sub-tile, so neighbours' words are a shuffle away.
+        bool skip = false;
         for (uint32_t t0 = 0; t0 < clen; t0 += LZF_TILE) {
+            const uint32_t tile = t0 / LZF_TILE;
+            const bool sample = tile == 0 || (tile % LZF_SAMPLE) == 1;
+            if (skip && !sample) {
+                // nothing to find here (the last sample tile said so): no candidates, no table update
+                #pragma unroll
+                for (uint32_t k = 0; k < LZF_PER_THREAD; k++) {
+                    const uint32_t p = t0 + k * LZF_THREADS + tid;
+                    if (p < clen) cand[p] = 0;
+                }
+                continue;
+            }
+            uint32_t found = 0;
             uint32_t w4[LZF_PER_THREAD], w8[LZF_PER_THREAD], hq[LZF_PER_THREAD];
             #pragma unroll
             for (uint32_t k = 0; k < LZF_PER_THREAD; k++) {
@@ -208,9 +234,25 @@ lz77_fast_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t nchunks, u
                     if (!best) bdist = 0;
                 }
                 if (p < clen) cand[p] = (uint16_t)bdist;   // 32768 == 0x8000 still fits
+                found += bdist != 0;
+            }
+            {
+                // candidates of this tile: per segment (phase C takes a literal-only loop for segments without any) and,
+                // for a sample tile, in total
+                const uint32_t wsum = __reduce_add_sync(FULL, found);
+                if (lane == 0 && wsum) {
+                    atomicAdd(&s_segcnt[tile >> 2], wsum);
+                    if (sample && tile) atomicAdd(&s_segcnt[NSEG], wsum);
+                }
             }
             __syncthreads();                               // inserts land before the next tile looks up
+            if (sample && tile && adaptive) {
+                skip = s_segcnt[NSEG] < LZF_SAMPLE_MIN;
+                __syncthreads();                           // everybody has read the count
+                if (tid == 0) s_segcnt[NSEG] = 0;
+            }
         }
+        __syncthreads();
         // the block-wide barrier above also orders this CTA's cand[] stores before the loads below
 
         // ---- phase C: greedy parse, one warp per segment ----------------------------------------------
@@ -219,7 +261,15 @@ lz77_fast_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t nchunks, u
         uint32_t* hs = s_hist + warp * HIST_WORDS;
         uint32_t* mytok = tok + chunk * CHUNK + seg_lo;
         uint32_t nt = 0;
-        if (seg_lo < clen) {
+        if (seg_lo < clen && s_segcnt[warp] == 0) {
+            // not one candidate in this segment: every byte is a literal
+            for (uint32_t p = seg_lo + lane; p < seg_hi; p += 32) {
+                const uint32_t b = s_data[p];
+                mytok[p - seg_lo] = b;
+                hist_add(hs, b);
+            }
+            nt = seg_hi - seg_lo;
+        } else if (seg_lo < clen) {
             uint32_t pos = seg_lo;
             // candidates travel through a per-warp ring of four 32-entry blocks in shared memory, filled by
             // cp.async (no destination register: a register queue has to be shifted one step after the load
@@ -300,7 +350,7 @@ lz77_fast_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t nchunks, u
         }
         __syncwarp();
         if (lane == 0) ntok[chunk * NSEG + warp] = nt;
-        hist_store(hs, hist + (chunk * NSEG + warp) * NSYM, lane);
+        hist_store(hs, hist + (size_t)(chunk * NSEG + warp) * NSYM, lane);
     }
 }
 
@@ -321,7 +371,8 @@ lz77_fast_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t nchunks, u
 //            (a match is deferred when the next position has a longer one), emit tokens in place and
 //            build the histograms, exactly as the fast kernel does.
 // =====================================================================================================
-constexpr uint32_t LZB_THREADS = 512;
+constexpr uint32_t LZB_THREADS = 1024;          // 32 warps: the chain search is a chase of dependent shared-memory loads, one CTA per SM
+                                                // (224 KB) -- twice the warps hide twice the latency; 16 of them parse afterwards
 constexpr uint32_t LZB_HASH_BITS = 13;          // 8 K heads x u32 (atomicExch needs 32-bit words)
 constexpr uint32_t LZB_NIL = 0xFFFFu;           // position 65535 can never be anybody's predecessor
 constexpr uint32_t LZB_GOOD = 32;               // once a match this long is in hand, cut the remaining search to a quarter
@@ -332,7 +383,7 @@ __device__ __forceinline__ uint32_t lzb_hash(uint32_t w4) { return ((w4 & 0xFFFF
 
 __global__ void __launch_bounds__(LZB_THREADS, 1)
 lz77_better_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t* __restrict__ tok,
-                   uint32_t* __restrict__ ntok, uint32_t* __restrict__ hist, uint32_t depth, uint32_t nice,
+                   uint32_t* __restrict__ ntok, uint16_t* __restrict__ hist, uint32_t depth, uint32_t nice,
                    const ChunkSrc* __restrict__ srcs) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* s_data = smem;
@@ -365,14 +416,21 @@ lz77_better_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t* __restr
     // previous head as its predecessor, so a bucket is one linked list through all its positions,
     // newest first.  Steps are ordered; inside a step the hardware serialises lanes that hit the same
     // bucket (the search below tolerates either order by skipping predecessors that are not earlier).
+    // Four steps are in flight at a time: a warp's atomics on one address execute in program order, so the chains are
+    // the same as with one step at a time, but the ~150-cycle round trip of the exchange is paid once per four steps.
     if (warp == 0) {
-        for (uint32_t t0 = 0; t0 < clen; t0 += 32) {
-            const uint32_t p = t0 + lane;
-            if (p + 3 <= clen) {
-                const uint32_t h = lzb_hash(ld4_unaligned(s_data, p));
-                s_prev[p] = (uint16_t)atomicExch(&s_head[h], p);
-            } else if (p < clen) {
-                s_prev[p] = (uint16_t)LZB_NIL;
+        for (uint32_t t0 = 0; t0 < clen; t0 += 128) {
+            uint32_t old[4];
+            #pragma unroll
+            for (uint32_t k = 0; k < 4; k++) {
+                const uint32_t p = t0 + k * 32 + lane;
+                old[k] = LZB_NIL;
+                if (p + 3 <= clen) old[k] = atomicExch(&s_head[lzb_hash(ld4_unaligned(s_data, p))], p);
+            }
+            #pragma unroll
+            for (uint32_t k = 0; k < 4; k++) {
+                const uint32_t p = t0 + k * 32 + lane;
+                if (p < clen) s_prev[p] = (uint16_t)old[k];
             }
         }
     }
@@ -477,7 +535,7 @@ lz77_better_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t* __restr
     }
     __syncwarp();
     if (lane == 0) ntok[chunk * NSEG + warp] = nt;
-    hist_store(h, hist + (chunk * NSEG + warp) * NSYM, lane);
+    hist_store(h, hist + (size_t)(chunk * NSEG + warp) * NSYM, lane);
 }
 
 }  // namespace b200

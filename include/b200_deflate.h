@@ -38,6 +38,7 @@ extern "C" {
 #define B200_E_CUDA 4     /* CUDA runtime / driver error, or no sm_100 device: there is no CPU path */
 #define B200_E_ARG 5      /* bad argument */
 #define B200_E_NOMEM 6    /* host or device allocation failed */
+#define B200_E_IO 7       /* file API: a file could not be opened, read or written */
 
 /* Compression levels: the reference's `int compression_level` (deflate.hpp:675-680). */
 #define B200_LEVEL_STORED 0  /* stored blocks only */
@@ -51,6 +52,9 @@ extern "C" {
 #define B200_F_NO_INDEX 2u /* do not put the segment index (320 bytes of empty stored blocks whose padding bits \
                               hold the bit length of every 4 KiB segment) in front of full 64 KiB chunks: the   \
                               stream is 0.3-0.5 % smaller and inflates one warp per chunk instead of 16 threads */
+#define B200_F_ZLIB 4u     /* wrap the stream in zlib framing (RFC 1950): 78 9C in front, the Adler-32 of the INPUT behind,  \
+                              computed on the GPU (what zlib.decompress / inflate::decompressZlib read) */
+#define B200_F_GZIP 8u     /* wrap it in one gzip member (RFC 1952): 10-byte header, CRC-32 of the input + ISIZE behind */
 /* Flags for the inflater. */
 #define B200_F_STRICT 1u   /* reject what the reference silently accepts: distance beyond the output \
                               produced so far, NLEN != ~LEN, BTYPE 3, and for zlib streams a bad header or   \
@@ -89,6 +93,11 @@ size_t b200_deflate_bound(size_t n);
  * than for CUDA / memory errors (the reference compressor never throws to its caller either). */
 int b200_deflate_compress(const void* in, size_t n, int level, void** out, size_t* out_n);
 
+/* The same two calls with compressor flags (B200_F_NO_INDEX, B200_F_ZLIB, B200_F_GZIP): framed output for the wire formats
+ * next to the path (the reference only has the inflate side, inflate.hpp:326-361). */
+int b200_deflate_compress_ex(const void* in, size_t n, int level, unsigned flags, void** out, size_t* out_n);
+int b200_deflate_compress_into_ex(const void* in, size_t n, int level, unsigned flags, void* out, size_t cap, size_t* out_n);
+
 /* Same, into a caller buffer of `cap` bytes (B200_E_OUTPUT if cap < compressed size; cap >=
  * b200_deflate_bound(n) always suffices).  Pinned host memory is streamed without staging. */
 int b200_deflate_compress_into(const void* in, size_t n, int level, void* out, size_t cap, size_t* out_n);
@@ -113,7 +122,35 @@ int b200_inflate_zlib(const void* in, size_t n, void* out, size_t cap, size_t* o
                       unsigned flags);
 int b200_inflate_zlib_alloc(const void* in, size_t n, void** out, size_t* out_n, unsigned flags);
 
+/* gzip (RFC 1952): first member of a .gz buffer; header fields FEXTRA / FNAME / FCOMMENT / FHCRC are skipped.  With
+ * B200_F_STRICT the CRC-32 (computed on the GPU over the decoded bytes) and ISIZE must match, else B200_E_DATA. */
+int b200_inflate_gzip(const void* in, size_t n, void* out, size_t cap, size_t* out_n, size_t* full_n,
+                      unsigned flags);
+int b200_inflate_gzip_alloc(const void* in, size_t n, void** out, size_t* out_n, unsigned flags);
+
 void b200_free(void* p);
+
+/* Views (what the header-only drop-ins use for the std::vector-returning overloads): the result is left in the library's
+ * pinned host arena -- written there by the DMA engine, no page faults, no intermediate malloc -- and *view points at it
+ * until b200_view_release(); the caller copies it once into its own storage (one std::vector::assign).  A successful
+ * *_view call keeps the default context locked until b200_view_release() (same thread).  framing: 0 raw, 1 zlib. */
+int b200_deflate_compress_view(const void* in, size_t n, int level, unsigned flags, const void** view, size_t* out_n);
+int b200_inflate_view(const void* in, size_t n, unsigned flags, int framing, const void** view, size_t* out_n);
+void b200_view_release(void);
+
+/* ---- file-path API -------------------------------------------------------------------------- */
+/* Replaces deflate::compress(std::string file_path, std::string new_file, int level) (reference include/deflate.hpp:755-777):
+ * the file is streamed through the GPU in slices of 64 MiB with bounded memory -- pinned host staging, slice k + 1 is
+ * read while slice k is compressed and slice k - 1 is written.  The output is byte-identical to compressing the whole
+ * file in memory.  flags: B200_F_NO_INDEX, B200_F_ZLIB, B200_F_GZIP (checksum accumulated on the device across slices).
+ * *in_n / *out_n (may be NULL): bytes read / written.  B200_E_IO on file errors. */
+int b200_deflate_compress_file(const char* in_path, const char* out_path, int level, unsigned flags, size_t* in_n,
+                               size_t* out_n);
+/* Replaces inflate::decompress(std::string file_path, std::string new_file) (include/inflate.hpp:390-408; the reference
+ * fails on multi-block files).  Streams of this library's chunk format are decoded window by window with bounded
+ * memory (the next window is read and the previous output written while the current one is on the GPU); any other raw
+ * DEFLATE stream goes through the memory API as a whole. */
+int b200_inflate_file(const char* in_path, const char* out_path, unsigned flags, size_t* in_n, size_t* out_n);
 
 /* ---- device-resident API (benchmarks, pipelines, multi-GPU shards) -------------------------- */
 /* All pointers prefixed d_ are device pointers on ctx's device; `stream` is a cudaStream_t passed as
@@ -184,6 +221,10 @@ int b200_inflate_batch_dev(b200_ctx* ctx, const void* d_in, const uint64_t* d_in
 /* Adler-32 (RFC 1950) of d_data[0..n) computed on the device; the result goes to *h_out (synchronizes the
  * stream) and / or *d_out (device, no sync).  What B200_F_STRICT uses to check a zlib stream's trailer. */
 int b200_adler32_dev(b200_ctx* ctx, const void* d_data, size_t n, uint32_t* h_out, uint32_t* d_out, void* stream);
+
+/* CRC-32 (RFC 1952 / zlib crc32) of d_data[0..n) computed on the device: one CTA per 64 KiB block, blocks combined with the
+ * GF(2) identity crc(A || B) = crc(A) * x^(8|B|) + crc(B).  Same result conventions as b200_adler32_dev. */
+int b200_crc32_dev(b200_ctx* ctx, const void* d_data, size_t n, uint32_t* h_out, uint32_t* d_out, void* stream);
 
 /* Synthetic corpus of BASELINE config 3/5 (definition: oracle/corpus_oracle.c):
  * chunks first_chunk .. first_chunk+n_chunks-1 of 64 KiB each, written to d_out. */

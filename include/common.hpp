@@ -37,6 +37,11 @@ struct Api {
     decltype(&::b200_inflate_alloc) inflate_alloc = nullptr;
     decltype(&::b200_inflate_zlib) inflate_zlib = nullptr;
     decltype(&::b200_inflate_zlib_alloc) inflate_zlib_alloc = nullptr;
+    decltype(&::b200_deflate_compress_view) compress_view = nullptr;
+    decltype(&::b200_inflate_view) inflate_view = nullptr;
+    decltype(&::b200_view_release) view_release = nullptr;
+    decltype(&::b200_deflate_compress_file) compress_file = nullptr;
+    decltype(&::b200_inflate_file) inflate_file = nullptr;
     decltype(&::b200_free) free_ = nullptr;
     decltype(&::b200_strerror) strerror_ = nullptr;
     decltype(&::b200_abi_version) abi_version = nullptr;
@@ -61,6 +66,11 @@ inline const Api& api() {
         x.inflate_alloc = reinterpret_cast<decltype(x.inflate_alloc)>(sym("b200_inflate_alloc"));
         x.inflate_zlib = reinterpret_cast<decltype(x.inflate_zlib)>(sym("b200_inflate_zlib"));
         x.inflate_zlib_alloc = reinterpret_cast<decltype(x.inflate_zlib_alloc)>(sym("b200_inflate_zlib_alloc"));
+        x.compress_view = reinterpret_cast<decltype(x.compress_view)>(sym("b200_deflate_compress_view"));
+        x.inflate_view = reinterpret_cast<decltype(x.inflate_view)>(sym("b200_inflate_view"));
+        x.view_release = reinterpret_cast<decltype(x.view_release)>(sym("b200_view_release"));
+        x.compress_file = reinterpret_cast<decltype(x.compress_file)>(sym("b200_deflate_compress_file"));
+        x.inflate_file = reinterpret_cast<decltype(x.inflate_file)>(sym("b200_inflate_file"));
         x.free_ = reinterpret_cast<decltype(x.free_)>(sym("b200_free"));
         x.strerror_ = reinterpret_cast<decltype(x.strerror_)>(sym("b200_strerror"));
         x.abi_version = reinterpret_cast<decltype(x.abi_version)>(sym("b200_abi_version"));
@@ -85,6 +95,14 @@ inline std::vector<uint8_t> take(void* p, size_t n) {
     return v;
 }
 
+// the library's pinned arena -> the vector the reference API returns: one pass (assign), then the arena is released
+inline std::vector<uint8_t> take_view(const void* p, size_t n) {
+    struct Release { ~Release() { api().view_release(); } } release;
+    std::vector<uint8_t> v;
+    v.assign(static_cast<const uint8_t*>(p), static_cast<const uint8_t*>(p) + n);
+    return v;
+}
+
 inline std::vector<uint8_t> read_file(const std::string& path) {
     std::ifstream f(path, std::ios::binary);
     if (!f) throw std::runtime_error("Failed to read file " + path);
@@ -94,6 +112,8 @@ inline std::vector<uint8_t> read_file(const std::string& path) {
 inline void write_file(const std::string& path, const uint8_t* p, size_t n) {
     std::ofstream f(path, std::ios::binary);
     f.write(reinterpret_cast<const char*>(p), static_cast<std::streamsize>(n));
+    f.flush();
+    if (!f) throw std::runtime_error("Failed to write file " + path);
 }
 
 }  // namespace b200_detail

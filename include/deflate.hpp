@@ -19,22 +19,23 @@
 class deflate {
 public:
     static std::vector<uint8_t> compress(char* data, size_t data_size, int compression_level) {
-        void* out = nullptr;
+        const void* view = nullptr;
         size_t n = 0;
-        const int rc = b200_detail::api().compress(data, data_size, compression_level, &out, &n);
+        const int rc = b200_detail::api().compress_view(data, data_size, compression_level, 0, &view, &n);
         if (rc) b200_detail::fail(rc);
-        return b200_detail::take(out, n);
+        return b200_detail::take_view(view, n);
     }
     static std::vector<uint8_t> compress(std::vector<uint8_t>& data, int compression_level) {
         return compress(reinterpret_cast<char*>(data.data()), data.size(), compression_level);
     }
     // Streams file_path -> new_file.  The reference always returns 0 here (deflate.hpp:681,751,776);
     // this returns the number of compressed bytes written.
+    // The file is streamed through the GPU in 64 MiB slices (pinned, double-buffered; bounded memory for any file size).
     static size_t compress(std::string file_path, std::string new_file, int compression_level) {
-        std::vector<uint8_t> in = b200_detail::read_file(file_path);
-        std::vector<uint8_t> out = compress(in, compression_level);
-        b200_detail::write_file(new_file, out.data(), out.size());
-        return out.size();
+        size_t out_n = 0;
+        const int rc = b200_detail::api().compress_file(file_path.c_str(), new_file.c_str(), compression_level, 0, nullptr, &out_n);
+        if (rc) b200_detail::fail(rc);
+        return out_n;
     }
 
     // README form: bool selects fast (false) or better (true).  Templates constrained to exactly `bool`, so every

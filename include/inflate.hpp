@@ -30,24 +30,25 @@ public:
         return n;
     }
     static std::vector<uint8_t> decompress(void* in, size_t in_size) {
-        void* out = nullptr;
+        const void* view = nullptr;
         size_t n = 0;
-        const int rc = b200_detail::api().inflate_alloc(in, in_size, &out, &n, 0);
-        if (rc) { if (out) b200_detail::api().free_(out); b200_detail::fail(rc); }
-        return b200_detail::take(out, n);
+        const int rc = b200_detail::api().inflate_view(in, in_size, 0, 0, &view, &n);
+        if (rc) b200_detail::fail(rc);
+        return b200_detail::take_view(view, n);
     }
     static std::vector<uint8_t> decompressZlib(void* in, size_t in_size) {
-        void* out = nullptr;
+        if (!in || in_size < 2) b200_detail::fail(B200_E_OVERRUN);
+        const void* view = nullptr;
         size_t n = 0;
-        const int rc = b200_detail::api().inflate_zlib_alloc(in, in_size, &out, &n, 0);
-        if (rc) { if (out) b200_detail::api().free_(out); b200_detail::fail(rc); }
-        return b200_detail::take(out, n);
+        const int rc = b200_detail::api().inflate_view(in, in_size, 0, 1, &view, &n);
+        if (rc) b200_detail::fail(rc);
+        return b200_detail::take_view(view, n);
     }
     static std::vector<uint8_t> decompress(std::vector<uint8_t> in) { return decompress(in.data(), in.size()); }
     static size_t decompress(std::string file_path, std::string new_file) {
-        std::vector<uint8_t> in = b200_detail::read_file(file_path);
-        std::vector<uint8_t> out = decompress(in.data(), in.size());
-        b200_detail::write_file(new_file, out.data(), out.size());
-        return out.size();
+        size_t out_n = 0;
+        const int rc = b200_detail::api().inflate_file(file_path.c_str(), new_file.c_str(), 0, nullptr, &out_n);
+        if (rc) b200_detail::fail(rc);
+        return out_n;
     }
 };

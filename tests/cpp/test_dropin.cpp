@@ -103,6 +103,26 @@ int main(int argc, char** argv) {
         std::remove((tmp + "deflated").c_str());
         std::remove((tmp + "inflated.bmp").c_str());
     }
+    // a multi-block FILE through the file-path overloads (the reference's inflate side fails on these):
+    // 1.2 MB = 19 chunks, made from the fixture so that the test needs no other input
+    {
+        const std::string tmp = "/tmp/b200_dropin_big_";
+        std::vector<uint8_t> one = b200_detail::read_file(dir + "test.bmp"), big;
+        for (int k = 0; k < 55; k++) { big.insert(big.end(), one.begin(), one.end()); big.push_back((uint8_t)k); }
+        b200_detail::write_file(tmp + "in", big.data(), big.size());
+        for (int level : {0, 2, 3}) {
+            size_t cn = deflate::compress(tmp + "in", tmp + "deflated", level);
+            std::vector<uint8_t> comp = b200_detail::read_file(tmp + "deflated"), zout;
+            bool ok = zlib_raw_inflate(comp, zout, big.size() + 64);
+            CHECK(cn == comp.size() && ok && zout == big, "multi-block file, level " + std::to_string(level) + ": deflate(file) -> zlib");
+            size_t n = inflate::decompress(tmp + "deflated", tmp + "inflated");
+            CHECK(n == big.size() && b200_detail::read_file(tmp + "inflated") == big, "multi-block file: inflate(file) matches");
+        }
+        bool threw = false;
+        try { deflate::compress(tmp + "no_such_file", tmp + "x", 2); } catch (const std::runtime_error&) { threw = true; }
+        CHECK(threw, "missing input file throws std::runtime_error");
+        for (const char* f : {"in", "deflated", "inflated"}) std::remove((tmp + f).c_str());
+    }
     // error behaviour: truncated stream throws std::runtime_error (inflate.hpp:82)
     {
         std::vector<uint8_t> original = b200_detail::read_file(dir + "test.bmp");

@@ -1,0 +1,174 @@
+"""Robustness of the inflaters on damaged input: bit flips, truncations and splices of
+streams from many producers.  The inflater parses untrusted bytes; whatever they are it must not crash, hang or write
+outside the caller's buffer, a stream zlib accepts must decode to zlib's bytes, and the parallel decoders must take the
+same decisions as the sequential one (same status, same bytes)."""
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+from conftest import gold
+import datagen
+
+pytestmark = pytest.mark.gpu
+
+GUARD = 64
+
+
+def producers(data):
+    s = dict(datagen.foreign_streams(data))
+    return s
+
+
+def mutate(stream, rng):
+    s = bytearray(stream)
+    kind = int(rng.integers(0, 6))
+    if kind == 0 and len(s) > 2:                       # truncate
+        return bytes(s[:int(rng.integers(1, len(s)))])
+    if kind == 1:                                      # 1-3 bit flips
+        for _ in range(int(rng.integers(1, 4))):
+            p = int(rng.integers(0, len(s)))
+            s[p] ^= 1 << int(rng.integers(0, 8))
+        return bytes(s)
+    if kind == 2 and len(s) > 40:                      # garble a short region
+        p = int(rng.integers(0, len(s) - 16))
+        s[p:p + 16] = bytes(rng.integers(0, 256, 16, dtype=np.uint8))
+        return bytes(s)
+    if kind == 3 and len(s) > 40:                      # drop a region (everything behind it shifts)
+        p = int(rng.integers(0, len(s) - 8))
+        del s[p:p + int(rng.integers(1, 8))]
+        return bytes(s)
+    if kind == 4:                                      # flip a bit in the first bytes (block header / code lengths)
+        p = int(rng.integers(0, min(len(s), 60)))
+        s[p] ^= 1 << int(rng.integers(0, 8))
+        return bytes(s)
+    return bytes(s) + bytes(rng.integers(0, 256, int(rng.integers(1, 40)), dtype=np.uint8))      # trailing garbage
+
+
+def zlib_verdict(stream, limit):
+    """(True, bytes) if zlib decodes the raw stream to completion, else (False, None)"""
+    try:
+        o = zlib.decompressobj(-15)
+        out = o.decompress(stream, limit)
+        if o.eof and not o.unconsumed_tail:
+            return True, out
+    except zlib.error:
+        pass
+    return False, None
+
+
+def build_cases(seed, count):
+    rng = np.random.default_rng(seed)
+    kinds = sorted(datagen.KINDS)
+    bases = []
+    for i in range(12):
+        n = int(rng.integers(300, 40000))
+        data = datagen.KINDS[kinds[i % len(kinds)]](n, seed=200 + i)
+        for name, st in producers(data).items():
+            bases.append((st, len(data)))
+    for f in ("zlib.dat", "weird.dat"):
+        raw = gold(f)[2:]
+        bases.append((raw, len(zlib.decompressobj(-15).decompress(raw))))
+    cases = []
+    for k in range(count):
+        st, n = bases[int(rng.integers(0, len(bases)))]
+        cases.append((mutate(st, rng) if k % 10 else st, n))       # every 10th stays intact
+    return cases
+
+
+@pytest.mark.parametrize("seed,two_pass", [(1, False), (2, False), (3, True)])
+def test_fuzz_batch(b200, seed, two_pass, monkeypatch):
+    """3 000 damaged streams in one batch launch, canaries between the outputs"""
+    import torch
+    if two_pass:
+        monkeypatch.setenv("B200_BATCH_TP", "1")
+    cases = build_cases(seed, 3000)
+    caps = [n + 4096 for _, n in cases]
+    in_off, out_off = [], []
+    pi = po = 0
+    for (st, n), cap in zip(cases, caps):
+        in_off.append(pi); pi += (len(st) + 15) & ~15
+        out_off.append(po); po += ((cap + 15) & ~15) + GUARD
+    blob = np.zeros(pi + 64, dtype=np.uint8)
+    for (st, _), o in zip(cases, in_off):
+        blob[o:o + len(st)] = np.frombuffer(st, dtype=np.uint8)
+    dev = "cuda"
+    t = lambda a: torch.tensor(a, dtype=torch.int64, device=dev)
+    d_blob = torch.from_numpy(blob).to(dev)
+    d_out = torch.full((po + 64,), 0xA5, dtype=torch.uint8, device=dev)
+    d_in_off, d_in_len, d_out_off, d_out_cap = t(in_off), t([len(s) for s, _ in cases]), t(out_off), t(caps)
+    d_len = torch.zeros(len(cases), dtype=torch.int64, device=dev)
+    d_st = torch.full((len(cases),), -7, dtype=torch.int32, device=dev)
+    ctx = b200.Context(0)
+    ctx.inflate_batch_dev(d_blob.data_ptr(), d_in_off.data_ptr(), d_in_len.data_ptr(), d_out.data_ptr(), d_out_off.data_ptr(),
+                          d_out_cap.data_ptr(), d_len.data_ptr(), d_st.data_ptr(), len(cases))
+    torch.cuda.synchronize()
+    out = d_out.cpu().numpy()
+    status = d_st.cpu().numpy()
+    lens = d_len.cpu().numpy()
+    assert set(np.unique(status)) <= {0, 1, 2}
+    n_valid = 0
+    for k, ((st, n), cap, oo) in enumerate(zip(cases, caps, out_off)):
+        region_end = oo + ((cap + 15) & ~15)
+        assert (out[oo + cap:region_end + GUARD] == 0xA5).all(), ("wrote past its capacity", k)
+        ok, zout = zlib_verdict(st, cap + 1)
+        if ok and len(zout) <= cap:
+            n_valid += 1
+            assert status[k] == 0 and lens[k] == len(zout), (k, status[k], lens[k], len(zout))
+            assert out[oo:oo + len(zout)].tobytes() == zout, k
+    assert n_valid >= 300          # the intact tenth, plus mutations that happen to leave a valid stream
+
+
+def test_fuzz_single_stream_api(b200):
+    """the same kind of damage through inflate::decompress (host API, one stream per call): B200Error or zlib's bytes"""
+    cases = build_cases(7, 250)
+    for st, n in cases:
+        ok, zout = zlib_verdict(st, n + 4096)
+        try:
+            got = b200.decompress(st, out_size=n + 4096)
+        except b200.B200Error as e:
+            assert e.code in (1, 2)
+            assert not ok
+            continue
+        if ok:
+            assert got == zout
+
+
+def test_fuzz_own_streams_parallel_vs_sequential(b200, monkeypatch):
+    """damaged streams of THIS library's format (segment index bits, separators, payload): the chunk-parallel two-pass
+    path, the block-parallel foreign path and the sequential one-warp decoder must agree on status and bytes"""
+    rng = np.random.default_rng(99)
+    data = datagen.text_like(400_000, seed=1) + datagen.image_like(300_000) + datagen.random_bytes(100_000) + datagen.runs(200_000)
+    base = b200.compress(data, 2)
+    cases = [base]
+    for k in range(40):
+        s = bytearray(base)
+        kind = k % 4
+        if kind == 0:                                   # inside some chunk's segment index
+            p = int(rng.integers(0, len(s) - 400))
+            q = s.find(b"\x00\x00\xff\xff", p)
+            if q > 0:
+                s[q - 1] ^= 1 << int(rng.integers(3, 7))
+        elif kind == 1:
+            p = int(rng.integers(0, len(s)))
+            s[p] ^= 1 << int(rng.integers(0, 8))
+        elif kind == 2:
+            s = s[:int(rng.integers(100, len(s)))]
+        else:
+            p = int(rng.integers(0, len(s) - 32))
+            s[p:p + 8] = bytes(rng.integers(0, 256, 8, dtype=np.uint8))
+        cases.append(bytes(s))
+
+    def run(s):
+        try:
+            return ("ok", b200.decompress(s, out_size=len(data) + 70000))
+        except b200.B200Error as e:
+            return ("err", e.code)
+    for k, s in enumerate(cases):
+        got = run(s)
+        monkeypatch.setenv("B200_INFLATE_SEQUENTIAL", "1")
+        want = run(s)
+        monkeypatch.delenv("B200_INFLATE_SEQUENTIAL")
+        assert got == want, k
+    assert run(base) == ("ok", data)

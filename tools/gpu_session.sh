@@ -8,7 +8,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > 
 for step in "$@"; do
   case $step in
     pytest)
-      timeout 1500 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest.log 2>&1; echo "pytest exit $?" >> $out/${tag}_pytest.log ;;
+      timeout 1500 python -m pytest tests -m gpu --maxfail=12 -q > $out/${tag}_pytest.log 2>&1; echo "pytest exit $?" >> $out/${tag}_pytest.log ;;
     bench)
       timeout 900 python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err; echo "bench exit $?" >> $out/${tag}_bench.err ;;
     bench_quick)
