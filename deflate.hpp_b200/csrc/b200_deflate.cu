@@ -217,7 +217,6 @@ int set_attrs(b200_ctx* c) {
     CK(cudaFuncSetAttribute(inflate_symbols_kernel<BatchUnits>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM_BYTES));
     CK(cudaFuncSetAttribute(foreign_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM_BYTES));
     CK(cudaFuncSetAttribute(foreign_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM_BYTES));
-    CK(cudaFuncSetAttribute(foreign_find_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FB_SMEM_BYTES));
     CK(cudaFuncSetAttribute(foreign_window_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FW_SMEM_BYTES));
     CK(cudaFuncSetAttribute(foreign_window_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FW_SMEM_BYTES));
     CK(cudaFuncSetAttribute(foreign_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FW_SMEM_BYTES));
@@ -880,6 +879,9 @@ static int inflate_chunked(b200_ctx* c, const uint8_t* in, uint64_t n, uint64_t 
     CK(cudaMemcpyAsync(&nmark, d_result + 2, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (nmark + 1 > cand_cap) return B200_OK;          // not ours: far too many separators
+    // not ours either: no separator at all in more bytes than one chunk can take (a foreign stream; without this its first
+    // 64 KiB would be decoded by the one-warp decoder just to find out)
+    if (nmark == 0 && first_is_start && n > (uint64_t)CHUNK + INDEX_BYTES + 64) return B200_OK;
     CK(cudaMemsetAsync(cand0, 0, 8, st));               // cand0[0] = 0
     if (nmark) {
         PROF_BEGIN(c, K_FIND_SYNC, st);
@@ -1031,7 +1033,7 @@ static int inflate_foreign(b200_ctx* c, const uint8_t* in, uint64_t n, uint8_t* 
     const uint64_t npieces = (n + FB_PIECE - 1) / FB_PIECE;
     if ((rc = c->f_cand.ensure(npieces * 8))) return B200_OK;
     PROF_BEGIN(c, K_F_FIND, st);
-    foreign_find_blocks_kernel<<<(uint32_t)((npieces + FB_WARPS - 1) / FB_WARPS), FB_THREADS, FB_SMEM_BYTES, st>>>(
+    foreign_find_blocks_kernel<<<(uint32_t)((npieces + FB_WARPS - 1) / FB_WARPS), FB_THREADS, 0, st>>>(
         in, n, npieces, (unsigned long long*)c->f_cand.p);
     LAUNCHED();
     PROF_END(c, st);
@@ -1132,34 +1134,55 @@ static int inflate_foreign(b200_ctx* c, const uint8_t* in, uint64_t n, uint8_t* 
     if (total == 0) { *done = true; return B200_OK; }
     if (c->f_sym.ensure(total * 2 + 64) || c->f_ops.ensure((total_ops + 64) * 8)) return B200_OK;     // no memory: sequential
     if ((rc = c->f_starts.ensure(nu * 8)) || (rc = c->f_stops.ensure(nu * 8)) || (rc = c->f_res.ensure(nu * sizeof(FUnitRes))) ||
-        (rc = c->f_base.ensure((nu + 1) * 8)) || (rc = c->f_opsbase.ensure((nu + 1) * 8)) || (rc = c->f_misc.ensure(64)))
+        (rc = c->f_base.ensure((nu + 1) * 8)) || (rc = c->f_opsbase.ensure((nu + 1) * 8)) || (rc = c->f_misc.ensure(256)))
         return B200_OK;
     CK(cudaMemcpyAsync(c->f_starts.p, hs.data(), nu * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(c->f_stops.p, hp.data(), nu * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(c->f_base.p, hbase.data(), (nu + 1) * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(c->f_opsbase.p, hops.data(), (nu + 1) * 8, cudaMemcpyHostToDevice, st));
-    CK(cudaMemsetAsync(c->f_misc.p, 0, 64, st));
+    CK(cudaMemsetAsync(c->f_misc.p, 0, 256, st));
     unsigned long long* d_counter = (unsigned long long*)c->f_misc.p;
     unsigned int* d_err = (unsigned int*)((unsigned long long*)c->f_misc.p + 1);
     uint16_t* S = (uint16_t*)c->f_sym.p;
     const uint64_t* d_base = (const uint64_t*)c->f_base.p;
 
-    // ---- F3: decode with known offsets ----
-    PROF_BEGIN(c, K_F_EMIT, st);
-    foreign_decode_kernel<true><<<(uint32_t)((nu + FD_THREADS - 1) / FD_THREADS), FD_THREADS, TP_SMEM_BYTES, st>>>(
-        in, n, (const uint64_t*)c->f_starts.p, (const uint64_t*)c->f_stops.p, nu, (FUnitRes*)c->f_res.p, d_base,
-        (const uint64_t*)c->f_opsbase.p, S, (uint64_t*)c->f_ops.p, flags);
-    LAUNCHED();
-    PROF_END(c, st);
-    // ---- F4: ops inside the symbol image ----
+    // ---- F3 + F4: decode with known offsets, then the ops inside the symbol image.  The decode kernel runs four warps per
+    // SM (its private tables fill the shared memory) and is bound by latency, the copy kernel needs no shared memory: the
+    // units are cut into parts, and the copies of part k run on a side stream under the decode of part k + 1 ----
     {
-        const uint64_t want = (nu + INF_WARPS - 1) / INF_WARPS;
+        const uint64_t parts = nu >= 8192 ? 4 : 1;
+        while (c->group_events.size() < 2 * parts) {
+            cudaEvent_t e;
+            CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            c->group_events.push_back(e);
+        }
         const uint64_t gmax = (uint64_t)(c->inf_grid / INF_MAX_CTAS_PER_SM) * 12;
-        PROF_BEGIN(c, K_F_COPY, st);
-        foreign_copy_kernel<<<(uint32_t)(want < gmax ? want : gmax), INF_THREADS, 0, st>>>(
-            in, (const FUnitRes*)c->f_res.p, d_base, (const uint64_t*)c->f_opsbase.p, nu, S, (const uint64_t*)c->f_ops.p, d_counter, d_err);
-        LAUNCHED();
-        PROF_END(c, st);
+        for (uint64_t k = 0; k < parts; k++) {
+            const uint64_t u0 = nu * k / parts, u1 = nu * (k + 1) / parts, m = u1 - u0;
+            if (!m) continue;
+            PROF_BEGIN(c, K_F_EMIT, st);
+            foreign_decode_kernel<true><<<(uint32_t)((m + FD_THREADS - 1) / FD_THREADS), FD_THREADS, TP_SMEM_BYTES, st>>>(
+                in, n, (const uint64_t*)c->f_starts.p + u0, (const uint64_t*)c->f_stops.p + u0, m, (FUnitRes*)c->f_res.p + u0, d_base + u0,
+                (const uint64_t*)c->f_opsbase.p + u0, S, (uint64_t*)c->f_ops.p, flags);
+            LAUNCHED();
+            PROF_END(c, st);
+            cudaStream_t cs = parts > 1 ? c->s_side : st;
+            if (parts > 1) {
+                CK(cudaEventRecord(c->group_events[2 * k], st));
+                CK(cudaStreamWaitEvent(cs, c->group_events[2 * k], 0));
+            }
+            const uint64_t want = (m + INF_WARPS - 1) / INF_WARPS;
+            PROF_BEGIN(c, K_F_COPY, cs);
+            foreign_copy_kernel<<<(uint32_t)(want < gmax ? want : gmax), INF_THREADS, 0, cs>>>(
+                in, (const FUnitRes*)c->f_res.p + u0, d_base + u0, (const uint64_t*)c->f_opsbase.p + u0, m, S, (const uint64_t*)c->f_ops.p,
+                d_counter + 8 + k, d_err);
+            LAUNCHED();
+            PROF_END(c, cs);
+            if (parts > 1 && k + 1 == parts) {
+                CK(cudaEventRecord(c->group_events[2 * k + 1], cs));
+                CK(cudaStreamWaitEvent(st, c->group_events[2 * k + 1], 0));
+            }
+        }
     }
     // ---- F5: window propagation, two levels ----
     uint32_t G = c->foreign_group;

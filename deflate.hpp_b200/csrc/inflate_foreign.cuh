@@ -39,31 +39,34 @@
 namespace b200 {
 
 constexpr uint32_t FB_PIECE = 16384;                 // input bytes whose bit offsets one warp tests
-constexpr uint32_t FB_SLACK = 1024;                  // staged behind the piece: a dynamic header is < 2400 bits long
 constexpr uint32_t FB_WARPS = 4;
 constexpr uint32_t FB_THREADS = FB_WARPS * 32;
 constexpr uint32_t FB_QUEUE = 96;                    // survivors per stage queue (flushed when >= 32 are waiting)
-constexpr uint32_t FB_STAGE_WORDS = (FB_PIECE + FB_SLACK) / 4 + 4;
+constexpr uint32_t FB_HDR_MAX_BITS = 2400;           // 17 + 19 * 3 + 316 * (7 + 7) rounded up: no dynamic header is longer
 struct __align__(16) FbWarp {
-    uint32_t data[FB_STAGE_WORDS];
     uint32_t q1[FB_QUEUE], q2[FB_QUEUE];             // bit offsets relative to the piece
     uint8_t pre[128 * 32];                           // per-lane 7-bit precode table: entry e of lane l at [e * 32 + l]
 };
-constexpr size_t FB_SMEM_BYTES = FB_WARPS * sizeof(FbWarp);
 
-// 64 bits of the staged piece starting at bit q (q + 64 <= staged bits)
-__device__ __forceinline__ uint64_t fb_bits64(const uint32_t* w, uint32_t q) {
+// The piece is read straight from global memory: the 32 lanes of a warp look at 32 consecutive bit offsets, i.e. at the
+// same two or three words -- one L1 line, broadcast.  (A shared-memory copy of the piece costs 17 KB per warp, which
+// leaves 8 warps per SM; the scan is a chain of dependent loads and wants the occupancy more than the lower latency:
+// measured 23.5 ms -> see DESIGN.md.)  w = the stream as aligned 32-bit words, word indices are clamped to the last
+// word of the stream (offsets that close to the end cannot start a block that matters).
+struct FbSrc { const uint32_t* w; uint32_t last; };  // last: highest word index that may be read, relative to w
+__device__ __forceinline__ uint32_t fb_word(const FbSrc& s, uint32_t i) { return __ldg(s.w + min(i, s.last)); }
+__device__ __forceinline__ uint64_t fb_bits64(const FbSrc& s, uint32_t q) {
     const uint32_t i = q >> 5, sh = q & 31;
-    const uint32_t a = w[i], b = w[i + 1], c = w[i + 2];
+    const uint32_t a = fb_word(s, i), b = fb_word(s, i + 1), c = fb_word(s, i + 2);
     return (uint64_t)__funnelshift_r(a, b, sh) | ((uint64_t)__funnelshift_r(b, c, sh) << 32);
 }
-__device__ __forceinline__ uint32_t fb_bits32(const uint32_t* w, uint32_t q) {
+__device__ __forceinline__ uint32_t fb_bits32(const FbSrc& s, uint32_t q) {
     const uint32_t i = q >> 5;
-    return __funnelshift_r(w[i], w[i + 1], q & 31);
+    return __funnelshift_r(fb_word(s, i), fb_word(s, i + 1), q & 31);
 }
 
 // stage 2: the precode (HCLEN x 3 bits from bit 17) must be a complete prefix code
-__device__ __forceinline__ bool fb_precode_complete(const uint32_t* w, uint32_t q) {
+__device__ __forceinline__ bool fb_precode_complete(const FbSrc& w, uint32_t q) {
     const uint64_t h = fb_bits64(w, q);
     const uint32_t hclen = ((uint32_t)(h >> 13) & 15u) + 4;
     const uint64_t lo = h >> 17;                                   // 47 bits = 15 lengths
@@ -78,7 +81,7 @@ __device__ __forceinline__ bool fb_precode_complete(const uint32_t* w, uint32_t 
 }
 
 // stage 3: decode HLIT + HDIST code lengths through the precode and check what a valid block guarantees
-__device__ bool fb_header_valid(const uint32_t* w, uint32_t q, uint8_t* pre /* this lane's column */) {
+__device__ bool fb_header_valid(const FbSrc& w, uint32_t q, uint8_t* pre /* this lane's column */) {
     const uint64_t h = fb_bits64(w, q);
     const uint32_t hlit = ((uint32_t)(h >> 3) & 31u) + 257, hdist = ((uint32_t)(h >> 8) & 31u) + 1;
     const uint32_t hclen = ((uint32_t)(h >> 13) & 15u) + 4;
@@ -111,6 +114,7 @@ __device__ bool fb_header_valid(const uint32_t* w, uint32_t q, uint8_t* pre /* t
         for (uint32_t k = rev; k < 128; k += 1u << l) pre[k * 32] = (uint8_t)(s | (l << 5));
     }
     uint32_t pos = q + 17 + 3 * hclen;
+    const uint32_t pos_max = q + FB_HDR_MAX_BITS;
     const uint32_t total = hlit + hdist;
     uint32_t i = 0, prev = 0, klit = 0, kdist = 0, ndist = 0, eob = 0;
     while (i < total) {
@@ -136,7 +140,8 @@ __device__ bool fb_header_valid(const uint32_t* w, uint32_t q, uint8_t* pre /* t
         }
         i += rep;
         prev = val;
-        if (pos > (FB_PIECE + FB_SLACK) * 8 - 64) return false;    // cannot happen for a real header (< 2400 bits)
+        // over-subscribed already: no need to read the rest (random bits get here after a few dozen lengths, a tenth of a header)
+        if (klit > 32768u || kdist > 32768u || pos > pos_max) return false;
     }
     if (!eob || klit != 32768u) return false;
     // distance code: complete, or a single code of length 1 (zlib accepts exactly that), or none at all
@@ -146,42 +151,33 @@ __device__ bool fb_header_valid(const uint32_t* w, uint32_t q, uint8_t* pre /* t
 // cand[p] = absolute bit offset of the first valid-looking dynamic block header that STARTS in piece p, or ~0
 __global__ void __launch_bounds__(FB_THREADS)
 foreign_find_blocks_kernel(const uint8_t* __restrict__ in, uint64_t n, uint64_t npieces, unsigned long long* __restrict__ cand) {
-    extern __shared__ __align__(16) uint8_t fb_smem[];
+    __shared__ FbWarp fb_warps[FB_WARPS];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint64_t p = (uint64_t)blockIdx.x * FB_WARPS + warp;
     if (p >= npieces) return;
-    FbWarp* W = reinterpret_cast<FbWarp*>(fb_smem) + warp;
+    FbWarp* W = &fb_warps[warp];
     const uint32_t FULL = 0xFFFFFFFFu;
     const uint64_t byte0 = p * FB_PIECE;
-    // stage the piece (+ slack), zero-filled past the end of the stream; `in` is only byte-aligned in general
+    // the stream as aligned words: the piece starts `qoff` bits into word `word0`
+    const uint32_t skip = (uint32_t)(reinterpret_cast<uintptr_t>(in) & 3);
+    const uint32_t* wall = reinterpret_cast<const uint32_t*>(in - skip);
+    const uint64_t nwords = (skip + n + 3) >> 2;
+    const uint64_t word0 = (skip + byte0) >> 2;
+    const uint32_t qoff = (uint32_t)((skip + byte0) & 3) * 8;
+    FbSrc w;
+    w.w = wall + word0;
+    w.last = (uint32_t)min(nwords - 1 - word0, (uint64_t)0x7FFFFFFFu);
     const uint64_t avail = n - byte0;
-    if ((reinterpret_cast<uintptr_t>(in + byte0) & 3) == 0) {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(in + byte0);
-        const uint32_t full_words = (uint32_t)min((uint64_t)FB_STAGE_WORDS, avail >> 2);
-        for (uint32_t i = lane; i < full_words; i += 32) W->data[i] = __ldg(src + i);
-        for (uint32_t i = full_words + lane; i < FB_STAGE_WORDS; i += 32) {
-            uint32_t v = 0;
-            for (uint32_t k = 0; k < 4; k++) { const uint64_t b = (uint64_t)i * 4 + k; if (b < avail) v |= (uint32_t)in[byte0 + b] << (8 * k); }
-            W->data[i] = v;
-        }
-    } else {
-        for (uint32_t i = lane; i < FB_STAGE_WORDS; i += 32) {
-            uint32_t v = 0;
-            for (uint32_t k = 0; k < 4; k++) { const uint64_t b = (uint64_t)i * 4 + k; if (b < avail) v |= (uint32_t)in[byte0 + b] << (8 * k); }
-            W->data[i] = v;
-        }
-    }
-    __syncwarp();
-    const uint32_t nbits = (uint32_t)min((uint64_t)FB_PIECE, avail) * 8;     // offsets tested: [0, nbits)
-    // a header needs at least 17 + 12 bits and an end-of-block: offsets in the stream's last bytes cannot start a block
+    // offsets tested: [0, nbits) of the piece; the last bytes of the stream cannot hold a header plus a block worth finding
+    uint32_t nbits = (uint32_t)min((uint64_t)FB_PIECE, avail) * 8;
+    if (avail < FB_PIECE + 16) nbits = avail > 16 ? (uint32_t)(avail - 16) * 8 : 0;
     uint32_t best = 0xFFFFFFFFu;
     uint32_t n1 = 0, n2 = 0;
-    const uint32_t* w = W->data;
     auto drain2 = [&](uint32_t count) {          // stage 3 on the first `count` entries of q2
         const bool have = lane < count;
         const uint32_t q = have ? W->q2[lane] : 0;
         bool ok = false;
-        if (have && q < best) ok = fb_header_valid(w, q, W->pre + lane);
+        if (have && q < best) ok = fb_header_valid(w, q + qoff, W->pre + lane);
         uint32_t m = __ballot_sync(FULL, ok);
         while (m) {
             const uint32_t j = __ffs(m) - 1;
@@ -204,7 +200,7 @@ foreign_find_blocks_kernel(const uint8_t* __restrict__ in, uint64_t n, uint64_t 
     auto drain1 = [&](uint32_t count) {          // stage 2 on the first `count` entries of q1
         const bool have = lane < count;
         const uint32_t q = have ? W->q1[lane] : 0;
-        const bool ok = have && q < best && fb_precode_complete(w, q);
+        const bool ok = have && q < best && fb_precode_complete(w, q + qoff);
         const uint32_t m = __ballot_sync(FULL, ok);
         if (ok) W->q2[n2 + __popc(m & ((1u << lane) - 1u))] = q;
         n2 += __popc(m);
@@ -223,7 +219,7 @@ foreign_find_blocks_kernel(const uint8_t* __restrict__ in, uint64_t n, uint64_t 
     for (uint32_t b0 = 0; b0 < nbits; b0 += 32) {
         if (b0 > best) break;                    // only the FIRST hit of the piece matters
         const uint32_t q = b0 + lane;
-        const uint32_t h = fb_bits32(w, q);
+        const uint32_t h = fb_bits32(w, q + qoff);
         // stage 1: BFINAL = 0, BTYPE = 10 (bits 1, 2 = 0, 1), HLIT <= 29, HDIST <= 29
         const bool ok = q < nbits && (h & 7u) == 4u && ((h >> 3) & 31u) <= 29u && ((h >> 8) & 31u) <= 29u;
         const uint32_t m = __ballot_sync(FULL, ok);

@@ -8,7 +8,11 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > 
 for step in "$@"; do
   case $step in
     pytest)
-      timeout 1500 python -m pytest tests -m gpu --maxfail=12 -q > $out/${tag}_pytest.log 2>&1; echo "pytest exit $?" >> $out/${tag}_pytest.log ;;
+      # one process per file, each under its own timeout: a hang costs one file, not the session; slowest tests are listed
+      for f in ${PYTEST_FILES:-tests/test_gpu_misc.py tests/test_gpu_compress.py tests/test_gpu_inflate.py tests/test_gpu_foreign.py tests/test_gpu_framing.py tests/test_gpu_fuzz.py tests/test_gpu_configs.py}; do
+        echo "=== $f $(date +%T)" >> $out/${tag}_pytest.log
+        timeout ${PYTEST_TIMEOUT:-600} python -m pytest $f -m gpu --maxfail=8 -v --durations=6 -o faulthandler_timeout=150 >> $out/${tag}_pytest.log 2>&1; echo "exit $? $(date +%T)" >> $out/${tag}_pytest.log
+      done ;;
     bench)
       timeout 900 python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err; echo "bench exit $?" >> $out/${tag}_bench.err ;;
     bench_quick)
@@ -23,7 +27,7 @@ for step in "$@"; do
       timeout 1500 compute-sanitizer --tool memcheck --log-file $out/${tag}_memcheck.log python -m pytest tests -m gpu -x -q -k "${SAN_K:-edge or fixture or quirk or fuzz}" > $out/${tag}_memcheck_pytest.log 2>&1
       timeout 1500 compute-sanitizer --tool racecheck --log-file $out/${tag}_racecheck.log python -m pytest tests -m gpu -x -q -k "${SAN_K:-edge or fixture or quirk or fuzz}" > $out/${tag}_racecheck_pytest.log 2>&1 ;;
     probe)
-      timeout 900 python tools/dev_probe.py ${PROBE_ARGS} > $out/${tag}_probe.log 2>&1 ;;
+      timeout 1200 python tools/probe_r02.py ${PROBE_ARGS} > $out/${tag}_probe.log 2>&1 ;;
     *) echo "unknown step $step" ;;
   esac
 done
