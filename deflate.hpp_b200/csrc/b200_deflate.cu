@@ -146,12 +146,12 @@ struct b200_ctx {
     int device = 0;
     bool attrs_set = false;
     uint32_t batch_chunks = 4096;
-    uint32_t better_depth = 128, better_nice = 258;   // "better" level: chain depth / good-enough length
+    uint32_t better_depth = 8, better_nice = 32;   // "better" level: chain depth / good-enough length
     // compress scratch
     Buf tok, ntok, hist, codes, hdr, desc, sizes, offsets, total;
     // inflate scratch
     Buf counts, woffs, cand, res, result, one_off, counter, cand16, ops, tpres, segnops, chunk_list, group_cnt, sync_cache, adler_parts, batch_nch, batch_first, batch_srcs;
-    Buf f_cand, f_starts, f_stops, f_res, f_base, f_opsbase, f_sym, f_ops, f_gmap, f_gwin, f_slabs, f_misc;   // foreign streams
+    Buf f_cand, f_starts, f_stops, f_res, f_base, f_opsbase, f_sym, f_ops, f_gmap, f_gwin, f_slabs, f_misc, f_order;   // foreign streams
     bool size_probe = false;                  // set by inflate_host while it does not know the decoded size yet
     size_t foreign_min = (size_t)256 << 10;   // streams shorter than this stay with the one-warp decoder (B200_FOREIGN_MIN)
     uint32_t foreign_group = 0;               // units per window-propagation group (0 = auto); B200_FOREIGN_GROUP
@@ -161,6 +161,7 @@ struct b200_ctx {
     bool inflate_overlap = false;        // B200_INFLATE_OVERLAP=1: copy pass of group g on a side stream while group g + 1 is in
                                          // pass A (measured: +1 % on a 4 GiB stream, so off by default)
     bool with_index = true;          // B200_NO_INDEX=1 / B200_F_NO_INDEX: no segment index in front of full chunks
+    bool with_split = true;          // B200_NO_SPLIT=1: never cut a chunk into two blocks (huffman.cuh: block splitting)
     int sg_occ = 12, copy_occ = 8;   // resident CTAs per SM the two inflate passes are compiled for (tuning knobs; 8 x 4 warps at
                                      // 64 registers: no spills in the lane-local copies, measured best of 6 / 8 / 12)
     uint32_t sg_pad = 0;             // B200_SG_PAD: extra dynamic shared memory per pass-A CTA (occupancy experiments)
@@ -169,6 +170,7 @@ struct b200_ctx {
                                      // slower than one warp per stream on 1-64 KiB zlib streams: 15 vs 75 GB/s; kept for
                                      // workloads with very many tiny streams)
     bool inflate_warp_path = false;  // B200_INFLATE_WARP=1: the one-warp-per-unit decoder only (A/B comparisons)
+    uint32_t num_sms = 148;
     uint32_t lzf_grid = 148 * 2;     // persistent two-phase matcher: SMs x resident CTAs
     uint32_t lzf_adaptive = 1;       // skip the match search where sample tiles find nothing (lz77.cuh); B200_LZF_ADAPTIVE=0: off
     uint32_t inf_grid = 148 * 7;     // persistent inflate grid: SMs x resident CTAs
@@ -408,6 +410,7 @@ int b200_ctx_create(int device, b200_ctx** ctx) {
     c->device = device;
     DeviceGuard dev_guard__(device);
     if (!dev_guard__.ok) { cudaGetLastError(); delete c; return B200_E_CUDA; }
+    c->num_sms = (uint32_t)prop.multiProcessorCount;
     c->inf_grid = (uint32_t)prop.multiProcessorCount * INF_MAX_CTAS_PER_SM;
     c->lzf_grid = (uint32_t)prop.multiProcessorCount * 2;
     // B200_RESERVE_SMS=k: leave k SMs out of the persistent matcher's grid so that concurrently running
@@ -419,6 +422,7 @@ int b200_ctx_create(int device, b200_ctx** ctx) {
     if (const char* e = getenv("B200_BETTER_DEPTH")) { int v = atoi(e); if (v > 0) c->better_depth = (uint32_t)v; }
     if (const char* e = getenv("B200_BETTER_NICE")) { int v = atoi(e); if (v >= 3) c->better_nice = (uint32_t)v; }
     if (const char* e = getenv("B200_LZF_ADAPTIVE")) c->lzf_adaptive = atoi(e) != 0;
+    if (const char* e = getenv("B200_NO_SPLIT")) c->with_split = atoi(e) == 0;
     if (const char* e = getenv("B200_NO_INDEX")) c->with_index = atoi(e) == 0;
     if (const char* e = getenv("B200_INFLATE_GROUP")) { long v = atol(e); if (v > 0) c->inflate_group_chunks = (uint64_t)v; }
     if (const char* e = getenv("B200_INFLATE_OVERLAP")) c->inflate_overlap = atoi(e) != 0;
@@ -452,7 +456,7 @@ void b200_ctx_destroy(b200_ctx* c) {
     Buf* all[] = {&c->tok, &c->ntok, &c->hist, &c->codes, &c->hdr, &c->desc, &c->sizes, &c->offsets, &c->total,
                   &c->counts, &c->woffs, &c->cand, &c->res, &c->result, &c->one_off, &c->counter, &c->cand16, &c->ops, &c->tpres, &c->segnops, &c->chunk_list, &c->group_cnt, &c->sync_cache, &c->adler_parts, &c->batch_nch, &c->batch_first, &c->batch_srcs,
                   &c->d_in, &c->d_out, &c->f_cand, &c->f_starts, &c->f_stops, &c->f_res, &c->f_base, &c->f_opsbase, &c->f_sym, &c->f_ops,
-                  &c->f_gmap, &c->f_gwin, &c->f_slabs, &c->f_misc};
+                  &c->f_gmap, &c->f_gwin, &c->f_slabs, &c->f_misc, &c->f_order};
     for (Buf* b : all) b->release();
     c->prof.destroy();
     for (auto e : c->events) cudaEventDestroy(e);
@@ -548,7 +552,7 @@ static int compress_batch(b200_ctx* c, const uint8_t* bin, uint64_t bn, uint32_t
     }
     PROF_BEGIN(c, K_HUFFMAN, st);
     huffman_kernel<<<(nb + HUF_WARPS - 1) / HUF_WARPS, HUF_THREADS, 0, st>>>(
-        (const uint16_t*)c->hist.p, bn, nb, level, final_batch ? 1 : 0, c->with_index ? 1 : 0, srcs, (uint32_t*)c->codes.p,
+        (const uint16_t*)c->hist.p, bn, nb, level, final_batch ? 1 : 0, c->with_index ? 1 : 0, c->with_split ? 1 : 0, srcs, (uint32_t*)c->codes.p,
         (uint32_t*)c->hdr.p, (BlockDesc*)c->desc.p, (uint32_t*)c->sizes.p);
     LAUNCHED();
     PROF_END(c, st);
@@ -652,8 +656,8 @@ int b200_deflate_compress_dev(b200_ctx* c, const void* d_in, size_t n, int level
     if ((rc = c->tok.ensure(B * CHUNK * 4))) return rc;
     if ((rc = c->ntok.ensure(B * NSEG * 4))) return rc;
     if ((rc = c->hist.ensure(B * NSEG * NSYM * 2))) return rc;
-    if ((rc = c->codes.ensure(B * NSYM * 4))) return rc;
-    if ((rc = c->hdr.ensure(B * HDR_WORDS * 4))) return rc;
+    if ((rc = c->codes.ensure(B * 2 * NSYM * 4))) return rc;
+    if ((rc = c->hdr.ensure(B * 2 * HDR_WORDS * 4))) return rc;
     if ((rc = c->desc.ensure(B * sizeof(BlockDesc)))) return rc;
     if ((rc = c->sizes.ensure(B * 4))) return rc;
     uint64_t* offs = d_chunk_off;
@@ -722,8 +726,8 @@ int b200_deflate_compress_batch_dev(b200_ctx* c, const void* d_in, const uint64_
     if ((rc = c->tok.ensure(B * CHUNK * 4))) return rc;
     if ((rc = c->ntok.ensure(B * NSEG * 4))) return rc;
     if ((rc = c->hist.ensure(B * NSEG * NSYM * 2))) return rc;
-    if ((rc = c->codes.ensure(B * NSYM * 4))) return rc;
-    if ((rc = c->hdr.ensure(B * HDR_WORDS * 4))) return rc;
+    if ((rc = c->codes.ensure(B * 2 * NSYM * 4))) return rc;
+    if ((rc = c->hdr.ensure(B * 2 * HDR_WORDS * 4))) return rc;
     if ((rc = c->desc.ensure(B * sizeof(BlockDesc)))) return rc;
     if ((rc = c->sizes.ensure(B * 4))) return rc;
     if ((rc = c->offsets.ensure((nchunks + 1) * 8))) return rc;
@@ -763,8 +767,8 @@ int b200_deflate_compress_stage1_dev(b200_ctx* c, const void* d_in, size_t n, in
     if ((rc = c->tok.ensure(B * CHUNK * 4))) return rc;
     if ((rc = c->ntok.ensure(B * NSEG * 4))) return rc;
     if ((rc = c->hist.ensure(B * NSEG * NSYM * 2))) return rc;
-    if ((rc = c->codes.ensure(B * NSYM * 4))) return rc;
-    if ((rc = c->hdr.ensure(B * HDR_WORDS * 4))) return rc;
+    if ((rc = c->codes.ensure(B * 2 * NSYM * 4))) return rc;
+    if ((rc = c->hdr.ensure(B * 2 * HDR_WORDS * 4))) return rc;
     if ((rc = c->desc.ensure(B * sizeof(BlockDesc)))) return rc;
     if ((rc = c->sizes.ensure(B * 4))) return rc;
     if ((rc = c->offsets.ensure((nchunks + 1) * 8))) return rc;
@@ -1060,12 +1064,25 @@ static int inflate_foreign(b200_ctx* c, const uint8_t* in, uint64_t n, uint8_t* 
             if (!units[i].have) { hs.push_back(units[i].start); hp.push_back(units[i].stop); idx.push_back(i); }
         const uint64_t m = hs.size();
         if (m) {
-            if ((rc = c->f_starts.ensure(m * 8)) || (rc = c->f_stops.ensure(m * 8)) || (rc = c->f_res.ensure(m * sizeof(FUnitRes)))) return B200_OK;
+            if ((rc = c->f_starts.ensure(m * 8)) || (rc = c->f_stops.ensure(m * 8)) || (rc = c->f_res.ensure(m * sizeof(FUnitRes))) ||
+                (rc = c->f_order.ensure(m * 4)) || (rc = c->f_misc.ensure(256)))
+                return B200_OK;
+            // longest first: the compressed span is the estimate (the last unit's is unknown: first)
+            std::vector<uint32_t> order(m);
+            for (uint64_t k = 0; k < m; k++) order[k] = (uint32_t)k;
+            std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+                const uint64_t sa = hp[a] == ~0ull ? ~0ull : hp[a] - hs[a], sb = hp[b] == ~0ull ? ~0ull : hp[b] - hs[b];
+                return sa != sb ? sa > sb : a < b;
+            });
             CK(cudaMemcpyAsync(c->f_starts.p, hs.data(), m * 8, cudaMemcpyHostToDevice, st));
             CK(cudaMemcpyAsync(c->f_stops.p, hp.data(), m * 8, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(c->f_order.p, order.data(), m * 4, cudaMemcpyHostToDevice, st));
+            CK(cudaMemsetAsync(c->f_misc.p, 0, 256, st));
+            const uint64_t want_ctas = (m + FD_THREADS - 1) / FD_THREADS;
             PROF_BEGIN(c, K_F_COUNT, st);
-            foreign_decode_kernel<false><<<(uint32_t)((m + FD_THREADS - 1) / FD_THREADS), FD_THREADS, TP_SMEM_BYTES, st>>>(
-                in, n, (const uint64_t*)c->f_starts.p, (const uint64_t*)c->f_stops.p, m, (FUnitRes*)c->f_res.p, nullptr, nullptr, nullptr, nullptr, flags);
+            foreign_decode_kernel<false><<<(uint32_t)(want_ctas < c->num_sms ? want_ctas : c->num_sms), FD_THREADS, TP_SMEM_BYTES, st>>>(
+                in, n, (const uint64_t*)c->f_starts.p, (const uint64_t*)c->f_stops.p, m, (FUnitRes*)c->f_res.p, nullptr, nullptr, nullptr, nullptr, flags,
+                (const uint32_t*)c->f_order.p, (unsigned long long*)c->f_misc.p + 16);
             LAUNCHED();
             PROF_END(c, st);
             std::vector<FUnitRes> hr(m);
@@ -1146,43 +1163,35 @@ static int inflate_foreign(b200_ctx* c, const uint8_t* in, uint64_t n, uint8_t* 
     uint16_t* S = (uint16_t*)c->f_sym.p;
     const uint64_t* d_base = (const uint64_t*)c->f_base.p;
 
-    // ---- F3 + F4: decode with known offsets, then the ops inside the symbol image.  The decode kernel runs four warps per
-    // SM (its private tables fill the shared memory) and is bound by latency, the copy kernel needs no shared memory: the
-    // units are cut into parts, and the copies of part k run on a side stream under the decode of part k + 1 ----
+    // ---- F3: decode with known offsets (longest units first) ----
     {
-        const uint64_t parts = nu >= 8192 ? 4 : 1;
-        while (c->group_events.size() < 2 * parts) {
-            cudaEvent_t e;
-            CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-            c->group_events.push_back(e);
-        }
+        std::vector<uint32_t> order(nu);
+        for (uint64_t k = 0; k < nu; k++) order[k] = (uint32_t)k;
+        std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+            const uint64_t la = hbase[a + 1] - hbase[a], lb = hbase[b + 1] - hbase[b];
+            return la != lb ? la > lb : a < b;
+        });
+        if ((rc = c->f_order.ensure(nu * 4))) return B200_OK;
+        CK(cudaMemcpyAsync(c->f_order.p, order.data(), nu * 4, cudaMemcpyHostToDevice, st));
+        const uint64_t want_ctas = (nu + FD_THREADS - 1) / FD_THREADS;
+        PROF_BEGIN(c, K_F_EMIT, st);
+        foreign_decode_kernel<true><<<(uint32_t)(want_ctas < c->num_sms ? want_ctas : c->num_sms), FD_THREADS, TP_SMEM_BYTES, st>>>(
+            in, n, (const uint64_t*)c->f_starts.p, (const uint64_t*)c->f_stops.p, nu, (FUnitRes*)c->f_res.p, d_base,
+            (const uint64_t*)c->f_opsbase.p, S, (uint64_t*)c->f_ops.p, flags, (const uint32_t*)c->f_order.p, d_counter + 17);
+        LAUNCHED();
+        PROF_END(c, st);
+        CK(cudaStreamSynchronize(st));            // `order` lives on this stack frame
+    }
+    // ---- F4: ops inside the symbol image (measured: running this on a side stream under the decode of the next part
+    // of the units makes both slower -- the decode is bound by the length of its longest unit, not by throughput) ----
+    {
+        const uint64_t want = (nu + INF_WARPS - 1) / INF_WARPS;
         const uint64_t gmax = (uint64_t)(c->inf_grid / INF_MAX_CTAS_PER_SM) * 12;
-        for (uint64_t k = 0; k < parts; k++) {
-            const uint64_t u0 = nu * k / parts, u1 = nu * (k + 1) / parts, m = u1 - u0;
-            if (!m) continue;
-            PROF_BEGIN(c, K_F_EMIT, st);
-            foreign_decode_kernel<true><<<(uint32_t)((m + FD_THREADS - 1) / FD_THREADS), FD_THREADS, TP_SMEM_BYTES, st>>>(
-                in, n, (const uint64_t*)c->f_starts.p + u0, (const uint64_t*)c->f_stops.p + u0, m, (FUnitRes*)c->f_res.p + u0, d_base + u0,
-                (const uint64_t*)c->f_opsbase.p + u0, S, (uint64_t*)c->f_ops.p, flags);
-            LAUNCHED();
-            PROF_END(c, st);
-            cudaStream_t cs = parts > 1 ? c->s_side : st;
-            if (parts > 1) {
-                CK(cudaEventRecord(c->group_events[2 * k], st));
-                CK(cudaStreamWaitEvent(cs, c->group_events[2 * k], 0));
-            }
-            const uint64_t want = (m + INF_WARPS - 1) / INF_WARPS;
-            PROF_BEGIN(c, K_F_COPY, cs);
-            foreign_copy_kernel<<<(uint32_t)(want < gmax ? want : gmax), INF_THREADS, 0, cs>>>(
-                in, (const FUnitRes*)c->f_res.p + u0, d_base + u0, (const uint64_t*)c->f_opsbase.p + u0, m, S, (const uint64_t*)c->f_ops.p,
-                d_counter + 8 + k, d_err);
-            LAUNCHED();
-            PROF_END(c, cs);
-            if (parts > 1 && k + 1 == parts) {
-                CK(cudaEventRecord(c->group_events[2 * k + 1], cs));
-                CK(cudaStreamWaitEvent(st, c->group_events[2 * k + 1], 0));
-            }
-        }
+        PROF_BEGIN(c, K_F_COPY, st);
+        foreign_copy_kernel<<<(uint32_t)(want < gmax ? want : gmax), INF_THREADS, 0, st>>>(
+            in, (const FUnitRes*)c->f_res.p, d_base, (const uint64_t*)c->f_opsbase.p, nu, S, (const uint64_t*)c->f_ops.p, d_counter + 8, d_err);
+        LAUNCHED();
+        PROF_END(c, st);
     }
     // ---- F5: window propagation, two levels ----
     uint32_t G = c->foreign_group;
@@ -1413,8 +1422,8 @@ static int compress_host(b200_ctx* c, const uint8_t* in, size_t n, int level, un
     if ((rc = c->tok.ensure(B * CHUNK * 4))) return rc;
     if ((rc = c->ntok.ensure(B * NSEG * 4))) return rc;
     if ((rc = c->hist.ensure(B * NSEG * NSYM * 2))) return rc;
-    if ((rc = c->codes.ensure(B * NSYM * 4))) return rc;
-    if ((rc = c->hdr.ensure(B * HDR_WORDS * 4))) return rc;
+    if ((rc = c->codes.ensure(B * 2 * NSYM * 4))) return rc;
+    if ((rc = c->hdr.ensure(B * 2 * HDR_WORDS * 4))) return rc;
     if ((rc = c->desc.ensure(B * sizeof(BlockDesc)))) return rc;
     if ((rc = c->sizes.ensure(B * 4))) return rc;
     if ((rc = c->offsets.ensure((nchunks + 1) * 8))) return rc;
@@ -1772,7 +1781,8 @@ static int inflate_host(const uint8_t* in, size_t n, void* out, size_t cap, void
         if (cudaStreamSynchronize(c->stream) != cudaSuccess) { free(buf); return B200_E_CUDA; }
         *out_alloc = buf;
     } else if (written && !piped) {
-        if ((rc = copy_d2h(c, out, c->d_out.p, written, c->stream))) return rc;
+        const int rc2 = copy_d2h(c, out, c->d_out.p, written, c->stream);      // (rc keeps the decoder's verdict)
+        if (rc2) return rc2;
         CK(cudaStreamSynchronize(c->stream));
     }
     if (out_n) *out_n = written;

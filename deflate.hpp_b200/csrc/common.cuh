@@ -55,9 +55,14 @@ struct BlockDesc {
     uint32_t nbytes;         // bytes this chunk occupies in the stream (incl. sync marker if any)
     uint32_t clen;           // uncompressed bytes in this chunk
     uint32_t last;           // 1 = carries BFINAL, no sync marker
-    uint32_t eob;            // bit-reversed EOB code | len << 16
+    uint32_t eob;            // (unused)
     uint32_t index_bytes;    // 0, or INDEX_BYTES when the chunk is preceded by the segment index
     uint32_t seg_bitoff[NSEG];  // bit offset of each segment's first token, relative to block start
+    // a chunk split into two blocks (huffman.cuh): segments [0, split_seg) use codes[0] / hdr[0], the rest codes[1] / hdr[1]
+    uint32_t split_seg;      // 0 = one block
+    uint32_t btype2;         // second block: 1 fixed, 2 dynamic
+    uint32_t hdr_bits2;      // bits of the second block's header
+    uint32_t block2_bit;     // bit offset of the second block's header, relative to the first block's start
 };
 
 // ---- RFC 1951 3.2.5 symbol arithmetic ------------------------------------------------------

@@ -52,7 +52,7 @@ scan_sizes_kernel(const uint32_t* __restrict__ sizes, uint32_t n, const uint64_t
 // ---- K4: encode ------------------------------------------------------------------------------------
 constexpr uint32_t ENC_THREADS = NSEG * 32;
 constexpr uint32_t ENC_STAGE_BYTES = CHUNK + 80;       // block bytes (<= stored size) + phase + marker
-constexpr size_t ENC_SMEM_BYTES = ENC_STAGE_BYTES + NSYM * 4;
+constexpr size_t ENC_SMEM_BYTES = ENC_STAGE_BYTES + 2 * NSYM * 4;     // staging image + the code tables of up to two blocks
 
 // OR `nbits` (<= 48) of v into the staging bit array at absolute bit position `bit`.
 __device__ __forceinline__ void stage_bits(uint32_t* stage, uint32_t bit, uint64_t v, uint32_t nbits) {
@@ -88,7 +88,8 @@ encode_kernel(const uint8_t* __restrict__ in, const uint32_t* __restrict__ tok, 
     const uint32_t stage_words = (stage_bytes + 3) / 4;
 
     for (uint32_t i = tid; i < ((stage_words + 3) & ~3u) + 4; i += ENC_THREADS) stage[i] = 0;
-    if (d.btype) for (uint32_t i = tid; i < NSYM; i += ENC_THREADS) s_codes[i] = codes[chunk * NSYM + i];
+    const uint32_t split = d.btype ? d.split_seg : 0u;     // segments [split, 16) belong to the chunk's second block
+    if (d.btype) for (uint32_t i = tid; i < (split ? 2 * NSYM : NSYM); i += ENC_THREADS) s_codes[i] = codes[chunk * 2 * NSYM + i];
     __syncthreads();
 
     if (d.btype == 0) {
@@ -123,11 +124,21 @@ encode_kernel(const uint8_t* __restrict__ in, const uint32_t* __restrict__ tok, 
         // header bits
         const uint32_t hw = (d.hdr_bits + 31) / 32;
         for (uint32_t i = tid; i < hw; i += ENC_THREADS) {
-            uint32_t v = hdr[chunk * HDR_WORDS + i];
+            uint32_t v = hdr[chunk * 2 * HDR_WORDS + i];
             const uint32_t rem = d.hdr_bits - i * 32;
             if (rem < 32) v &= (1u << rem) - 1u;
             stage_bits(stage, bit0 + i * 32, v, 32);
         }
+        if (split) {
+            const uint32_t hw2 = (d.hdr_bits2 + 31) / 32;
+            for (uint32_t i = tid; i < hw2; i += ENC_THREADS) {
+                uint32_t v = hdr[(chunk * 2 + 1) * HDR_WORDS + i];
+                const uint32_t rem = d.hdr_bits2 - i * 32;
+                if (rem < 32) v &= (1u << rem) - 1u;
+                stage_bits(stage, bit0 + d.block2_bit + i * 32, v, 32);
+            }
+        }
+        const uint32_t* cd = s_codes + ((split && warp >= split) ? NSYM : 0u);
         // payload: warp = segment; 32 tokens per step, warp scan of bit lengths
         const uint32_t nt = d.clen ? ntok[chunk * NSEG + warp] : 0u;      // an empty input: header + end of block only
         const uint32_t* mytok = tok + chunk * CHUNK + warp * SEG;
@@ -146,17 +157,17 @@ encode_kernel(const uint8_t* __restrict__ in, const uint32_t* __restrict__ tok, 
             if (i < nt) {
                 const uint32_t dist = tok_dist(t);
                 if (dist == 0) {
-                    const uint32_t c = s_codes[t & 0xFFu];
+                    const uint32_t c = cd[t & 0xFFu];
                     v = c >> 8; nb = c & 0xFFu;
                 } else {
                     uint32_t idx, ne, ev;
                     len_symbol(tok_len(t), idx, ne, ev);
-                    uint32_t c = s_codes[257 + idx];
+                    uint32_t c = cd[257 + idx];
                     v = c >> 8; nb = c & 0xFFu;
                     v |= (uint64_t)ev << nb; nb += ne;
                     uint32_t ds;
                     dist_symbol(dist, ds, ne, ev);
-                    c = s_codes[NLIT + ds];
+                    c = cd[NLIT + ds];
                     v |= (uint64_t)(c >> 8) << nb; nb += c & 0xFFu;
                     v |= (uint64_t)ev << nb; nb += ne;
                 }
@@ -170,7 +181,11 @@ encode_kernel(const uint8_t* __restrict__ in, const uint32_t* __restrict__ tok, 
             bit += __shfl_sync(0xFFFFFFFFu, incl, 31);
         }
         if (tid == 0) {
-            const uint32_t c = s_codes[256];
+            if (split) {                                   // end of the first block, right in front of the second header
+                const uint32_t c1 = s_codes[256];
+                stage_bits(stage, bit0 + d.block2_bit - (c1 & 0xFFu), c1 >> 8, c1 & 0xFFu);
+            }
+            const uint32_t c = s_codes[(split ? NSYM : 0u) + 256];
             const uint32_t eob_len = c & 0xFFu;
             stage_bits(stage, bit0 + d.total_bits - eob_len, c >> 8, eob_len);
             if (!d.last) {   // separator: 3 zero bits, pad, 00 00 FF FF, then 00 | 00 00 FF FF

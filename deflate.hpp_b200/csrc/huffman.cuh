@@ -211,59 +211,36 @@ __device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
     return v;
 }
 
-// grid = ceil(nchunks / HUF_WARPS), block = 128.
-//   hist   : [nchunks][NSEG][NSYM] u16 from K1 (a segment has at most 4096 tokens)
-//   codes  : [nchunks][NSYM]   len | reversed code << 8   (what the encoder indexes by symbol)
-//   hdr    : [nchunks][HDR_WORDS] block header bits (BFINAL/BTYPE + dynamic tables)
-//   desc   : [nchunks] BlockDesc;  sizes: [nchunks] bytes per chunk (input of the offset scan)
-// level 0 forces stored blocks.  last_is_final: the final chunk of this buffer carries BFINAL.
-__global__ void __launch_bounds__(HUF_THREADS)
-huffman_kernel(const uint16_t* __restrict__ hist, uint64_t n, uint32_t nchunks, int level, int last_is_final,
-               int with_index, const ChunkSrc* __restrict__ srcs, uint32_t* __restrict__ codes, uint32_t* __restrict__ hdr, BlockDesc* __restrict__ desc,
-               uint32_t* __restrict__ sizes) {
-    __shared__ HufScratch scratch[HUF_WARPS];
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t chunk = blockIdx.x * HUF_WARPS + warp;
-    if (chunk >= nchunks) return;
-    HufScratch* s = &scratch[warp];
-    const uint32_t clen = srcs ? srcs[chunk].clen : (uint32_t)min((uint64_t)CHUNK, n - (uint64_t)chunk * CHUNK);
-    const bool last = srcs ? srcs[chunk].last != 0 : (last_is_final && chunk == nchunks - 1);
-    const uint16_t* h = hist + (size_t)chunk * NSEG * NSYM;
-    uint32_t* mycodes = codes + (size_t)chunk * NSYM;
-    uint32_t* myhdr = hdr + (size_t)chunk * HDR_WORDS;
-    BlockDesc* d = desc + chunk;
+// What one candidate block would cost, and what the emitter needs to write it (the code lengths, the run-length coded
+// header and the precode stay in the warp's HufScratch: a block is emitted right after it was planned).
+struct BlockPlan {
+    uint32_t use_dyn;        // 1: dynamic codes are smaller than the fixed ones
+    uint32_t bits;           // whole block: 3-bit header (+ dynamic tables) + symbols + end of block
+    uint32_t hdr_bits;       // 3 + dynamic tables (3 for a fixed block)
+    uint32_t hlit, hdist, hclen, nr;
+    uint32_t ok;             // code construction succeeded (always, in practice)
+};
 
-    const uint32_t nstored = (clen + 65534u) / 65535u;
-    // an empty input (batch compression only) still needs a block: stored is not an option, the fixed block wins (03 00)
-    const uint32_t stored_bytes = clen ? clen + 5u * nstored + (last ? 0u : SYNC_BYTES_ALIGNED) : 0xFFFFFFFFu;
-
-    if (level == 0 && clen) {
-        if (lane == 0) {
-            d->btype = 0; d->hdr_bits = 0; d->total_bits = 0; d->nbytes = stored_bytes; d->clen = clen;
-            d->last = last; d->eob = 0; d->index_bytes = 0;
-            sizes[chunk] = stored_bytes;
-        }
-        return;
-    }
-
+// Plans the block that covers segments [seg_lo, seg_hi) of the chunk whose per-segment histograms are h.
+__device__ __noinline__ BlockPlan plan_block(HufScratch* s, const uint16_t* __restrict__ h, uint32_t seg_lo, uint32_t seg_hi, bool have_tokens,
+                                uint32_t lane) {
+    BlockPlan P;
     // ---- reduce the per-segment histograms ------------------------------------------------
     for (uint32_t i = lane; i < NSYM; i += 32) {
         uint32_t f = 0;
-        if (clen) for (uint32_t sgm = 0; sgm < NSEG; sgm++) f += h[sgm * NSYM + i];     // (level 0 runs no tokeniser)
+        if (have_tokens) for (uint32_t sgm = seg_lo; sgm < seg_hi; sgm++) f += h[sgm * NSYM + i];     // (level 0 runs no tokeniser)
         s->freq[i] = f + (i == 256 ? 1u : 0u);
     }
     __syncwarp();
-
-    // ---- code lengths + canonical codes ----------------------------------------------------
+    // ---- code lengths ------------------------------------------------------------------------
     bool ok = build_lengths(s, s->freq, s->lens, 286, 15, lane);
     ok &= build_lengths(s, s->freq + NLIT, s->lens + NLIT, 30, 15, lane);
     if (lane < 2) s->lens[286 + lane] = 0;
     if (lane < 2) s->lens[NLIT + 30 + lane] = 0;
     __syncwarp();
-
     // ---- dynamic header: HLIT/HDIST, RLE of both lists (separately), precode ---------------
-    uint32_t hlit = 286, hdist = 30;
     if (lane == 0) {
+        uint32_t hlit = 286, hdist = 30;
         while (hlit > 257 && s->lens[hlit - 1] == 0) hlit--;
         while (hdist > 1 && s->lens[NLIT + hdist - 1] == 0) hdist--;
         uint32_t nr = rle_lengths(s, s->lens, hlit, 0);
@@ -273,8 +250,7 @@ huffman_kernel(const uint16_t* __restrict__ hist, uint64_t n, uint32_t nchunks, 
         s->misc[0] = hlit; s->misc[1] = hdist; s->misc[2] = nr;
     }
     __syncwarp();
-    hlit = s->misc[0]; hdist = s->misc[1];
-    const uint32_t nr = s->misc[2];
+    P.hlit = s->misc[0]; P.hdist = s->misc[1]; P.nr = s->misc[2];
     ok &= build_lengths(s, s->pfreq, s->plens, 19, 7, lane);
     {   // precode canonical codes: 19 symbols, one batch
         uint32_t tmp = 0;
@@ -294,7 +270,6 @@ huffman_kernel(const uint16_t* __restrict__ hist, uint64_t n, uint32_t nchunks, 
         if (lane < 32) s->pcodes[lane] = (uint16_t)tmp;
         __syncwarp();
     }
-
     // ---- exact sizes -----------------------------------------------------------------------
     uint32_t dyn = 0, fix = 0;
     for (uint32_t i = lane; i < NSYM; i += 32) {
@@ -312,13 +287,12 @@ huffman_kernel(const uint16_t* __restrict__ hist, uint64_t n, uint32_t nchunks, 
     }
     dyn = warp_sum(dyn);
     fix = warp_sum(fix);
-    const uint8_t* ORDER = PRECODE_ORDER;
     uint32_t hclen = 19;
-    while (hclen > 4 && s->plens[ORDER[hclen - 1]] == 0) hclen--;
+    while (hclen > 4 && s->plens[PRECODE_ORDER[hclen - 1]] == 0) hclen--;
     uint32_t hdr_bits = 3 + 5 + 5 + 4 + 3 * hclen;
     {
         uint32_t hb = 0;
-        for (uint32_t i = lane; i < nr; i += 32) {
+        for (uint32_t i = lane; i < P.nr; i += 32) {
             const uint32_t r = s->rle[i], sym = r & 31u;
             hb += s->plens[sym] + (sym == 16 ? 2u : sym == 17 ? 3u : sym == 18 ? 7u : 0u);
         }
@@ -326,20 +300,21 @@ huffman_kernel(const uint16_t* __restrict__ hist, uint64_t n, uint32_t nchunks, 
     }
     const uint32_t dyn_bits = ok ? hdr_bits + dyn : 0xFFFFFFFFu;
     const uint32_t fix_bits = 3 + fix;
-    const uint32_t use_dyn = dyn_bits < fix_bits;
-    const uint32_t bits = use_dyn ? dyn_bits : fix_bits;
-    // full chunks carry the segment index (common.cuh) so that they can be inflated by 16 threads
-    // (only where it costs little: the chunk must save at least four times the index's size)
-    const uint32_t huff_plain = last ? (bits + 7) / 8 : (bits + 3 + 7) / 8 + (SYNC_BYTES_ALIGNED - 1);
-    const uint32_t index_bytes = (with_index && clen == CHUNK && huff_plain + 4 * INDEX_BYTES <= stored_bytes) ? INDEX_BYTES : 0u;
-    const uint32_t huff_bytes = index_bytes + huff_plain;
-    const uint32_t btype = huff_bytes < stored_bytes ? (use_dyn ? 2u : 1u) : 0u;
+    P.use_dyn = dyn_bits < fix_bits;
+    P.bits = P.use_dyn ? dyn_bits : fix_bits;
+    P.hdr_bits = P.use_dyn ? hdr_bits : 3u;
+    P.hclen = hclen;
+    P.ok = ok;
+    return P;
+}
 
-    // ---- emit codes, header, descriptor ---------------------------------------------------
+// Writes the planned block's codes (what the encoder indexes by symbol) and its header bits.  btype 2 dynamic / 1 fixed.
+__device__ __noinline__ void emit_block(HufScratch* s, const BlockPlan& P, uint32_t btype, bool last, uint32_t* __restrict__ mycodes,
+                           uint32_t* __restrict__ myhdr, uint32_t lane) {
     if (btype == 2) {
         assign_codes(s, s->lens, NLIT, mycodes, lane);
         assign_codes(s, s->lens + NLIT, NDIST, mycodes + NLIT, lane);
-    } else if (btype == 1) {
+    } else {
         for (uint32_t i = lane; i < NSYM; i += 32) {
             uint32_t v;
             if (i < NLIT) {   // common.hpp:442-482 (RFC 1951 3.2.6)
@@ -353,16 +328,15 @@ huffman_kernel(const uint16_t* __restrict__ hist, uint64_t n, uint32_t nchunks, 
         }
     }
     __syncwarp();
-    const uint32_t hb_final = btype == 2 ? hdr_bits : btype == 1 ? 3u : 0u;
     if (lane == 0) {
         if (btype == 2) {
             BitSink bs{myhdr, 0, 0, 0};
             bs.put((last ? 1u : 0u) | (2u << 1), 3);
-            bs.put(hlit - 257, 5);
-            bs.put(hdist - 1, 5);
-            bs.put(hclen - 4, 4);
-            for (uint32_t i = 0; i < hclen; i++) bs.put(s->plens[ORDER[i]], 3);
-            for (uint32_t i = 0; i < nr; i++) {
+            bs.put(P.hlit - 257, 5);
+            bs.put(P.hdist - 1, 5);
+            bs.put(P.hclen - 4, 4);
+            for (uint32_t i = 0; i < P.hclen; i++) bs.put(s->plens[PRECODE_ORDER[i]], 3);
+            for (uint32_t i = 0; i < P.nr; i++) {
                 const uint32_t r = s->rle[i], sym = r & 31u;
                 bs.put(s->pcodes[sym], s->plens[sym]);
                 if (sym == 16) bs.put(r >> 8, 2);
@@ -370,38 +344,194 @@ huffman_kernel(const uint16_t* __restrict__ hist, uint64_t n, uint32_t nchunks, 
                 else if (sym == 18) bs.put(r >> 8, 7);
             }
             bs.flush();
-        } else if (btype == 1) {
+        } else {
             myhdr[0] = (last ? 1u : 0u) | (1u << 1);
         }
     }
-    // segment bit offsets (exclusive scan of per-segment payload bits)
-    uint32_t off = hb_final;
-    for (uint32_t sgm = 0; sgm < NSEG; sgm++) {
+    __syncwarp();
+}
+
+// payload bits of segments [seg_lo, seg_hi) under the code lengths currently in the scratch; offsets go to d->seg_bitoff
+__device__ __noinline__ uint32_t segment_offsets(HufScratch* s, const uint16_t* __restrict__ h, uint32_t btype, uint32_t seg_lo, uint32_t seg_hi,
+                                    bool have_tokens, uint32_t off, BlockDesc* d, uint32_t lane) {
+    for (uint32_t sgm = seg_lo; sgm < seg_hi; sgm++) {
         uint32_t sb = 0;
-        if (btype) {
-            for (uint32_t i = lane; i < NSYM; i += 32) {
-                const uint32_t f = clen ? h[sgm * NSYM + i] : 0u;
-                if (!f) continue;
-                const uint32_t cl = btype == 2 ? s->lens[i] : (i < NLIT ? fixed_lit_len(i) : 5u);
-                const uint32_t ex = i < NLIT ? (i > 256 ? len_extra_bits(i - 257) : 0u) : dist_extra_bits(i - NLIT);
-                sb += f * (cl + ex);
-            }
-            sb = warp_sum(sb);
+        for (uint32_t i = lane; i < NSYM; i += 32) {
+            const uint32_t f = have_tokens ? h[sgm * NSYM + i] : 0u;
+            if (!f) continue;
+            const uint32_t cl = btype == 2 ? s->lens[i] : (i < NLIT ? fixed_lit_len(i) : 5u);
+            const uint32_t ex = i < NLIT ? (i > 256 ? len_extra_bits(i - 257) : 0u) : dist_extra_bits(i - NLIT);
+            sb += f * (cl + ex);
         }
+        sb = warp_sum(sb);
         if (lane == 0) d->seg_bitoff[sgm] = off;
         off += sb;
     }
+    return off;
+}
+
+// Block splitting (the reference emits a block per 32 KB, deflate.hpp:692-749).  A full chunk may
+// be cut at a segment boundary into TWO blocks with their own code tables when the statistics change inside it.  Cost
+// model: the zero-order entropy of the literal/length + distance histograms (already in HBM per 4 KiB segment) of the
+// two sides against the whole, for the cuts at 16, 32 and 48 KiB; the best cut is taken to the exact stage -- both
+// blocks are planned for real -- only if the estimate beats the price of a second header by a margin, and is used only
+// if the exact bit count is smaller.  A split chunk carries no segment index (it is decoded by the one-warp decoder).
+__device__ __noinline__ uint32_t split_candidate(const uint16_t* __restrict__ h, uint32_t hdr_bits, uint32_t lane) {
+    float gain[3] = {0.f, 0.f, 0.f};
+    uint32_t nA[3][2] = {{0, 0}, {0, 0}, {0, 0}}, nS[2] = {0, 0};
+    // per-lane symbols: counts left of each cut and in total
+    uint32_t fA[3][NSYM / 32], fS[NSYM / 32];
+    #pragma unroll
+    for (uint32_t k = 0; k < NSYM / 32; k++) {
+        const uint32_t i = lane + 32 * k;
+        uint32_t run = 0;
+        for (uint32_t sgm = 0; sgm < NSEG; sgm++) {
+            if (sgm == 4) fA[0][k] = run;
+            if (sgm == 8) fA[1][k] = run;
+            if (sgm == 12) fA[2][k] = run;
+            run += h[sgm * NSYM + i];
+        }
+        fS[k] = run;
+        const uint32_t alpha = i < NLIT ? 0 : 1;
+        nS[alpha] += run;
+        #pragma unroll
+        for (uint32_t c = 0; c < 3; c++) nA[c][alpha] += fA[c][k];
+    }
+    #pragma unroll
+    for (uint32_t a = 0; a < 2; a++) {
+        nS[a] = warp_sum(nS[a]);
+        #pragma unroll
+        for (uint32_t c = 0; c < 3; c++) nA[c][a] = warp_sum(nA[c][a]);
+    }
+    // sum f log2(N / f): bits of the side under its own ideal code
+    #pragma unroll
+    for (uint32_t k = 0; k < NSYM / 32; k++) {
+        const uint32_t i = lane + 32 * k;
+        const uint32_t a = i < NLIT ? 0 : 1;
+        const float s_bits = fS[k] ? (float)fS[k] * (__log2f((float)nS[a]) - __log2f((float)fS[k])) : 0.f;
+        #pragma unroll
+        for (uint32_t c = 0; c < 3; c++) {
+            const uint32_t fa = fA[c][k], fb = fS[k] - fa, na = nA[c][a], nb = nS[a] - na;
+            const float a_bits = fa ? (float)fa * (__log2f((float)na) - __log2f((float)fa)) : 0.f;
+            const float b_bits = fb ? (float)fb * (__log2f((float)nb) - __log2f((float)fb)) : 0.f;
+            gain[c] += s_bits - a_bits - b_bits;
+        }
+    }
+    uint32_t best = 0;
+    float bestg = 0.f;
+    #pragma unroll
+    for (uint32_t c = 0; c < 3; c++) {
+        float g = gain[c];
+        for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(0xFFFFFFFFu, g, o);
+        if (g > bestg) { bestg = g; best = 4 * (c + 1); }
+    }
+    // worth the exact stage only if the ideal-code saving pays a second header twice over
+    return bestg > 2.0f * (float)hdr_bits + 256.f ? best : 0u;
+}
+
+// grid = ceil(nchunks / HUF_WARPS), block = 128.
+//   hist   : [nchunks][NSEG][NSYM] u16 from K1 (a segment has at most 4096 tokens)
+//   codes  : [nchunks][2][NSYM]   len | reversed code << 8   (what the encoder indexes by symbol; [1] = second block of a split chunk)
+//   hdr    : [nchunks][2][HDR_WORDS] block header bits (BFINAL/BTYPE + dynamic tables)
+//   desc   : [nchunks] BlockDesc;  sizes: [nchunks] bytes per chunk (input of the offset scan)
+// level 0 forces stored blocks.  last_is_final: the final chunk of this buffer carries BFINAL.
+__global__ void __launch_bounds__(HUF_THREADS)
+huffman_kernel(const uint16_t* __restrict__ hist, uint64_t n, uint32_t nchunks, int level, int last_is_final,
+               int with_index, int with_split, const ChunkSrc* __restrict__ srcs, uint32_t* __restrict__ codes, uint32_t* __restrict__ hdr,
+               BlockDesc* __restrict__ desc, uint32_t* __restrict__ sizes) {
+    __shared__ HufScratch scratch[HUF_WARPS];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t chunk = blockIdx.x * HUF_WARPS + warp;
+    if (chunk >= nchunks) return;
+    HufScratch* s = &scratch[warp];
+    const uint32_t clen = srcs ? srcs[chunk].clen : (uint32_t)min((uint64_t)CHUNK, n - (uint64_t)chunk * CHUNK);
+    const bool last = srcs ? srcs[chunk].last != 0 : (last_is_final && chunk == nchunks - 1);
+    const uint16_t* h = hist + (size_t)chunk * NSEG * NSYM;
+    uint32_t* mycodes = codes + (size_t)chunk * 2 * NSYM;
+    uint32_t* myhdr = hdr + (size_t)chunk * 2 * HDR_WORDS;
+    BlockDesc* d = desc + chunk;
+
+    const uint32_t nstored = (clen + 65534u) / 65535u;
+    // an empty input (batch compression only) still needs a block: stored is not an option, the fixed block wins (03 00)
+    const uint32_t stored_bytes = clen ? clen + 5u * nstored + (last ? 0u : SYNC_BYTES_ALIGNED) : 0xFFFFFFFFu;
+
+    if (level == 0 && clen) {
+        if (lane == 0) {
+            d->btype = 0; d->hdr_bits = 0; d->total_bits = 0; d->nbytes = stored_bytes; d->clen = clen;
+            d->last = last; d->eob = 0; d->index_bytes = 0; d->split_seg = 0;
+            sizes[chunk] = stored_bytes;
+        }
+        return;
+    }
+    const bool have_tokens = clen != 0;
+
+    // ---- one block for the whole chunk ---------------------------------------------------------------------
+    BlockPlan S = plan_block(s, h, 0, NSEG, have_tokens, lane);
+    // ---- or two?  (full chunks only: the cut is a segment boundary) -------------------------------------------
+    uint32_t split = 0;
+    bool scratch_is_S = true;                     // the scratch still holds the whole-chunk plan
+    BlockPlan A = S, B = S;
+    if (with_split && clen == CHUNK) {
+        const uint32_t cut = split_candidate(h, S.hdr_bits, lane);
+        if (cut) {
+            A = plan_block(s, h, 0, cut, true, lane);
+            B = plan_block(s, h, cut, NSEG, true, lane);
+            scratch_is_S = false;
+            if (A.bits + B.bits < S.bits) split = cut;
+        }
+    }
+    const uint32_t bits = split ? A.bits + B.bits : S.bits;
+    // full chunks carry the segment index (common.cuh) so that they can be inflated by 16 threads
+    // (only where it costs little: the chunk must save at least four times the index's size; never for a split chunk)
+    const uint32_t huff_plain = last ? (bits + 7) / 8 : (bits + 3 + 7) / 8 + (SYNC_BYTES_ALIGNED - 1);
+    const uint32_t index_bytes = (with_index && !split && clen == CHUNK && huff_plain + 4 * INDEX_BYTES <= stored_bytes) ? INDEX_BYTES : 0u;
+    const uint32_t huff_bytes = index_bytes + huff_plain;
+    const bool huffman = huff_bytes < stored_bytes;
+
+    if (!huffman) {
+        if (lane == 0) {
+            d->btype = 0; d->hdr_bits = 0; d->total_bits = 0; d->nbytes = stored_bytes; d->clen = clen;
+            d->last = last; d->eob = 0; d->index_bytes = 0; d->split_seg = 0;
+            sizes[chunk] = stored_bytes;
+        }
+        return;
+    }
+    // ---- emit: the scratch holds the LAST planned block, so each block is planned again right before it is written ----
+    uint32_t btype, off;
+    if (!split) {
+        if (!scratch_is_S) S = plan_block(s, h, 0, NSEG, have_tokens, lane);
+        btype = S.use_dyn ? 2u : 1u;
+        emit_block(s, S, btype, last, mycodes, myhdr, lane);
+        off = segment_offsets(s, h, btype, 0, NSEG, have_tokens, S.hdr_bits, d, lane);
+        if (lane == 0) {
+            const uint32_t eob_len = btype == 2 ? s->lens[256] : 7u;
+            d->btype = btype; d->hdr_bits = S.hdr_bits; d->total_bits = off + eob_len;
+            d->split_seg = 0; d->btype2 = 0; d->hdr_bits2 = 0; d->block2_bit = 0;
+        }
+    } else {
+        A = plan_block(s, h, 0, split, true, lane);
+        btype = A.use_dyn ? 2u : 1u;
+        emit_block(s, A, btype, false, mycodes, myhdr, lane);
+        off = segment_offsets(s, h, btype, 0, split, true, A.hdr_bits, d, lane);
+        const uint32_t eobA = btype == 2 ? s->lens[256] : 7u;
+        const uint32_t block2 = off + eobA;                    // first bit of the second block's header
+        B = plan_block(s, h, split, NSEG, true, lane);
+        const uint32_t btype2 = B.use_dyn ? 2u : 1u;
+        emit_block(s, B, btype2, last, mycodes + NSYM, myhdr + HDR_WORDS, lane);
+        off = segment_offsets(s, h, btype2, split, NSEG, true, block2 + B.hdr_bits, d, lane);
+        if (lane == 0) {
+            const uint32_t eobB = btype2 == 2 ? s->lens[256] : 7u;
+            d->btype = btype; d->hdr_bits = A.hdr_bits; d->total_bits = off + eobB;
+            d->split_seg = split; d->btype2 = btype2; d->hdr_bits2 = B.hdr_bits; d->block2_bit = block2;
+        }
+    }
     if (lane == 0) {
-        const uint32_t eob_len = btype == 2 ? s->lens[256] : 7u;
-        d->btype = btype;
-        d->hdr_bits = hb_final;
-        d->total_bits = btype ? off + eob_len : 0;
-        d->nbytes = btype ? huff_bytes : stored_bytes;
+        d->nbytes = huff_bytes;
         d->clen = clen;
         d->last = last;
-        d->index_bytes = btype ? index_bytes : 0;
-        d->eob = btype ? mycodes[256] : 0;   // written above by this warp (same-thread visibility not needed: recomputed by encoder)
-        sizes[chunk] = d->nbytes;
+        d->index_bytes = index_bytes;
+        d->eob = 0;
+        sizes[chunk] = huff_bytes;
     }
 }
 

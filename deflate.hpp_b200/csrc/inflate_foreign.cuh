@@ -41,10 +41,11 @@ namespace b200 {
 constexpr uint32_t FB_PIECE = 16384;                 // input bytes whose bit offsets one warp tests
 constexpr uint32_t FB_WARPS = 4;
 constexpr uint32_t FB_THREADS = FB_WARPS * 32;
-constexpr uint32_t FB_QUEUE = 96;                    // survivors per stage queue (flushed when >= 32 are waiting)
+constexpr uint32_t FB_QUEUE1 = 1024 + 64;            // stage-1 survivors of one sweep of 32 words (all 1024 offsets in the worst case)
+constexpr uint32_t FB_QUEUE = 96;                    // stage-2 survivors (flushed when >= 32 are waiting)
 constexpr uint32_t FB_HDR_MAX_BITS = 2400;           // 17 + 19 * 3 + 316 * (7 + 7) rounded up: no dynamic header is longer
 struct __align__(16) FbWarp {
-    uint32_t q1[FB_QUEUE], q2[FB_QUEUE];             // bit offsets relative to the piece
+    uint32_t q1[FB_QUEUE1], q2[FB_QUEUE];            // bit offsets relative to the piece
     uint8_t pre[128 * 32];                           // per-lane 7-bit precode table: entry e of lane l at [e * 32 + l]
 };
 
@@ -65,18 +66,15 @@ __device__ __forceinline__ uint32_t fb_bits32(const FbSrc& s, uint32_t q) {
     return __funnelshift_r(fb_word(s, i), fb_word(s, i + 1), q & 31);
 }
 
-// stage 2: the precode (HCLEN x 3 bits from bit 17) must be a complete prefix code
-__device__ __forceinline__ bool fb_precode_complete(const FbSrc& w, uint32_t q) {
-    const uint64_t h = fb_bits64(w, q);
-    const uint32_t hclen = ((uint32_t)(h >> 13) & 15u) + 4;
-    const uint64_t lo = h >> 17;                                   // 47 bits = 15 lengths
-    const uint32_t hi = fb_bits32(w, q + 62);                      // lengths 15..18
-    uint32_t kraft = 0;
-    #pragma unroll
-    for (uint32_t i = 0; i < 19; i++) {
-        const uint32_t l = i < 15 ? (uint32_t)(lo >> (3 * i)) & 7u : (hi >> (3 * (i - 15))) & 7u;
-        if (i < hclen && l) kraft += 128u >> l;
-    }
+// stage 2: the precode (HCLEN x 3 bits from bit 17) must be a complete prefix code: sum of 2^-len == 1.  The sum comes
+// from a table indexed by four lengths at a time (klut[i] = sum over the four 3-bit fields of i of 128 >> len, 0 for len 0).
+__device__ __forceinline__ bool fb_precode_complete(const FbSrc& w, uint32_t q, const uint16_t* __restrict__ klut) {
+    const uint32_t hclen = (fb_bits32(w, q + 13) & 15u) + 4;
+    uint64_t pb = fb_bits64(w, q + 17);
+    const uint32_t nb = 3 * hclen;                                 // 12 .. 57
+    pb &= (1ull << nb) - 1ull;
+    const uint32_t kraft = klut[(uint32_t)pb & 4095u] + klut[(uint32_t)(pb >> 12) & 4095u] + klut[(uint32_t)(pb >> 24) & 4095u] +
+                           klut[(uint32_t)(pb >> 36) & 4095u] + klut[(uint32_t)(pb >> 48) & 4095u];
     return kraft == 128u;
 }
 
@@ -152,6 +150,14 @@ __device__ bool fb_header_valid(const FbSrc& w, uint32_t q, uint8_t* pre /* this
 __global__ void __launch_bounds__(FB_THREADS)
 foreign_find_blocks_kernel(const uint8_t* __restrict__ in, uint64_t n, uint64_t npieces, unsigned long long* __restrict__ cand) {
     __shared__ FbWarp fb_warps[FB_WARPS];
+    __shared__ uint16_t klut[4096];
+    for (uint32_t i = threadIdx.x; i < 4096; i += FB_THREADS) {
+        uint32_t k = 0;
+        #pragma unroll
+        for (uint32_t f = 0; f < 4; f++) { const uint32_t l = (i >> (3 * f)) & 7u; k += l ? (128u >> l) : 0u; }
+        klut[i] = (uint16_t)k;
+    }
+    __syncthreads();
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint64_t p = (uint64_t)blockIdx.x * FB_WARPS + warp;
     if (p >= npieces) return;
@@ -197,38 +203,57 @@ foreign_find_blocks_kernel(const uint8_t* __restrict__ in, uint64_t n, uint64_t 
         n2 = rest;
         __syncwarp();
     };
-    auto drain1 = [&](uint32_t count) {          // stage 2 on the first `count` entries of q1
-        const bool have = lane < count;
-        const uint32_t q = have ? W->q1[lane] : 0;
-        const bool ok = have && q < best && fb_precode_complete(w, q + qoff);
-        const uint32_t m = __ballot_sync(FULL, ok);
-        if (ok) W->q2[n2 + __popc(m & ((1u << lane) - 1u))] = q;
-        n2 += __popc(m);
+    // Stage 1 is bit-parallel: a lane takes ONE word of the piece and tests its 32 bit offsets at once on a 64-bit window
+    // x (bit j of every term below speaks for the header that starts at bit j):
+    //   BFINAL = 0, BTYPE = 10      ~x & ~(x >> 1) & (x >> 2)
+    //   HLIT  <= 29  (bits 3..7)    not all of bits 4..7 set
+    //   HDIST <= 29  (bits 8..12)   not all of bits 9..12 set
+    // 1 offset in 9 survives; the survivors of 32 words are queued in offset order and go through stage 2, 32 at a time.
+    const uint32_t nwords_piece = (qoff + nbits + 31) >> 5;
+    for (uint32_t w0 = 0; w0 < nwords_piece; w0 += 32) {
+        if (best != 0xFFFFFFFFu && w0 * 32 > best + qoff) break;       // only the FIRST hit of the piece matters
+        const uint32_t wi = w0 + lane;
+        const uint64_t x = (uint64_t)fb_word(w, wi) | ((uint64_t)fb_word(w, wi + 1) << 32);
+        uint64_t m64 = ~x & ~(x >> 1) & (x >> 2);
+        m64 &= ~((x >> 4) & (x >> 5) & (x >> 6) & (x >> 7));
+        m64 &= ~((x >> 9) & (x >> 10) & (x >> 11) & (x >> 12));
+        uint32_t m = (uint32_t)m64;
+        // offsets of this word that lie inside [qoff, qoff + nbits)
+        const uint32_t lo = wi * 32, hi = lo + 32;
+        if (wi >= nwords_piece) m = 0;
+        else {
+            if (lo < qoff) m &= 0xFFFFFFFFu << (qoff - lo);
+            if (hi > qoff + nbits) m &= (qoff + nbits > lo) ? (0xFFFFFFFFu >> (hi - (qoff + nbits))) : 0u;
+        }
+        const uint32_t cnt = __popc(m);
+        uint32_t incl = cnt;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(FULL, incl, o);
+            if ((int)lane >= o) incl += u;
+        }
+        uint32_t slot = n1 + incl - cnt;
+        while (m) {
+            const uint32_t j = __ffs(m) - 1;
+            m &= m - 1;
+            W->q1[slot++] = lo + j - qoff;
+        }
+        n1 += __shfl_sync(FULL, incl, 31);
         __syncwarp();
-        const uint32_t rest = n1 - count;
-        uint32_t v = 0, v2 = 0;
-        if (lane < rest) v = W->q1[count + lane];
-        if (lane + 32 < rest) v2 = W->q1[count + lane + 32];
+        // stage 2 over everything queued (the queue is in offset order, so is what survives)
+        for (uint32_t r0 = 0; r0 < n1; r0 += 32) {
+            const bool have = r0 + lane < n1;
+            const uint32_t q = have ? W->q1[r0 + lane] : 0;
+            const bool ok = have && q < best && fb_precode_complete(w, q + qoff, klut);
+            const uint32_t mk = __ballot_sync(FULL, ok);
+            if (ok) W->q2[n2 + __popc(mk & ((1u << lane) - 1u))] = q;
+            n2 += __popc(mk);
+            __syncwarp();
+            if (n2 >= 32) drain2(32);
+        }
+        n1 = 0;
         __syncwarp();
-        if (lane < rest) W->q1[lane] = v;
-        if (lane + 32 < rest) W->q1[lane + 32] = v2;
-        n1 = rest;
-        __syncwarp();
-        if (n2 >= 32) drain2(32);
-    };
-    for (uint32_t b0 = 0; b0 < nbits; b0 += 32) {
-        if (b0 > best) break;                    // only the FIRST hit of the piece matters
-        const uint32_t q = b0 + lane;
-        const uint32_t h = fb_bits32(w, q + qoff);
-        // stage 1: BFINAL = 0, BTYPE = 10 (bits 1, 2 = 0, 1), HLIT <= 29, HDIST <= 29
-        const bool ok = q < nbits && (h & 7u) == 4u && ((h >> 3) & 31u) <= 29u && ((h >> 8) & 31u) <= 29u;
-        const uint32_t m = __ballot_sync(FULL, ok);
-        if (ok) W->q1[n1 + __popc(m & ((1u << lane) - 1u))] = q;
-        n1 += __popc(m);
-        __syncwarp();
-        if (n1 >= 32) drain1(32);
     }
-    while (n1) drain1(min(n1, 32u));
     while (n2) drain2(min(n2, 32u));
     if (lane == 0) cand[p] = best == 0xFFFFFFFFu ? ~0ull : (unsigned long long)(byte0 * 8 + best);
 }
@@ -329,19 +354,22 @@ __device__ __noinline__ void fd_block(FdState& s, uint16_t* lit, uint16_t* dst, 
     else if (tb_bitpos(br) >= stop_bit) { s.flags |= FU_REACHED; s.state = TS_DONE; }
 }
 
+// Persistent: the grid is one CTA per SM (the private tables fill the shared memory) and every THREAD pulls the next
+// unit from a global counter when it has finished one -- units differ a lot in length (a wave of fixed assignments takes
+// as long as its longest unit; measured: 2 waves x the longest = 18 ms, pulled from a queue in order of decreasing
+// compressed size = see DESIGN.md).  order[q] = unit taken by the q-th pull (NULL: q itself).
 template <bool EMIT>
 __global__ void __launch_bounds__(FD_THREADS)
 foreign_decode_kernel(const uint8_t* __restrict__ in, uint64_t n, const uint64_t* __restrict__ starts, const uint64_t* __restrict__ stops,
                       uint64_t nunits, FUnitRes* __restrict__ res, const uint64_t* __restrict__ out_base, const uint64_t* __restrict__ ops_base,
-                      uint16_t* __restrict__ S, uint64_t* __restrict__ ops_all, unsigned flags) {
+                      uint16_t* __restrict__ S, uint64_t* __restrict__ ops_all, unsigned flags, const uint32_t* __restrict__ order,
+                      unsigned long long* __restrict__ queue) {
     extern __shared__ __align__(16) uint8_t tp_smem[];
     __shared__ uint32_t s_ring[TB_RING * FD_THREADS];
     uint32_t* s_lut = reinterpret_cast<uint32_t*>(tp_smem);
     uint16_t* tabs = reinterpret_cast<uint16_t*>(tp_smem + TP_LUT_WORDS * 4);
     tp_lut_init(s_lut, threadIdx.x);
     __syncthreads();
-    const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = u < nunits;
     const uint32_t NT = blockDim.x;
     uint16_t* lit = tabs + threadIdx.x;
     uint16_t* dst = tabs + threadIdx.x + (size_t)(1u << TP_LIT_BITS) * NT;
@@ -357,29 +385,48 @@ foreign_decode_kernel(const uint8_t* __restrict__ in, uint64_t n, const uint64_t
     s.br.ring_stride = NT * 4;
     s.br.skip = (uint32_t)(reinterpret_cast<uintptr_t>(in) & 3);
     s.br.wp = reinterpret_cast<const uint32_t*>(in - s.br.skip);
-    s.br.nw = live ? (uint32_t)((s.br.skip + n + 3) >> 2) : 0;
+    s.br.nw = (uint32_t)((s.br.skip + n + 3) >> 2);
     s.br.wi = 0; s.br.w0 = 0; s.br.bb = 0; s.br.bc = 0;
     s.pos = 0; s.nops = 0; s.bfinal = 0; s.flags = 0; s.st = ST_OK;
-    s.state = live ? TS_BLOCK : TS_DONE;
-    uint64_t stop_bit = ~0ull, start_bit = 0;
+    s.state = TS_DONE;
+    uint64_t stop_bit = ~0ull, u = 0;
     uint16_t* Su = nullptr;
     uint64_t* ops = nullptr;
-    if (live) {
-        start_bit = starts[u];
-        stop_bit = stops[u];
-        tb_seek(s.br, start_bit >> 3);
-        tb_drop(s.br, (uint32_t)(start_bit & 7));
-        if (EMIT) { Su = S + out_base[u]; ops = ops_all + ops_base[u]; }
-    }
-    const bool first_unit = live && start_bit == 0;           // knows its absolute position: the too-far quirk is decided here
+    bool first_unit = false;                                  // the unit at bit 0 knows its absolute position: the too-far quirk is decided there
+    bool have = false, more = true;
     // A unit that started on a false candidate decodes garbage; it normally dies within a few thousand symbols (an
     // end-of-block turns up, what follows is no header), but nothing guarantees that: it may not read more than 1 MiB
     // past its stop offset (no real producer writes blocks that long; if one did, the stream goes to the sequential decoder)
     const uint32_t wi_end = s.br.nw + 4;
-    const uint64_t stop_word = stop_bit == ~0ull ? (uint64_t)wi_end : ((stop_bit + (uint64_t)s.br.skip * 8) >> 5) + (1u << 18);
-    const uint32_t wi_lim = (uint32_t)min((uint64_t)wi_end, stop_word);
+    uint32_t wi_lim = wi_end;
 
-    while (__any_sync(0xFFFFFFFFu, s.state != TS_DONE)) {
+    while (__any_sync(0xFFFFFFFFu, more)) {
+        if (s.state == TS_DONE) {
+            if (!more) continue;
+            if (have) {                                       // publish the unit that has just ended
+                asm volatile("cp.async.wait_all;" ::: "memory");
+                if (s.st == ST_OK && tb_bitpos(s.br) > in_bits) s.st = ST_OVERRUN;
+                FUnitRes r;
+                r.end_bit = tb_bitpos(s.br); r.out_len = s.pos; r.nops = s.nops; r.status = s.st; r.flags = s.flags; r.pad = 0;
+                res[u] = r;
+                have = false;
+            }
+            const unsigned long long q = atomicAdd(queue, 1ull);
+            if (q >= nunits) { more = false; continue; }
+            u = order ? order[q] : q;
+            const uint64_t start_bit = starts[u];
+            stop_bit = stops[u];
+            tb_seek(s.br, start_bit >> 3);
+            tb_drop(s.br, (uint32_t)(start_bit & 7));
+            if (EMIT) { Su = S + out_base[u]; ops = ops_all + ops_base[u]; }
+            first_unit = start_bit == 0;
+            const uint64_t stop_word = stop_bit == ~0ull ? (uint64_t)wi_end : ((stop_bit + (uint64_t)s.br.skip * 8) >> 5) + (1u << 18);
+            wi_lim = (uint32_t)min((uint64_t)wi_end, stop_word);
+            s.pos = 0; s.nops = 0; s.bfinal = 0; s.flags = 0; s.st = ST_OK;
+            s.state = TS_BLOCK;
+            have = true;
+            continue;
+        }
         if (s.state == TS_SYM) {
             TBits& br = s.br;
             if (s.pos > FD_MAX_OUT || br.wi > wi_lim) {
@@ -451,12 +498,7 @@ foreign_decode_kernel(const uint8_t* __restrict__ in, uint64_t n, const uint64_t
             fd_block<EMIT>(s, lit, dst, NT, T, n, in_bits, strict, stop_bit, Su, ops, in);
         }
     }
-    if (!live) return;
     asm volatile("cp.async.wait_all;" ::: "memory");
-    if (s.st == ST_OK && tb_bitpos(s.br) > in_bits) s.st = ST_OVERRUN;
-    FUnitRes r;
-    r.end_bit = tb_bitpos(s.br); r.out_len = s.pos; r.nops = s.nops; r.status = s.st; r.flags = s.flags; r.pad = 0;
-    res[u] = r;
 }
 
 // ---- F4: ops inside the symbol image, one warp per unit ----------------------------------------------------------

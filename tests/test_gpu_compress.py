@@ -198,3 +198,41 @@ def test_batch_compress(b200, oracle, level):
     with pytest.raises(b200.B200Error):                         # the capacity is checked against the worst case
         ctx.compress_batch_dev(d_in.data_ptr(), d_off.data_ptr(), d_len.data_ptr(), len(files), level, d_out.data_ptr(), cap - 1,
                                d_out_off.data_ptr())
+
+
+@pytest.mark.parametrize("level", [1, 2, 3])
+def test_block_split(b200, oracle, ref, level, monkeypatch):
+    """a chunk whose statistics change inside it is cut into two blocks with their own code
+    tables (the reference emits a block per 32 KB, deflate.hpp:692-749).  Chunks made of two different halves must come
+    out smaller than with one table, homogeneous chunks must not change, and every stream still decodes everywhere."""
+    import torch
+    import numpy as np
+    rng = np.random.default_rng(5)
+    halves = [datagen.text_like(32768, seed=1), bytes(rng.integers(0, 16, 32768, dtype=np.uint8) + 200),
+              datagen.image_like(49152), bytes(rng.integers(0, 4, 16384, dtype=np.uint8)),
+              bytes(rng.integers(0, 64, 16384, dtype=np.uint8)), datagen.text_like(49152, seed=3)]
+    mixed = b"".join(halves) * 3 + datagen.text_like(30000, seed=9)          # 9 full chunks + a partial one
+    plain = datagen.text_like(4 * 65536, seed=2)
+
+    def sizes(data):
+        out = {}
+        for env in ("0", "1"):
+            monkeypatch.setenv("B200_NO_SPLIT", env)
+            ctx = b200.Context(0)
+            src = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
+            cap = b200.deflate_bound(len(data))
+            dst = torch.empty(cap, dtype=torch.uint8, device="cuda")
+            n = ctx.compress_dev(src.data_ptr(), len(data), level, dst.data_ptr(), cap)
+            c = bytes(dst[:n].cpu().numpy())
+            check_stream(c, data, oracle)
+            assert b200.decompress(c) == data
+            got, r_out = ref.inflate(c)
+            assert got == len(data) and r_out == data
+            out[env] = (n, c)
+            ctx.close()
+        monkeypatch.delenv("B200_NO_SPLIT")
+        return out
+    m = sizes(mixed)
+    assert m["0"][0] < 0.97 * m["1"][0], (m["0"][0], m["1"][0])          # two tables pay off on these chunks
+    p = sizes(plain)
+    assert p["0"][1] == p["1"][1]                                         # nothing to gain: byte-identical to the unsplit stream

@@ -11,7 +11,7 @@ for step in "$@"; do
       # one process per file, each under its own timeout: a hang costs one file, not the session; slowest tests are listed
       for f in ${PYTEST_FILES:-tests/test_gpu_misc.py tests/test_gpu_compress.py tests/test_gpu_inflate.py tests/test_gpu_foreign.py tests/test_gpu_framing.py tests/test_gpu_fuzz.py tests/test_gpu_configs.py}; do
         echo "=== $f $(date +%T)" >> $out/${tag}_pytest.log
-        timeout ${PYTEST_TIMEOUT:-600} python -m pytest $f -m gpu --maxfail=8 -v --durations=6 -o faulthandler_timeout=150 >> $out/${tag}_pytest.log 2>&1; echo "exit $? $(date +%T)" >> $out/${tag}_pytest.log
+        timeout ${PYTEST_TIMEOUT:-600} python -m pytest $f -m gpu -k "${PYTEST_K:-test}" --maxfail=8 -v --durations=6 -o faulthandler_timeout=150 >> $out/${tag}_pytest.log 2>&1; echo "exit $? $(date +%T)" >> $out/${tag}_pytest.log
       done ;;
     bench)
       timeout 900 python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err; echo "bench exit $?" >> $out/${tag}_bench.err ;;
@@ -28,6 +28,23 @@ for step in "$@"; do
       timeout 1500 compute-sanitizer --tool racecheck --log-file $out/${tag}_racecheck.log python -m pytest tests -m gpu -x -q -k "${SAN_K:-edge or fixture or quirk or fuzz}" > $out/${tag}_racecheck_pytest.log 2>&1 ;;
     probe)
       timeout 1200 python tools/probe_r02.py ${PROBE_ARGS} > $out/${tag}_probe.log 2>&1 ;;
+    probe_e2e)
+      for slice in 67108864 134217728 268435456; do
+        B200_HOST_INFLATE_SLICE=$slice timeout 300 python tools/probe_e2e.py >> $out/${tag}_probe_e2e.log 2>&1
+      done
+      B200_STAGE=0 timeout 300 python tools/probe_e2e.py >> $out/${tag}_probe_e2e.log 2>&1
+      B200_STAGE_THREADS=4 timeout 300 python tools/probe_e2e.py >> $out/${tag}_probe_e2e.log 2>&1
+      B200_STAGE_THREADS=16 timeout 300 python tools/probe_e2e.py >> $out/${tag}_probe_e2e.log 2>&1 ;;
+    bisect)
+      for k in 0 1 2 3 4 5 6 7; do
+        for mode in par seq; do
+          echo "--- long case $k $mode" >> $out/${tag}_bisect.log
+          if [ $mode = seq ]; then export B200_NO_FOREIGN_PARALLEL=1; else unset B200_NO_FOREIGN_PARALLEL; fi
+          B200_DEBUG=1 timeout 40 python tools/long_case.py $k >> $out/${tag}_bisect.log 2>&1; echo "exit $?" >> $out/${tag}_bisect.log
+        done
+      done
+      unset B200_NO_FOREIGN_PARALLEL
+      timeout 600 python tools/fuzz_bisect.py >> $out/${tag}_bisect.log 2>&1; echo "exit $?" >> $out/${tag}_bisect.log ;;
     *) echo "unknown step $step" ;;
   esac
 done
