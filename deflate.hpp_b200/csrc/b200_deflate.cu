@@ -146,7 +146,10 @@ struct b200_ctx {
     int device = 0;
     bool attrs_set = false;
     uint32_t batch_chunks = 4096;
-    uint32_t better_depth = 8, better_nice = 32;   // "better" level: chain depth / good-enough length
+    // "better" level: chain depth / good-enough length.  0 = by input size: small inputs (< 1 MiB, where the time does not
+    // matter) search like the reference does -- its level 3 looks at EVERY earlier position (deflate.hpp:280-296), and on
+    // test.bmp that is worth 5 % -- large ones use 8 / 32 (the depth sweep in profiles/: 6.6 -> 18 GB/s for +0.4 % size)
+    uint32_t better_depth = 0, better_nice = 0;
     // compress scratch
     Buf tok, ntok, hist, codes, hdr, desc, sizes, offsets, total;
     // inflate scratch
@@ -155,6 +158,8 @@ struct b200_ctx {
     bool size_probe = false;                  // set by inflate_host while it does not know the decoded size yet
     size_t foreign_min = (size_t)256 << 10;   // streams shorter than this stay with the one-warp decoder (B200_FOREIGN_MIN)
     uint32_t foreign_group = 0;               // units per window-propagation group (0 = auto); B200_FOREIGN_GROUP
+    int foreign_tab = 0;                      // decode-kernel variant (inflate_foreign.cuh): 0 = 9/8-bit tables x 128 threads per SM,
+                                              // 1 = 8/7 x 256, 2 = 8/6 x 320, 3 = 7/6 x 448; B200_FOREIGN_TAB
     std::vector<cudaEvent_t> group_events;
     cudaStream_t s_side = nullptr;   // inflate: copy pass of group g while group g + 1 is in pass A
     uint64_t inflate_group_chunks = 0;   // 0 = auto (32768 chunks); B200_INFLATE_GROUP
@@ -217,8 +222,11 @@ int set_attrs(b200_ctx* c) {
     CK(cudaFuncSetAttribute(inflate_segments_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM_BYTES + 65536));
     CK(cudaFuncSetAttribute(inflate_segments_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM_BYTES));
     CK(cudaFuncSetAttribute(inflate_symbols_kernel<BatchUnits>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM_BYTES));
-    CK(cudaFuncSetAttribute(foreign_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM_BYTES));
-    CK(cudaFuncSetAttribute(foreign_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM_BYTES));
+#define FD_ATTR(LB, DB, NTH)                                                                                                    \
+    CK(cudaFuncSetAttribute(foreign_decode_kernel<false, LB, DB, NTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fd_smem_bytes(LB, DB, NTH))); \
+    CK(cudaFuncSetAttribute(foreign_decode_kernel<true, LB, DB, NTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fd_smem_bytes(LB, DB, NTH)));
+    FD_ATTR(9, 8, 128) FD_ATTR(8, 7, 256) FD_ATTR(8, 6, 320) FD_ATTR(7, 6, 448)
+#undef FD_ATTR
     CK(cudaFuncSetAttribute(foreign_window_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FW_SMEM_BYTES));
     CK(cudaFuncSetAttribute(foreign_window_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FW_SMEM_BYTES));
     CK(cudaFuncSetAttribute(foreign_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FW_SMEM_BYTES));
@@ -434,6 +442,7 @@ int b200_ctx_create(int device, b200_ctx** ctx) {
     if (const char* e = getenv("B200_INFLATE_WARP")) c->inflate_warp_path = atoi(e) != 0;
     if (const char* e = getenv("B200_FOREIGN_MIN")) { long long v = atoll(e); if (v >= 0) c->foreign_min = (size_t)v; }
     if (const char* e = getenv("B200_FOREIGN_GROUP")) { int v = atoi(e); if (v > 0) c->foreign_group = (uint32_t)v; }
+    if (const char* e = getenv("B200_FOREIGN_TAB")) { int v = atoi(e); if (v >= 0 && v <= 3) c->foreign_tab = v; }
     if (const char* e = getenv("B200_STAGE")) c->stage_pageable = atoi(e) != 0;
     if (const char* e = getenv("B200_STAGE_THREADS")) c->stg_threads = atoi(e);
     if (const char* e = getenv("B200_FILE_SLICE")) { long long v = atoll(e); if (v >= (long long)CHUNK) c->file_slice = (size_t)v / CHUNK * CHUNK; }
@@ -536,9 +545,14 @@ static int compress_batch(b200_ctx* c, const uint8_t* bin, uint64_t bn, uint32_t
     }
     if (level >= 1) {
         PROF_BEGIN(c, K_LZ77, st);
-        if (level == 3)
+        if (level == 3) {
+            const uint64_t total_hint = srcs ? (uint64_t)nb * CHUNK : b0 * CHUNK + bn;      // bytes of the whole input
+            const bool small = total_hint < ((uint64_t)1 << 20);
+            const uint32_t depth = c->better_depth ? c->better_depth : (small ? 128u : 8u);
+            const uint32_t nice = c->better_nice ? c->better_nice : (small ? 258u : 32u);
             lz77_better_kernel<<<nb, LZB_THREADS, LZB_SMEM_BYTES, st>>>(bin, bn, (uint32_t*)c->tok.p, (uint32_t*)c->ntok.p,
-                                                                     (uint16_t*)c->hist.p, c->better_depth, c->better_nice, srcs);
+                                                                     (uint16_t*)c->hist.p, depth, nice, srcs);
+        }
         else if (level == 2) {
             const uint32_t grid = nb < c->lzf_grid ? nb : c->lzf_grid;
             lz77_fast_kernel<<<grid, LZF_THREADS, LZF_SMEM_BYTES, st>>>(bin, bn, nb, (uint32_t*)c->tok.p, (uint32_t*)c->ntok.p,
@@ -955,6 +969,28 @@ static int inflate_chunked(b200_ctx* c, const uint8_t* in, uint64_t n, uint64_t 
 static int inflate_foreign(b200_ctx* c, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t cap, unsigned flags, cudaStream_t st,
                            bool* done, uint64_t* full);
 
+// foreign_decode_kernel in the table-width / CTA-size variant the context asks for (c->foreign_tab, B200_FOREIGN_TAB)
+extern "C++" {
+template <bool EMIT>
+static void launch_foreign_decode(b200_ctx* c, cudaStream_t st, const uint8_t* in, uint64_t n, const uint64_t* starts, const uint64_t* stops,
+                                  uint64_t nunits, FUnitRes* res, const uint64_t* out_base, const uint64_t* ops_base, uint16_t* S, uint64_t* ops,
+                                  unsigned flags, const uint32_t* order, unsigned long long* queue) {
+#define FD_LAUNCH(LB, DB, NTH)                                                                                                       \
+    {                                                                                                                                \
+        const uint64_t want = (nunits + NTH - 1) / NTH;                                                                              \
+        foreign_decode_kernel<EMIT, LB, DB, NTH><<<(uint32_t)(want < c->num_sms ? want : c->num_sms), NTH, fd_smem_bytes(LB, DB, NTH), st>>>( \
+            in, n, starts, stops, nunits, res, out_base, ops_base, S, ops, flags, order, queue);                                     \
+    }
+    switch (c->foreign_tab) {
+        case 0: FD_LAUNCH(9, 8, 128) break;
+        case 2: FD_LAUNCH(8, 6, 320) break;
+        case 3: FD_LAUNCH(7, 6, 448) break;
+        default: FD_LAUNCH(8, 7, 256) break;
+    }
+#undef FD_LAUNCH
+}
+}  // extern "C++"
+
 // Single stream.  Synchronizes `stream` internally (the candidate count and the validation verdict
 // steer the launches).
 int b200_inflate_dev(b200_ctx* c, const void* d_in, size_t n, void* d_out, size_t cap, uint64_t* d_out_n,
@@ -1078,11 +1114,9 @@ static int inflate_foreign(b200_ctx* c, const uint8_t* in, uint64_t n, uint8_t* 
             CK(cudaMemcpyAsync(c->f_stops.p, hp.data(), m * 8, cudaMemcpyHostToDevice, st));
             CK(cudaMemcpyAsync(c->f_order.p, order.data(), m * 4, cudaMemcpyHostToDevice, st));
             CK(cudaMemsetAsync(c->f_misc.p, 0, 256, st));
-            const uint64_t want_ctas = (m + FD_THREADS - 1) / FD_THREADS;
             PROF_BEGIN(c, K_F_COUNT, st);
-            foreign_decode_kernel<false><<<(uint32_t)(want_ctas < c->num_sms ? want_ctas : c->num_sms), FD_THREADS, TP_SMEM_BYTES, st>>>(
-                in, n, (const uint64_t*)c->f_starts.p, (const uint64_t*)c->f_stops.p, m, (FUnitRes*)c->f_res.p, nullptr, nullptr, nullptr, nullptr, flags,
-                (const uint32_t*)c->f_order.p, (unsigned long long*)c->f_misc.p + 16);
+            launch_foreign_decode<false>(c, st, in, n, (const uint64_t*)c->f_starts.p, (const uint64_t*)c->f_stops.p, m, (FUnitRes*)c->f_res.p, nullptr,
+                                         nullptr, nullptr, nullptr, flags, (const uint32_t*)c->f_order.p, (unsigned long long*)c->f_misc.p + 16);
             LAUNCHED();
             PROF_END(c, st);
             std::vector<FUnitRes> hr(m);
@@ -1173,11 +1207,9 @@ static int inflate_foreign(b200_ctx* c, const uint8_t* in, uint64_t n, uint8_t* 
         });
         if ((rc = c->f_order.ensure(nu * 4))) return B200_OK;
         CK(cudaMemcpyAsync(c->f_order.p, order.data(), nu * 4, cudaMemcpyHostToDevice, st));
-        const uint64_t want_ctas = (nu + FD_THREADS - 1) / FD_THREADS;
         PROF_BEGIN(c, K_F_EMIT, st);
-        foreign_decode_kernel<true><<<(uint32_t)(want_ctas < c->num_sms ? want_ctas : c->num_sms), FD_THREADS, TP_SMEM_BYTES, st>>>(
-            in, n, (const uint64_t*)c->f_starts.p, (const uint64_t*)c->f_stops.p, nu, (FUnitRes*)c->f_res.p, d_base,
-            (const uint64_t*)c->f_opsbase.p, S, (uint64_t*)c->f_ops.p, flags, (const uint32_t*)c->f_order.p, d_counter + 17);
+        launch_foreign_decode<true>(c, st, in, n, (const uint64_t*)c->f_starts.p, (const uint64_t*)c->f_stops.p, nu, (FUnitRes*)c->f_res.p, d_base,
+                                    (const uint64_t*)c->f_opsbase.p, S, (uint64_t*)c->f_ops.p, flags, (const uint32_t*)c->f_order.p, d_counter + 17);
         LAUNCHED();
         PROF_END(c, st);
         CK(cudaStreamSynchronize(st));            // `order` lives on this stack frame

@@ -374,9 +374,13 @@ __device__ __noinline__ uint32_t segment_offsets(HufScratch* s, const uint16_t* 
 // be cut at a segment boundary into TWO blocks with their own code tables when the statistics change inside it.  Cost
 // model: the zero-order entropy of the literal/length + distance histograms (already in HBM per 4 KiB segment) of the
 // two sides against the whole, for the cuts at 16, 32 and 48 KiB; the best cut is taken to the exact stage -- both
-// blocks are planned for real -- only if the estimate beats the price of a second header by a margin, and is used only
-// if the exact bit count is smaller.  A split chunk carries no segment index (it is decoded by the one-warp decoder).
-__device__ __noinline__ uint32_t split_candidate(const uint16_t* __restrict__ h, uint32_t hdr_bits, uint32_t lane) {
+// blocks are planned for real -- only if the estimate beats the price of a second header plus SPLIT_MARGIN of the chunk,
+// and is used only if the exact bit count is smaller by that margin.  The margin is what the segment index is worth: a
+// split chunk carries none (two code tables per chunk do not fit pass A's per-chunk table slot) and is inflated by the
+// one-warp decoder, ~10x slower than an indexed chunk -- so drifting statistics (a few hundred bytes to gain) do not
+// split, a boundary between two kinds of content (tar members, the halves in tests/test_gpu_compress.py) does.
+constexpr uint32_t SPLIT_MARGIN_SHIFT = 5;       // 1/32 of the one-block size (3 %)
+__device__ __noinline__ uint32_t split_candidate(const uint16_t* __restrict__ h, uint32_t hdr_bits, uint32_t one_block_bits, uint32_t lane) {
     float gain[3] = {0.f, 0.f, 0.f};
     uint32_t nA[3][2] = {{0, 0}, {0, 0}, {0, 0}}, nS[2] = {0, 0};
     // per-lane symbols: counts left of each cut and in total
@@ -425,8 +429,8 @@ __device__ __noinline__ uint32_t split_candidate(const uint16_t* __restrict__ h,
         for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(0xFFFFFFFFu, g, o);
         if (g > bestg) { bestg = g; best = 4 * (c + 1); }
     }
-    // worth the exact stage only if the ideal-code saving pays a second header twice over
-    return bestg > 2.0f * (float)hdr_bits + 256.f ? best : 0u;
+    // worth the exact stage only if the ideal-code saving pays a second header and the margin
+    return bestg > (float)hdr_bits + 256.f + (float)(one_block_bits >> SPLIT_MARGIN_SHIFT) ? best : 0u;
 }
 
 // grid = ceil(nchunks / HUF_WARPS), block = 128.
@@ -472,12 +476,12 @@ huffman_kernel(const uint16_t* __restrict__ hist, uint64_t n, uint32_t nchunks, 
     bool scratch_is_S = true;                     // the scratch still holds the whole-chunk plan
     BlockPlan A = S, B = S;
     if (with_split && clen == CHUNK) {
-        const uint32_t cut = split_candidate(h, S.hdr_bits, lane);
+        const uint32_t cut = split_candidate(h, S.hdr_bits, S.bits, lane);
         if (cut) {
             A = plan_block(s, h, 0, cut, true, lane);
             B = plan_block(s, h, cut, NSEG, true, lane);
             scratch_is_S = false;
-            if (A.bits + B.bits < S.bits) split = cut;
+            if (A.bits + B.bits + (S.bits >> SPLIT_MARGIN_SHIFT) < S.bits) split = cut;
         }
     }
     const uint32_t bits = split ? A.bits + B.bits : S.bits;

@@ -447,7 +447,16 @@ __device__ int inflate_warp(InfWarp* S, const ModLut* ML, const uint8_t* in, uin
                 const uint32_t ne = (e >> 20) & 15u;
                 const uint32_t length = ((e >> 8) & 0x1FFu) + br_peek(br, ne);
                 br_drop(br, ne);
-                br_need32(S, br, lane);
+                if (br.bc < 32) {
+                    // the same refill AND the same limit checks as at the top of the loop: a run of back-references with
+                    // short codes (e.g. the zero bits behind a truncated stream) refills only here, never up there
+                    br.bb |= (uint64_t)S->ring[br.wi & (RING_WORDS - 1)] << br.bc;
+                    br.bc += 32;
+                    br.wi++;
+                    if ((br.wi & 127) == 0) ring_fill(S, br, (br.wi >> 7) + 1, lane);
+                    if (br.wi > wi_limit || op > max_out) break;        // resolved after the loop
+                    if (op >= REBASE) rebase();
+                }
                 uint32_t de = S->dst[br_peek(br, DST_BITS)];
                 uint32_t dl = de & 15u;
                 if (((de >> 4) & 3u) == K_LONG) {

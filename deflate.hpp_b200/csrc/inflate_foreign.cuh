@@ -259,7 +259,11 @@ foreign_find_blocks_kernel(const uint8_t* __restrict__ in, uint64_t n, uint64_t 
 }
 
 // ---- F2 / F3: one thread per unit ---------------------------------------------------------------------------
-constexpr uint32_t FD_THREADS = TP_THREADS;                       // 128 threads, private interleaved tables (TP_SMEM_BYTES)
+// Threads per CTA x table widths: every thread owns private, interleaved u16 tables in shared memory, so the table size
+// decides how many threads (= units in flight) an SM holds.  The decode is a chain of dependent shared-memory lookups:
+// with 4 warps per SM every one of its latencies is exposed.  Smaller tables send more (rarer) codes through the
+// canonical search in tp_slow_symbol, more threads hide more latency; variants are measured in DESIGN.md.
+constexpr uint32_t fd_smem_bytes(uint32_t lb, uint32_t db, uint32_t nth) { return ((1u << lb) + (1u << db)) * 2u * nth + TP_LUT_WORDS * 4u; }
 constexpr uint32_t FU_FINAL = 1;                                  // the unit ended with a BFINAL block
 constexpr uint32_t FU_REACHED = 2;                                // ... at a block end at or behind its stop offset
 struct FUnitRes { uint64_t end_bit; uint64_t out_len; uint32_t nops; int32_t status; uint32_t flags; uint32_t pad; };
@@ -276,7 +280,9 @@ struct FdState {
 };
 
 // One block header (single thread): stored blocks become ops, Huffman blocks get their tables built.
-template <bool EMIT>
+// LB / DB: index widths of the thread's private literal/length and distance tables (the 7-bit precode table borrows the
+// literal table's space, which is not built yet when it is needed).
+template <bool EMIT, uint32_t LB, uint32_t DB>
 __device__ __noinline__ void fd_block(FdState& s, uint16_t* lit, uint16_t* dst, uint32_t NT, TpTables& T, uint64_t in_len, uint64_t in_bits,
                                       bool strict, uint64_t stop_bit, uint16_t* S, uint64_t* ops, const uint8_t* in) {
     TBits& br = s.br;
@@ -318,13 +324,14 @@ __device__ __noinline__ void fd_block(FdState& s, uint16_t* lit, uint16_t* dst, 
                 tb_refill(br);
                 pl[C_PRECODE_ORDER[i]] = (uint8_t)tb_get(br, 3);
             }
-            if (!tp_build(dst, NT, T, pl, 19, 1, 7, false)) { s.st = ST_DATA; s.state = TS_DONE; return; }
+            static_assert(LB >= 7, "the precode table needs 128 entries");
+            if (!tp_build(lit, NT, T, pl, 19, 1, 7, false)) { s.st = ST_DATA; s.state = TS_DONE; return; }
             const uint32_t total = hlit + hdist;
             uint32_t i = 0, prev = 0;
             #pragma unroll 1
             while (i < total) {
                 tb_refill(br);
-                const uint32_t e = dst[tb_peek(br, 7) * NT];
+                const uint32_t e = lit[tb_peek(br, 7) * NT];
                 const uint32_t l = e & 15u, sym = e >> 4;
                 if (l == 0) { s.st = ST_OVERRUN; s.state = TS_DONE; return; }
                 tb_drop(br, l);
@@ -343,8 +350,8 @@ __device__ __noinline__ void fd_block(FdState& s, uint16_t* lit, uint16_t* dst, 
             }
             if (T.lens[256] == 0) { s.st = ST_DATA; s.state = TS_DONE; return; }
         }
-        if (!tp_build(lit, NT, T, T.lens, hlit, 0, TP_LIT_BITS, true)) { s.st = ST_DATA; s.state = TS_DONE; return; }
-        if (!tp_build(dst, NT, T, T.lens + NLIT, hdist, 1, TP_DST_BITS, false)) { s.st = ST_DATA; s.state = TS_DONE; return; }
+        if (!tp_build(lit, NT, T, T.lens, hlit, 0, LB, true)) { s.st = ST_DATA; s.state = TS_DONE; return; }
+        if (!tp_build(dst, NT, T, T.lens + NLIT, hdist, 1, DB, false)) { s.st = ST_DATA; s.state = TS_DONE; return; }
         s.state = TS_SYM;
         return;
     }
@@ -358,21 +365,21 @@ __device__ __noinline__ void fd_block(FdState& s, uint16_t* lit, uint16_t* dst, 
 // unit from a global counter when it has finished one -- units differ a lot in length (a wave of fixed assignments takes
 // as long as its longest unit; measured: 2 waves x the longest = 18 ms, pulled from a queue in order of decreasing
 // compressed size = see DESIGN.md).  order[q] = unit taken by the q-th pull (NULL: q itself).
-template <bool EMIT>
-__global__ void __launch_bounds__(FD_THREADS)
+template <bool EMIT, uint32_t LB, uint32_t DB, uint32_t NTH>
+__global__ void __launch_bounds__(NTH)
 foreign_decode_kernel(const uint8_t* __restrict__ in, uint64_t n, const uint64_t* __restrict__ starts, const uint64_t* __restrict__ stops,
                       uint64_t nunits, FUnitRes* __restrict__ res, const uint64_t* __restrict__ out_base, const uint64_t* __restrict__ ops_base,
                       uint16_t* __restrict__ S, uint64_t* __restrict__ ops_all, unsigned flags, const uint32_t* __restrict__ order,
                       unsigned long long* __restrict__ queue) {
     extern __shared__ __align__(16) uint8_t tp_smem[];
-    __shared__ uint32_t s_ring[TB_RING * FD_THREADS];
+    __shared__ uint32_t s_ring[TB_RING * NTH];
     uint32_t* s_lut = reinterpret_cast<uint32_t*>(tp_smem);
     uint16_t* tabs = reinterpret_cast<uint16_t*>(tp_smem + TP_LUT_WORDS * 4);
     tp_lut_init(s_lut, threadIdx.x);
     __syncthreads();
     const uint32_t NT = blockDim.x;
     uint16_t* lit = tabs + threadIdx.x;
-    uint16_t* dst = tabs + threadIdx.x + (size_t)(1u << TP_LIT_BITS) * NT;
+    uint16_t* dst = tabs + threadIdx.x + (size_t)(1u << LB) * NT;
     const uint32_t lit_sa = (uint32_t)__cvta_generic_to_shared(lit);
     const uint32_t dst_sa = (uint32_t)__cvta_generic_to_shared(dst);
     const uint32_t lut_sa = (uint32_t)__cvta_generic_to_shared(s_lut);
@@ -433,10 +440,10 @@ foreign_decode_kernel(const uint8_t* __restrict__ in, uint64_t n, const uint64_t
                 s.st = br.wi > wi_end ? ST_OVERRUN : ST_FALLBACK; s.state = TS_DONE;
             } else {
                 if (br.bc < 33) tb_take(br);
-                uint32_t e = lds_u16(lit_sa + tb_peek(br, TP_LIT_BITS) * ntb);
+                uint32_t e = lds_u16(lit_sa + tb_peek(br, LB) * ntb);
                 bool ok = true;
                 if ((e & 15u) == 0) {
-                    const int r = tp_slow_symbol(T, 0, (uint32_t)br.bb, TP_LIT_BITS + 1);
+                    const int r = tp_slow_symbol(T, 0, (uint32_t)br.bb, LB + 1);
                     if (r < 0) { s.st = ST_OVERRUN; s.state = TS_DONE; ok = false; }
                     else e = tp_lit_entry((uint32_t)r & 0xFFFFu, (uint32_t)r >> 16);
                 }
@@ -449,7 +456,7 @@ foreign_decode_kernel(const uint8_t* __restrict__ in, uint64_t n, const uint64_t
                     #pragma unroll
                     for (uint32_t k = 0; k < TP_LIT_RUN; k++) {
                         if (k) tb_refill(br);
-                        const uint32_t e2 = lds_u16(lit_sa + tb_peek(br, TP_LIT_BITS) * ntb);
+                        const uint32_t e2 = lds_u16(lit_sa + tb_peek(br, LB) * ntb);
                         const uint32_t l2 = e2 & 15u, p2 = e2 >> 4;
                         if (l2 == 0) break;
                         if (p2 < 256) { tb_drop(br, l2); if (EMIT) Su[s.pos] = (uint16_t)p2; s.pos++; continue; }
@@ -462,10 +469,10 @@ foreign_decode_kernel(const uint8_t* __restrict__ in, uint64_t n, const uint64_t
                     const uint32_t lt = lds_u32(lut_sa + (p & 31u) * 4);
                     const uint32_t length = (lt & 0xFFFFu) + tb_get(br, lt >> 16);
                     tb_refill(br);
-                    const uint32_t de = lds_u16(dst_sa + tb_peek(br, TP_DST_BITS) * ntb);
+                    const uint32_t de = lds_u16(dst_sa + tb_peek(br, DB) * ntb);
                     uint32_t dl = de & 15u, dsym = de >> 4;
                     if (dl == 0) {
-                        const int r = tp_slow_symbol(T, 1, (uint32_t)br.bb, TP_DST_BITS + 1);
+                        const int r = tp_slow_symbol(T, 1, (uint32_t)br.bb, DB + 1);
                         dsym = r < 0 ? 99u : ((uint32_t)r & 0xFFFFu);
                         dl = r < 0 ? 0u : ((uint32_t)r >> 16);
                     }
@@ -495,7 +502,7 @@ foreign_decode_kernel(const uint8_t* __restrict__ in, uint64_t n, const uint64_t
                 }
             }
         } else if (s.state == TS_BLOCK) {
-            fd_block<EMIT>(s, lit, dst, NT, T, n, in_bits, strict, stop_bit, Su, ops, in);
+            fd_block<EMIT, LB, DB>(s, lit, dst, NT, T, n, in_bits, strict, stop_bit, Su, ops, in);
         }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");

@@ -68,6 +68,26 @@ def test_foreign_parallel_vs_zlib(b200, oracle, producer, monkeypatch):
         assert rc == 0 and o == data
 
 
+@pytest.mark.parametrize("tab", [0, 1, 2, 3])
+def test_foreign_table_variants(b200, tab, monkeypatch):
+    """every table-width / CTA-size variant of the decode kernels (B200_FOREIGN_TAB) gives the same bytes: text (long
+    literal codes -> the canonical search behind the direct table), image-like data and a Huffman-only stream"""
+    import torch
+    monkeypatch.setenv("B200_FOREIGN_TAB", str(tab))
+    ctx = b200.Context(0)
+    data = mixed(5_000_000, seed=21)
+    for stream in (raw(data, 6), raw(data, 9, zlib.Z_FILTERED), raw(data[:2_000_000], 6, zlib.Z_HUFFMAN_ONLY)):
+        want = zlib.decompressobj(-15).decompress(stream)
+        comp = torch.frombuffer(bytearray(stream), dtype=torch.uint8).cuda()
+        out = torch.zeros(len(want) + 64, dtype=torch.uint8, device="cuda")
+        ctx.profile(True)
+        w, full = ctx.inflate_dev(comp.data_ptr(), comp.numel(), out.data_ptr(), len(want) + 64)
+        ctx.profile(False)
+        assert "foreign_decode_kernel<emit>" in ctx.profile_read()
+        assert w == full == len(want) and bytes(out[:w].cpu().numpy()) == want
+    ctx.close()
+
+
 def test_foreign_parallel_is_taken(b200):
     """the block-parallel kernels really run for a long zlib stream (and not for a short one)"""
     import torch

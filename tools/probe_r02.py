@@ -78,7 +78,7 @@ if "foreign" in want:
     print("zlib-6 stream", len(stream), "bytes in", round(time.time() - t0, 1), "s", flush=True)
     import numpy as np
     comp = torch.from_numpy(np.frombuffer(stream, dtype=np.uint8).copy()).to(dev)
-    for env in ({},):
+    for env in ({"B200_FOREIGN_TAB": 0}, {"B200_FOREIGN_TAB": 1}, {"B200_FOREIGN_TAB": 2}, {"B200_FOREIGN_TAB": 3}):
         ctx = with_env(env)
         ms, (w, full) = timed(lambda: ctx.inflate_dev(comp.data_ptr(), comp.numel(), back.data_ptr(), n), 3)
         ctx.profile(True)
