@@ -145,7 +145,8 @@ struct Buf {
 struct b200_ctx {
     int device = 0;
     bool attrs_set = false;
-    uint32_t batch_chunks = 4096;
+    uint32_t batch_chunks = 16384;   // chunks per compress batch (B200_BATCH_CHUNKS): 1 GiB of input, 4.4 GiB of scratch -- measured 4096 /
+                                     // 8192 / 16384: 80.0 / 82.5 / 83.9 GB/s (fewer tails of the persistent matcher, fewer launches)
     // "better" level: chain depth / good-enough length.  0 = by input size: small inputs (< 1 MiB, where the time does not
     // matter) search like the reference does -- its level 3 looks at EVERY earlier position (deflate.hpp:280-296), and on
     // test.bmp that is worth 5 % -- large ones use 8 / 32 (the depth sweep in profiles/: 6.6 -> 18 GB/s for +0.4 % size)
@@ -262,7 +263,7 @@ __global__ void batch_srcs_kernel(const uint64_t* __restrict__ in_off, const uin
         ChunkSrc s;
         s.off = off + j * CHUNK;
         s.clen = (uint32_t)(len - j * CHUNK < CHUNK ? len - j * CHUNK : CHUNK);
-        s.last = j + 1 == k;
+        s.last = (j + 1 == k ? 1u : 0u) | (len < SMALL_INPUT_BYTES ? 2u : 0u);
         srcs[c0 + j] = s;
     }
 }
@@ -546,12 +547,12 @@ static int compress_batch(b200_ctx* c, const uint8_t* bin, uint64_t bn, uint32_t
     if (level >= 1) {
         PROF_BEGIN(c, K_LZ77, st);
         if (level == 3) {
-            const uint64_t total_hint = srcs ? (uint64_t)nb * CHUNK : b0 * CHUNK + bn;      // bytes of the whole input
-            const bool small = total_hint < ((uint64_t)1 << 20);
-            const uint32_t depth = c->better_depth ? c->better_depth : (small ? 128u : 8u);
-            const uint32_t nice = c->better_nice ? c->better_nice : (small ? 258u : 32u);
-            lz77_better_kernel<<<nb, LZB_THREADS, LZB_SMEM_BYTES, st>>>(bin, bn, (uint32_t*)c->tok.p, (uint32_t*)c->ntok.p,
-                                                                     (uint16_t*)c->hist.p, depth, nice, srcs);
+            // bytes of the whole input (a batch says it per chunk, in ChunkSrc)
+            const bool small = !srcs && b0 * CHUNK + bn < SMALL_INPUT_BYTES;
+            lz77_better_kernel<<<nb, LZB_THREADS, LZB_SMEM_BYTES, st>>>(bin, bn, (uint32_t*)c->tok.p, (uint32_t*)c->ntok.p, (uint16_t*)c->hist.p,
+                                                                     c->better_depth ? c->better_depth : 8u, c->better_nice ? c->better_nice : 32u,
+                                                                     c->better_depth ? c->better_depth : 128u, c->better_nice ? c->better_nice : 258u,
+                                                                     small ? 1u : 0u, srcs);
         }
         else if (level == 2) {
             const uint32_t grid = nb < c->lzf_grid ? nb : c->lzf_grid;

@@ -43,9 +43,11 @@ __host__ __device__ __forceinline__ uint32_t tok_dist(uint32_t t) { return t >> 
 __host__ __device__ __forceinline__ uint32_t tok_len(uint32_t t) { return t & 0x1FFu; }
 
 // Batch compression (many independent inputs in one launch sequence): chunk c of the batch is bytes
-// [off, off + clen) of the input buffer; `last` = it closes its stream (BFINAL, no separator after it).
+// [off, off + clen) of the input buffer; `last` bit 0 = it closes its stream (BFINAL, no separator after it), bit 1 = its
+// input is a small one (< SMALL_INPUT_BYTES: the better level searches deeper there).
 // Kernels take a `const ChunkSrc*` that is NULL for one contiguous input (chunk c = bytes [c * CHUNK, ...)).
 struct ChunkSrc { uint64_t off; uint32_t clen; uint32_t last; };
+constexpr uint64_t SMALL_INPUT_BYTES = 1ull << 20;
 
 // Block descriptor written by the Huffman kernel, read by the encoder.
 struct BlockDesc {

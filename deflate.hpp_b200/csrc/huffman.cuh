@@ -449,7 +449,7 @@ huffman_kernel(const uint16_t* __restrict__ hist, uint64_t n, uint32_t nchunks, 
     if (chunk >= nchunks) return;
     HufScratch* s = &scratch[warp];
     const uint32_t clen = srcs ? srcs[chunk].clen : (uint32_t)min((uint64_t)CHUNK, n - (uint64_t)chunk * CHUNK);
-    const bool last = srcs ? srcs[chunk].last != 0 : (last_is_final && chunk == nchunks - 1);
+    const bool last = srcs ? (srcs[chunk].last & 1u) != 0 : (last_is_final && chunk == nchunks - 1);
     const uint16_t* h = hist + (size_t)chunk * NSEG * NSYM;
     uint32_t* mycodes = codes + (size_t)chunk * 2 * NSYM;
     uint32_t* myhdr = hdr + (size_t)chunk * 2 * HDR_WORDS;

@@ -279,12 +279,43 @@ struct FdState {
     int st;
 };
 
+// Codes longer than the direct table's index.  tp_slow_symbol() walks the lengths one by one with two local-memory loads
+// per step (~300 cycles), and in a warp whose 32 lanes decode 32 different units the other lanes wait for it: with a
+// 9-bit table one trip in three has such a lane.  The canonical code makes a search without a loop possible: left-aligned
+// to 15 bits, the codes of length l fill [first[l] << (15 - l), (first[l] + count[l]) << (15 - l)), and these ranges follow one
+// another in order of length -- so the length of a code is the smallest l whose upper bound lies above it.  Per thread and
+// per length above the table width one word in shared memory ([slot][thread], conflict-free):
+//   [15:0] upper bound (left-aligned, <= 0x8000), [31:16] offs[l] - first[l] (mod 2^16): index into sorted[] = that + code.
+template <uint32_t TB>
+__device__ __forceinline__ void fd_slow_fill(uint32_t* slow /* this thread's slot 0 */, uint32_t NT, const TpTables& T, uint32_t which) {
+    #pragma unroll 1
+    for (uint32_t l = TB + 1; l <= 15; l++) {
+        const uint32_t lim = ((uint32_t)T.first[which][l] + T.count[which][l]) << (15 - l);
+        const uint32_t base = ((uint32_t)T.offs[which][l] - T.first[which][l]) & 0xFFFFu;
+        slow[(l - TB - 1) * NT] = lim | (base << 16);
+    }
+}
+// returns symbol | length << 16, or -1 (no code starts with these bits); sorted: the alphabet's part of TpTables::sorted
+template <uint32_t TB>
+__device__ __forceinline__ int fd_slow_symbol(uint32_t slow_sa, uint32_t stride, const uint16_t* sorted, uint32_t bits32) {
+    const uint32_t code15 = __brev(bits32) >> 17;
+    uint32_t sel = 0, len = 0;
+    #pragma unroll
+    for (int k = (int)(15 - TB) - 1; k >= 0; k--) {             // descending: the smallest length that fits is assigned last
+        const uint32_t w = lds_u32(slow_sa + (uint32_t)k * stride);
+        if (code15 < (w & 0xFFFFu)) { sel = w; len = TB + 1 + (uint32_t)k; }
+    }
+    if (!len) return -1;
+    const uint32_t idx = ((sel >> 16) + (code15 >> (15 - len))) & 0xFFFFu;
+    return (int)(sorted[idx] | (len << 16));
+}
+
 // One block header (single thread): stored blocks become ops, Huffman blocks get their tables built.
 // LB / DB: index widths of the thread's private literal/length and distance tables (the 7-bit precode table borrows the
 // literal table's space, which is not built yet when it is needed).
 template <bool EMIT, uint32_t LB, uint32_t DB>
-__device__ __noinline__ void fd_block(FdState& s, uint16_t* lit, uint16_t* dst, uint32_t NT, TpTables& T, uint64_t in_len, uint64_t in_bits,
-                                      bool strict, uint64_t stop_bit, uint16_t* S, uint64_t* ops, const uint8_t* in) {
+__device__ __noinline__ void fd_block(FdState& s, uint16_t* lit, uint16_t* dst, uint32_t* slow, uint32_t NT, TpTables& T, uint64_t in_len,
+                                      uint64_t in_bits, bool strict, uint64_t stop_bit, uint16_t* S, uint64_t* ops, const uint8_t* in) {
     TBits& br = s.br;
     if (tb_bitpos(br) + 3 > in_bits) { s.st = ST_OVERRUN; s.state = TS_DONE; return; }
     tb_refill(br);
@@ -351,7 +382,9 @@ __device__ __noinline__ void fd_block(FdState& s, uint16_t* lit, uint16_t* dst, 
             if (T.lens[256] == 0) { s.st = ST_DATA; s.state = TS_DONE; return; }
         }
         if (!tp_build(lit, NT, T, T.lens, hlit, 0, LB, true)) { s.st = ST_DATA; s.state = TS_DONE; return; }
+        fd_slow_fill<LB>(slow, NT, T, 0);                    // before the distance build reuses nothing of alphabet 0
         if (!tp_build(dst, NT, T, T.lens + NLIT, hdist, 1, DB, false)) { s.st = ST_DATA; s.state = TS_DONE; return; }
+        fd_slow_fill<DB>(slow + (15 - LB) * NT, NT, T, 1);
         s.state = TS_SYM;
         return;
     }
@@ -373,6 +406,7 @@ foreign_decode_kernel(const uint8_t* __restrict__ in, uint64_t n, const uint64_t
                       unsigned long long* __restrict__ queue) {
     extern __shared__ __align__(16) uint8_t tp_smem[];
     __shared__ uint32_t s_ring[TB_RING * NTH];
+    __shared__ uint32_t s_slow[((15 - LB) + (15 - DB)) * NTH];          // long-code search words, [slot][thread]
     uint32_t* s_lut = reinterpret_cast<uint32_t*>(tp_smem);
     uint16_t* tabs = reinterpret_cast<uint16_t*>(tp_smem + TP_LUT_WORDS * 4);
     tp_lut_init(s_lut, threadIdx.x);
@@ -387,6 +421,9 @@ foreign_decode_kernel(const uint8_t* __restrict__ in, uint64_t n, const uint64_t
     const bool strict = flags & 1u;
     const uint64_t in_bits = n * 8;
     TpTables T;
+    uint32_t* slow = s_slow + threadIdx.x;
+    const uint32_t slow_lit_sa = (uint32_t)__cvta_generic_to_shared(slow);
+    const uint32_t slow_dst_sa = slow_lit_sa + (15 - LB) * NTH * 4;
     FdState s;
     s.br.ring_sa = (uint32_t)__cvta_generic_to_shared(s_ring + threadIdx.x);
     s.br.ring_stride = NT * 4;
@@ -443,7 +480,7 @@ foreign_decode_kernel(const uint8_t* __restrict__ in, uint64_t n, const uint64_t
                 uint32_t e = lds_u16(lit_sa + tb_peek(br, LB) * ntb);
                 bool ok = true;
                 if ((e & 15u) == 0) {
-                    const int r = tp_slow_symbol(T, 0, (uint32_t)br.bb, LB + 1);
+                    const int r = fd_slow_symbol<LB>(slow_lit_sa, NTH * 4, T.sorted, (uint32_t)br.bb);
                     if (r < 0) { s.st = ST_OVERRUN; s.state = TS_DONE; ok = false; }
                     else e = tp_lit_entry((uint32_t)r & 0xFFFFu, (uint32_t)r >> 16);
                 }
@@ -472,7 +509,7 @@ foreign_decode_kernel(const uint8_t* __restrict__ in, uint64_t n, const uint64_t
                     const uint32_t de = lds_u16(dst_sa + tb_peek(br, DB) * ntb);
                     uint32_t dl = de & 15u, dsym = de >> 4;
                     if (dl == 0) {
-                        const int r = tp_slow_symbol(T, 1, (uint32_t)br.bb, DB + 1);
+                        const int r = fd_slow_symbol<DB>(slow_dst_sa, NTH * 4, T.sorted + NLIT, (uint32_t)br.bb);
                         dsym = r < 0 ? 99u : ((uint32_t)r & 0xFFFFu);
                         dl = r < 0 ? 0u : ((uint32_t)r >> 16);
                     }
@@ -502,7 +539,7 @@ foreign_decode_kernel(const uint8_t* __restrict__ in, uint64_t n, const uint64_t
                 }
             }
         } else if (s.state == TS_BLOCK) {
-            fd_block<EMIT, LB, DB>(s, lit, dst, NT, T, n, in_bits, strict, stop_bit, Su, ops, in);
+            fd_block<EMIT, LB, DB>(s, lit, dst, slow, NT, T, n, in_bits, strict, stop_bit, Su, ops, in);
         }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");

@@ -383,8 +383,8 @@ __device__ __forceinline__ uint32_t lzb_hash(uint32_t w4) { return ((w4 & 0xFFFF
 
 __global__ void __launch_bounds__(LZB_THREADS, 1)
 lz77_better_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t* __restrict__ tok,
-                   uint32_t* __restrict__ ntok, uint16_t* __restrict__ hist, uint32_t depth, uint32_t nice,
-                   const ChunkSrc* __restrict__ srcs) {
+                   uint32_t* __restrict__ ntok, uint16_t* __restrict__ hist, uint32_t depth_large, uint32_t nice_large,
+                   uint32_t depth_small, uint32_t nice_small, uint32_t input_is_small, const ChunkSrc* __restrict__ srcs) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* s_data = smem;
     uint16_t* s_prev = reinterpret_cast<uint16_t*>(smem + CHUNK + LZ_DATA_PAD);
@@ -398,6 +398,10 @@ lz77_better_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t* __restr
     const uint32_t clen = srcs ? srcs[chunk].clen : (uint32_t)min((uint64_t)CHUNK, n - base);
     const uint8_t* src = in + base;
     const uint32_t FULL = 0xFFFFFFFFu;
+    // search effort by the size of the INPUT this chunk belongs to (a batch mixes small and large files: ChunkSrc says which)
+    const bool small_input = srcs ? (srcs[chunk].last & 2u) != 0 : input_is_small != 0;
+    const uint32_t depth = small_input ? depth_small : depth_large;
+    const uint32_t nice = small_input ? nice_small : nice_large;
 
     const bool aligned = ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
     const uint32_t bulk = aligned ? (clen & ~15u) : 0;

@@ -176,7 +176,7 @@ int b200_deflate_compress_batch_dev(b200_ctx* ctx, const void* d_in, const uint6
                                     void* d_out, size_t cap, uint64_t* d_out_off, size_t* h_total, void* stream);
 
 /* Multi-GPU gather fused into the encoder.  Stage 1 runs tokenise / code construction / sizing for one
- * batch (n <= 4096 chunks) and leaves this shard's compressed byte count in *d_local_n (device).  The
+ * batch (n <= the batch size: 16384 chunks unless B200_BATCH_CHUNKS says otherwise) and leaves this shard's compressed byte count in *d_local_n (device).  The
  * caller exchanges the counts between ranks (an 8-byte all_gather) and computes *d_base, the offset of
  * this shard inside the joined stream.  Stage 2 bit-packs and writes every chunk of the shard at
  * d_out + *d_base + (offset inside the shard): d_out may be ANOTHER GPU's memory mapped over NVLink

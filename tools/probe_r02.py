@@ -64,12 +64,12 @@ def compress_point(env, level, steps=3):
 
 
 if "fast" in want:
-    for env in ({}, {"B200_LZF_ADAPTIVE": 0}):
+    for env in ({}, {"B200_NO_SPLIT": 1}, {"B200_BATCH_CHUNKS": 8192}, {"B200_BATCH_CHUNKS": 16384}):
         compress_point(env, 2, steps=5)
 
 if "better" in want:
-    for depth, nice in ((8, 32), (6, 32), (4, 32), (4, 16), (12, 32)):
-        compress_point({"B200_BETTER_DEPTH": depth, "B200_BETTER_NICE": nice}, 3, steps=2)
+    for env in ({}, {"B200_NO_SPLIT": 1}):
+        compress_point(env, 3, steps=2)
 
 if "foreign" in want:
     host = src.cpu().numpy()
