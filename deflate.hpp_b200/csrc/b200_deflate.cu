@@ -19,6 +19,7 @@
 #include <cstdio>
 #include <fcntl.h>
 #include <future>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 #include <cstdlib>
@@ -192,7 +193,8 @@ struct b200_ctx {
     uint32_t host_slice_chunks = 1024;   // 64 MiB: measured best (smaller slices starve the persistent matcher)
     // pageable caller memory: a ring of pinned staging buffers, filled / drained by a few host threads (host-buffer API)
     static constexpr int STG_N = 4;
-    static constexpr size_t STG_BYTES = (size_t)8 << 20;
+    static constexpr size_t STG_BYTES = (size_t)32 << 20;      // per slot; a piece is copied by a few short-lived host threads, so few large
+                                                               // pieces (8 MiB pieces: the thread start-up alone cost ~40 ms per GiB)
     void* stg_in[STG_N] = {};
     void* stg_out[STG_N] = {};
     cudaEvent_t stg_in_ev[STG_N] = {}, stg_out_ev[STG_N] = {};
@@ -1597,6 +1599,36 @@ int b200_inflate_view(const void* in, size_t n, unsigned flags, int framing, con
     return B200_OK;
 }
 
+// Touch every page of [p, p + n) from a few threads.  The std::vector a drop-in call returns is fresh memory: its first
+// write faults in 4 KiB at a time, single-threaded, at ~3 GB/s -- slower than everything the GPU did.  The header reserves
+// the vector, calls this (the faults, i.e. the kernel's page zeroing, then run on several cores at once) and only then
+// assigns.  Transparent huge pages are asked for where the system offers them on request.  Writes one zero byte per page:
+// only for memory whose contents do not matter yet.
+void b200_host_prefault(void* p, size_t n) {
+    if (!p || n < ((size_t)4 << 20)) return;
+    uint8_t* b = (uint8_t*)p;
+    const unsigned hw = std::thread::hardware_concurrency();
+    const int T = hw >= 16 ? 8 : hw >= 8 ? 4 : hw >= 4 ? 2 : 1;
+    const size_t page = 4096;
+#ifdef MADV_HUGEPAGE
+    {
+        const uintptr_t lo = ((uintptr_t)b + (((size_t)2 << 20) - 1)) & ~(uintptr_t)(((size_t)2 << 20) - 1);
+        const uintptr_t hi = ((uintptr_t)b + n) & ~(uintptr_t)(((size_t)2 << 20) - 1);
+        if (hi > lo) madvise((void*)lo, hi - lo, MADV_HUGEPAGE);
+    }
+#endif
+    std::vector<std::thread> pool;
+    const size_t per = ((n + T - 1) / T + page - 1) & ~(page - 1);
+    auto touch = [b, n, page](size_t lo, size_t hi) {
+        if (hi > n) hi = n;
+        for (size_t o = lo; o < hi; o += page) ((volatile uint8_t*)b)[o] = 0;
+    };
+    for (int t = 1; t < T; t++) pool.emplace_back(touch, (size_t)t * per, (size_t)(t + 1) * per);
+    touch(0, per);
+    for (auto& th : pool) th.join();
+    ((volatile uint8_t*)b)[n - 1] = 0;
+}
+
 void b200_view_release(void) {
     std::lock_guard<std::mutex> g(g_default_mu);
     if (g_default && g_default->view_locked) {
@@ -1641,9 +1673,23 @@ static int inflate_host_pipelined(b200_ctx* c, const uint8_t* in, size_t n, uint
     *handled = false;
     *in_resident = false;
     const size_t S = c->host_inflate_slice & ~(size_t)15;
-    if (!S || n < 2 * S || !cap || c->inflate_warp_path) return B200_OK;
+    const size_t first = (S / 8 > 65536 ? S / 8 : 65536) & ~(size_t)15;         // 32 MiB with the default slice of 256 MiB
+    if (!S || n < 3 * first || !cap || c->inflate_warp_path) return B200_OK;
     int rc;
-    const size_t nsl = (n + S - 1) / S;
+    // Slice ends.  The device -> host copy of the output is the long pole (1.6x the bytes of the input), so what counts is how
+    // early it can start: the first slices are small (32, 64, 128 MiB ...: the first output is on its way back after ~1.5 ms
+    // instead of ~7), the later ones have the full size (small groups of chunks run as partial waves of the decoder).
+    std::vector<size_t> ends;
+    {
+        size_t pos = 0, step = first;
+        while (pos < n) {
+            const size_t cur = step < S ? step : S;
+            pos = n - pos <= cur + cur / 2 ? n : pos + cur;      // no tiny last slice
+            ends.push_back(pos);
+            step <<= 1;
+        }
+    }
+    const size_t nsl = ends.size();
     if ((rc = c->d_in.ensure(n + 64))) return rc;
     if ((rc = c->d_out.ensure(cap + 64))) return rc;
     if ((rc = c->result.ensure(64))) return rc;
@@ -1663,7 +1709,7 @@ static int inflate_host_pipelined(b200_ctx* c, const uint8_t* in, size_t n, uint
     std::thread feeder([&]() {
         cudaSetDevice(c->device);
         for (size_t k = 0; k < nsl; k++) {
-            const size_t off = k * S, len = off + S < n ? S : n - off;
+            const size_t off = k ? ends[k - 1] : 0, len = ends[k] - off;
             int r = copy_h2d(c, d_in + off, in + off, len, c->s_in);
             if (r == B200_OK && cudaEventRecord(c->events[k], c->s_in) != cudaSuccess) r = B200_E_CUDA;
             if (r) { feed_rc.store(r); arrived.store(nsl, std::memory_order_release); return; }
@@ -1678,7 +1724,7 @@ static int inflate_host_pipelined(b200_ctx* c, const uint8_t* in, size_t n, uint
         if (feed_rc.load()) return feed_rc.load();
         CK(cudaStreamWaitEvent(st, c->events[k], 0));
         const bool last = k + 1 == nsl;
-        const uint64_t avail = last ? n : (k + 1) * S;
+        const uint64_t avail = ends[k];
         const uint64_t base = start & ~15ull, rel0 = start - base, region = avail - base;
         const uint8_t* rin = d_in + base;
         const uint64_t nwarps = (region + SYNC_REGION - 1) / SYNC_REGION;

@@ -137,6 +137,9 @@ void b200_free(void* p);
 int b200_deflate_compress_view(const void* in, size_t n, int level, unsigned flags, const void** view, size_t* out_n);
 int b200_inflate_view(const void* in, size_t n, unsigned flags, int framing, const void** view, size_t* out_n);
 void b200_view_release(void);
+/* Fault in the pages of fresh host memory [p, p + n) from several threads (one zero byte is written per page, so only for
+ * memory whose contents do not matter yet): what the drop-in headers do to the std::vector they are about to fill. */
+void b200_host_prefault(void* p, size_t n);
 
 /* ---- file-path API -------------------------------------------------------------------------- */
 /* Replaces deflate::compress(std::string file_path, std::string new_file, int level) (reference include/deflate.hpp:755-777):

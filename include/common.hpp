@@ -40,6 +40,7 @@ struct Api {
     decltype(&::b200_deflate_compress_view) compress_view = nullptr;
     decltype(&::b200_inflate_view) inflate_view = nullptr;
     decltype(&::b200_view_release) view_release = nullptr;
+    decltype(&::b200_host_prefault) host_prefault = nullptr;
     decltype(&::b200_deflate_compress_file) compress_file = nullptr;
     decltype(&::b200_inflate_file) inflate_file = nullptr;
     decltype(&::b200_free) free_ = nullptr;
@@ -69,6 +70,7 @@ inline const Api& api() {
         x.compress_view = reinterpret_cast<decltype(x.compress_view)>(sym("b200_deflate_compress_view"));
         x.inflate_view = reinterpret_cast<decltype(x.inflate_view)>(sym("b200_inflate_view"));
         x.view_release = reinterpret_cast<decltype(x.view_release)>(sym("b200_view_release"));
+        x.host_prefault = reinterpret_cast<decltype(x.host_prefault)>(sym("b200_host_prefault"));
         x.compress_file = reinterpret_cast<decltype(x.compress_file)>(sym("b200_deflate_compress_file"));
         x.inflate_file = reinterpret_cast<decltype(x.inflate_file)>(sym("b200_inflate_file"));
         x.free_ = reinterpret_cast<decltype(x.free_)>(sym("b200_free"));
@@ -95,10 +97,13 @@ inline std::vector<uint8_t> take(void* p, size_t n) {
     return v;
 }
 
-// the library's pinned arena -> the vector the reference API returns: one pass (assign), then the arena is released
+// the library's pinned arena -> the vector the reference API returns: the vector's fresh pages are faulted in from several
+// threads first (b200_host_prefault), then one pass (assign), then the arena is released
 inline std::vector<uint8_t> take_view(const void* p, size_t n) {
     struct Release { ~Release() { api().view_release(); } } release;
     std::vector<uint8_t> v;
+    v.reserve(n);
+    api().host_prefault(v.data(), n);
     v.assign(static_cast<const uint8_t*>(p), static_cast<const uint8_t*>(p) + n);
     return v;
 }

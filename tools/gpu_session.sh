@@ -15,6 +15,10 @@ for step in "$@"; do
       done ;;
     bench)
       timeout 900 python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err; echo "bench exit $?" >> $out/${tag}_bench.err ;;
+    bench_args)
+      timeout 900 python bench.py ${BENCH_ARGS} > $out/${tag}_bencha.json 2> $out/${tag}_bencha.err; echo "bench exit $?" >> $out/${tag}_bencha.err ;;
+    bench_multi)
+      timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-2} --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus ${NGPU:-2} ${BENCH_ARGS} > $out/${tag}_bench_${NGPU:-2}gpu.json 2> $out/${tag}_bench_${NGPU:-2}gpu.err; echo "bench exit $?" >> $out/${tag}_bench_${NGPU:-2}gpu.err ;;
     bench_quick)
       timeout 600 python bench.py --steps 3 --warmup 3 --skip config5,dropin > $out/${tag}_benchq.json 2> $out/${tag}_benchq.err; echo "bench exit $?" >> $out/${tag}_benchq.err ;;
     ncu_list)
@@ -22,7 +26,7 @@ for step in "$@"; do
         python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --skip config5,dropin,batch > $out/${tag}_ncu_list.log 2>&1 ;;
     ncu_full)
       timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"${NCU_KERNELS:-lz77_fast_kernel|encode_kernel|huffman_kernel}" -c ${NCU_COUNT:-4} \
-        -o $out/${tag}_full -f python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --only none > $out/${tag}_ncu_full.log 2>&1 ;;
+        -o $out/${tag}_full${NCU_TAG} -f python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --only ${NCU_ONLY:-none} > $out/${tag}_ncu_full${NCU_TAG}.log 2>&1 ;;
     sanitizer)
       timeout 1500 compute-sanitizer --tool memcheck --log-file $out/${tag}_memcheck.log python -m pytest tests -m gpu -x -q -k "${SAN_K:-edge or fixture or quirk or fuzz}" > $out/${tag}_memcheck_pytest.log 2>&1
       timeout 1500 compute-sanitizer --tool racecheck --log-file $out/${tag}_racecheck.log python -m pytest tests -m gpu -x -q -k "${SAN_K:-edge or fixture or quirk or fuzz}" > $out/${tag}_racecheck_pytest.log 2>&1 ;;
