@@ -312,14 +312,17 @@ __device__ __forceinline__ int fd_slow_symbol(uint32_t slow_sa, uint32_t stride,
     return (int)(sorted[idx] | (len << 16));
 }
 
-// One block header (single thread): stored blocks become ops, Huffman blocks get their tables built.
+// One block header (single thread): stored blocks become ops, Huffman blocks get their tables built.  The decoder state
+// travels BY VALUE (as in tp_step_block): passed by reference to this non-inlined function it has an address, lives in local
+// memory for the whole kernel, and every bit-buffer operation of the symbol loop becomes a local load and store (the first
+// version did exactly that: 955 LDL / STL instructions in the kernel, F2 + F3 = 37.6 ms).
 // LB / DB: index widths of the thread's private literal/length and distance tables (the 7-bit precode table borrows the
 // literal table's space, which is not built yet when it is needed).
 template <bool EMIT, uint32_t LB, uint32_t DB>
-__device__ __noinline__ void fd_block(FdState& s, uint16_t* lit, uint16_t* dst, uint32_t* slow, uint32_t NT, TpTables& T, uint64_t in_len,
+__device__ __noinline__ FdState fd_block(FdState s, uint16_t* lit, uint16_t* dst, uint32_t* slow, uint32_t NT, TpTables& T, uint64_t in_len,
                                       uint64_t in_bits, bool strict, uint64_t stop_bit, uint16_t* S, uint64_t* ops, const uint8_t* in) {
     TBits& br = s.br;
-    if (tb_bitpos(br) + 3 > in_bits) { s.st = ST_OVERRUN; s.state = TS_DONE; return; }
+    if (tb_bitpos(br) + 3 > in_bits) { s.st = ST_OVERRUN; s.state = TS_DONE; return s; }
     tb_refill(br);
     const uint32_t hdr = tb_get(br, 3);
     s.bfinal = hdr & 1;
@@ -329,9 +332,9 @@ __device__ __noinline__ void fd_block(FdState& s, uint16_t* lit, uint16_t* dst, 
         tb_refill(br);
         const uint32_t len = tb_get(br, 16);
         const uint32_t nlen = tb_get(br, 16);
-        if (strict && (len ^ nlen) != 0xFFFFu) { s.st = ST_DATA; s.state = TS_DONE; return; }
+        if (strict && (len ^ nlen) != 0xFFFFu) { s.st = ST_DATA; s.state = TS_DONE; return s; }
         const uint64_t bpos = tb_bitpos(br) >> 3;
-        if (bpos + len > in_len) { s.st = ST_OVERRUN; s.state = TS_DONE; return; }
+        if (bpos + len > in_len) { s.st = ST_OVERRUN; s.state = TS_DONE; return s; }
         if (len) {
             if (EMIT) { ops[s.nops] = tp_op(s.pos, len, 0); ops[s.nops + 1] = bpos; }
             s.nops += 2;
@@ -339,7 +342,7 @@ __device__ __noinline__ void fd_block(FdState& s, uint16_t* lit, uint16_t* dst, 
         }
         tb_seek(br, bpos + len);
     } else if (btype == 3) {
-        if (strict) { s.st = ST_DATA; s.state = TS_DONE; return; }           // the reference's switch has no case 3: skipped
+        if (strict) { s.st = ST_DATA; s.state = TS_DONE; return s; }           // the reference's switch has no case 3: skipped
     } else {
         uint32_t hlit = NLIT, hdist = NDIST;
         if (btype == 1) {
@@ -358,7 +361,7 @@ __device__ __noinline__ void fd_block(FdState& s, uint16_t* lit, uint16_t* dst, 
                 pl[C_PRECODE_ORDER[i]] = (uint8_t)tb_get(br, 3);
             }
             static_assert(LB >= 7, "the precode table needs 128 entries");
-            if (!tp_build(lit, NT, T, pl, 19, 1, 7, false)) { s.st = ST_DATA; s.state = TS_DONE; return; }
+            if (!tp_build(lit, NT, T, pl, 19, 1, 7, false)) { s.st = ST_DATA; s.state = TS_DONE; return s; }
             const uint32_t total = hlit + hdist;
             uint32_t i = 0, prev = 0;
             #pragma unroll 1
@@ -366,13 +369,13 @@ __device__ __noinline__ void fd_block(FdState& s, uint16_t* lit, uint16_t* dst, 
                 tb_refill(br);
                 const uint32_t e = lit[tb_peek(br, 7) * NT];
                 const uint32_t l = e & 15u, sym = e >> 4;
-                if (l == 0) { s.st = ST_OVERRUN; s.state = TS_DONE; return; }
+                if (l == 0) { s.st = ST_OVERRUN; s.state = TS_DONE; return s; }
                 tb_drop(br, l);
                 uint32_t rep = 1, val = sym;
                 if (sym == 16) { rep = 3 + tb_get(br, 2); val = prev; }
                 else if (sym == 17) { rep = 3 + tb_get(br, 3); val = 0; }
                 else if (sym == 18) { rep = 11 + tb_get(br, 7); val = 0; }
-                if (i + rep > total) { s.st = ST_DATA; s.state = TS_DONE; return; }
+                if (i + rep > total) { s.st = ST_DATA; s.state = TS_DONE; return s; }
                 #pragma unroll 1
                 for (uint32_t j = 0; j < rep; j++) {
                     const uint32_t p = i + j;
@@ -381,19 +384,20 @@ __device__ __noinline__ void fd_block(FdState& s, uint16_t* lit, uint16_t* dst, 
                 i += rep;
                 prev = val;
             }
-            if (T.lens[256] == 0) { s.st = ST_DATA; s.state = TS_DONE; return; }
+            if (T.lens[256] == 0) { s.st = ST_DATA; s.state = TS_DONE; return s; }
         }
-        if (!tp_build(lit, NT, T, T.lens, hlit, 0, LB, true)) { s.st = ST_DATA; s.state = TS_DONE; return; }
+        if (!tp_build(lit, NT, T, T.lens, hlit, 0, LB, true)) { s.st = ST_DATA; s.state = TS_DONE; return s; }
         fd_slow_fill<LB>(slow, NT, T, 0);                    // before the distance build reuses nothing of alphabet 0
-        if (!tp_build(dst, NT, T, T.lens + NLIT, hdist, 1, DB, false)) { s.st = ST_DATA; s.state = TS_DONE; return; }
+        if (!tp_build(dst, NT, T, T.lens + NLIT, hdist, 1, DB, false)) { s.st = ST_DATA; s.state = TS_DONE; return s; }
         fd_slow_fill<DB>(slow + (15 - LB) * NT, NT, T, 1);
         s.state = TS_SYM;
-        return;
+        return s;
     }
     // stored or skipped block: what follows every block
     if (s.pos > FD_MAX_OUT) { s.st = ST_FALLBACK; s.state = TS_DONE; }
     else if (s.bfinal) { s.flags |= FU_FINAL; s.state = TS_DONE; }
     else if (tb_bitpos(br) >= stop_bit) { s.flags |= FU_REACHED; s.state = TS_DONE; }
+    return s;
 }
 
 // Persistent: the grid is one CTA per SM (the private tables fill the shared memory) and every THREAD pulls the next
@@ -541,7 +545,7 @@ foreign_decode_kernel(const uint8_t* __restrict__ in, uint64_t n, const uint64_t
                 }
             }
         } else if (s.state == TS_BLOCK) {
-            fd_block<EMIT, LB, DB>(s, lit, dst, slow, NT, T, n, in_bits, strict, stop_bit, Su, ops, in);
+            s = fd_block<EMIT, LB, DB>(s, lit, dst, slow, NT, T, n, in_bits, strict, stop_bit, Su, ops, in);
         }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
