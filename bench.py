@@ -335,11 +335,12 @@ def gpu_numa_bind(local_rank):
     root) and, where the cpuset allows it, run on that node's cores.  Best effort; returns a description."""
     try:
         import torch
-        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id if hasattr(torch.cuda.get_device_properties(local_rank), "pci_bus_id") else None
-        if bus is None:
-            out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local_rank)],
+        pr = torch.cuda.get_device_properties(local_rank)
+        if all(hasattr(pr, a) for a in ("pci_domain_id", "pci_bus_id", "pci_device_id")):
+            bus = "%04x:%02x:%02x.0" % (int(pr.pci_domain_id), int(pr.pci_bus_id), int(pr.pci_device_id))
+        else:
+            bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local_rank)],
                                  capture_output=True, text=True).stdout.strip()
-            bus = out
         bus = bus.lower()
         if bus.count(":") == 2 and len(bus.split(":")[0]) == 8:
             bus = bus[4:]

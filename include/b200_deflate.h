@@ -11,7 +11,8 @@
  *
  * Stream format produced by the compressor (one valid RFC 1951 raw stream):
  *   input is cut into independent 64 KiB chunks; each chunk is ONE block (dynamic, fixed or stored,
- *   whichever is smallest by exact bit count) that starts byte-aligned; every chunk except the last
+ *   whichever is smallest by exact bit count; two blocks where the chunk's statistics change enough
+ *   to pay for a second code table) that starts byte-aligned; every chunk except the last
  *   is followed by TWO empty non-final stored blocks (pad bits, 00 00 FF FF, 00, 00 00 FF FF) so
  *   that the next chunk is byte-aligned again and its start can be found by scanning for the 9-byte
  *   pattern 00 00 FF FF 00 00 00 FF FF (a single sync marker would turn up by chance in compressed
