@@ -1063,6 +1063,22 @@ int b200_inflate_shard_dev(b200_ctx* c, const void* d_in, size_t n, size_t lo, s
     return B200_OK;
 }
 
+// order[] = unit indices by decreasing key, in O(n): keys are bucketed by their top bits (a comparison sort of 40 000 units
+// costs ~1.5 ms of host time per pass while the GPU waits; the queue only needs "long units first", not a total order)
+static void order_longest_first(const std::vector<uint64_t>& key, std::vector<uint32_t>& order) {
+    const size_t n = key.size();
+    order.resize(n);
+    uint64_t mx = 1;
+    for (size_t k = 0; k < n; k++) if (key[k] != ~0ull && key[k] > mx) mx = key[k];
+    int shift = 0;
+    while ((mx >> shift) >= 4096) shift++;
+    std::vector<uint32_t> head(4098, 0);
+    auto bucket = [&](uint64_t v) -> uint32_t { return v == ~0ull ? 0u : 4096u - (uint32_t)(v >> shift); };   // 0: unknown length (first)
+    for (size_t k = 0; k < n; k++) head[bucket(key[k]) + 1]++;
+    for (size_t b = 1; b < head.size(); b++) head[b] += head[b - 1];
+    for (size_t k = 0; k < n; k++) order[head[bucket(key[k])]++] = (uint32_t)k;
+}
+
 // Block-parallel inflate of a stream that is not made of this library's chunks (inflate_foreign.cuh).  *done = false:
 // nothing was decided (too small, too few blocks found, an error, no memory): the caller decodes sequentially, which
 // also produces the right error code.  Synchronizes `st` several times (candidate list, chain walk, verdict).
@@ -1107,12 +1123,12 @@ static int inflate_foreign(b200_ctx* c, const uint8_t* in, uint64_t n, uint8_t* 
                 (rc = c->f_order.ensure(m * 4)) || (rc = c->f_misc.ensure(256)))
                 return B200_OK;
             // longest first: the compressed span is the estimate (the last unit's is unknown: first)
-            std::vector<uint32_t> order(m);
-            for (uint64_t k = 0; k < m; k++) order[k] = (uint32_t)k;
-            std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
-                const uint64_t sa = hp[a] == ~0ull ? ~0ull : hp[a] - hs[a], sb = hp[b] == ~0ull ? ~0ull : hp[b] - hs[b];
-                return sa != sb ? sa > sb : a < b;
-            });
+            std::vector<uint32_t> order;
+            {
+                std::vector<uint64_t> key(m);
+                for (uint64_t k = 0; k < m; k++) key[k] = hp[k] == ~0ull ? ~0ull : hp[k] - hs[k];
+                order_longest_first(key, order);
+            }
             CK(cudaMemcpyAsync(c->f_starts.p, hs.data(), m * 8, cudaMemcpyHostToDevice, st));
             CK(cudaMemcpyAsync(c->f_stops.p, hp.data(), m * 8, cudaMemcpyHostToDevice, st));
             CK(cudaMemcpyAsync(c->f_order.p, order.data(), m * 4, cudaMemcpyHostToDevice, st));
@@ -1202,12 +1218,12 @@ static int inflate_foreign(b200_ctx* c, const uint8_t* in, uint64_t n, uint8_t* 
 
     // ---- F3: decode with known offsets (longest units first) ----
     {
-        std::vector<uint32_t> order(nu);
-        for (uint64_t k = 0; k < nu; k++) order[k] = (uint32_t)k;
-        std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
-            const uint64_t la = hbase[a + 1] - hbase[a], lb = hbase[b + 1] - hbase[b];
-            return la != lb ? la > lb : a < b;
-        });
+        std::vector<uint32_t> order;
+        {
+            std::vector<uint64_t> key(nu);
+            for (uint64_t k = 0; k < nu; k++) key[k] = hbase[k + 1] - hbase[k];
+            order_longest_first(key, order);
+        }
         if ((rc = c->f_order.ensure(nu * 4))) return B200_OK;
         CK(cudaMemcpyAsync(c->f_order.p, order.data(), nu * 4, cudaMemcpyHostToDevice, st));
         PROF_BEGIN(c, K_F_EMIT, st);

@@ -27,9 +27,20 @@ for step in "$@"; do
     ncu_full)
       timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"${NCU_KERNELS:-lz77_fast_kernel|encode_kernel|huffman_kernel}" -c ${NCU_COUNT:-4} \
         -o $out/${tag}_full${NCU_TAG} -f python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --only ${NCU_ONLY:-none} > $out/${tag}_ncu_full${NCU_TAG}.log 2>&1 ;;
+    ncu_each)
+      # one `--set full` capture per kernel (first launch that matches), each from its own short bench run
+      for spec in ${NCU_EACH:-lz77_fast_kernel:none huffman_kernel:none encode_kernel:none inflate_segments_kernel:none inflate_copy_kernel:none lz77_better_kernel:better inflate_batch_kernel:batch foreign_decode_kernel:foreign foreign_find_blocks_kernel:foreign foreign_copy_kernel:foreign}; do
+        k=${spec%%:*}; only=${spec##*:}
+        timeout 600 ncu --set full --clock-control none --import-source on -k regex:"$k" -c 1 -o $out/${tag}_ncu_$k -f \
+          python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --only $only > $out/${tag}_ncu_$k.log 2>&1
+      done ;;
     sanitizer)
-      timeout 1500 compute-sanitizer --tool memcheck --log-file $out/${tag}_memcheck.log python -m pytest tests -m gpu -x -q -k "${SAN_K:-edge or fixture or quirk or fuzz}" > $out/${tag}_memcheck_pytest.log 2>&1
-      timeout 1500 compute-sanitizer --tool racecheck --log-file $out/${tag}_racecheck.log python -m pytest tests -m gpu -x -q -k "${SAN_K:-edge or fixture or quirk or fuzz}" > $out/${tag}_racecheck_pytest.log 2>&1 ;;
+      # memcheck and racecheck over a bounded subset (small inputs: the tools slow kernels down 10-100x); the summary lines
+      # (ERROR SUMMARY / RACECHECK SUMMARY) are what profiles/ keeps
+      timeout ${SAN_TIMEOUT:-480} compute-sanitizer --tool memcheck --log-file $out/${tag}_memcheck.log python -m pytest tests -m gpu -x -q -p no:cacheprovider \
+        -k "${SAN_K:-fixture or quirks or edge_sizes or fuzz_single or segment_index or errors}" > $out/${tag}_memcheck_pytest.log 2>&1; echo "exit $?" >> $out/${tag}_memcheck_pytest.log
+      timeout ${SAN_TIMEOUT:-480} compute-sanitizer --tool racecheck --log-file $out/${tag}_racecheck.log python -m pytest tests -m gpu -x -q -p no:cacheprovider \
+        -k "${SAN_RACE_K:-fixture or quirks or segment_index_streams or test_edge_sizes}" > $out/${tag}_racecheck_pytest.log 2>&1; echo "exit $?" >> $out/${tag}_racecheck_pytest.log ;;
     probe)
       timeout 1200 python tools/probe_r02.py ${PROBE_ARGS} > $out/${tag}_probe.log 2>&1 ;;
     probe_e2e)
