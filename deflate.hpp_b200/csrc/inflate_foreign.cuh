@@ -276,8 +276,17 @@ struct FdState {
     uint32_t pos;            // bytes produced by this unit
     uint32_t nops;
     uint32_t state, bfinal, flags;
+    uint32_t btype;          // of the block whose tables are about to be built (TS_TABLES)
     int st;
 };
+constexpr uint32_t TS_TABLES = 3;        // a Huffman block's 3 header bits are read, its tables are not built yet
+// Table builds are ~16 000 instructions of single-thread work per block (code lengths through the precode, two table
+// fills); run by whichever lane happens to reach one they serialise: 31 lanes wait while one works, 32 times per round
+// of blocks -- a third of the decode kernels' instruction stream.  A lane that reaches a Huffman block therefore WAITS
+// (the others keep decoding) until FD_TAB_BATCH lanes are waiting, nobody is decoding any more, or FD_TAB_WAIT trips of
+// the symbol loop have passed; the waiting lanes then build their tables together, the same instructions side by side.
+constexpr uint32_t FD_TAB_BATCH = 4;
+constexpr uint32_t FD_TAB_WAIT = 1024;
 
 // Codes longer than the direct table's index.  tp_slow_symbol() walks the lengths one by one with two local-memory loads
 // per step (~300 cycles), and in a warp whose 32 lanes decode 32 different units the other lanes wait for it: with a
@@ -318,9 +327,8 @@ __device__ __forceinline__ int fd_slow_symbol(uint32_t slow_sa, uint32_t stride,
 // version did exactly that: 955 LDL / STL instructions in the kernel, F2 + F3 = 37.6 ms).
 // LB / DB: index widths of the thread's private literal/length and distance tables (the 7-bit precode table borrows the
 // literal table's space, which is not built yet when it is needed).
-template <bool EMIT, uint32_t LB, uint32_t DB>
-__device__ __noinline__ FdState fd_block(FdState s, uint16_t* lit, uint16_t* dst, uint32_t* slow, uint32_t NT, TpTables& T, uint64_t in_len,
-                                      uint64_t in_bits, bool strict, uint64_t stop_bit, uint16_t* S, uint64_t* ops, const uint8_t* in) {
+template <bool EMIT>
+__device__ __noinline__ FdState fd_block(FdState s, uint64_t in_len, uint64_t in_bits, bool strict, uint64_t stop_bit, uint64_t* ops) {
     TBits& br = s.br;
     if (tb_bitpos(br) + 3 > in_bits) { s.st = ST_OVERRUN; s.state = TS_DONE; return s; }
     tb_refill(br);
@@ -344,59 +352,69 @@ __device__ __noinline__ FdState fd_block(FdState s, uint16_t* lit, uint16_t* dst
     } else if (btype == 3) {
         if (strict) { s.st = ST_DATA; s.state = TS_DONE; return s; }           // the reference's switch has no case 3: skipped
     } else {
-        uint32_t hlit = NLIT, hdist = NDIST;
-        if (btype == 1) {
-            for (uint32_t i = 0; i < NLIT; i++) T.lens[i] = (uint8_t)fixed_lit_len(i);
-            for (uint32_t i = 0; i < NDIST; i++) T.lens[NLIT + i] = 5;
-        } else {
-            hlit = tb_get(br, 5) + 257;
-            hdist = tb_get(br, 5) + 1;
-            const uint32_t hclen = tb_get(br, 4) + 4;
-            uint8_t pl[19];
-            #pragma unroll 1
-            for (uint32_t i = 0; i < 19; i++) pl[i] = 0;
-            #pragma unroll 1
-            for (uint32_t i = 0; i < hclen; i++) {
-                tb_refill(br);
-                pl[C_PRECODE_ORDER[i]] = (uint8_t)tb_get(br, 3);
-            }
-            static_assert(LB >= 7, "the precode table needs 128 entries");
-            if (!tp_build(lit, NT, T, pl, 19, 1, 7, false)) { s.st = ST_DATA; s.state = TS_DONE; return s; }
-            const uint32_t total = hlit + hdist;
-            uint32_t i = 0, prev = 0;
-            #pragma unroll 1
-            while (i < total) {
-                tb_refill(br);
-                const uint32_t e = lit[tb_peek(br, 7) * NT];
-                const uint32_t l = e & 15u, sym = e >> 4;
-                if (l == 0) { s.st = ST_OVERRUN; s.state = TS_DONE; return s; }
-                tb_drop(br, l);
-                uint32_t rep = 1, val = sym;
-                if (sym == 16) { rep = 3 + tb_get(br, 2); val = prev; }
-                else if (sym == 17) { rep = 3 + tb_get(br, 3); val = 0; }
-                else if (sym == 18) { rep = 11 + tb_get(br, 7); val = 0; }
-                if (i + rep > total) { s.st = ST_DATA; s.state = TS_DONE; return s; }
-                #pragma unroll 1
-                for (uint32_t j = 0; j < rep; j++) {
-                    const uint32_t p = i + j;
-                    T.lens[p < hlit ? p : NLIT + (p - hlit)] = (uint8_t)val;
-                }
-                i += rep;
-                prev = val;
-            }
-            if (T.lens[256] == 0) { s.st = ST_DATA; s.state = TS_DONE; return s; }
-        }
-        if (!tp_build(lit, NT, T, T.lens, hlit, 0, LB, true)) { s.st = ST_DATA; s.state = TS_DONE; return s; }
-        fd_slow_fill<LB>(slow, NT, T, 0);                    // before the distance build reuses nothing of alphabet 0
-        if (!tp_build(dst, NT, T, T.lens + NLIT, hdist, 1, DB, false)) { s.st = ST_DATA; s.state = TS_DONE; return s; }
-        fd_slow_fill<DB>(slow + (15 - LB) * NT, NT, T, 1);
-        s.state = TS_SYM;
+        s.btype = btype;
+        s.state = TS_TABLES;
         return s;
     }
     // stored or skipped block: what follows every block
     if (s.pos > FD_MAX_OUT) { s.st = ST_FALLBACK; s.state = TS_DONE; }
     else if (s.bfinal) { s.flags |= FU_FINAL; s.state = TS_DONE; }
     else if (tb_bitpos(br) >= stop_bit) { s.flags |= FU_REACHED; s.state = TS_DONE; }
+    return s;
+}
+
+// The tables of a fixed (btype 1) or dynamic (btype 2) block whose 3 header bits have been read.
+template <uint32_t LB, uint32_t DB>
+__device__ __noinline__ FdState fd_tables(FdState s, uint16_t* lit, uint16_t* dst, uint32_t* slow, uint32_t NT, TpTables& T) {
+    TBits& br = s.br;
+    uint32_t hlit = NLIT, hdist = NDIST;
+    if (s.btype == 1) {
+        for (uint32_t i = 0; i < NLIT; i++) T.lens[i] = (uint8_t)fixed_lit_len(i);
+        for (uint32_t i = 0; i < NDIST; i++) T.lens[NLIT + i] = 5;
+    } else {
+        tb_refill(br);
+        hlit = tb_get(br, 5) + 257;
+        hdist = tb_get(br, 5) + 1;
+        const uint32_t hclen = tb_get(br, 4) + 4;
+        uint8_t pl[19];
+        #pragma unroll 1
+        for (uint32_t i = 0; i < 19; i++) pl[i] = 0;
+        #pragma unroll 1
+        for (uint32_t i = 0; i < hclen; i++) {
+            tb_refill(br);
+            pl[C_PRECODE_ORDER[i]] = (uint8_t)tb_get(br, 3);
+        }
+        static_assert(LB >= 7, "the precode table needs 128 entries");
+        if (!tp_build(lit, NT, T, pl, 19, 1, 7, false)) { s.st = ST_DATA; s.state = TS_DONE; return s; }
+        const uint32_t total = hlit + hdist;
+        uint32_t i = 0, prev = 0;
+        #pragma unroll 1
+        while (i < total) {
+            tb_refill(br);
+            const uint32_t e = lit[tb_peek(br, 7) * NT];
+            const uint32_t l = e & 15u, sym = e >> 4;
+            if (l == 0) { s.st = ST_OVERRUN; s.state = TS_DONE; return s; }
+            tb_drop(br, l);
+            uint32_t rep = 1, val = sym;
+            if (sym == 16) { rep = 3 + tb_get(br, 2); val = prev; }
+            else if (sym == 17) { rep = 3 + tb_get(br, 3); val = 0; }
+            else if (sym == 18) { rep = 11 + tb_get(br, 7); val = 0; }
+            if (i + rep > total) { s.st = ST_DATA; s.state = TS_DONE; return s; }
+            #pragma unroll 1
+            for (uint32_t j = 0; j < rep; j++) {
+                const uint32_t p = i + j;
+                T.lens[p < hlit ? p : NLIT + (p - hlit)] = (uint8_t)val;
+            }
+            i += rep;
+            prev = val;
+        }
+        if (T.lens[256] == 0) { s.st = ST_DATA; s.state = TS_DONE; return s; }
+    }
+    if (!tp_build(lit, NT, T, T.lens, hlit, 0, LB, true)) { s.st = ST_DATA; s.state = TS_DONE; return s; }
+    fd_slow_fill<LB>(slow, NT, T, 0);
+    if (!tp_build(dst, NT, T, T.lens + NLIT, hdist, 1, DB, false)) { s.st = ST_DATA; s.state = TS_DONE; return s; }
+    fd_slow_fill<DB>(slow + (15 - LB) * NT, NT, T, 1);
+    s.state = TS_SYM;
     return s;
 }
 
@@ -437,7 +455,7 @@ foreign_decode_kernel(const uint8_t* __restrict__ in, uint64_t n, const uint64_t
     s.br.wp = reinterpret_cast<const uint32_t*>(in - s.br.skip);
     s.br.nw = (uint32_t)((s.br.skip + n + 3) >> 2);
     s.br.wi = 0; s.br.w0 = 0; s.br.bb = 0; s.br.bc = 0;
-    s.pos = 0; s.nops = 0; s.bfinal = 0; s.flags = 0; s.st = ST_OK;
+    s.pos = 0; s.nops = 0; s.bfinal = 0; s.flags = 0; s.st = ST_OK; s.btype = 0;
     s.state = TS_DONE;
     uint64_t stop_bit = ~0ull, u = 0;
     uint16_t* Su = nullptr;
@@ -450,7 +468,13 @@ foreign_decode_kernel(const uint8_t* __restrict__ in, uint64_t n, const uint64_t
     const uint32_t wi_end = s.br.nw + 4;
     uint32_t wi_lim = wi_end;
 
+    uint32_t waited = 0;                                      // trips since a lane began to wait for its tables (warp-uniform)
     while (__any_sync(0xFFFFFFFFu, more)) {
+        const uint32_t m_tab = __ballot_sync(0xFFFFFFFFu, s.state == TS_TABLES);
+        const uint32_t m_sym = __ballot_sync(0xFFFFFFFFu, s.state == TS_SYM);
+        waited = m_tab ? waited + 1 : 0;
+        const bool build_now = m_tab && (__popc(m_tab) >= FD_TAB_BATCH || m_sym == 0 || waited >= FD_TAB_WAIT);
+        if (build_now) waited = 0;
         if (s.state == TS_DONE) {
             if (!more) continue;
             if (have) {                                       // publish the unit that has just ended
@@ -545,7 +569,9 @@ foreign_decode_kernel(const uint8_t* __restrict__ in, uint64_t n, const uint64_t
                 }
             }
         } else if (s.state == TS_BLOCK) {
-            s = fd_block<EMIT, LB, DB>(s, lit, dst, slow, NT, T, n, in_bits, strict, stop_bit, Su, ops, in);
+            s = fd_block<EMIT>(s, n, in_bits, strict, stop_bit, ops);
+        } else if (s.state == TS_TABLES && build_now) {
+            s = fd_tables<LB, DB>(s, lit, dst, slow, NT, T);
         }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
