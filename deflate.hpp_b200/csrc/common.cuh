@@ -48,6 +48,8 @@ __host__ __device__ __forceinline__ uint32_t tok_len(uint32_t t) { return t & 0x
 // Kernels take a `const ChunkSrc*` that is NULL for one contiguous input (chunk c = bytes [c * CHUNK, ...)).
 struct ChunkSrc { uint64_t off; uint32_t clen; uint32_t last; };
 constexpr uint64_t SMALL_INPUT_BYTES = 1ull << 20;
+// ntok[] entry of a segment that consists of literals only: bit 31 set, no tokens in tok[] -- token i is input byte i
+constexpr uint32_t NTOK_LITERALS = 0x80000000u;
 
 // Block descriptor written by the Huffman kernel, read by the encoder.
 struct BlockDesc {

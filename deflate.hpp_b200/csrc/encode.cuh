@@ -140,20 +140,24 @@ encode_kernel(const uint8_t* __restrict__ in, const uint32_t* __restrict__ tok, 
         }
         const uint32_t* cd = s_codes + ((split && warp >= split) ? NSYM : 0u);
         // payload: warp = segment; 32 tokens per step, warp scan of bit lengths
-        const uint32_t nt = d.clen ? ntok[chunk * NSEG + warp] : 0u;      // an empty input: header + end of block only
+        const uint32_t nt_raw = d.clen ? ntok[chunk * NSEG + warp] : 0u;  // an empty input: header + end of block only
+        const uint32_t nt = nt_raw & ~NTOK_LITERALS;
+        const bool lit_only = (nt_raw & NTOK_LITERALS) != 0;               // no tokens were written: token i = input byte i
         const uint32_t* mytok = tok + chunk * CHUNK + warp * SEG;
+        const uint8_t* mysrc = in + (srcs ? srcs[chunk].off : chunk * CHUNK) + warp * SEG;
+        auto ld_tok = [&](uint32_t k) -> uint32_t { return lit_only ? (uint32_t)mysrc[k] : mytok[k]; };
         uint32_t bit = bit0 + d.seg_bitoff[warp];
         // the tokens of the step after the current one are always in flight (a step is ~60 instructions: shorter than
         // an L2 / DRAM round trip; ncu r01f: 13 % of this kernel's stall samples were long-scoreboard)
-        uint32_t t_next = lane < nt ? mytok[lane] : 0u;
-        uint32_t t_next2 = 32 + lane < nt ? mytok[32 + lane] : 0u;
+        uint32_t t_next = lane < nt ? ld_tok(lane) : 0u;
+        uint32_t t_next2 = 32 + lane < nt ? ld_tok(32 + lane) : 0u;
         for (uint32_t b = 0; b < nt; b += 32) {
             const uint32_t i = b + lane;
             uint64_t v = 0;
             uint32_t nb = 0;
             const uint32_t t = t_next;
             t_next = t_next2;
-            if (b + 64 + lane < nt) t_next2 = mytok[b + 64 + lane];
+            if (b + 64 + lane < nt) t_next2 = ld_tok(b + 64 + lane);
             if (i < nt) {
                 const uint32_t dist = tok_dist(t);
                 if (dist == 0) {

@@ -78,14 +78,11 @@ lz77_literal_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t* __rest
     __syncthreads();
     const uint32_t seg_lo = warp * SEG, seg_hi = min(clen, seg_lo + SEG);
     uint32_t* hs = s_hist + warp * HIST_WORDS;
-    uint32_t* mytok = tok + chunk * CHUNK + seg_lo;
-    for (uint32_t p = seg_lo + lane; p < seg_hi; p += 32) {
-        const uint32_t b = in[base + p];
-        mytok[p - seg_lo] = b;
-        hist_add(hs, b);
-    }
+    // a segment of nothing but literals writes no tokens: the encoder reads the bytes from the input (NTOK_LITERALS)
+    for (uint32_t p = seg_lo + lane; p < seg_hi; p += 32) hist_add(hs, in[base + p]);
     __syncwarp();
-    if (lane == 0) ntok[chunk * NSEG + warp] = seg_lo < clen ? seg_hi - seg_lo : 0;
+    if (lane == 0) ntok[chunk * NSEG + warp] = seg_lo < clen ? ((seg_hi - seg_lo) | NTOK_LITERALS) : 0;
+    (void)tok;
     hist_store(hs, hist + (size_t)(chunk * NSEG + warp) * NSYM, lane);
 }
 
@@ -262,13 +259,10 @@ lz77_fast_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t nchunks, u
         uint32_t* mytok = tok + chunk * CHUNK + seg_lo;
         uint32_t nt = 0;
         if (seg_lo < clen && s_segcnt[warp] == 0) {
-            // not one candidate in this segment: every byte is a literal
-            for (uint32_t p = seg_lo + lane; p < seg_hi; p += 32) {
-                const uint32_t b = s_data[p];
-                mytok[p - seg_lo] = b;
-                hist_add(hs, b);
-            }
-            nt = seg_hi - seg_lo;
+            // not one candidate in this segment: every byte is a literal, and no tokens are written -- the encoder reads
+            // the bytes from the input (a quarter of a MB per random chunk that neither kernel has to move)
+            for (uint32_t p = seg_lo + lane; p < seg_hi; p += 32) hist_add(hs, s_data[p]);
+            nt = (seg_hi - seg_lo) | NTOK_LITERALS;
         } else if (seg_lo < clen) {
             uint32_t pos = seg_lo;
             // candidates travel through a per-warp ring of four 32-entry blocks in shared memory, filled by
