@@ -97,3 +97,22 @@ int main() {
 ''' % (ROOT, ROOT))
     r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", str(probe)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_host_prefault_touches_without_changing_zeroed_memory(b200):
+    """b200_host_prefault (what the drop-in headers call on the std::vector they are about to fill) needs no GPU: it writes
+    one zero byte per page from several threads -- fresh (zero) memory stays zero, sizes below its threshold and odd
+    sizes / alignments are fine, NULL is ignored."""
+    import mmap
+    L = ctypes.CDLL(b200.lib_path())
+    L.b200_host_prefault.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
+    L.b200_host_prefault.restype = None
+    L.b200_host_prefault(None, 1 << 20)
+    for n in (1, 4095, (4 << 20) + 123, (37 << 20) + 1):
+        m = mmap.mmap(-1, n + 4096)
+        buf = (ctypes.c_char * (n + 4096)).from_buffer(m)
+        addr = ctypes.addressof(buf) + 3                   # unaligned start
+        L.b200_host_prefault(addr, n)
+        assert m[:n + 4096].count(b"\0") == n + 4096
+        del buf
+        m.close()

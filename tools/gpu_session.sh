@@ -28,12 +28,22 @@ for step in "$@"; do
       timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"${NCU_KERNELS:-lz77_fast_kernel|encode_kernel|huffman_kernel}" -c ${NCU_COUNT:-4} \
         -o $out/${tag}_full${NCU_TAG} -f python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --only ${NCU_ONLY:-none} > $out/${tag}_ncu_full${NCU_TAG}.log 2>&1 ;;
     ncu_each)
-      # one `--set full` capture per kernel (first launch that matches), each from its own short bench run
-      for spec in ${NCU_EACH:-lz77_fast_kernel:none huffman_kernel:none encode_kernel:none inflate_segments_kernel:none inflate_copy_kernel:none lz77_better_kernel:better inflate_batch_kernel:batch foreign_decode_kernel:foreign foreign_find_blocks_kernel:foreign foreign_copy_kernel:foreign}; do
+      # one `--set full` capture per kernel (first launch that matches), each from its own short bench run.  The reports are
+      # 10-16 MB each and gpurun brings back at most 64 MiB: they are condensed HERE (tools/ncu_summary.py, tools/ncu_lines.py
+      # work without a GPU but need ncu + nvdisasm, which the box has) and only the text travels; NCU_KEEP names the one report to keep.
+      rm -f $out/${tag}_ncu_summary.md $out/${tag}_traffic.json
+      for spec in ${NCU_EACH:-lz77_fast_kernel:none huffman_kernel:none encode_kernel:none find_sync_kernel:none inflate_segments_kernel:none inflate_copy_kernel:none lz77_better_kernel:better inflate_batch_kernel:batch foreign_find_blocks_kernel:foreign foreign_decode_kernel:foreign foreign_copy_kernel:foreign foreign_window_kernel:foreign}; do
         k=${spec%%:*}; only=${spec##*:}
         timeout 600 ncu --set full --clock-control none --import-source on -k regex:"$k" -c 1 -o $out/${tag}_ncu_$k -f \
           python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --only $only > $out/${tag}_ncu_$k.log 2>&1
-      done ;;
+        if [ -f $out/${tag}_ncu_$k.ncu-rep ]; then
+          python tools/ncu_summary.py $out/${tag}_ncu_$k.ncu-rep $out/${tag}_ncu_summary.md $out/${tag}_traffic.json > /dev/null 2>&1
+          python tools/ncu_lines.py $out/${tag}_ncu_$k.ncu-rep $k 40 > $out/${tag}_lines_$k.txt 2>&1
+          [ "$k" = "${NCU_KEEP:-lz77_fast_kernel}" ] || rm -f $out/${tag}_ncu_$k.ncu-rep
+        fi
+        tail -c 2000 $out/${tag}_ncu_$k.log > $out/${tag}_ncu_$k.log.tail; mv $out/${tag}_ncu_$k.log.tail $out/${tag}_ncu_$k.log
+      done
+      du -sh $out > $out/${tag}_du.txt ;;
     sanitizer)
       # memcheck and racecheck over a bounded subset (small inputs: the tools slow kernels down 10-100x); the summary lines
       # (ERROR SUMMARY / RACECHECK SUMMARY) are what profiles/ keeps
