@@ -305,29 +305,19 @@ lz77_fast_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t nchunks, u
                 }
                 const uint32_t byte = s_data[p];
                 const uint32_t valid = min(32u, seg_hi - pos);
-                // greedy in-order selection (first match lane at or after the frontier, jump to its end, repeat) without the
-                // serial walk: every match lane knows its successor -- the first match lane at or behind its own end -- so the
-                // selected set is what is reachable from the window's first match, and a window holds at most 8 selected
-                // matches (each covers >= 4 positions): three rounds of pointer doubling reach them all.  (The walk, one
-                // ffs + shuffle + mask per selected match, was 23 % of this kernel's stall samples.)
-                const uint32_t mm = __ballot_sync(FULL, len >= 4);
+                // greedy in-order selection: the serial part only walks from match to match
+                // (first match lane at or after the frontier, jump to its end) ...
+                // (Measured and rejected: the walk replaced by three rounds of pointer doubling over per-lane successor
+                // links -- the selected set is what is reachable from the window's first match, at most 8 matches -- gives the
+                // same bytes in the same 9.5 ms: the walk's latency is hidden by the other 31 warps of the SM.)
+                uint32_t mm = __ballot_sync(FULL, len >= 4);
                 const uint32_t endl = lane + len;                        // where this lane's match would end
                 uint32_t selmask = 0, cur = 0;
-                if (mm) {
-                    uint32_t J = 32;                                     // successor lane (32: none)
-                    if (len >= 4 && endl < 32) {
-                        const uint32_t later = mm & (FULL << endl);
-                        J = later ? __ffs(later) - 1 : 32;
-                    }
-                    selmask = 1u << (__ffs(mm) - 1);
-                    #pragma unroll
-                    for (int r = 0; r < 3; r++) {
-                        const bool on = (selmask >> lane) & 1u;
-                        selmask |= __reduce_or_sync(FULL, (on && J < 32) ? (1u << J) : 0u);
-                        const uint32_t JJ = __shfl_sync(FULL, J, J & 31);
-                        J = J < 32 ? JJ : 32;
-                    }
-                    cur = __reduce_max_sync(FULL, ((selmask >> lane) & 1u) ? endl : 0u);
+                while (mm) {
+                    const uint32_t j = __ffs(mm) - 1;
+                    selmask |= 1u << j;
+                    cur = __shfl_sync(FULL, endl, j);
+                    mm = cur < 32 ? mm & (FULL << cur) : 0;
                 }
                 // ... and every lane then decides for itself whether a selected match covers it: the
                 // nearest selected lane at or below it is the only one that can (matches do not overlap)

@@ -50,7 +50,8 @@ for step in "$@"; do
       timeout ${SAN_TIMEOUT:-480} compute-sanitizer --tool memcheck --log-file $out/${tag}_memcheck.log python -m pytest tests -m gpu -x -q -p no:cacheprovider \
         -k "${SAN_K:-fixture or quirks or edge_sizes or fuzz_single or segment_index or errors}" > $out/${tag}_memcheck_pytest.log 2>&1; echo "exit $?" >> $out/${tag}_memcheck_pytest.log
       timeout ${SAN_TIMEOUT:-480} compute-sanitizer --tool racecheck --log-file $out/${tag}_racecheck.log python -m pytest tests -m gpu -x -q -p no:cacheprovider \
-        -k "${SAN_RACE_K:-fixture or quirks or segment_index_streams or test_edge_sizes}" > $out/${tag}_racecheck_pytest.log 2>&1; echo "exit $?" >> $out/${tag}_racecheck_pytest.log ;;
+        -k "${SAN_RACE_K:-fixture or quirks or segment_index_streams or test_edge_sizes}" > $out/${tag}_racecheck_pytest.log 2>&1; echo "exit $?" >> $out/${tag}_racecheck_pytest.log
+      for f in $out/${tag}_memcheck.log $out/${tag}_racecheck.log; do [ -f $f ] && { head -c 1500000 $f > $f.cut; mv $f.cut $f; }; done ;;
     probe)
       timeout 1200 python tools/probe_r02.py ${PROBE_ARGS} > $out/${tag}_probe.log 2>&1 ;;
     probe_e2e)
