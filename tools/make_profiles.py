@@ -44,7 +44,25 @@ def main():
     # ---- ncu --set full captures ----
     md = os.path.join(PROF, f"{rnd}_ncu_summary.md")
     reps = sorted(glob.glob(os.path.join(OUT, f"{tag}_ncu_*.ncu-rep")))
-    if reps:
+    boxmd = os.path.join(OUT, f"{tag}_ncu_summary.md")
+    if os.path.exists(boxmd):
+        # the session condensed its captures on the GPU box (tools/gpu_session.sh ncu_each): one table from its rows
+        lines = [ln for ln in open(boxmd).read().splitlines() if ln.startswith("|")]
+        head, rows_ = lines[:2], [ln for ln in lines if not ln.startswith("| kernel") and not ln.startswith("|---")]
+        with open(md, "w") as f:
+            f.write(f"# Round {rnd[1:]} -- `ncu --set full --clock-control none --import-source on`, one capture per kernel (first launch), B200\n\n"
+                    "Each row comes from its own run of `python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --only <section>` under ncu\n"
+                    "(`tools/gpu_session.sh ncu_each`), after the same bench command had exited 0 without ncu; the reports were condensed on the box\n"
+                    "(`tools/ncu_summary.py`), the lz77_fast_kernel report also came back.  Compress kernels see one batch = 16 384 chunks = 1 GiB per\n"
+                    "launch, the inflate kernels the whole 1 GiB stream.  Times are cold-cache and serialised.  `traffic.json` holds dram read + write\n"
+                    "bytes of these launches (what `bench.py` reports as `roofline.traffic`).\n\n" + "\n".join(head + rows_) + "\n")
+        if os.path.exists(os.path.join(OUT, f"{tag}_traffic.json")):
+            shutil.copy(os.path.join(OUT, f"{tag}_traffic.json"), os.path.join(PROF, "traffic.json"))
+        for lf in sorted(glob.glob(os.path.join(OUT, f"{tag}_lines_*.txt"))):
+            short = os.path.basename(lf)[len(tag) + 7:].replace("_kernel.txt", ".txt")
+            shutil.copy(lf, os.path.join(PROF, f"{rnd}_lines_{short}"))
+        notes.append(f"{rnd}_ncu_summary.md / traffic.json / {rnd}_lines_<kernel>.txt: {len(rows_)} `--set full` captures, condensed on the box")
+    elif reps:
         with open(md, "w") as f:
             f.write(f"# Round {rnd[1:]} -- `ncu --set full --clock-control none --import-source on`, one capture per kernel (first launch), B200\n\n"
                     "Each row comes from its own run of `python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --only <section>` under ncu\n"
@@ -97,8 +115,15 @@ def main():
         mu = hdr.index("Metric Unit")
         scale = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3, "nsecond": 1e-6, "usecond": 1e-3, "msecond": 1.0, "second": 1e3}
         agg = {}
+        seen_main = False
         for r_ in rows[1:]:
             name = r_[kn].split("(")[0].replace("void ", "").replace("b200::", "").split("<")[0]
+            # only the headline section (warm-up + one step on the 1 GiB corpus): it ends where bench.py's next section starts
+            # (torch kernels checking the round trip, then the small-file calls of config 1)
+            if name == "lz77_fast_kernel":
+                seen_main = True
+            if seen_main and name.startswith("at::"):
+                break
             agg[name] = agg.get(name, 0.0) + float(r_[mv].replace(",", "")) * scale.get(r_[mu], 1e-6)
         comp = {"lz77_kernel": agg.get("lz77_fast_kernel", 0), "huffman_kernel": agg.get("huffman_kernel", 0),
                 "scan_sizes_kernel": None, "encode_kernel": agg.get("encode_kernel", 0)}
