@@ -150,7 +150,7 @@ struct b200_ctx {
                                      // 8192 / 16384: 80.0 / 82.5 / 83.9 GB/s (fewer tails of the persistent matcher, fewer launches)
     // "better" level: chain depth / good-enough length.  0 = by input size: small inputs (< 1 MiB, where the time does not
     // matter) search like the reference does -- its level 3 looks at EVERY earlier position (deflate.hpp:280-296), and on
-    // test.bmp that is worth 5 % -- large ones use 8 / 32 (the depth sweep in profiles/: 6.6 -> 18 GB/s for +0.4 % size)
+    // test.bmp that is worth 5 % -- large ones use 6 / 32 (the depth sweep in profiles/: 6.6 -> 21 GB/s for +1 % size)
     uint32_t better_depth = 0, better_nice = 0;
     // compress scratch
     Buf tok, ntok, hist, codes, hdr, desc, sizes, offsets, total;
@@ -188,6 +188,7 @@ struct b200_ctx {
     std::vector<cudaEvent_t> events;
     uint64_t* mailbox = nullptr;     // pinned: per-slice end offsets
     size_t mailbox_cap = 0;
+    unsigned long long* ctl = nullptr;   // pinned, 16 words: results the pipelined host inflate reads (publish_kernel)
     size_t host_inflate_slice = (size_t)256 << 20;  // host-buffer inflate: bytes of input per pipeline slice (0 = off; measured best of
                                                     // 64..384 MiB: smaller groups of chunks run as partial waves); B200_HOST_INFLATE_SLICE
     uint32_t host_slice_chunks = 1024;   // 64 MiB: measured best (smaller slices starve the persistent matcher)
@@ -292,6 +293,29 @@ int default_ctx(b200_ctx** out) {
 }
 
 
+// Control words between host and device WITHOUT the copy engines.  A cudaMemcpyAsync of 8 bytes is queued on the same
+// DMA engine as the bulk copies of the host-buffer pipeline and waits for whatever slice is on the wire (a 256 MiB slice:
+// 5 ms) -- and the compute stream waits with it.  So the pipelined host inflate passes its few words through kernels:
+// the device writes results straight into pinned (UVA-mapped) host memory, the host passes values as kernel arguments.
+__global__ void publish_kernel(volatile unsigned long long* __restrict__ host, const unsigned long long* __restrict__ a, uint32_t na,
+                               const unsigned long long* __restrict__ b, uint32_t nb) {
+    const uint32_t t = threadIdx.x;
+    if (t < na) host[t] = a[t];
+    else if (t < na + nb) host[t] = b[t - na];
+    __threadfence_system();
+}
+__global__ void poke_kernel(unsigned long long* p0, unsigned long long v0, unsigned long long* p1, unsigned long long v1,
+                            unsigned long long* p2, unsigned long long v2, unsigned long long* p3, unsigned long long v3) {
+    if (p0) *p0 = v0;
+    if (p1) *p1 = v1;
+    if (p2) *p2 = v2;
+    if (p3) *p3 = v3;
+}
+__global__ void zero_words_kernel(unsigned long long* __restrict__ p, uint64_t nwords) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nwords) p[i] = 0;
+}
+
 // Two-pass fast path (inflate_tp.cuh) for a set of units: pass A (one thread per unit: symbols, literals,
 // op lists), the one-warp decoder for the units pass A gave up on, pass B (one warp per unit: copies).
 // `res` receives one TpResult per unit.  cnt: 32 zeroed u64 counter words ([1] fallback queue, [2] copy queue,
@@ -360,7 +384,8 @@ static int inflate_chunks_two_pass(b200_ctx* c, const uint8_t* in, uint64_t n, c
     if ((rc = c->segnops.ensure(ncand * NSEG * 2))) return rc;
     if ((rc = c->ops.ensure(nslots * G * OPS_PER_CHUNK * 8))) return rc;
     if ((rc = c->group_cnt.ensure(ngroups * 256))) return rc;
-    CK(cudaMemsetAsync(c->group_cnt.p, 0, ngroups * 256, st));
+    zero_words_kernel<<<(uint32_t)((ngroups * 32 + 255) / 256), 256, 0, st>>>((unsigned long long*)c->group_cnt.p, ngroups * 32);   // (not a memset:
+    LAUNCHED();                                                                    // see publish_kernel)
     while (c->group_events.size() < 2 * ngroups) {
         cudaEvent_t e;
         CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -475,6 +500,7 @@ void b200_ctx_destroy(b200_ctx* c) {
     for (auto e : c->group_events) cudaEventDestroy(e);
     if (c->s_side) cudaStreamDestroy(c->s_side);
     if (c->mailbox) cudaFreeHost(c->mailbox);
+    if (c->ctl) cudaFreeHost(c->ctl);
     if (c->arena) cudaFreeHost(c->arena);
     for (int k = 0; k < b200_ctx::STG_N; k++) {
         if (c->stg_in[k]) cudaFreeHost(c->stg_in[k]);
@@ -552,7 +578,7 @@ static int compress_batch(b200_ctx* c, const uint8_t* bin, uint64_t bn, uint32_t
             // bytes of the whole input (a batch says it per chunk, in ChunkSrc)
             const bool small = !srcs && b0 * CHUNK + bn < SMALL_INPUT_BYTES;
             lz77_better_kernel<<<nb, LZB_THREADS, LZB_SMEM_BYTES, st>>>(bin, bn, (uint32_t*)c->tok.p, (uint32_t*)c->ntok.p, (uint16_t*)c->hist.p,
-                                                                     c->better_depth ? c->better_depth : 8u, c->better_nice ? c->better_nice : 32u,
+                                                                     c->better_depth ? c->better_depth : 6u, c->better_nice ? c->better_nice : 32u,
                                                                      c->better_depth ? c->better_depth : 128u, c->better_nice ? c->better_nice : 258u,
                                                                      small ? 1u : 0u, srcs);
         }
@@ -1516,7 +1542,9 @@ static int compress_host(b200_ctx* c, const uint8_t* in, size_t n, int level, un
         if ((rc = compress_batch(c, d_in + off, n - off, nb, b0, b0 + nb == nchunks, level, offs, d_total, d_out, c->stream, 3, nullptr,
                                  nullptr, d_first_base)))
             return rc;
-        CK(cudaMemcpyAsync(&c->mailbox[k], offs + b0 + nb, 8, cudaMemcpyDeviceToHost, c->stream));
+        // the slice's end offset goes to the mailbox by a kernel, not by a copy that would queue behind the bulk copies
+        publish_kernel<<<1, 32, 0, c->stream>>>((volatile unsigned long long*)&c->mailbox[k], (const unsigned long long*)(offs + b0 + nb), 1, nullptr, 0);
+        LAUNCHED();
         CK(cudaEventRecord(c->events[2 * k + 1], c->stream));
         // slices that are finished already start their way back now instead of after the last slice was enqueued
         while (drained + 1 < k && cudaEventQuery(c->events[2 * drained + 1]) == cudaSuccess) {
@@ -1532,7 +1560,8 @@ static int compress_host(b200_ctx* c, const uint8_t* in, size_t n, int level, un
         if ((rc = checksum_dev(c, d_in, n, frame, (uint32_t*)(d_total + 4), c->stream))) return rc;
         write_trailer_kernel<<<1, 1, 0, c->stream>>>(d_out, d_total, (const uint32_t*)(d_total + 4), (uint64_t)n, frame);
         LAUNCHED();
-        CK(cudaMemcpyAsync(&c->mailbox[nslices], d_total, 8, cudaMemcpyDeviceToHost, c->stream));
+        publish_kernel<<<1, 32, 0, c->stream>>>((volatile unsigned long long*)&c->mailbox[nslices], (const unsigned long long*)d_total, 1, nullptr, 0);
+        LAUNCHED();
     }
     // drain: as each slice finishes, copy its compressed bytes out on s_out
     for (uint64_t k = drained; k < nslices; k++) {
@@ -1718,6 +1747,8 @@ static int inflate_host_pipelined(b200_ctx* c, const uint8_t* in, size_t n, uint
     uint8_t* d_out = (uint8_t*)c->d_out.p;
     unsigned long long* d_result = (unsigned long long*)c->result.p;
     cudaStream_t st = c->stream;
+    if (!c->ctl) CK(cudaHostAlloc((void**)&c->ctl, 16 * 8, cudaHostAllocDefault));
+    volatile unsigned long long* ctl = c->ctl;
     // the input travels on its own host thread: with pageable caller memory every slice is staged through the pinned
     // ring by host threads (copy_h2d), which must not hold up the decode loop below
     std::atomic<size_t> arrived{0};
@@ -1758,14 +1789,20 @@ static int inflate_host_pipelined(b200_ctx* c, const uint8_t* in, size_t n, uint
         scan_sizes_kernel<<<1, SCAN_THREADS, 0, st>>>((const uint32_t*)c->counts.p, (uint32_t)nwarps, nullptr, (uint64_t*)c->woffs.p,
                                                      (uint64_t*)d_result + 2);
         LAUNCHED();
-        uint64_t nmark = 0;
-        CK(cudaMemcpyAsync(&nmark, d_result + 2, 8, cudaMemcpyDeviceToHost, st));
+        // (control words travel through kernels, not through the copy engines the slices are on: see publish_kernel)
+        publish_kernel<<<1, 32, 0, st>>>(ctl, d_result + 2, 1, nullptr, 0);
+        LAUNCHED();
         CK(cudaStreamSynchronize(st));
+        const uint64_t nmark = ctl[0];
         if (nmark + 2 > cand_cap) { ok = false; break; }
         const uint64_t ncand = nmark + 1;
         const uint64_t units = last ? ncand : ncand - 1;      // the last candidate of a slice starts a chunk that is still arriving
         if (units == 0) continue;
-        CK(cudaMemcpyAsync(cand, &rel0, 8, cudaMemcpyHostToDevice, st));
+        // cand[0] = where this slice's first chunk starts, the sentinel behind the last slice's candidates (the last chunk
+        // ends at n), and the verdict words {valid = 1, total = 0}
+        poke_kernel<<<1, 1, 0, st>>>((unsigned long long*)cand, rel0, last ? (unsigned long long*)cand + ncand : nullptr, region,
+                                     d_result, 1ull, d_result + 1, 0ull);
+        LAUNCHED();
         if (nmark) {
             PROF_BEGIN(c, K_FIND_SYNC, st);
             find_sync_kernel<true><<<g, 256, 0, st>>>(rin, region, (uint32_t*)c->counts.p, (uint32_t*)c->sync_cache.p,
@@ -1773,9 +1810,6 @@ static int inflate_host_pipelined(b200_ctx* c, const uint8_t* in, size_t n, uint
             LAUNCHED();
             PROF_END(c, st);
         }
-        if (last) CK(cudaMemcpyAsync(cand + ncand, &region, 8, cudaMemcpyHostToDevice, st));     // sentinel: the last chunk ends at n
-        const unsigned long long init[2] = {1ull, 0ull};
-        CK(cudaMemcpyAsync(d_result, init, 16, cudaMemcpyHostToDevice, st));
         const uint64_t o0 = chunk0 * CHUNK;
         if ((rc = inflate_chunks_two_pass(c, rin, region, cand, units, d_out + o0, cap > o0 ? cap - o0 : 0, flags, st))) return rc;
         PROF_BEGIN(c, K_VALIDATE, st);
@@ -1783,11 +1817,11 @@ static int inflate_host_pipelined(b200_ctx* c, const uint8_t* in, size_t n, uint
                                                                               last ? 1 : 0);
         LAUNCHED();
         PROF_END(c, st);
-        unsigned long long verdict[2] = {0, 0};
-        uint64_t next_rel = 0;
-        CK(cudaMemcpyAsync(verdict, d_result, 16, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(&next_rel, cand + units, 8, cudaMemcpyDeviceToHost, st));
+        publish_kernel<<<1, 32, 0, st>>>(ctl + 4, d_result, 2, (const unsigned long long*)cand + units, 1);
+        LAUNCHED();
         CK(cudaStreamSynchronize(st));
+        const unsigned long long verdict[2] = {ctl[4], ctl[5]};
+        const uint64_t next_rel = ctl[6];
         if (verdict[0] != 1) { ok = false; break; }
         const uint64_t lo = o0 < cap ? o0 : cap, hi = o0 + verdict[1] < cap ? o0 + verdict[1] : cap;
         if (hi > lo && (rc = copy_d2h(c, out + lo, d_out + lo, hi - lo, c->s_out))) return rc;

@@ -61,6 +61,12 @@ for step in "$@"; do
       B200_STAGE=0 timeout 300 python tools/probe_e2e.py >> $out/${tag}_probe_e2e.log 2>&1
       B200_STAGE_THREADS=4 timeout 300 python tools/probe_e2e.py >> $out/${tag}_probe_e2e.log 2>&1
       B200_STAGE_THREADS=16 timeout 300 python tools/probe_e2e.py >> $out/${tag}_probe_e2e.log 2>&1 ;;
+    probe_pcie)
+      # what the PCIe link moves raw, then the pinned host-buffer calls at several inflate slice sizes
+      timeout 300 python tools/probe_e2e.py 1024 pinned raw >> $out/${tag}_probe_pcie.log 2>&1
+      for slice in ${PCIE_SLICES:-33554432 67108864 134217728}; do
+        B200_HOST_INFLATE_SLICE=$slice timeout 300 python tools/probe_e2e.py 1024 pinned >> $out/${tag}_probe_pcie.log 2>&1
+      done ;;
     bisect)
       for k in 0 1 2 3 4 5 6 7; do
         for mode in par seq; do

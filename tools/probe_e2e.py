@@ -1,5 +1,6 @@
 """e2e probe of the host-buffer C ABI (pinned and pageable buffers); knobs come from the environment of THIS process
-(the per-process default context reads them once).  usage: python tools/probe_e2e.py [MiB]"""
+(the per-process default context reads them once).  usage: python tools/probe_e2e.py [MiB] [pinned|pageable|both] [raw]
+`raw` adds what the PCIe link of this box moves for the same byte counts with nothing else going on (the ceiling of any e2e number)."""
 import ctypes
 import json
 import os
@@ -18,7 +19,55 @@ src = torch.empty(n, dtype=torch.uint8, device="cuda")
 d.Context.corpus_generate_dev(src.data_ptr(), 20261018, 0, n // 65536)
 cap = d.deflate_bound(n)
 res = {"env": {k: v for k, v in os.environ.items() if k.startswith("B200_")}, "mib": mib}
-for kind in ("pinned", "pageable"):
+kinds = ("pinned", "pageable")
+if len(sys.argv) > 2 and sys.argv[2] in ("pinned", "pageable"):
+    kinds = (sys.argv[2],)
+if "raw" in sys.argv[2:]:
+    # pinned 1 GiB one way, then n bytes in + 0.62 n bytes out at the same time (compress), and the reverse (inflate)
+    a = torch.empty(n, dtype=torch.uint8).pin_memory()
+    b = torch.empty(n, dtype=torch.uint8).pin_memory()
+    da = torch.empty(n, dtype=torch.uint8, device="cuda")
+    db = torch.empty(n, dtype=torch.uint8, device="cuda")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    m = int(n * 0.6207)
+
+    def timed(fn, reps=4):
+        ts = []
+        for i in range(reps + 1):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            fn()
+            torch.cuda.synchronize()
+            if i:
+                ts.append(time.perf_counter() - t0)
+        return sum(ts) / len(ts)
+
+    def h2d():
+        with torch.cuda.stream(s1):
+            da.copy_(a, non_blocking=True)
+
+    def d2h():
+        with torch.cuda.stream(s2):
+            b.copy_(db, non_blocking=True)
+
+    def both_c():
+        with torch.cuda.stream(s1):
+            da.copy_(a, non_blocking=True)
+        with torch.cuda.stream(s2):
+            b[:m].copy_(db[:m], non_blocking=True)
+
+    def both_i():
+        with torch.cuda.stream(s1):
+            da[:m].copy_(a[:m], non_blocking=True)
+        with torch.cuda.stream(s2):
+            b.copy_(db, non_blocking=True)
+
+    res["raw_pcie"] = {"h2d_GBps": round(n / timed(h2d) / 1e9, 2), "d2h_GBps": round(n / timed(d2h) / 1e9, 2),
+                       "compress_shape_ceiling_GBps": round(n / timed(both_c) / 1e9, 2),
+                       "inflate_shape_ceiling_GBps": round(n / timed(both_i) / 1e9, 2),
+                       "note": "ceilings: n bytes one way + 0.62 n the other way at the same time, per n"}
+    del a, b, da, db
+for kind in kinds:
     h_in = torch.empty(n, dtype=torch.uint8)
     h_out = torch.empty(cap, dtype=torch.uint8)
     h_back = torch.empty(n, dtype=torch.uint8)
