@@ -189,8 +189,9 @@ struct b200_ctx {
     uint64_t* mailbox = nullptr;     // pinned: per-slice end offsets
     size_t mailbox_cap = 0;
     unsigned long long* ctl = nullptr;   // pinned, 16 words: results the pipelined host inflate reads (publish_kernel)
-    size_t host_inflate_slice = (size_t)256 << 20;  // host-buffer inflate: bytes of input per pipeline slice (0 = off; measured best of
-                                                    // 64..384 MiB: smaller groups of chunks run as partial waves); B200_HOST_INFLATE_SLICE
+    size_t host_inflate_slice = (size_t)128 << 20;  // host-buffer inflate: bytes of input per pipeline slice (0 = off; measured 32 / 64 /
+                                                    // 128 / 256 MiB: 25.5 / 42.1 / 44.2 / 42.8 GB/s -- smaller groups of chunks run as
+                                                    // partial waves, larger ones start the way back later); B200_HOST_INFLATE_SLICE
     uint32_t host_slice_chunks = 1024;   // 64 MiB: measured best (smaller slices starve the persistent matcher)
     // pageable caller memory: a ring of pinned staging buffers, filled / drained by a few host threads (host-buffer API)
     static constexpr int STG_N = 4;
@@ -1495,7 +1496,18 @@ static int compress_host(b200_ctx* c, const uint8_t* in, size_t n, int level, un
         return B200_OK;
     }
     const uint64_t B = nchunks < c->host_slice_chunks ? nchunks : c->host_slice_chunks;
-    const uint64_t nslices = (nchunks + B - 1) / B;
+    // slice k = chunks [cuts[k], cuts[k + 1]).  What the call cannot hide behind the host -> device copies is the last slice's
+    // kernels and its way back, so a long input ends with slices of B/2, B/4, B/4 chunks (64 MiB slices in between: smaller
+    // ones starve the persistent matcher)
+    std::vector<uint64_t> cuts;
+    {
+        const uint64_t tail = (nchunks >= 4 * B && B >= 4) ? B : 0;
+        uint64_t pos = 0;
+        while (pos < nchunks - tail) { cuts.push_back(pos); pos += (nchunks - tail - pos < B) ? nchunks - tail - pos : B; }
+        if (tail) { cuts.push_back(pos); pos += B / 2; cuts.push_back(pos); pos += B / 4; cuts.push_back(pos); }
+        cuts.push_back(nchunks);
+    }
+    const uint64_t nslices = cuts.size() - 1;
     if ((rc = c->tok.ensure(B * CHUNK * 4))) return rc;
     if ((rc = c->ntok.ensure(B * NSEG * 4))) return rc;
     if ((rc = c->hist.ensure(B * NSEG * NSYM * 2))) return rc;
@@ -1532,8 +1544,8 @@ static int compress_host(b200_ctx* c, const uint8_t* in, size_t n, int level, un
     int result = B200_OK;
     // enqueue every slice: H2D on s_in, kernels on stream (after the slice's H2D), mailbox write
     for (uint64_t k = 0; k < nslices; k++) {
-        const uint64_t b0 = k * B;
-        const uint32_t nb = (uint32_t)((nchunks - b0 < B) ? nchunks - b0 : B);
+        const uint64_t b0 = cuts[k];
+        const uint32_t nb = (uint32_t)(cuts[k + 1] - b0);
         const size_t off = (size_t)b0 * CHUNK;
         const size_t len = (size_t)((b0 + nb == nchunks) ? n - off : (size_t)nb * CHUNK);
         if ((rc = copy_h2d(c, d_in + off, in + off, len, c->s_in))) return rc;          // pageable input: the host stages slice k
@@ -1718,7 +1730,7 @@ static int inflate_host_pipelined(b200_ctx* c, const uint8_t* in, size_t n, uint
     *handled = false;
     *in_resident = false;
     const size_t S = c->host_inflate_slice & ~(size_t)15;
-    const size_t first = (S / 8 > 65536 ? S / 8 : 65536) & ~(size_t)15;         // 32 MiB with the default slice of 256 MiB
+    const size_t first = (S / 8 > 65536 ? S / 8 : 65536) & ~(size_t)15;         // 16 MiB with the default slice of 128 MiB
     if (!S || n < 3 * first || !cap || c->inflate_warp_path) return B200_OK;
     int rc;
     // Slice ends.  The device -> host copy of the output is the long pole (1.6x the bytes of the input), so what counts is how
