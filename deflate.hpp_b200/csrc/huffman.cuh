@@ -61,15 +61,23 @@ __device__ __forceinline__ void warp_sort(uint32_t* keys, uint32_t N, uint32_t l
 // Warp-cooperative: sort and scatter are parallel, the O(n) tree pass runs on lane 0.
 __device__ bool build_lengths(HufScratch* s, const uint32_t* freq, uint8_t* lens, uint32_t nsym,
                               uint32_t maxbits, uint32_t lane) {
-    const uint32_t N = nsym > 32 ? 512 : 32;
-    for (uint32_t i = lane; i < N; i += 32) {
-        uint32_t f = i < nsym ? freq[i] : 0;
-        s->keys[i] = f ? ((f << 9) | i) : 0xFFFFFFFFu;
+    // The symbols in use are packed to the front (keys are unique, so the sorted order does not depend on where they start)
+    // and only the next power of two of them is sorted: a text chunk uses ~100 of the 288 literal/length symbols, and the
+    // bitonic network over 128 keys is a sixth of the one over 512.
+    const uint32_t NP = nsym > 32 ? 512 : 32;
+    uint32_t used = 0;
+    for (uint32_t i0 = 0; i0 < NP; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        const uint32_t f = i < nsym ? freq[i] : 0;
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, f != 0);
+        if (f) s->keys[used + __popc(m & ((1u << lane) - 1u))] = (f << 9) | i;
+        used += __popc(m);
     }
+    uint32_t N = 32;
+    while (N < used) N <<= 1;
+    for (uint32_t i = used + lane; i < N; i += 32) s->keys[i] = 0xFFFFFFFFu;
     for (uint32_t i = lane; i < nsym; i += 32) lens[i] = 0;
     __syncwarp();
-    uint32_t used = 0;
-    for (uint32_t i = lane; i < N; i += 32) used += __popc(__ballot_sync(0xFFFFFFFFu, s->keys[i] != 0xFFFFFFFFu));
     // force at least two symbols (zlib build_tree does the same): add the lowest unused symbols, freq 1
     if (used < 2) {
         if (lane == 0) {

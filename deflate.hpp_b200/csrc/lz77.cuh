@@ -310,15 +310,19 @@ lz77_fast_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t nchunks, u
                 // (Measured and rejected: the walk replaced by three rounds of pointer doubling over per-lane successor
                 // links -- the selected set is what is reachable from the window's first match, at most 8 matches -- gives the
                 // same bytes in the same 9.5 ms: the walk's latency is hidden by the other 31 warps of the SM.)
-                uint32_t mm = __ballot_sync(FULL, len >= 4);
+                // Every lane works out beforehand which matches start at or behind the end of its own (`after`), so a step of the
+                // walk is: lowest set bit, OR it in, fetch that lane's `after` -- 7 instructions instead of 12.
+                const uint32_t mm = __ballot_sync(FULL, len >= 4);
                 const uint32_t endl = lane + len;                        // where this lane's match would end
-                uint32_t selmask = 0, cur = 0;
-                while (mm) {
-                    const uint32_t j = __ffs(mm) - 1;
-                    selmask |= 1u << j;
-                    cur = __shfl_sync(FULL, endl, j);
-                    mm = cur < 32 ? mm & (FULL << cur) : 0;
+                const uint32_t after = endl < 32 ? mm & (FULL << endl) : 0u;
+                uint32_t selmask = 0;
+                for (uint32_t m = mm; m;) {
+                    selmask |= m & (0u - m);
+                    m = __shfl_sync(FULL, after, __clz(__brev(m)));
                 }
+                // end of the last selected match (0 if there is none)
+                const uint32_t lastsel = __shfl_sync(FULL, endl, (31 - __clz(selmask)) & 31);
+                const uint32_t cur = selmask ? lastsel : 0u;
                 // ... and every lane then decides for itself whether a selected match covers it: the
                 // nearest selected lane at or below it is the only one that can (matches do not overlap)
                 const uint32_t below = selmask & (FULL >> (31 - lane));
