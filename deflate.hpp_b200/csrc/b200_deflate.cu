@@ -232,6 +232,7 @@ int set_attrs(b200_ctx* c) {
     CK(cudaFuncSetAttribute(foreign_decode_kernel<true, LB, DB, NTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fd_smem_bytes(LB, DB, NTH)));
     FD_ATTR(9, 8, 128) FD_ATTR(8, 7, 256) FD_ATTR(8, 6, 320) FD_ATTR(7, 6, 448)
 #undef FD_ATTR
+    CK(cudaFuncSetAttribute(inflate_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_OUT_BYTES + 16));
     CK(cudaFuncSetAttribute(foreign_window_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FW_SMEM_BYTES));
     CK(cudaFuncSetAttribute(foreign_window_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FW_SMEM_BYTES));
     CK(cudaFuncSetAttribute(foreign_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FW_SMEM_BYTES));
@@ -1032,9 +1033,30 @@ int b200_inflate_dev(b200_ctx* c, const void* d_in, size_t n, void* d_out, size_
     const uint8_t* in = (const uint8_t*)d_in;
     int status = B200_OK;
     uint64_t full = 0;
-    bool done = false;
+    bool done = false, small_done = false;
 
-    if (n >= 8 && !getenv("B200_INFLATE_SEQUENTIAL")) {
+    // ---- a short stream into a small buffer: one warp, output window in shared memory (inflate_small_kernel) ----
+    // (size_probe: the host does not know the decoded size yet -- if it fits the window the call is done, else the
+    // regular paths run; with a caller buffer that small there is nothing to lose, the decoder counts beyond it anyway)
+    if (n && n <= SMALL_IN_BYTES && (cap <= SMALL_OUT_BYTES || c->size_probe) && !c->inflate_warp_path &&
+        !getenv("B200_NO_SMALL_INFLATE") && !getenv("B200_INFLATE_SEQUENTIAL")) {
+        if ((rc = c->one_off.ensure(64))) return rc;
+        if (!c->ctl) CK(cudaHostAlloc((void**)&c->ctl, 16 * 8, cudaHostAllocDefault));
+        const uint32_t scap = (uint32_t)(cap < SMALL_OUT_BYTES ? cap : SMALL_OUT_BYTES);
+        PROF_BEGIN(c, K_INFLATE_BATCH, st);
+        inflate_small_kernel<<<1, SMALL_THREADS, scap + 16, st>>>(in, n, (uint8_t*)d_out, scap, flags, (unsigned long long*)c->one_off.p, c->ctl + 8);
+        LAUNCHED();
+        PROF_END(c, st);
+        CK(cudaStreamSynchronize(st));
+        const uint64_t got = c->ctl[8];
+        if (got <= scap || cap <= scap) {       // everything is in the buffer, or the caller's buffer truncates anyway
+            full = got;
+            status = (int)(int32_t)(c->ctl[9] & 0xFFFFFFFFu);
+            done = true;
+            small_done = true;
+        }
+    }
+    if (!small_done && n >= 8 && !getenv("B200_INFLATE_SEQUENTIAL")) {
         // ---- this library's own chunked streams ----
         if ((rc = inflate_chunked(c, in, n, 0, n, true, true, (uint8_t*)d_out, cap, flags, st, &done, &full, nullptr, nullptr))) return rc;
         // ---- anything else that is big enough to be worth it: block-parallel (inflate_foreign.cuh) ----

@@ -164,6 +164,68 @@ def test_own_streams_chunk_parallel_vs_sequential(b200, monkeypatch):
     assert b200.decompress(c) == data
 
 
+def test_small_streams_shared_memory_window(b200, oracle, monkeypatch):
+    """Short streams into small buffers are decoded by one warp with the output window in shared memory
+    (inflate_small_kernel); B200_NO_SMALL_INFLATE=1 sends them down the regular paths.  Same bytes, same sizes, same
+    errors -- own streams of every level, ten foreign producers, the reference's fixtures, truncating buffers, damaged
+    input -- and the oracle agrees."""
+    from conftest import gold
+    bmp = gold("test.bmp")
+    cases = []
+    for data in (bmp, gold("tiny.bmp"), datagen.text_like(150000), datagen.image_like(70000), datagen.random_bytes(5000),
+                 b"", b"a", b"\x00" * 160000, datagen.text_like(163840)):
+        for level in (0, 1, 2, 3):
+            c = b200.compress(data, level)
+            if len(c) <= 65536:
+                cases.append((c, data))
+    for name, z in datagen.foreign_streams(bmp + datagen.text_like(60000)).items():
+        if len(z) <= 65536:
+            cases.append((z, bmp + datagen.text_like(60000)))
+    assert len(cases) > 30
+    raw = [gold("zlib.dat")[2:], gold("weird.dat")[2:], datagen.too_far_stream()]
+
+    def run():
+        out = []
+        for c, data in cases:
+            out.append(b200.decompress(c))                                    # size unknown: probe, then exact
+            out.append(b200.decompress(c, out_size=len(data)))                # exact buffer
+            out.append(b200.decompress(c, out_size=len(data) // 3))           # truncating buffer (inflate.hpp:345)
+            out.append(b200.decompress(c, out_size=len(data) + 1000))
+        for z in raw:
+            out.append(b200.decompress(z))
+            out.append(b200.decompress(z, out_size=100))
+        for c, data in cases[::5]:                                             # damaged input: same outcome either way
+            for cut in (len(c) // 2, max(len(c) - 1, 0)):
+                try:
+                    out.append(b200.decompress(c[:cut], out_size=len(data)))
+                except b200.B200Error as e:
+                    out.append(("error", e.code))
+            bad = bytearray(c)
+            if bad:
+                bad[len(bad) // 2] ^= 0x5A
+            try:
+                out.append(b200.decompress(bytes(bad), out_size=len(data)))
+            except b200.B200Error as e:
+                out.append(("error", e.code))
+        return out
+
+    small = run()
+    monkeypatch.setenv("B200_NO_SMALL_INFLATE", "1")
+    regular = run()
+    monkeypatch.delenv("B200_NO_SMALL_INFLATE")
+    assert len(small) == len(regular)
+    for k, (a, b) in enumerate(zip(small, regular)):
+        assert a == b, k
+    k = 0
+    for c, data in cases:
+        assert small[k] == data and small[k + 1] == data and small[k + 2] == data[:len(data) // 3] and small[k + 3] == data
+        k += 4
+    for z in raw:
+        rc, o = oracle.inflate(z)
+        assert rc == 0 and small[k] == o and small[k + 1] == o[:100]
+        k += 2
+
+
 def test_false_sync_markers(b200):
     """Stored data full of 00 00 FF FF patterns must not confuse the chunk-parallel path."""
     data = (b"\x00\x00\xff\xff" * 40000) + datagen.random_bytes(70000) + b"\x00\x00\xff\xff" * 10
