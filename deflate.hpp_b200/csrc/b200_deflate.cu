@@ -1049,7 +1049,9 @@ int b200_inflate_dev(b200_ctx* c, const void* d_in, size_t n, void* d_out, size_
         PROF_END(c, st);
         CK(cudaStreamSynchronize(st));
         const uint64_t got = c->ctl[8];
-        if (got <= scap || cap <= scap) {       // everything is in the buffer, or the caller's buffer truncates anyway
+        if (c->ctl[9] == SMALL_ST_INDEXED) {
+            // this library's stream with a segment index: the chunked path below
+        } else if (got <= scap || cap <= scap) {       // everything is in the buffer, or the caller's buffer truncates anyway
             full = got;
             status = (int)(int32_t)(c->ctl[9] & 0xFFFFFFFFu);
             done = true;

@@ -26,15 +26,16 @@ constexpr uint32_t MAX_DIST = 32768;
 constexpr uint32_t SYNC_BYTES_ALIGNED = 10;   // bytes the separator takes when it starts byte-aligned
 constexpr uint32_t SYNC_PATTERN_BYTES = 9;
 
-// Segment index (parallel inflate inside a chunk).  A full 64 KiB chunk that is Huffman-coded is preceded by
-// INDEX_GROUPS empty non-final stored blocks, each starting byte-aligned: byte 0 = 1pppp000 (BFINAL 0,
-// BTYPE 00, then five "ignored up to the byte boundary" bits, RFC 1951 3.2.4), then 00 00 FF FF.  The four p
-// bits of the 64 groups spell 16 little-endian u16 words: word 0 = INDEX_MAGIC | (segments - 1) << 10,
-// word s (1..15) = the number of bits segment s-1's symbols take.  Every inflater skips these blocks; this
+// Segment index (parallel inflate inside a chunk).  A Huffman-coded chunk of S >= 2 segments (S = 16 for a full 64 KiB
+// chunk, fewer for the short last chunk of a stream) is preceded by 4 S empty non-final stored blocks, each starting
+// byte-aligned: byte 0 = 1pppp000 (BFINAL 0, BTYPE 00, then five "ignored up to the byte boundary" bits, RFC 1951 3.2.4),
+// then 00 00 FF FF.  The four p bits of the groups spell S little-endian u16 words: word 0 = INDEX_MAGIC | (S - 1) << 10,
+// word s (1..S-1) = the number of bits segment s-1's symbols take.  Every inflater skips these blocks; this
 // one reads them and starts one thread per 4 KiB segment.  Bit 7 of byte 0 is always set so that a group can
 // never look like a chunk separator (below) -- the separator's stored blocks have all-zero padding.
-constexpr uint32_t INDEX_GROUPS = 64;
+constexpr uint32_t INDEX_GROUPS = 64;                       // of a full chunk
 constexpr uint32_t INDEX_BYTES = INDEX_GROUPS * 5;          // 320
+constexpr uint32_t INDEX_BYTES_PER_SEG = 20;                // four groups of 5 bytes per 16-bit word
 constexpr uint32_t INDEX_MAGIC = 0x2B5;                     // 10 bits
 
 // Token: literal -> byte value (dist field 0); match -> length in bits [0,9), distance in [16,32).
@@ -60,7 +61,7 @@ struct BlockDesc {
     uint32_t clen;           // uncompressed bytes in this chunk
     uint32_t last;           // 1 = carries BFINAL, no sync marker
     uint32_t eob;            // (unused)
-    uint32_t index_bytes;    // 0, or INDEX_BYTES when the chunk is preceded by the segment index
+    uint32_t index_bytes;    // 0, or 20 bytes per segment when the chunk is preceded by the segment index
     uint32_t seg_bitoff[NSEG];  // bit offset of each segment's first token, relative to block start
     // a chunk split into two blocks (huffman.cuh): segments [0, split_seg) use codes[0] / hdr[0], the rest codes[1] / hdr[1]
     uint32_t split_seg;      // 0 = one block

@@ -153,10 +153,10 @@ encode_kernel(const uint8_t* __restrict__ in, const uint32_t* __restrict__ tok, 
             sb[o + 5] = 0; sb[o + 6] = 0; sb[o + 7] = 0; sb[o + 8] = 0xFF; sb[o + 9] = 0xFF;
         }
     } else {
-        // segment index: 64 empty stored blocks whose padding bits carry the segments' bit lengths
-        if (d.index_bytes && tid < INDEX_GROUPS) {
+        // segment index: four empty stored blocks per segment whose padding bits carry the segments' bit lengths
+        if (tid < d.index_bytes / 5) {
             const uint32_t w = tid >> 2;
-            const uint32_t word = w == 0 ? (INDEX_MAGIC | ((NSEG - 1) << 10)) : d.seg_bitoff[w] - d.seg_bitoff[w - 1];
+            const uint32_t word = w == 0 ? (INDEX_MAGIC | ((d.index_bytes / INDEX_BYTES_PER_SEG - 1) << 10)) : d.seg_bitoff[w] - d.seg_bitoff[w - 1];
             const uint32_t nib = (word >> (4 * (tid & 3))) & 15u;
             stage_bits(stage, (phase + 5 * tid) * 8, (uint64_t)(0x80u | (nib << 3)) | (0xFFFFull << 24), 40);
         }

@@ -570,6 +570,7 @@ inflate_batch_kernel(const uint8_t* __restrict__ in, const uint64_t* __restrict_
 constexpr uint32_t SMALL_THREADS = 256;
 constexpr uint32_t SMALL_OUT_BYTES = 160u << 10;
 constexpr uint32_t SMALL_IN_BYTES = 64u << 10;
+constexpr unsigned long long SMALL_ST_INDEXED = 0x100;      // result[1]: not decoded, the stream carries a segment index
 __global__ void __launch_bounds__(SMALL_THREADS)
 inflate_small_kernel(const uint8_t* __restrict__ in, uint64_t n, uint8_t* __restrict__ out, uint32_t cap, unsigned flags,
                      unsigned long long* __restrict__ result, volatile unsigned long long* __restrict__ host_result) {
@@ -577,6 +578,15 @@ inflate_small_kernel(const uint8_t* __restrict__ in, uint64_t n, uint8_t* __rest
     __shared__ InfWarp S;
     __shared__ ModLut ML;
     __shared__ unsigned long long s_res[2];
+    // a stream that opens with a segment index group (common.cuh) is this library's: the segment-parallel path decodes
+    // it several times faster than one warp can -- say so and leave
+    if (n >= 7 && (in[0] & 0x87u) == 0x80u && in[1] == 0 && in[2] == 0 && in[3] == 0xFF && in[4] == 0xFF) {
+        if (threadIdx.x == 0) {
+            result[0] = 0; result[1] = SMALL_ST_INDEXED;
+            if (host_result) { host_result[0] = 0; host_result[1] = SMALL_ST_INDEXED; __threadfence_system(); }
+        }
+        return;
+    }
     modlut_init(&ML, threadIdx.x, SMALL_THREADS);
     __syncthreads();
     if (threadIdx.x < 32) {

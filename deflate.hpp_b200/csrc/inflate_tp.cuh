@@ -630,17 +630,23 @@ struct __align__(16) SgChunk {
 constexpr uint32_t SG_SMEM_BYTES = SG_CHUNKS * sizeof(SgChunk) + TP_LUT_WORDS * 4 + 16;
 
 // reads the segment index at the start of a chunk (common.cuh); returns the number of segments or 0
+// (the index takes INDEX_BYTES_PER_SEG bytes per segment: word 0 says how many)
 __device__ uint32_t sg_read_index(const uint8_t* in, uint64_t in_len, uint32_t* words /* [NSEG] */) {
-    if (in_len < INDEX_BYTES + 2) return 0;
+    if (in_len < INDEX_BYTES_PER_SEG + 2) return 0;
     for (uint32_t w = 0; w < NSEG; w++) words[w] = 0;
-    for (uint32_t g = 0; g < INDEX_GROUPS; g++) {
+    uint32_t ngroups = 4;
+    for (uint32_t g = 0; g < ngroups; g++) {
         const uint8_t* b = in + 5 * g;
         const uint32_t b0 = b[0];
         if ((b0 & 0x87u) != 0x80u || b[1] != 0 || b[2] != 0 || b[3] != 0xFF || b[4] != 0xFF) return 0;
         words[g >> 2] |= ((b0 >> 3) & 15u) << (4 * (g & 3));
+        if (g == 3) {
+            if ((words[0] & 0x3FFu) != INDEX_MAGIC || (words[0] >> 14) != 0) return 0;
+            ngroups = 4 * (((words[0] >> 10) & 15u) + 1);
+            if (in_len < (uint64_t)5 * ngroups + 2) return 0;
+        }
     }
-    if ((words[0] & 0x3FFu) != INDEX_MAGIC || (words[0] >> 14) != 0) return 0;
-    return ((words[0] >> 10) & 15u) + 1;
+    return ngroups / 4;
 }
 
 // Pass A0: one thread per chunk.  Indexed chunks are appended to `list` (the segment kernel then works on a
@@ -716,7 +722,7 @@ inflate_segments_kernel(ChunkUnits U, const uint32_t* __restrict__ blist, const 
             const uint32_t nseg = sg_read_index(u.in, u.in_len, words);
             tp_state_init(s, c, u, true, s_ring, SG_THREADS);
             if (nseg >= 2) {
-                tb_seek(s.br, INDEX_BYTES);
+                tb_seek(s.br, nseg * INDEX_BYTES_PER_SEG);
                 s = tp_step_block(c, s);
             }
             if (nseg >= 2 && s.state == TS_SYM) {

@@ -50,9 +50,10 @@ extern "C" {
 /* Flags for the compressor. */
 #define B200_F_NOT_LAST 1u /* this buffer is a shard that is NOT the end of the stream: its last chunk \
                               is closed with the byte-aligning empty stored block instead of BFINAL */
-#define B200_F_NO_INDEX 2u /* do not put the segment index (320 bytes of empty stored blocks whose padding bits \
-                              hold the bit length of every 4 KiB segment) in front of full 64 KiB chunks: the   \
-                              stream is 0.3-0.5 % smaller and inflates one warp per chunk instead of 16 threads */
+#define B200_F_NO_INDEX 2u /* do not put the segment index (20 bytes per 4 KiB segment -- 320 for a full chunk -- of  \
+                              empty stored blocks whose padding bits hold the bit length of every segment) in      \
+                              front of chunks of two segments or more: the stream is 0.3-0.5 % smaller and         \
+                              inflates one warp per chunk instead of one thread per segment */
 #define B200_F_ZLIB 4u     /* wrap the stream in zlib framing (RFC 1950): 78 9C in front, the Adler-32 of the INPUT behind,  \
                               computed on the GPU (what zlib.decompress / inflate::decompressZlib read) */
 #define B200_F_GZIP 8u     /* wrap it in one gzip member (RFC 1952): 10-byte header, CRC-32 of the input + ISIZE behind */

@@ -282,7 +282,7 @@ def test_segment_index_streams(b200, oracle, level):
     assert words is not None and (words[0] & 0x3FF) == 0x2B5 and (words[0] >> 10) == 15
     assert all(0 < w < 65536 for w in words[1:])
     assert _index_at(plain, 0) is None
-    assert len(c) - len(plain) == 5 * INDEX_BYTES          # five full chunks, the partial one has none
+    assert len(c) - len(plain) == 5 * INDEX_BYTES          # five full chunks; the partial one is a single segment: no index
     for s in (c, plain):
         out, unused = zlib_raw_inflate(s)
         assert out == data and unused == b""
@@ -290,6 +290,38 @@ def test_segment_index_streams(b200, oracle, level):
         assert rc == 0 and o == data
         assert b200.decompress(s) == data
         assert b200.decompress(s, out_size=100000) == data[:100000]     # truncating overload
+
+
+@pytest.mark.parametrize("level", [2, 3])
+def test_segment_index_short_chunk(b200, oracle, ref, level):
+    """The short last chunk of a stream (a small file is nothing else) carries an index of its own size -- four groups
+    per segment, word 0 says how many -- so that it is decoded by one thread per segment too.  test.bmp: 6 segments."""
+    from conftest import gold
+    for data in (gold("test.bmp"), datagen.text_like(65536 + 3 * 4096 + 17, seed=9), datagen.text_like(4097, seed=10)):
+        nseg = (len(data) % 65536 + 4095) // 4096
+        c = _compress_dev(b200, data, level)
+        plain = _compress_dev(b200, data, level, flags=b200.F_NO_INDEX)
+        full = len(data) // 65536
+        assert len(c) - len(plain) == full * INDEX_BYTES + 20 * nseg
+        # the short chunk's index: find it behind the full chunks' bytes by parsing from the end of `plain`'s shared prefix
+        if full == 0:
+            words = [0] * nseg
+            for g in range(4 * nseg):
+                b = c[5 * g: 5 * g + 5]
+                assert (b[0] & 0x87) == 0x80 and b[1:] == b"\x00\x00\xff\xff"
+                words[g >> 2] |= ((b[0] >> 3) & 15) << (4 * (g & 3))
+            assert (words[0] & 0x3FF) == 0x2B5 and (words[0] >> 10) == nseg - 1
+            assert all(0 < w < 65536 for w in words[1:])
+        for s in (c, plain):
+            out, unused = zlib_raw_inflate(s)
+            assert out == data and unused == b""
+            rc, o = oracle.inflate(s)
+            assert rc == 0 and o == data
+            n, r_out = ref.inflate(s)
+            assert n == len(data) and r_out == data
+            assert b200.decompress(s) == data
+            assert b200.decompress(s, out_size=len(data)) == data
+            assert b200.decompress(s, out_size=5000) == data[:5000]
 
 
 def test_segment_index_not_trusted(b200):
