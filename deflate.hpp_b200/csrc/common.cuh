@@ -26,8 +26,8 @@ constexpr uint32_t MAX_DIST = 32768;
 constexpr uint32_t SYNC_BYTES_ALIGNED = 10;   // bytes the separator takes when it starts byte-aligned
 constexpr uint32_t SYNC_PATTERN_BYTES = 9;
 
-// Segment index (parallel inflate inside a chunk).  A Huffman-coded chunk of S >= 2 segments (S = 16 for a full 64 KiB
-// chunk, fewer for the short last chunk of a stream) is preceded by 4 S empty non-final stored blocks, each starting
+// Segment index (parallel inflate inside a chunk).  A Huffman-coded chunk of S segments (S = 16 for a full 64 KiB
+// chunk, 8..15 for the short last chunk of a stream; shorter ones have none) is preceded by 4 S empty non-final stored blocks, each starting
 // byte-aligned: byte 0 = 1pppp000 (BFINAL 0, BTYPE 00, then five "ignored up to the byte boundary" bits, RFC 1951 3.2.4),
 // then 00 00 FF FF.  The four p bits of the groups spell S little-endian u16 words: word 0 = INDEX_MAGIC | (S - 1) << 10,
 // word s (1..S-1) = the number of bits segment s-1's symbols take.  Every inflater skips these blocks; this
@@ -36,6 +36,7 @@ constexpr uint32_t SYNC_PATTERN_BYTES = 9;
 constexpr uint32_t INDEX_GROUPS = 64;                       // of a full chunk
 constexpr uint32_t INDEX_BYTES = INDEX_GROUPS * 5;          // 320
 constexpr uint32_t INDEX_BYTES_PER_SEG = 20;                // four groups of 5 bytes per 16-bit word
+constexpr uint32_t INDEX_MIN_SEGS = 8;                      // chunks shorter than this many segments get no index (huffman.cuh)
 constexpr uint32_t INDEX_MAGIC = 0x2B5;                     // 10 bits
 
 // Token: literal -> byte value (dist field 0); match -> length in bits [0,9), distance in [16,32).

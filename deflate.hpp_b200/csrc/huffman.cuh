@@ -493,13 +493,15 @@ huffman_kernel(const uint16_t* __restrict__ hist, uint64_t n, uint32_t nchunks, 
         }
     }
     const uint32_t bits = split ? A.bits + B.bits : S.bits;
-    // chunks of two segments or more carry the segment index (common.cuh) so that they can be inflated by one thread per
-    // segment -- the short last chunk of a stream too: a small file IS that chunk, and one warp decodes 21 KB in 0.6 ms,
-    // six threads in a tenth of that (only where it costs little: the chunk must save at least four times the index's size;
-    // never for a split chunk)
+    // chunks carry the segment index (common.cuh) so that they can be inflated by one thread per segment -- the short last
+    // chunk of a stream too if it has INDEX_MIN_SEGS segments or more.  (Measured, tools/probe_small.py: a lone thread takes
+    // 0.4-0.9 ms for its 4 KiB segment and the copy pass 0.2 ms more, whatever the chunk's size; one warp with the output
+    // window in shared memory -- inflate_small_kernel -- needs 26-45 us per KiB: it wins below ~30 KiB, e.g. test.bmp,
+    // 21 KB: 0.56 against 0.73 ms.)  Only where it costs little: the chunk must save at least four times the index's size;
+    // never for a split chunk.
     const uint32_t huff_plain = last ? (bits + 7) / 8 : (bits + 3 + 7) / 8 + (SYNC_BYTES_ALIGNED - 1);
     const uint32_t nseg_used = (clen + SEG - 1) / SEG;
-    const uint32_t index_want = nseg_used >= 2 ? nseg_used * INDEX_BYTES_PER_SEG : 0u;
+    const uint32_t index_want = nseg_used >= INDEX_MIN_SEGS ? nseg_used * INDEX_BYTES_PER_SEG : 0u;
     const uint32_t index_bytes = (with_index && !split && index_want && huff_plain + 4 * index_want <= stored_bytes) ? index_want : 0u;
     const uint32_t huff_bytes = index_bytes + huff_plain;
     const bool huffman = huff_bytes < stored_bytes;

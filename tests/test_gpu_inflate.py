@@ -294,17 +294,18 @@ def test_segment_index_streams(b200, oracle, level):
 
 @pytest.mark.parametrize("level", [2, 3])
 def test_segment_index_short_chunk(b200, oracle, ref, level):
-    """The short last chunk of a stream (a small file is nothing else) carries an index of its own size -- four groups
-    per segment, word 0 says how many -- so that it is decoded by one thread per segment too.  test.bmp: 6 segments."""
+    """The short last chunk of a stream carries an index of its own size -- four groups per segment, word 0 says how
+    many -- if it has 8 segments or more, so that it is decoded by one thread per segment too; shorter ones (test.bmp: 6
+    segments) have none and go to the one-warp decoder with the shared-memory window, which is faster there."""
     from conftest import gold
-    for data in (gold("test.bmp"), datagen.text_like(65536 + 3 * 4096 + 17, seed=9), datagen.text_like(4097, seed=10)):
+    for data in (gold("test.bmp"), datagen.text_like(65536 + 9 * 4096 + 17, seed=9), datagen.text_like(40000, seed=10),
+                 datagen.text_like(65536 + 3 * 4096 + 17, seed=11), datagen.text_like(7 * 4096 + 1, seed=12)):
         nseg = (len(data) % 65536 + 4095) // 4096
         c = _compress_dev(b200, data, level)
         plain = _compress_dev(b200, data, level, flags=b200.F_NO_INDEX)
         full = len(data) // 65536
-        assert len(c) - len(plain) == full * INDEX_BYTES + 20 * nseg
-        # the short chunk's index: find it behind the full chunks' bytes by parsing from the end of `plain`'s shared prefix
-        if full == 0:
+        assert len(c) - len(plain) == full * INDEX_BYTES + (20 * nseg if nseg >= 8 else 0)
+        if full == 0 and nseg >= 8:
             words = [0] * nseg
             for g in range(4 * nseg):
                 b = c[5 * g: 5 * g + 5]

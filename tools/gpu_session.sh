@@ -61,6 +61,8 @@ for step in "$@"; do
       B200_STAGE=0 timeout 300 python tools/probe_e2e.py >> $out/${tag}_probe_e2e.log 2>&1
       B200_STAGE_THREADS=4 timeout 300 python tools/probe_e2e.py >> $out/${tag}_probe_e2e.log 2>&1
       B200_STAGE_THREADS=16 timeout 300 python tools/probe_e2e.py >> $out/${tag}_probe_e2e.log 2>&1 ;;
+    probe_small)
+      timeout 300 python tools/probe_small.py > $out/${tag}_probe_small.log 2>&1 ;;
     probe_pcie)
       # what the PCIe link moves raw, then the pinned host-buffer calls at several inflate slice sizes
       timeout 300 python tools/probe_e2e.py 1024 pinned raw >> $out/${tag}_probe_pcie.log 2>&1
