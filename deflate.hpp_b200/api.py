@@ -107,6 +107,8 @@ def lib():
     L.b200_deflate_compress_batch_dev.restype = c_int
     L.b200_adler32_dev.argtypes = [c_void_p, c_void_p, c_size_t, P(ctypes.c_uint32), c_void_p, c_void_p]
     L.b200_adler32_dev.restype = c_int
+    L.b200_publish_dev.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    L.b200_publish_dev.restype = c_int
     for f in ("b200_ctx_create", "b200_deflate_compress", "b200_deflate_compress_into", "b200_inflate",
               "b200_inflate_alloc", "b200_inflate_zlib", "b200_inflate_zlib_alloc", "b200_deflate_compress_dev",
               "b200_inflate_dev", "b200_inflate_batch_dev", "b200_corpus_generate_dev"):
@@ -336,6 +338,12 @@ class Context:
         if rc:
             raise B200Error(rc, "b200_crc32_dev")
         return out.value
+
+    def publish_dev(self, h_pinned_dst, d_src, n_words, stream=0):
+        """n_words u64 from device memory into pinned host memory by a kernel on `stream` (no copy engine involved)."""
+        rc = lib().b200_publish_dev(self._h, h_pinned_dst, d_src, n_words, stream or None)
+        if rc:
+            raise B200Error(rc, "b200_publish_dev")
 
     @staticmethod
     def corpus_generate_dev(d_out, seed, first_chunk, n_chunks, stream=0):

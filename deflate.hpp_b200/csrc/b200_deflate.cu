@@ -1377,6 +1377,16 @@ int b200_crc32_dev(b200_ctx* c, const void* d_data, size_t n, uint32_t* h_out, u
     return B200_OK;
 }
 
+int b200_publish_dev(b200_ctx* c, void* h_pinned_dst, const void* d_src, size_t n_words, void* stream_) {
+    if (!c || !h_pinned_dst || !d_src || n_words == 0 || n_words > 32) return B200_E_ARG;
+    ON_DEVICE(c);
+    publish_kernel<<<1, 32, 0, (cudaStream_t)stream_>>>((volatile unsigned long long*)h_pinned_dst, (const unsigned long long*)d_src,
+                                                       (uint32_t)n_words, nullptr, 0);
+    LAUNCHED();
+    CK(cudaGetLastError());
+    return B200_OK;
+}
+
 int b200_corpus_generate_dev(void* d_out, uint64_t seed, uint64_t first_chunk, uint64_t n_chunks, void* stream_) {
     if (!d_out && n_chunks) return B200_E_ARG;
     if (!n_chunks) return B200_OK;

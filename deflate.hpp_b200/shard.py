@@ -10,6 +10,7 @@ compressed bytes to a destination rank.
 
 Works with any torch.distributed backend: NCCL on GPUs, gloo on CPU tensors (tests/test_shard_gloo.py).
 """
+import os
 from typing import List, Tuple
 
 import torch
@@ -175,15 +176,29 @@ WINDOW_SLACK = CHUNK + 4096          # a chunk that starts just below a range's 
                                      # goes in front of chunks that save at least 1280 bytes)
 
 
-def round_plan(chunks_per_rank: int, min_round: int = 1024) -> List[int]:
+def round_plan(chunks_per_rank: int, min_round: int = 1024, world: int = 0) -> List[int]:
     """Chunks per round for one rank.  Two costs pull against each other: what a step cannot hide is the copy of the LAST
     round (so it should be small), and every round costs the tail of the persistent matcher, ~0.2 ms in which the SMs run
-    dry one after the other (so there should be few).  8/16, 5/16, 2/16, 1/16 of the shard -- as long as the smallest
-    round keeps `min_round` chunks (below 64 MiB the matcher starves); smaller shards get four equal
-    rounds, or one.  (Measured at 8 GPUs, 2 GiB per rank: six rounds 4-4-4-2-1-1 lost 1.2 ms of 26.8 to tails.)"""
+    dry one after the other (so there should be few).  A third one shows at 8 GPUs: all slices of a round go into ONE GPU,
+    whose NVLink ingest (~750 GB/s) takes (world - 1) x 0.08 of the time the round took to compress -- 0.56 at 8 GPUs --
+    so a round may not be smaller than that fraction of the round before it, or its copy is still waiting for the link
+    when its compression is done (8/16, 5/16, 2/16, 1/16 at 8 GPUs: 1.3 + 0.2 + 0.9 ms exposed, model and measurement
+    agree).  With `world` given: geometric rounds, ratio max(0.2, 0.07 x (world - 1)), as many (<= 6) as keep the last one at
+    `min_round` chunks (below 64 MiB the matcher starves).  Without: 8/16, 5/16, 2/16, 1/16 of the
+    shard; smaller shards get four equal rounds, or one.  (Measured at 8 GPUs, 2 GiB per rank: six rounds 4-4-4-2-1-1 lost
+    1.2 ms of 26.8 to tails.)"""
     c = int(chunks_per_rank)
     if c <= 0:
         return []
+    if world >= 2 and os.environ.get("B200_ROUND_PLAN", "geo") == "geo":
+        rho = max(0.2, 0.07 * (world - 1))
+        for k in range(6, 1, -1):
+            w = [rho ** i for i in range(k)]
+            plan = [int(c * x / sum(w)) for x in w]
+            if plan[-1] >= min_round:
+                plan[0] += c - sum(plan)
+                return plan
+        return [c]
     if c // 16 >= min_round:
         u = c // 16
         plan = [8 * u, 5 * u, 2 * u, u]
@@ -230,7 +245,7 @@ class ShardedDeflate:
                  not_last_flag: int = 1, bound=None, transport: str = "auto"):
         self.codec, self.device, self.dst = codec, device, dst
         self.world, self.rank = dist.get_world_size(), dist.get_rank()
-        self.plan = list(plan) if plan else round_plan(chunks_per_rank)
+        self.plan = list(plan) if plan else round_plan(chunks_per_rank, world=self.world)
         assert sum(self.plan) == chunks_per_rank
         self.layout = round_layout(self.plan, self.rank, self.world)
         self.not_last = not_last_flag
@@ -279,7 +294,12 @@ class ShardedDeflate:
             # the sizes of this round: on the compute stream, BETWEEN two rounds (a collective posted on a side stream
             # waits for an SM until the persistent matcher of the next round ends)
             dist.all_gather_into_tensor(self.allsz_dev[k], self.sizes_dev[k:k + 1])
-            self.allsz_host[k].copy_(self.allsz_dev[k], non_blocking=True)
+            if self.cuda and self.world <= 32 and hasattr(self.codec, "publish_dev"):
+                # to the host by a kernel: a copy of a few bytes would queue on a copy engine behind the peer copies of the
+                # round before -- and the compute stream, on which the next round is about to start, with it
+                self.codec.publish_dev(self.allsz_host[k].data_ptr(), self.allsz_dev[k].data_ptr(), self.world, stream=st)
+            else:
+                self.allsz_host[k].copy_(self.allsz_dev[k], non_blocking=True)
             if self.cuda:
                 self.round_done[k].record(main)
         # trail the rounds on a side stream: each slice goes to its final offset as soon as its round's sizes are known

@@ -231,6 +231,13 @@ int b200_adler32_dev(b200_ctx* ctx, const void* d_data, size_t n, uint32_t* h_ou
  * GF(2) identity crc(A || B) = crc(A) * x^(8|B|) + crc(B).  Same result conventions as b200_adler32_dev. */
 int b200_crc32_dev(b200_ctx* ctx, const void* d_data, size_t n, uint32_t* h_out, uint32_t* d_out, void* stream);
 
+/* n_words (<= 32) 64-bit words from device memory to PINNED host memory (cudaHostAlloc / cudaHostRegister, mapped into the
+ * device's address space as all pinned memory is under unified addressing), written by a kernel on `stream` -- not by a
+ * copy: an 8-byte cudaMemcpyAsync is queued on the copy engine behind whatever bulk transfer is on the wire, and the
+ * stream it is on waits with it.  The multi-GPU gather (deflate.hpp_b200/shard.py) passes the sizes of a round to the host
+ * this way.  The words are visible to the host once work enqueued behind the call on `stream` has been waited for. */
+int b200_publish_dev(b200_ctx* ctx, void* h_pinned_dst, const void* d_src, size_t n_words, void* stream);
+
 /* Synthetic corpus of BASELINE config 3/5 (definition: oracle/corpus_oracle.c):
  * chunks first_chunk .. first_chunk+n_chunks-1 of 64 KiB each, written to d_out. */
 int b200_corpus_generate_dev(void* d_out, uint64_t seed, uint64_t first_chunk, uint64_t n_chunks,
