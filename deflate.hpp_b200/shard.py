@@ -176,6 +176,9 @@ WINDOW_SLACK = CHUNK + 4096          # a chunk that starts just below a range's 
                                      # goes in front of chunks that save at least 1280 bytes)
 
 
+BATCH_CHUNKS = 16384          # chunks per batch of one compress call (b200_ctx::batch_chunks)
+
+
 def round_plan(chunks_per_rank: int, min_round: int = 1024, world: int = 0) -> List[int]:
     """Chunks per round for one rank.  Two costs pull against each other: what a step cannot hide is the copy of the LAST
     round (so it should be small), and every round costs the tail of the persistent matcher, ~0.2 ms in which the SMs run
@@ -197,6 +200,14 @@ def round_plan(chunks_per_rank: int, min_round: int = 1024, world: int = 0) -> L
             plan = [int(c * x / sum(w)) for x in w]
             if plan[-1] >= min_round:
                 plan[0] += c - sum(plan)
+                # a compress call works in batches of 16 384 chunks (the size its scratch is laid out for): a round just
+                # above a multiple of that would end in a small batch of its own -- one more matcher tail -- so the
+                # excess moves into the next round
+                for i in range(k - 1):
+                    rem = plan[i] % BATCH_CHUNKS
+                    if plan[i] > BATCH_CHUNKS and rem < BATCH_CHUNKS // 4:
+                        plan[i] -= rem
+                        plan[i + 1] += rem
                 return plan
         return [c]
     if c // 16 >= min_round:
