@@ -378,7 +378,7 @@ constexpr uint32_t LZB_HASH_BITS = 13;          // 8 K heads x u32 (atomicExch n
 constexpr uint32_t LZB_NIL = 0xFFFFu;           // position 65535 can never be anybody's predecessor
 constexpr uint32_t LZB_GOOD = 32;               // once a match this long is in hand, cut the remaining search to a quarter
 constexpr uint32_t LZB_TOO_FAR = 4096;          // a 3-byte match farther than this costs more than literals
-constexpr size_t LZB_SMEM_BYTES = CHUNK + LZ_DATA_PAD + CHUNK * 2 + (4u << LZB_HASH_BITS) + 16;
+constexpr size_t LZB_SMEM_BYTES = CHUNK + LZ_DATA_PAD + CHUNK * 2 + (4u << LZB_HASH_BITS) + 16 + 80;      // + progress words
 
 __device__ __forceinline__ uint32_t lzb_hash(uint32_t w4) { return ((w4 & 0xFFFFFFu) * 0x9E3779B1u) >> (32 - LZB_HASH_BITS); }
 
@@ -407,7 +407,9 @@ lz77_better_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t* __restr
     const bool aligned = ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
     const uint32_t bulk = aligned ? (clen & ~15u) : 0;
     uint32_t* s_sync = reinterpret_cast<uint32_t*>(s_bar + 1);       // [0] positions linked so far, [1] next search tile
-    if (tid == 0) { mbar_init(s_bar, 1); s_sync[0] = 0; s_sync[1] = 0; }
+    uint32_t* s_segdone = s_sync + 4;                                // [NSEG] search tiles finished per segment; s_sync[2] = next segment to parse
+    if (tid == 0) mbar_init(s_bar, 1);
+    if (tid < 4 + NSEG) s_sync[tid] = 0;
     __syncthreads();
     if (tid == 0 && bulk) tma_load_1d(s_data, src, bulk, s_bar);
     for (uint32_t i = bulk + tid; i < clen; i += LZB_THREADS) s_data[i] = src[i];
@@ -494,16 +496,31 @@ lz77_better_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t* __restr
             if (best < 3 || (best == 3 && bdist > LZB_TOO_FAR)) { best = 0; bdist = 0; }
         }
         if (p < clen) cand[p] = best | (bdist << 16);
+        // this tile's candidates are in place: count it for its segment (the parser of that segment waits for all of them)
+        __syncwarp();
+        if (lane == 0) { __threadfence_block(); atomicAdd(&s_segdone[t0 / SEG], 1u); }
     }
-    __syncthreads();   // also orders the global cand[] stores before phase C's loads (same CTA)
 
     // ---- phase C: lazy parse, one warp per segment -----------------------------------------------
-    for (uint32_t i = tid; i < NSEG * HIST_WORDS; i += LZB_THREADS) s_hist[i] = 0;
-    __syncthreads();
-    if (warp >= NSEG) return;
-    const uint32_t seg_lo = warp * SEG;
+    // No barrier between the phases either: a warp that finds no search tile left takes the next segment, waits until the
+    // segment's tiles are all counted (and the linker is done with the head table, whose memory the histograms reuse) and
+    // parses it while other warps are still searching later segments.
+    for (;;) {
+    uint32_t seg = 0;
+    if (lane == 0) seg = atomicAdd(&s_sync[2], 1u);
+    seg = __shfl_sync(FULL, seg, 0);
+    if (seg >= NSEG) break;
+    const uint32_t seg_lo = seg * SEG;
     const uint32_t seg_hi = min(clen, seg_lo + SEG);
-    uint32_t* h = s_hist + warp * HIST_WORDS;
+    {
+        const uint32_t tiles = seg_lo < clen ? (seg_hi - seg_lo + 31u) / 32u : 0u;
+        while (*reinterpret_cast<volatile uint32_t*>(&s_segdone[seg]) < tiles ||
+               *reinterpret_cast<volatile uint32_t*>(&s_sync[0]) < clen) __nanosleep(64);
+        __threadfence_block();
+    }
+    uint32_t* h = s_hist + seg * HIST_WORDS;
+    for (uint32_t i = lane; i < HIST_WORDS; i += 32) h[i] = 0;
+    __syncwarp();
     uint32_t* mytok = tok + chunk * CHUNK + seg_lo;
     uint32_t nt = 0;
     if (seg_lo < clen) {
@@ -556,8 +573,9 @@ lz77_better_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t* __restr
         }
     }
     __syncwarp();
-    if (lane == 0) ntok[chunk * NSEG + warp] = nt;
-    hist_store(h, hist + (size_t)(chunk * NSEG + warp) * NSYM, lane);
+    if (lane == 0) ntok[chunk * NSEG + seg] = nt;
+    hist_store(h, hist + (size_t)(chunk * NSEG + seg) * NSYM, lane);
+    }
 }
 
 }  // namespace b200
