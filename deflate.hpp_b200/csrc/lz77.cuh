@@ -427,22 +427,25 @@ lz77_better_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t* __restr
     // Four steps are in flight at a time: a warp's atomics on one address execute in program order, so the chains are
     // the same as with one step at a time, but the ~150-cycle round trip of the exchange is paid once per four steps.
     if (warp == 0) {
-        for (uint32_t t0 = 0; t0 < clen; t0 += 128) {
-            uint32_t old[4];
+        constexpr uint32_t INFL = 8;          // steps in flight (the linker is the critical path once the search runs beside it)
+        for (uint32_t t0 = 0; t0 < clen; t0 += 32 * INFL) {
+            uint32_t old[INFL], hsh[INFL];
             #pragma unroll
-            for (uint32_t k = 0; k < 4; k++) {
+            for (uint32_t k = 0; k < INFL; k++) hsh[k] = lzb_hash(ld4_unaligned(s_data, t0 + k * 32 + lane));   // (the pad behind the chunk is readable)
+            #pragma unroll
+            for (uint32_t k = 0; k < INFL; k++) {
                 const uint32_t p = t0 + k * 32 + lane;
                 old[k] = LZB_NIL;
-                if (p + 3 <= clen) old[k] = atomicExch(&s_head[lzb_hash(ld4_unaligned(s_data, p))], p);
+                if (p + 3 <= clen) old[k] = atomicExch(&s_head[hsh[k]], p);
             }
             #pragma unroll
-            for (uint32_t k = 0; k < 4; k++) {
+            for (uint32_t k = 0; k < INFL; k++) {
                 const uint32_t p = t0 + k * 32 + lane;
                 if (p < clen) s_prev[p] = (uint16_t)old[k];
             }
             // publish: the searchers of phase B run right behind (see below)
             __syncwarp();
-            if (lane == 0) { __threadfence_block(); *reinterpret_cast<volatile uint32_t*>(&s_sync[0]) = t0 + 128; }
+            if (lane == 0) { __threadfence_block(); *reinterpret_cast<volatile uint32_t*>(&s_sync[0]) = t0 + 32 * INFL; }
         }
     }
 
@@ -460,7 +463,7 @@ lz77_better_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t* __restr
         if (t0 >= clen) break;
         {
             const uint32_t need = min(t0 + 32u, clen);
-            while (*reinterpret_cast<volatile uint32_t*>(&s_sync[0]) < need) __nanosleep(64);
+            while (*reinterpret_cast<volatile uint32_t*>(&s_sync[0]) < need) __nanosleep(256);
             __threadfence_block();
         }
         const uint32_t p = t0 + lane;
