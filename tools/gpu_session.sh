@@ -61,6 +61,17 @@ for step in "$@"; do
       B200_STAGE=0 timeout 300 python tools/probe_e2e.py >> $out/${tag}_probe_e2e.log 2>&1
       B200_STAGE_THREADS=4 timeout 300 python tools/probe_e2e.py >> $out/${tag}_probe_e2e.log 2>&1
       B200_STAGE_THREADS=16 timeout 300 python tools/probe_e2e.py >> $out/${tag}_probe_e2e.log 2>&1 ;;
+    env_sweep)
+      # ENV_SWEEP="A=1;B=2 C=3;" : one short bench run per ;-separated setting (space-separated assignments, may be empty)
+      IFS=';' read -ra settings <<< "${ENV_SWEEP}"
+      for setting in "${settings[@]}" ""; do
+        echo "### ${setting}" >> $out/${tag}_env_sweep.log
+        env ${setting} timeout 300 python bench.py --steps 5 --warmup 2 --only none --no-e2e --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1])
+print('compress', round(d['value'],2), d['roofline']['kernels_ms_per_step'])
+print('inflate', round(d['decompress']['value'],2), d['decompress']['roofline']['kernels_ms_per_step'])" >> $out/${tag}_env_sweep.log 2>&1
+      done ;;
     probe_small)
       timeout 300 python tools/probe_small.py > $out/${tag}_probe_small.log 2>&1 ;;
     probe_pcie)
