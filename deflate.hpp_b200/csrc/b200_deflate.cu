@@ -1380,7 +1380,11 @@ int b200_crc32_dev(b200_ctx* c, const void* d_data, size_t n, uint32_t* h_out, u
 int b200_publish_dev(b200_ctx* c, void* h_pinned_dst, const void* d_src, size_t n_words, void* stream_) {
     if (!c || !h_pinned_dst || !d_src || n_words == 0 || n_words > 32) return B200_E_ARG;
     ON_DEVICE(c);
-    publish_kernel<<<1, 32, 0, (cudaStream_t)stream_>>>((volatile unsigned long long*)h_pinned_dst, (const unsigned long long*)d_src,
+    // the address the DEVICE uses for this host memory (the same one under unified addressing for cudaHostAlloc memory; registered
+    // memory may differ); pageable memory is refused
+    void* dptr = nullptr;
+    if (cudaHostGetDevicePointer(&dptr, h_pinned_dst, 0) != cudaSuccess || !dptr) { cudaGetLastError(); return B200_E_ARG; }
+    publish_kernel<<<1, 32, 0, (cudaStream_t)stream_>>>((volatile unsigned long long*)dptr, (const unsigned long long*)d_src,
                                                        (uint32_t)n_words, nullptr, 0);
     LAUNCHED();
     CK(cudaGetLastError());

@@ -88,3 +88,6 @@ def test_publish_dev(b200):
         assert torch.equal(dst[:n], src[:n].cpu()) and int(dst[n:].abs().sum()) == 0
     with pytest.raises(b200.B200Error):
         ctx.publish_dev(dst.data_ptr(), src.data_ptr(), 33)
+    pageable = torch.zeros(4, dtype=torch.int64)
+    with pytest.raises(b200.B200Error):                      # not pinned: the device cannot write it
+        ctx.publish_dev(pageable.data_ptr(), src.data_ptr(), 4)
