@@ -330,6 +330,25 @@ def large_bmp_standin():
     return bytes(hdr) + rows.tobytes()
 
 
+def photo_bmp_standin():
+    """BASELINE config 2, second stand-in: a 2 048 x 2 048 x 24 bpp synthetic "photo" (the gradient + noise
+    of the corpus's image kind) behind test.bmp's header; the same generator as tests/test_gpu_configs.py."""
+    import numpy as np
+    src = open(os.path.join(ROOT, "tests", "golden", "test.bmp"), "rb").read()
+    off = struct.unpack_from("<I", src, 10)[0]
+    W = H = 2048
+    x = np.arange(W, dtype=np.uint32)[None, :]
+    y = np.arange(H, dtype=np.uint32)[:, None]
+    v = ((x >> 2) + (y >> 2)) & 255
+    noise = np.random.default_rng(7).integers(0, 3, size=(H, W), dtype=np.uint32)
+    px = np.stack([(v + noise) & 255, (2 * v) & 255, 255 - v], axis=2).astype(np.uint8)
+    hdr = bytearray(src[:off])
+    struct.pack_into("<I", hdr, 2, off + px.size)
+    struct.pack_into("<ii", hdr, 18, W, H)
+    struct.pack_into("<I", hdr, 34, px.size)
+    return bytes(hdr) + px.tobytes()
+
+
 def gpu_numa_bind(local_rank):
     """Prefer host memory on the NUMA node the rank's GPU hangs off (pinned staging then sits next to the GPU's PCIe
     root) and, where the cpuset allows it, run on that node's cores.  Best effort; returns a description."""
@@ -743,6 +762,24 @@ def section_better(B, S):
         except Exception as e:  # noqa: BLE001
             c2["cpu_baseline_error"] = str(e)
     out["config2"] = c2
+    # config 2, second stand-in: the synthetic photo (device timing, ratio against zlib -6 and, at the fast level, the reference)
+    photo = photo_bmp_standin()
+    psrc = torch.from_numpy(np.frombuffer(photo, dtype=np.uint8).copy()).to(dev)
+    c2p = {"workload": f"synthetic photo, 2048 x 2048 x 24 bpp ({len(photo)} bytes; BASELINE configs[1], stand-in B)",
+           "zlib6_ratio": len(zlib.compress(photo, 6)) / len(photo)}
+    for lv in (2, 3):
+        p, _, _, _ = B.codec_point(psrc, len(photo), lv, max(3, steps), 2)
+        c2p[f"level{lv}"] = p
+    if not args.no_cpu_baseline:
+        try:
+            ref = RefLib()
+            a = np.frombuffer(photo, dtype=np.uint8)
+            secs, comp2, _ = ref.compress_mt(a.ctypes.data, a.size, a.size, 2, 1)
+            c2p["level2"]["cpu_baseline"] = {"value": a.size / secs / 1e9, "unit": UNIT, "cores": 1, "kind": "reference",
+                                             "sample": "the whole file, one call of deflate::compress(char*, n, 2)", "ratio": comp2 / a.size}
+        except Exception as e:  # noqa: BLE001
+            c2p["cpu_baseline_error"] = str(e)
+    out["config2_photo"] = c2p
     return out
 
 

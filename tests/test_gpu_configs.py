@@ -1,6 +1,6 @@
 """GPU tests for the remaining BASELINE.json configurations (parity-test cases, not bench lines):
-  config 2  large.bmp at both levels (the file is missing from the reference checkout; the stand-in
-            is test.bmp's pixels upscaled x24)
+  config 2  large.bmp at both levels (the file is missing from the reference checkout; the stand-ins
+            are test.bmp's pixels upscaled x24 and a 2 048 x 2 048 synthetic photo)
   config 4  batch inflate of 100k independent small streams, one warp per stream
 """
 import struct
@@ -35,6 +35,48 @@ def large_bmp_standin():
     struct.pack_into("<ii", hdr, 18, W, H if h > 0 else -H)
     struct.pack_into("<I", hdr, 34, rows.size)
     return bytes(hdr) + rows.tobytes()
+
+
+def photo_bmp_standin():
+    """Second config-2 stand-in: a 2 048 x 2 048 x 24 bpp synthetic "photo" -- the gradient + noise of the
+    corpus's image kind, pixel (x, y): v = ((x >> 2) + (y >> 2)) & 255, bytes (v + noise % 3, 2 v & 255, 255 - v) -- behind
+    test.bmp's 138-byte header with the size fields patched.  Deterministic (numpy PCG64, seed 7)."""
+    src = gold("test.bmp")
+    off = struct.unpack_from("<I", src, 10)[0]
+    W = H = 2048
+    x = np.arange(W, dtype=np.uint32)[None, :]
+    y = np.arange(H, dtype=np.uint32)[:, None]
+    v = ((x >> 2) + (y >> 2)) & 255
+    noise = np.random.default_rng(7).integers(0, 3, size=(H, W), dtype=np.uint32)
+    px = np.stack([(v + noise) & 255, (2 * v) & 255, 255 - v], axis=2).astype(np.uint8)
+    hdr = bytearray(src[:off])
+    struct.pack_into("<I", hdr, 2, off + px.size)
+    struct.pack_into("<ii", hdr, 18, W, H)
+    struct.pack_into("<I", hdr, 34, px.size)
+    return bytes(hdr) + px.tobytes()
+
+
+@pytest.mark.parametrize("level", [2, 3])
+def test_photo_bmp_standin(b200, oracle, ref, level):
+    data = photo_bmp_standin()
+    assert len(data) == 138 + 2048 * 2048 * 3
+    c = b200.compress(data, level)
+    out, unused = zlib_raw_inflate(c)
+    assert out == data and unused == b""
+    assert b200.decompress(c) == data
+    n, r_out = ref.inflate(c, cap=len(data) + 16)          # the reference's inflater reads the stream too
+    assert n == len(data) and r_out == data
+    if level == 2:
+        theirs = len(ref.compress(data, 2))
+        assert len(c) <= 1.03 * theirs, (len(c), theirs)
+    else:
+        picks = [0, 77, 190, 301]                           # reference level 3: ~1 s per 32 KB piece
+        ours = theirs = 0
+        for p in picks:
+            piece = data[p * 32768:(p + 1) * 32768]
+            theirs += len(ref.compress(piece, 3))
+            ours += len(b200.compress(piece, 3))
+        assert ours <= 1.03 * theirs, (ours, theirs)
 
 
 @pytest.mark.parametrize("level", [2, 3])
