@@ -223,3 +223,36 @@ def test_segment_index_fixture(oracle, ref):
         assert c[sep:sep + 4] == b"\x00\x00\xff\xff" and c[sep + 4:sep + 9] == b"\x00\x00\x00\xff\xff"
         pos = sep + 9
     assert (c[pos] & 0x87) != 0x80 or c[pos + 1:pos + 5] != b"\x00\x00\xff\xff"          # the partial chunk has no index
+
+
+def test_segment_index_short_fixture(oracle, ref):
+    """tests/golden/b200_indexed_short.deflate: ONE short chunk (40 000 bytes of text, ten segments), compressed on a B200
+    (tools/make_index_fixture.py).  Its index has its own size -- four groups per segment, word 0 = magic | (10 - 1) << 10
+    (csrc/common.cuh) -- and states the bit lengths an independent decoder sees between 4 KiB output boundaries; the block
+    is final, nothing follows it; zlib, the oracle and the unmodified reference inflater skip the index."""
+    import datagen
+    c = gold("b200_indexed_short.deflate")
+    data = datagen.text_like(40000, seed=61)
+    nseg = (len(data) + 4095) // 4096
+    assert nseg == 10
+    rc, out = oracle.inflate(c)
+    assert rc == 0 and out == data
+    n, r_out = ref.inflate(c)
+    assert n == len(data) and r_out == data
+    o = zlib.decompressobj(-15)
+    assert o.decompress(c) == data and o.eof and o.unused_data == b""
+    words = [0] * nseg
+    for g in range(4 * nseg):
+        b = c[5 * g: 5 * g + 5]
+        assert (b[0] & 0x87) == 0x80 and b[1:] == b"\x00\x00\xff\xff", g
+        words[g >> 2] |= ((b[0] >> 3) & 15) << (4 * (g & 3))
+    assert words[0] == 0x2B5 | ((nseg - 1) << 10)
+    # the 41st group does not exist: the Huffman block starts right behind the index, and it is the final one
+    b = c[20 * nseg: 20 * nseg + 5]
+    assert not ((b[0] & 0x87) == 0x80 and b[1:] == b"\x00\x00\xff\xff")
+    assert c[20 * nseg] & 1 == 1
+    marks, produced, endbit = _dynamic_block_boundaries(c, 20 * nseg * 8)
+    assert produced == len(data) and sorted(marks) == [4096 * s for s in range(nseg)]
+    for s in range(1, nseg):
+        assert words[s] == marks[4096 * s] - marks[4096 * (s - 1)], s
+    assert (endbit + 7) // 8 == len(c)
