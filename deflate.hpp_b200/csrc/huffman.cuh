@@ -362,14 +362,23 @@ __device__ __noinline__ void emit_block(HufScratch* s, const BlockPlan& P, uint3
 // payload bits of segments [seg_lo, seg_hi) under the code lengths currently in the scratch; offsets go to d->seg_bitoff
 __device__ __noinline__ uint32_t segment_offsets(HufScratch* s, const uint16_t* __restrict__ h, uint32_t btype, uint32_t seg_lo, uint32_t seg_hi,
                                     bool have_tokens, uint32_t off, BlockDesc* d, uint32_t lane) {
+    // bits per symbol of this lane's ten symbols: the same for every segment
+    uint32_t cost[NSYM / 32];
+    #pragma unroll
+    for (uint32_t k = 0; k < NSYM / 32; k++) {
+        const uint32_t i = lane + 32 * k;
+        const uint32_t cl = btype == 2 ? s->lens[i] : (i < NLIT ? fixed_lit_len(i) : 5u);
+        const uint32_t ex = i < NLIT ? (i > 256 ? len_extra_bits(i - 257) : 0u) : dist_extra_bits(i - NLIT);
+        cost[k] = cl + ex;
+    }
     for (uint32_t sgm = seg_lo; sgm < seg_hi; sgm++) {
         uint32_t sb = 0;
-        for (uint32_t i = lane; i < NSYM; i += 32) {
-            const uint32_t f = have_tokens ? h[sgm * NSYM + i] : 0u;
-            if (!f) continue;
-            const uint32_t cl = btype == 2 ? s->lens[i] : (i < NLIT ? fixed_lit_len(i) : 5u);
-            const uint32_t ex = i < NLIT ? (i > 256 ? len_extra_bits(i - 257) : 0u) : dist_extra_bits(i - NLIT);
-            sb += f * (cl + ex);
+        if (have_tokens) {
+            uint32_t f[NSYM / 32];            // ten loads in flight instead of a load -> test -> multiply chain per symbol
+            #pragma unroll
+            for (uint32_t k = 0; k < NSYM / 32; k++) f[k] = h[sgm * NSYM + lane + 32 * k];
+            #pragma unroll
+            for (uint32_t k = 0; k < NSYM / 32; k++) sb += f[k] * cost[k];
         }
         sb = warp_sum(sb);
         if (lane == 0) d->seg_bitoff[sgm] = off;
