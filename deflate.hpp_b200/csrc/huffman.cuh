@@ -234,10 +234,17 @@ __device__ __noinline__ BlockPlan plan_block(HufScratch* s, const uint16_t* __re
                                 uint32_t lane) {
     BlockPlan P;
     // ---- reduce the per-segment histograms ------------------------------------------------
-    for (uint32_t i = lane; i < NSYM; i += 32) {
-        uint32_t f = 0;
-        if (have_tokens) for (uint32_t sgm = seg_lo; sgm < seg_hi; sgm++) f += h[sgm * NSYM + i];     // (level 0 runs no tokeniser)
-        s->freq[i] = f + (i == 256 ? 1u : 0u);
+    {
+        uint32_t f[NSYM / 32];                 // this lane's ten symbols; ten loads in flight per segment
+        #pragma unroll
+        for (uint32_t k = 0; k < NSYM / 32; k++) f[k] = 0;
+        if (have_tokens)                       // (level 0 runs no tokeniser)
+            for (uint32_t sgm = seg_lo; sgm < seg_hi; sgm++) {
+                #pragma unroll
+                for (uint32_t k = 0; k < NSYM / 32; k++) f[k] += h[sgm * NSYM + lane + 32 * k];
+            }
+        #pragma unroll
+        for (uint32_t k = 0; k < NSYM / 32; k++) s->freq[lane + 32 * k] = f[k] + (lane + 32 * k == 256 ? 1u : 0u);
     }
     __syncwarp();
     // ---- code lengths ------------------------------------------------------------------------
