@@ -248,3 +248,35 @@ def test_round_plan():
             seen.sort()
             assert seen[0][0] == 0 and seen[-1][1] == world * c
             assert all(a[1] == b[0] for a, b in zip(seen, seen[1:]))
+
+
+def test_round_plan_by_world(monkeypatch):
+    """round_plan(world): the sizes add up, every round keeps the matcher busy (>= 1 024 chunks), rounds shrink, and none
+    shrinks faster than the incast into rank 0 allows -- a round's slices take (world - 1) x 0.07 of the time the round took
+    to compress to arrive, so the next round may not be smaller than that fraction (minus the remainder that moved to avoid
+    a small trailing batch); no round sits just above a multiple of the 16 384-chunk compress batch; the layouts of all
+    ranks tile the corpus.  B200_ROUND_PLAN=fixed gives the 8/16, 5/16, 2/16, 1/16 plan."""
+    sh = _shard_mod()
+    for world in (2, 3, 4, 8):
+        for total_gib in (1, 4, 16):
+            c = total_gib * 16384 // world
+            plan = sh.round_plan(c, world=world)
+            assert sum(plan) == c and all(x > 0 for x in plan) and len(plan) <= 6
+            if len(plan) > 1:
+                assert plan[-1] >= 1024
+                assert all(a >= b for a, b in zip(plan, plan[1:]))
+                rho = max(0.2, 0.07 * (world - 1))
+                for a, b in zip(plan, plan[1:]):
+                    assert b >= rho * a * 0.75 - 1, (world, plan)
+                for x in plan[:-1]:
+                    assert not (x > sh.BATCH_CHUNKS and 0 < x % sh.BATCH_CHUNKS < sh.BATCH_CHUNKS // 4), (world, plan)
+            seen = []
+            for r in range(world):
+                seen += [(f, f + s) for f, s, _ in sh.round_layout(plan, r, world)]
+            seen.sort()
+            assert seen[0][0] == 0 and seen[-1][1] == world * c
+            assert all(a[1] == b[0] for a, b in zip(seen, seen[1:]))
+    assert sh.round_plan(32768, world=8) == [16384, 10041, 4257, 2086]
+    assert sh.round_plan(500, world=8) == [500]
+    monkeypatch.setenv("B200_ROUND_PLAN", "fixed")
+    assert sh.round_plan(32768, world=8) == [16384, 10240, 4096, 2048]
