@@ -11,7 +11,9 @@ import pytest
 from conftest import gold
 import datagen
 
-pytestmark = pytest.mark.gpu
+# watchdog: a decoder that never returns sits in a CUDA call no signal handler can interrupt -- pytest-timeout's thread
+# method dumps the stacks and ends the process instead (the hang round 2's fuzzing found showed up exactly like that)
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600, method="thread")]
 
 GUARD = 64
 
